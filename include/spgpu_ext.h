@@ -1,0 +1,102 @@
+/*
+ * spgpu_ext.h -- ADDITIVE entry points of the B200-native build.
+ *
+ * Nothing here exists in the reference library and nothing here changes a
+ * reference symbol; a consumer that only includes spgpu.h never sees them.
+ * They exist for (1) tuning / introspection used by bench.py and the tests,
+ * (2) Krylov loops that must not block the host: reductions that leave their
+ * result in device memory, and vector updates that take their scalars from
+ * device memory, so a whole CG iteration is stream-ordered and CUDA-graph
+ * capturable, (3) the row-partitioned multi-GPU layer: halo packing / pushing
+ * over NVLink peer pointers and CUDA IPC helpers to obtain those pointers
+ * across the one-process-per-GPU ranks.
+ */
+#ifndef SPGPU_EXT_H_
+#define SPGPU_EXT_H_
+
+#include "spgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- introspection / tuning ---------------------------------------------- */
+
+/* Version string of this build. */
+const char* spgpuB200Version(void);
+
+/* Kernels launched through this handle since spgpuCreate. */
+unsigned long long spgpuGetLaunchCount(spgpuHandle_t handle);
+
+/*
+ * Kernel-selection knobs (per handle).  Keys: hellVariant, hellBlock,
+ * hellLongFactor, hdiaVariant, hdiaBlock, diaBlock, streamLoads,
+ * redBlocksPerSm, vecBlocksPerSm.  Returns 0, or -1 for an unknown key.
+ */
+int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value);
+int spgpuGetTuning(spgpuHandle_t handle, const char* key);
+
+/* ---- non-blocking reductions: result left in DEVICE memory ---------------- */
+
+/*
+ * dRes[0] = sum a_i*b_i (unconjugated, like spgpu?dot), written on the handle's
+ * stream; no host synchronisation.  dRes must not alias a or b.
+ */
+#define SPGPU_DECL_DOT_DEV(S, T, R)                                          \
+	void spgpu##S##dotDev(spgpuHandle_t handle, int n, const __device T* a,  \
+		const __device T* b, __device T* dRes);                              \
+	void spgpu##S##nrm2sqDev(spgpuHandle_t handle, int n,                    \
+		const __device T* x, __device R* dRes);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_DOT_DEV)
+
+/*
+ * z = (*dBetaNum / *dBetaDen) * betaSign * y + (*dAlphaNum / *dAlphaDen) *
+ * alphaSign * x with the four scalars read from DEVICE memory at kernel time
+ * (pass NULL for a numerator/denominator pair to mean 1).  This is the shape of
+ * every CG update: x += (rr/pAp) p ; r -= (rr/pAp) Ap ; p = r + (rr'/rr) p.
+ */
+void spgpuDaxpbyDev(spgpuHandle_t handle, __device double* z, int n,
+	const __device double* dBetaNum, const __device double* dBetaDen,
+	double betaSign, const __device double* y,
+	const __device double* dAlphaNum, const __device double* dAlphaDen,
+	double alphaSign, const __device double* x);
+
+/* ---- fused Krylov kernels --------------------- */
+
+/*
+ * HELL SpMV z = A*x fused with dRes[0] = sum_i x[xOffset+i]*z[i] (the p.Ap of CG)
+ * in the SpMV epilogue.  xOffset = position of row 0's own entry inside x
+ * (0 on one GPU, the lower halo width on a partition).  dRes is zeroed by the call.
+ */
+void spgpuDhellspmvDot(spgpuHandle_t handle, __device double* z,
+	const __device double* cM, const __device int* rP, int hackSize,
+	const __device int* hackOffsets, const __device int* rS, int rows,
+	const __device double* x, int baseIndex, int xOffset,
+	__device double* dRes);
+
+/* ---- multi-GPU helpers ---------------------------------------------------- */
+
+/* 64-byte CUDA IPC handle of a cudaMalloc'ed pointer / open it in a peer process. */
+int spgpuIpcGetHandle(void* devPtr, void* handle64);
+int spgpuIpcOpenHandle(const void* handle64, void** devPtr);
+int spgpuIpcCloseHandle(void* devPtr);
+/* raw cudaMalloc / cudaFree (IPC needs allocations that are not sub-allocated) */
+int spgpuDeviceAlloc(void** devPtr, size_t bytes);
+int spgpuDeviceFree(void* devPtr);
+
+/*
+ * Halo push over NVLink: copy n elements src[0..n) of this GPU into a PEER
+ * pointer (obtained through spgpuIpcOpenHandle) with 128-bit stores, then
+ * release-store `flagValue` to the peer's flag word so the consumer can wait on
+ * it (spgpuWaitFlag).  One kernel, on the handle's stream.
+ */
+void spgpuDhaloPush(spgpuHandle_t handle, double* peerDst, const double* src,
+	int n, unsigned* peerFlag, unsigned flagValue);
+/* Stream-ordered wait until *flag >= value (bounded spin; traps on timeout). */
+void spgpuWaitFlag(spgpuHandle_t handle, const unsigned* flag, unsigned value);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SPGPU_EXT_H_ */

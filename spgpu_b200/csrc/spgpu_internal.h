@@ -1,0 +1,61 @@
+/*
+ * Private side of a spGPU handle (shared by the C host layer and the .cu files).
+ *
+ * The reference handle is a plain public struct (reference core.h:60-82) and its
+ * reductions keep their partial sums in file-static __device__ arrays (e.g.
+ * reference kernels/ddot.cu:35), so two handles on one device race.  Here each
+ * handle owns its scratch; the public struct is the first member, so a
+ * spgpuHandle_t can be cast to SpgpuHandlePriv* inside the library.
+ */
+#ifndef SPGPU_INTERNAL_H_
+#define SPGPU_INTERNAL_H_
+
+#include "spgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPGPU_PRIV_MAGIC 0x53504755u /* "SPGU" */
+
+/* Partial results of one reduction launch: up to SPGPU_RED_MAX_BLOCKS blocks,
+ * each writing up to 2 doubles (complex), plus a ticket counter. */
+#define SPGPU_RED_MAX_BLOCKS 2048
+#define SPGPU_RED_SLOT_BYTES 16
+
+/* Tunables that steer kernel selection; settable with spgpuSetTuning (ext). */
+typedef struct SpgpuTuning {
+	int hellVariant;     /* 0 auto, 1 row-per-lane, 2 two-rows-per-lane (128-bit), 3 bulk-async slabs */
+	int hellBlock;       /* threads per CTA for HELL/ELL kernels                */
+	int hellLongFactor;  /* a row is "long" when rS > factor*avgNnzPerRow (min 32) */
+	int hdiaVariant;     /* 0 auto, 1 direct, 2 bulk-async slabs                */
+	int hdiaBlock;
+	int diaBlock;
+	int streamLoads;     /* 1: matrix streams use evict-first loads            */
+	int redBlocksPerSm;  /* CTAs per SM for the reductions                      */
+	int vecBlocksPerSm;  /* CTAs per SM for grid-stride vector kernels          */
+} SpgpuTuning;
+
+typedef struct SpgpuHandlePriv {
+	SpgpuHandleStruct pub;         /* MUST stay first                            */
+	unsigned magic;
+	void* dPartials;               /* device: SPGPU_RED_MAX_BLOCKS slots          */
+	unsigned* dTicket;             /* device: last-block-done counter (kept 0)    */
+	void* hResult;                 /* pinned, mapped host: final reduction value  */
+	void* dResult;                 /* device alias of hResult                     */
+	int l2Bytes;
+	int smemPerBlockOptin;
+	unsigned long long launches;   /* kernels launched through this handle        */
+	SpgpuTuning tune;
+} SpgpuHandlePriv;
+
+static inline SpgpuHandlePriv* spgpuPriv(spgpuHandle_t h)
+{
+	return (SpgpuHandlePriv*)h;
+}
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
