@@ -1,0 +1,286 @@
+/*
+ * Reductions for sm_100a: dot, nrm2, amax, asum (+ multi-vector forms and the
+ * additive device-result variants of include/spgpu_ext.h).
+ *
+ * Replaces reference kernels/{s,d,c,z}dot.cu, {s,d,c,z}nrm2.cu, amax_base.cuh,
+ * asum_base.cuh.  Results: dot is NOT conjugated for C/Z (reference zdot.cu:54);
+ * nrm2 = sqrt(sum |x|^2) unscaled (dnrm2.cu:52-53,146); amax / asum are the
+ * documented full reductions (the reference's last warp steps discard lanes
+ * 2..31 and truncate doubles to float, SURVEY 2.3 -- not reproduced).
+ *
+ * One pass, one kernel: 128-bit loads in a grid-stride loop over
+ * (#SM x redBlocksPerSm) CTAs, warp-shuffle + shared-memory block reduction,
+ * one partial per CTA into the HANDLE's scratch (the reference uses a
+ * file-static __device__ array shared by every handle), and the last CTA to
+ * finish (ticket counter) folds the partials in a fixed order -- so the result
+ * is deterministic for a given n -- and stores the final value straight into
+ * mapped pinned host memory.  The blocking entry points then only need a
+ * stream synchronise; no cudaMemcpyFromSymbol on the legacy stream.
+ * Partials are combined in double for every type.
+ */
+#include <cstring>
+#include "launch.cuh"
+#include "numeric.cuh"
+
+#define RED_BLOCK 256
+
+template <typename T> struct alignas(16) RPack {
+	static constexpr int N = 16 / (int)sizeof(T);
+	T v[N];
+};
+
+/* accumulator: up to two doubles (re, im) or (value, unused) */
+struct alignas(16) Acc2 { double a, b; };
+
+/* ---- per-operation policy -------------------------------------------------- */
+/* Each op accumulates in the element's real precision per thread (short chains:
+ * n / (grid*block) terms) and hands over doubles for the cross-thread part.   */
+
+template <typename T> struct OpDot {
+	static constexpr int NIN = 2;
+	static constexpr bool IS_MAX = false;
+	T s;
+	__device__ __forceinline__ void init() { s = Num<T>::zero(); }
+	__device__ __forceinline__ void take(T x, T y) { s = Num<T>::fma(x, y, s); }
+	__device__ __forceinline__ Acc2 result() const;
+};
+template <> __device__ __forceinline__ Acc2 OpDot<float>::result() const { return { (double)s, 0.0 }; }
+template <> __device__ __forceinline__ Acc2 OpDot<double>::result() const { return { s, 0.0 }; }
+template <> __device__ __forceinline__ Acc2 OpDot<cuFloatComplex>::result() const { return { (double)s.x, (double)s.y }; }
+template <> __device__ __forceinline__ Acc2 OpDot<cuDoubleComplex>::result() const { return { s.x, s.y }; }
+
+template <typename T> struct OpSqSum {
+	static constexpr int NIN = 1;
+	static constexpr bool IS_MAX = false;
+	typename Num<T>::real s;
+	__device__ __forceinline__ void init() { s = 0; }
+	__device__ __forceinline__ void take(T x, T) { s += Num<T>::sqabs(x); }
+	__device__ __forceinline__ Acc2 result() const { return { (double)s, 0.0 }; }
+};
+
+template <typename T> struct OpAbsSum {
+	static constexpr int NIN = 1;
+	static constexpr bool IS_MAX = false;
+	typename Num<T>::real s;
+	__device__ __forceinline__ void init() { s = 0; }
+	__device__ __forceinline__ void take(T x, T) { s += Num<T>::abs(x); }
+	__device__ __forceinline__ Acc2 result() const { return { (double)s, 0.0 }; }
+};
+
+template <typename T> struct OpAbsMax {
+	static constexpr int NIN = 1;
+	static constexpr bool IS_MAX = true;
+	typename Num<T>::real s;
+	__device__ __forceinline__ void init() { s = 0; }
+	__device__ __forceinline__ void take(T x, T) { s = fmax(s, Num<T>::abs(x)); }
+	__device__ __forceinline__ Acc2 result() const { return { (double)s, 0.0 }; }
+};
+
+template <bool IS_MAX>
+__device__ __forceinline__ Acc2 combine(Acc2 p, Acc2 q)
+{
+	if (IS_MAX)
+		return { fmax(p.a, q.a), 0.0 };
+	return { p.a + q.a, p.b + q.b };
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ Acc2 block_reduce(Acc2 v, Acc2* smem)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1) {
+		Acc2 o = { __shfl_xor_sync(SPGPU_FULL_MASK, v.a, m), __shfl_xor_sync(SPGPU_FULL_MASK, v.b, m) };
+		v = combine<IS_MAX>(v, o);
+	}
+	if (lane == 0)
+		smem[warp] = v;
+	__syncthreads();
+	if (warp == 0) {
+		const int nwarps = blockDim.x >> 5;
+		v = lane < nwarps ? smem[lane] : Acc2{ 0.0, 0.0 };
+#pragma unroll
+		for (int m = 16; m > 0; m >>= 1) {
+			Acc2 o = { __shfl_xor_sync(SPGPU_FULL_MASK, v.a, m), __shfl_xor_sync(SPGPU_FULL_MASK, v.b, m) };
+			v = combine<IS_MAX>(v, o);
+		}
+	}
+	__syncthreads();
+	return v;          /* valid in warp 0 */
+}
+
+/*
+ * finish: 0 sum as is, 1 sqrt of the sum (nrm2).  outKind: how the final value
+ * is stored: 0 = as T (dot), 1 = as real of T.
+ */
+template <typename T, typename Op>
+__global__ void __launch_bounds__(RED_BLOCK)
+reduce_kernel(const T* x, const T* y, long long n, int vec, Acc2* partials,
+	unsigned* ticket, void* out, int finish, int outKind)
+{
+	__shared__ Acc2 smem[32];
+	__shared__ bool amLast;
+	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long nthreads = (long long)gridDim.x * blockDim.x;
+	constexpr int N = RPack<T>::N;
+
+	Op acc0, acc1;
+	acc0.init();
+	acc1.init();
+
+	if (vec) {
+		const long long npacks = n / N;
+		const RPack<T>* px = reinterpret_cast<const RPack<T>*>(x);
+		const RPack<T>* py = reinterpret_cast<const RPack<T>*>(y);
+		for (long long p = tid; p < npacks; p += 2 * nthreads) {
+			const long long q = p + nthreads;
+			const bool two = q < npacks;
+			RPack<T> a0 = px[p], b0, a1, b1;
+			if (Op::NIN > 1) b0 = py[p];
+			if (two) {
+				a1 = px[q];
+				if (Op::NIN > 1) b1 = py[q];
+			}
+#pragma unroll
+			for (int e = 0; e < N; ++e)
+				acc0.take(a0.v[e], b0.v[e]);
+			if (two) {
+#pragma unroll
+				for (int e = 0; e < N; ++e)
+					acc1.take(a1.v[e], b1.v[e]);
+			}
+		}
+		const long long done = npacks * N;
+		if (tid < n - done)
+			acc0.take(x[done + tid], Op::NIN > 1 ? y[done + tid] : Num<T>::zero());
+	} else {
+		for (long long e = tid; e < n; e += nthreads)
+			acc0.take(x[e], Op::NIN > 1 ? y[e] : Num<T>::zero());
+	}
+
+	Acc2 v = combine<Op::IS_MAX>(acc0.result(), acc1.result());
+	v = block_reduce<Op::IS_MAX>(v, smem);
+
+	if (threadIdx.x == 0) {
+		partials[blockIdx.x] = v;
+		__threadfence();
+		const unsigned t = atomicAdd(ticket, 1u);
+		amLast = (t == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!amLast)
+		return;
+
+	/* last CTA: fold the partials in index order (deterministic) */
+	__threadfence();
+	Acc2 total = { 0.0, 0.0 };
+	for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+		const double2 pv = __ldcg(reinterpret_cast<const double2*>(partials) + b);
+		total = combine<Op::IS_MAX>(total, Acc2{ pv.x, pv.y });
+	}
+	total = block_reduce<Op::IS_MAX>(total, smem);
+	if (threadIdx.x == 0) {
+		double a = total.a, b = total.b;
+		if (finish == 1)
+			a = sqrt(a);
+		typedef typename Num<T>::real R;
+		if (outKind == 1 || !Num<T>::is_complex) {
+			*reinterpret_cast<R*>(out) = (R)a;
+		} else {
+			reinterpret_cast<R*>(out)[0] = (R)a;
+			reinterpret_cast<R*>(out)[1] = (R)b;
+		}
+		*ticket = 0u;              /* ready for the next launch on this handle */
+		__threadfence_system();
+	}
+}
+
+static inline int r_aligned16(const void* p) { return ((size_t)p & 15) == 0; }
+
+template <typename T, typename Op>
+static void reduce_launch(spgpuHandle_t handle, const T* x, const T* y, long long n,
+	void* out, int finish, int outKind)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const int vec = r_aligned16(x) && (Op::NIN < 2 || r_aligned16(y));
+	const long long items = vec ? (n / RPack<T>::N + 1) / 2 + 1 : n;
+	long long want = (items + RED_BLOCK - 1) / RED_BLOCK;
+	long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 4);
+	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
+	if (cap < 1) cap = 1;
+	if (want > cap) want = cap;
+	if (want < 1) want = 1;
+	reduce_kernel<T, Op><<<(unsigned)want, RED_BLOCK, 0, handle->currentStream>>>(
+		x, y, n, vec, reinterpret_cast<Acc2*>(h->dPartials), h->dTicket, out, finish, outKind);
+	spgpu_count_launch(handle);
+}
+
+/* blocking form: result through the handle's mapped pinned slot */
+template <typename T, typename Op, typename Ret>
+static Ret reduce_blocking(spgpuHandle_t handle, const T* x, const T* y, int n, int finish, int outKind)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	Ret zero;
+	memset(&zero, 0, sizeof(zero));
+	if (n <= 0 || h->magic != SPGPU_PRIV_MAGIC || !h->dResult)
+		return zero;
+	reduce_launch<T, Op>(handle, x, y, n, h->dResult, finish, outKind);
+	cudaStreamSynchronize(handle->currentStream);
+	Ret r;
+	memcpy(&r, h->hResult, sizeof(r));
+	return r;
+}
+
+/* ---- C entry points -------------------------------------------------------- */
+
+#define SPGPU_DEFINE_REDUCE(S, T, R)                                           \
+	extern "C" T spgpu##S##dot(spgpuHandle_t h, int n, T* a, T* b)              \
+	{ return reduce_blocking<T, OpDot<T>, T>(h, a, b, n, 0, 0); }               \
+	extern "C" void spgpu##S##mdot(spgpuHandle_t h, T* y, int n, T* a, T* b,    \
+		int count, int pitch)                                                   \
+	{                                                                           \
+		for (int v = 0; v < count; ++v)                                         \
+			y[v] = spgpu##S##dot(h, n, a + (long long)v * pitch, b + (long long)v * pitch); \
+	}                                                                           \
+	extern "C" R spgpu##S##nrm2(spgpuHandle_t h, int n, T* x)                   \
+	{ return reduce_blocking<T, OpSqSum<T>, R>(h, x, (const T*)0, n, 1, 1); }   \
+	extern "C" void spgpu##S##mnrm2(spgpuHandle_t h, R* y, int n, T* x,         \
+		int count, int pitch)                                                   \
+	{                                                                           \
+		for (int v = 0; v < count; ++v)                                         \
+			y[v] = spgpu##S##nrm2(h, n, x + (long long)v * pitch);              \
+	}                                                                           \
+	extern "C" R spgpu##S##asum(spgpuHandle_t h, int n, T* x)                   \
+	{ return reduce_blocking<T, OpAbsSum<T>, R>(h, x, (const T*)0, n, 0, 1); }  \
+	extern "C" R spgpu##S##amax(spgpuHandle_t h, int n, T* x)                   \
+	{ return reduce_blocking<T, OpAbsMax<T>, R>(h, x, (const T*)0, n, 0, 1); }  \
+	extern "C" void spgpu##S##masum(spgpuHandle_t h, R* y, int n, T* x,         \
+		int count, int pitch)                                                   \
+	{                                                                           \
+		for (int v = 0; v < count; ++v)                                         \
+			y[v] = spgpu##S##asum(h, n, x + (long long)v * pitch);              \
+	}                                                                           \
+	extern "C" void spgpu##S##mamax(spgpuHandle_t h, R* y, int n, T* x,         \
+		int count, int pitch)                                                   \
+	{                                                                           \
+		for (int v = 0; v < count; ++v)                                         \
+			y[v] = spgpu##S##amax(h, n, x + (long long)v * pitch);              \
+	}                                                                           \
+	extern "C" void spgpu##S##dotDev(spgpuHandle_t h, int n, const T* a,        \
+		const T* b, T* dRes)                                                    \
+	{                                                                           \
+		if (n > 0) reduce_launch<T, OpDot<T> >(h, a, b, n, dRes, 0, 0);         \
+		else cudaMemsetAsync(dRes, 0, sizeof(T), h->currentStream);             \
+	}                                                                           \
+	extern "C" void spgpu##S##nrm2sqDev(spgpuHandle_t h, int n, const T* x,     \
+		R* dRes)                                                                \
+	{                                                                           \
+		if (n > 0) reduce_launch<T, OpSqSum<T> >(h, x, (const T*)0, n, dRes, 0, 1); \
+		else cudaMemsetAsync(dRes, 0, sizeof(R), h->currentStream);             \
+	}
+
+SPGPU_DEFINE_REDUCE(S, float, float)
+SPGPU_DEFINE_REDUCE(D, double, double)
+SPGPU_DEFINE_REDUCE(C, cuFloatComplex, float)
+SPGPU_DEFINE_REDUCE(Z, cuDoubleComplex, double)

@@ -1,0 +1,230 @@
+/*
+ * Additive entry points (include/spgpu_ext.h): Krylov helpers that keep their
+ * scalars on the device, the fused HELL SpMV + dot, and the NVLink halo push
+ * used by the row-partitioned multi-GPU layer.  No reference counterpart.
+ */
+#include <cstdio>
+#include <cstring>
+#include "launch.cuh"
+#include "spmv_slots.cuh"
+
+/* ---- z = b*y + a*x with a, b formed from device-resident scalars ----------- */
+
+__global__ void __launch_bounds__(256)
+daxpby_dev_kernel(double* z, long long n, const double* bNum, const double* bDen,
+	double bSign, const double* y, const double* aNum, const double* aDen,
+	double aSign, const double* x, int vec)
+{
+	double a = aSign, b = bSign;
+	if (aNum) a *= __ldg(aNum);
+	if (aDen) a /= __ldg(aDen);
+	if (bNum) b *= __ldg(bNum);
+	if (bDen) b /= __ldg(bDen);
+	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long nthreads = (long long)gridDim.x * blockDim.x;
+	if (vec) {
+		const long long np = n >> 1;
+		double2* zo = reinterpret_cast<double2*>(z);
+		const double2* y2 = reinterpret_cast<const double2*>(y);
+		const double2* x2 = reinterpret_cast<const double2*>(x);
+		for (long long p = tid; p < np; p += 2 * nthreads) {
+			const long long q = p + nthreads;
+			const bool two = q < np;
+			double2 y0 = y2[p], x0 = x2[p], y1 = y0, x1 = x0;
+			if (two) { y1 = y2[q]; x1 = x2[q]; }
+			zo[p] = make_double2(fma(b, y0.x, a * x0.x), fma(b, y0.y, a * x0.y));
+			if (two) zo[q] = make_double2(fma(b, y1.x, a * x1.x), fma(b, y1.y, a * x1.y));
+		}
+		if (tid == 0 && (n & 1))
+			z[n - 1] = fma(b, y[n - 1], a * x[n - 1]);
+	} else {
+		for (long long e = tid; e < n; e += nthreads)
+			z[e] = fma(b, y[e], a * x[e]);
+	}
+}
+
+extern "C" void spgpuDaxpbyDev(spgpuHandle_t handle, double* z, int n,
+	const double* dBetaNum, const double* dBetaDen, double betaSign,
+	const double* y, const double* dAlphaNum, const double* dAlphaDen,
+	double alphaSign, const double* x)
+{
+	if (n <= 0)
+		return;
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const int vec = (((size_t)z | (size_t)y | (size_t)x) & 15) == 0;
+	long long want = ((vec ? n / 4 : n) + 255) / 256 + 1;
+	const long long cap = (long long)handle->multiProcessorCount * (t->vecBlocksPerSm > 0 ? t->vecBlocksPerSm : 8);
+	if (cap > 0 && want > cap) want = cap;
+	daxpby_dev_kernel<<<(unsigned)want, 256, 0, handle->currentStream>>>(z, n, dBetaNum, dBetaDen,
+		betaSign, y, dAlphaNum, dAlphaDen, alphaSign, x, vec);
+	spgpu_count_launch(handle);
+}
+
+/* ---- HELL SpMV fused with p.Ap ---------------------------------------------- */
+
+template <int UNROLL>
+__global__ void __launch_bounds__(1024)
+dhell_spmv_dot_kernel(double* __restrict__ z, const double* __restrict__ cM,
+	const int* __restrict__ rP, int hackSize, const int* __restrict__ hackOffsets,
+	const int* __restrict__ rS, int rows, const double* __restrict__ x,
+	int baseIndex, int xOffset, int longCut, double* dRes)
+{
+	__shared__ double warpSums[32];
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const long long warpRow = i - lane;
+	double contrib = 0.0;
+	if (warpRow < rows) {
+		const bool live = i < rows;
+		const int hack = (int)(warpRow / hackSize);
+		const long long at = (long long)__ldg(hackOffsets + hack) + (warpRow % hackSize) + lane;
+		const int len = live ? ld_stream(rS + i) : 0;
+		double acc = warp_rows_dot<double, UNROLL>(cM + at, rP + at, hackSize, hackSize, len, longCut, x, baseIndex);
+		if (live) {
+			z[i] = acc;
+			contrib = acc * __ldg(x + xOffset + i);
+		}
+	}
+	contrib = warp_sum<double>(contrib);
+	if (lane == 0)
+		warpSums[warp] = contrib;
+	__syncthreads();
+	if (warp == 0) {
+		const int nwarps = blockDim.x >> 5;
+		double v = lane < nwarps ? warpSums[lane] : 0.0;
+		v = warp_sum<double>(v);
+		if (lane == 0)
+			atomicAdd(dRes, v);
+	}
+}
+
+extern "C" void spgpuDhellspmvDot(spgpuHandle_t handle, double* z, const double* cM,
+	const int* rP, int hackSize, const int* hackOffsets, const int* rS, int rows,
+	const double* x, int baseIndex, int xOffset, double* dRes)
+{
+	cudaMemsetAsync(dRes, 0, sizeof(double), handle->currentStream);
+	if (rows <= 0)
+		return;
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const int block = spgpu_block(t->hellBlock);
+	dhell_spmv_dot_kernel<8><<<spgpu_ceil_div(rows, block), block, 0, handle->currentStream>>>(
+		z, cM, rP, hackSize, hackOffsets, rS, rows, x, baseIndex, xOffset,
+		spgpu_long_cut(t, 8), dRes);
+	spgpu_count_launch(handle);
+}
+
+/* ---- CUDA IPC + raw allocation ---------------------------------------------- */
+
+extern "C" int spgpuIpcGetHandle(void* devPtr, void* handle64)
+{
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, devPtr);
+	if (e != cudaSuccess)
+		return (int)e;
+	memcpy(handle64, &h, sizeof(h));
+	return 0;
+}
+
+extern "C" int spgpuIpcOpenHandle(const void* handle64, void** devPtr)
+{
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	return (int)cudaIpcOpenMemHandle(devPtr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+extern "C" int spgpuIpcCloseHandle(void* devPtr)
+{
+	return (int)cudaIpcCloseMemHandle(devPtr);
+}
+
+extern "C" int spgpuDeviceAlloc(void** devPtr, size_t bytes)
+{
+	return (int)cudaMalloc(devPtr, bytes);
+}
+
+extern "C" int spgpuDeviceFree(void* devPtr)
+{
+	return (int)cudaFree(devPtr);
+}
+
+/* ---- halo push over NVLink --------------------------------------------------- */
+
+/*
+ * Copies src[0..n) into a peer GPU's memory with 128-bit stores; the last CTA
+ * to finish (ticket in local memory) makes the data visible system-wide and
+ * release-stores flagValue into the peer's flag word.
+ */
+__global__ void __launch_bounds__(256)
+halo_push_kernel(double* peerDst, const double* __restrict__ src, long long n, int vec,
+	unsigned* peerFlag, unsigned flagValue, unsigned* ticket)
+{
+	__shared__ bool amLast;
+	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long nthreads = (long long)gridDim.x * blockDim.x;
+	if (vec) {
+		const long long np = n >> 1;
+		double2* d2 = reinterpret_cast<double2*>(peerDst);
+		const double2* s2 = reinterpret_cast<const double2*>(src);
+		for (long long p = tid; p < np; p += nthreads)
+			d2[p] = s2[p];
+		if (tid == 0 && (n & 1))
+			peerDst[n - 1] = src[n - 1];
+	} else {
+		for (long long e = tid; e < n; e += nthreads)
+			peerDst[e] = src[e];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned t = atomicAdd(ticket, 1u);
+		amLast = (t == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (amLast && threadIdx.x == 0) {
+		*ticket = 0u;
+		if (peerFlag) {
+			__threadfence_system();
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(peerFlag), "r"(flagValue) : "memory");
+		}
+	}
+}
+
+extern "C" void spgpuDhaloPush(spgpuHandle_t handle, double* peerDst, const double* src,
+	int n, unsigned* peerFlag, unsigned flagValue)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	const int vec = (((size_t)peerDst | (size_t)src) & 15) == 0;
+	long long want = ((vec ? n / 2 : n) + 255) / 256;
+	if (want > 2 * handle->multiProcessorCount) want = 2 * handle->multiProcessorCount;
+	if (want < 1) want = 1;
+	/* the ticket word next to the reductions' one (offset 16 bytes) */
+	halo_push_kernel<<<(unsigned)want, 256, 0, handle->currentStream>>>(peerDst, src, n > 0 ? n : 0,
+		vec, peerFlag, flagValue, h->dTicket + 4);
+	spgpu_count_launch(handle);
+}
+
+/* Bounded spin on a flag in LOCAL device memory written by a peer GPU. */
+__global__ void wait_flag_kernel(const unsigned* flag, unsigned value, unsigned long long timeoutNs)
+{
+	unsigned long long t0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	for (;;) {
+		unsigned v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+		if ((int)(v - value) >= 0)
+			return;
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (t1 - t0 > timeoutNs) {
+			printf("spgpuWaitFlag: timed out waiting for %u (saw %u)\n", value, v);
+			return;
+		}
+		__nanosleep(200);
+	}
+}
+
+extern "C" void spgpuWaitFlag(spgpuHandle_t handle, const unsigned* flag, unsigned value)
+{
+	wait_flag_kernel<<<1, 1, 0, handle->currentStream>>>(flag, value, 2000000000ull);
+	spgpu_count_launch(handle);
+}

@@ -1,0 +1,74 @@
+/*
+ * ELL SpMV for sm_100a:  z = alpha*A*x + beta*y, A in pitched column-major
+ * ELLPACK.
+ *
+ * Replaces reference kernels/ell_spmv_base.cuh:99-146 (host entry),
+ * ell_spmv_base_template.cuh:178-425 (rS given) and ell_spmv_base_nors.cuh
+ * (rS == NULL: every row uses maxNnzPerRow slots, padding = value 0 with a
+ * valid index).  cMPitch / rPPitch are in elements and may differ.
+ *
+ * Same warp-per-32-rows walk as HELL (spmv_slots.cuh) with base = row and
+ * stride = pitch; the product k*pitch is formed in 64 bits (134 M rows x 7
+ * slots already passes 2^31).
+ */
+#include "launch.cuh"
+#include "spmv_slots.cuh"
+
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(1024)
+ell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
+	const T* __restrict__ cM, const int* __restrict__ rP, int cMPitch,
+	int rPPitch, const int* __restrict__ rS, const int* __restrict__ rIdx,
+	int maxNnzPerRow, int rows, const T* __restrict__ x, T beta, int baseIndex,
+	int longCut)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	if (i - lane >= rows)
+		return;
+	const bool live = i < rows;
+
+	const int len = live ? (rS ? ld_stream(rS + i) : maxNnzPerRow) : 0;
+	const bool useBeta = Num<T>::nonzero(beta);
+	const long long out = (live && rIdx) ? (long long)__ldg(rIdx + i) : i;
+	T yv = Num<T>::zero();
+	if (useBeta && live)
+		yv = y[out];
+
+	T acc = warp_rows_dot<T, UNROLL>(cM + i, rP + i, cMPitch, rPPitch, len, longCut, x, baseIndex);
+
+	if (live)
+		z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
+}
+
+template <typename T, int UNROLL>
+static void ell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
+	const T* cM, const int* rP, int cMPitch, int rPPitch, const int* rS,
+	const int* rIdx, int avgNnzPerRow, int maxNnzPerRow, int rows, const T* x,
+	T beta, int baseIndex)
+{
+	if (rows <= 0)
+		return;
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const int block = spgpu_block(t->hellBlock);
+	const unsigned grid = spgpu_ceil_div(rows, block);
+	ell_spmv_kernel<T, UNROLL><<<grid, block, 0, handle->currentStream>>>(
+		z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow, rows, x,
+		beta, baseIndex, spgpu_long_cut(t, avgNnzPerRow));
+	spgpu_count_launch(handle);
+}
+
+#define SPGPU_DEFINE_ELLSPMV(S, T, U)                                         \
+	extern "C" void spgpu##S##ellspmv(spgpuHandle_t handle, T* z, const T* y,  \
+		T alpha, const T* cM, const int* rP, int cMPitch, int rPPitch,         \
+		const int* rS, const int* rIdx, int avgNnzPerRow, int maxNnzPerRow,    \
+		int rows, const T* x, T beta, int baseIndex)                           \
+	{                                                                          \
+		ell_spmv_launch<T, U>(handle, z, y, alpha, cM, rP, cMPitch, rPPitch,   \
+			rS, rIdx, avgNnzPerRow, maxNnzPerRow, rows, x, beta, baseIndex);   \
+	}
+
+SPGPU_DEFINE_ELLSPMV(S, float, 8)
+SPGPU_DEFINE_ELLSPMV(D, double, 8)
+SPGPU_DEFINE_ELLSPMV(C, cuFloatComplex, 8)
+SPGPU_DEFINE_ELLSPMV(Z, cuDoubleComplex, 4)

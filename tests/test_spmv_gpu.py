@@ -1,0 +1,189 @@
+"""GPU parity: every spgpu?{ell,hell,dia,hdia}spmv entry point of OUR library,
+called through the C ABI on device buffers, against the CPU oracle on the same
+seeded inputs.  Tolerance (north_star): per row 1e-5 (S/C) / 1e-12 (D/Z) of
+|alpha| sum|a||x| + |beta||y|."""
+import numpy as np
+import pytest
+
+from spgpu_b200 import formats as F, generators as G
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DTYPES = [np.float32, np.float64, np.complex64, np.complex128]
+
+
+def scalars(dtype, beta_zero=False):
+    if np.dtype(dtype).kind == "c":
+        return (0.7 - 0.3j), (0.0 if beta_zero else (-0.5 + 0.25j))
+    return 2.0, (0.0 if beta_zero else -3.0)
+
+
+def build(fmt, coo, base, hack):
+    ell = F.coo_to_ell(coo, base)
+    if fmt == "ell":
+        return ell
+    if fmt == "hell":
+        return F.ell_to_hell(ell, hack)
+    if fmt == "dia":
+        return F.coo_to_dia(coo)
+    return F.coo_to_hdia(coo, hack)
+
+
+def check(ours, h, fmt, coo, A, x, y, alpha, beta, **kw):
+    s = util.sym_of(A.values.dtype)
+    dA = util.upload(A)
+    got = util.dev_spmv(ours, h, fmt, A, dA, x, y, alpha, beta, **kw)
+    okw = {k: v for k, v in kw.items() if k in ("base", "ridx", "rs_null")}
+    want = util.oracle_spmv(fmt, A, x, y if (beta != 0) else None, alpha, beta, **okw)
+    util.assert_rows_close(got, want, util.row_scale(coo, x, y, alpha, beta), s, f"{fmt}/{s}/{kw}")
+    return got
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("fmt", ["ell", "hell", "dia", "hdia"])
+@pytest.mark.parametrize("base", [0, 1])
+def test_random_ragged(ours, gpu_handle, dtype, fmt, base):
+    """ragged rows incl. empty ones, rows not a multiple of 32/hack, rect matrix"""
+    for nrows, ncols, hack in [(1, 7, 32), (31, 64, 32), (97, 83, 32), (1000, 1111, 64), (4099, 4099, 32)]:
+        coo = G.random_coo(nrows, ncols, (0, 13), nrows, dtype, base)
+        A = build(fmt, coo, base, hack)
+        x = G.random_vector(ncols, dtype, 1, -1, 1)
+        y = G.random_vector(nrows, dtype, 2, -1, 1)
+        alpha, beta = scalars(dtype)
+        check(ours, gpu_handle, fmt, coo, A, x, y, alpha, beta)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("fmt", ["ell", "hell", "dia", "hdia"])
+def test_beta_zero_never_reads_y(ours, gpu_handle, dtype, fmt):
+    coo = G.random_coo(515, 515, (0, 9), 9, dtype, 0)
+    A = build(fmt, coo, 0, 32)
+    x = G.random_vector(515, dtype, 1, -1, 1)
+    y = np.full(515, np.nan, dtype=dtype)
+    alpha, _ = scalars(dtype)
+    got = check(ours, gpu_handle, fmt, coo, A, x, y, alpha, 0.0)
+    assert np.isfinite(got.view(util.real_of(dtype))).all()
+    # and with y == NULL
+    s = util.sym_of(dtype)
+    dA = util.upload(A)
+    got2 = util.dev_spmv(ours, gpu_handle, fmt, A, dA, x, None, alpha, 0.0)
+    np.testing.assert_array_equal(got, got2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("fmt", ["ell", "hell", "dia", "hdia"])
+def test_inplace_z_aliases_y(ours, gpu_handle, dtype, fmt):
+    coo = G.random_coo(777, 777, (1, 9), 11, dtype, 0)
+    A = build(fmt, coo, 0, 32)
+    x = G.random_vector(777, dtype, 1, -1, 1)
+    y = G.random_vector(777, dtype, 2, -1, 1)
+    alpha, beta = scalars(dtype)
+    check(ours, gpu_handle, fmt, coo, A, x, y, alpha, beta, inplace=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+@pytest.mark.parametrize("fmt", ["ell", "hell"])
+def test_ridx_permutation(ours, gpu_handle, dtype, fmt):
+    """OELL / OHELL: rows sorted by length, rIdx sends results home
+    (reference hellPerf.cpp ELL == HELL == OELL)"""
+    coo = G.random_coo(1500, 1500, (0, 40), 5, dtype, 0)
+    ell = F.coo_to_ell(coo)
+    oell = F.ell_to_oell(ell)
+    A = oell if fmt == "ell" else F.ell_to_hell(oell, 32)
+    x = G.random_vector(1500, dtype, 1, -1, 1)
+    y = G.random_vector(1500, dtype, 2, -1, 1)
+    alpha, beta = scalars(dtype)
+    got = check(ours, gpu_handle, fmt, coo, A, x, y, alpha, beta, ridx=oell.ridx)
+    plain = util.oracle_spmv("ell", ell, x, y, alpha, beta)
+    util.assert_rows_close(got, plain, util.row_scale(coo, x, y, alpha, beta), util.sym_of(dtype), "ridx vs plain")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ell_without_row_sizes(ours, gpu_handle, dtype):
+    """rS == NULL: maxNnzPerRow slots per row, zero padding (reference hellPerf -DNO_ROW_SIZE)"""
+    coo = G.random_coo(999, 999, (0, 7), 3, dtype, 0)
+    A = F.coo_to_ell(coo)
+    x = G.random_vector(999, dtype, 1, -1, 1)
+    y = G.random_vector(999, dtype, 2, -1, 1)
+    alpha, beta = scalars(dtype)
+    check(ours, gpu_handle, "ell", coo, A, x, y, alpha, beta, rs_null=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("fmt", ["ell", "hell"])
+def test_spike_rows_take_the_cooperative_path(ours, gpu_handle, dtype, fmt):
+    """cfg3 in small: power-law lengths with spike rows far above the average ->
+    phase 2 of spmv_slots.cuh; HELL padding is NaN / invalid indices (formats.py)"""
+    coo = G.powerlaw(6000, mean=8, maxlen=1500, spike_every=512, seed=3, dtype=dtype)
+    A = build(fmt, coo, 0, 32)
+    x = G.random_vector(6000, dtype, 1, -1, 1)
+    y = G.random_vector(6000, dtype, 2, -1, 1)
+    alpha, beta = scalars(dtype)
+    for avg in (1, 8, 4000):          # tiny cut (everything cooperative) .. huge cut (none)
+        check(ours, gpu_handle, fmt, coo, A, x, y, alpha, beta, avg=avg)
+
+
+@pytest.mark.parametrize("hack", [32, 64, 128])
+@pytest.mark.parametrize("fmt", ["hell", "hdia"])
+def test_hack_sizes(ours, gpu_handle, fmt, hack):
+    coo = G.stencil3d_27pt(11)
+    A = build(fmt, coo, 0, hack)
+    n = coo.nrows
+    x = G.random_vector(n, np.float64, 1, 0, 1)
+    y = G.random_vector(n, np.float64, 2, 0, 1)
+    check(ours, gpu_handle, fmt, coo, A, x, y, 1.0, 0.5)
+
+
+@pytest.mark.parametrize("name,fmt,dtype", [
+    ("cfg1", "ell", np.float64), ("cfg2", "hdia", np.float64), ("cfg2", "dia", np.float64),
+    ("cfg3", "hell", np.float32), ("cfg4", "hell", np.complex128), ("cfg5", "hell", np.float64)])
+def test_baseline_configs_scaled_down(ours, gpu_handle, name, fmt, dtype):
+    """the five BASELINE.json configurations at sizes the oracle finishes in seconds"""
+    coo = {"cfg1": lambda: G.laplace2d_5pt(300),
+           "cfg2": lambda: G.stencil3d_27pt(40),
+           "cfg3": lambda: G.powerlaw(1 << 17, 16, 4096, 32768, 7, np.float32),
+           "cfg4": lambda: G.banded_complex(60000, 40, 1000, 11),
+           "cfg5": lambda: G.laplace3d_7pt(48)}[name]()
+    A = build(fmt, coo, 0, 32)
+    n = coo.nrows
+    x = G.random_vector(n, dtype, 12345, 0, 1)
+    y = G.random_vector(n, dtype, 54321, 0, 1)
+    if name == "cfg4":
+        alpha, beta = (0.7 - 0.3j), (-0.5 + 0.25j)
+    else:
+        alpha, beta = 1.0, 0.0
+    check(ours, gpu_handle, fmt, coo, A, x, y, alpha, beta)
+    if name == "cfg4":          # baseIndex exercised at 1 too
+        coo1 = G.banded_complex(60000, 40, 1000, 11, base=1)
+        A1 = build(fmt, coo1, 1, 32)
+        check(ours, gpu_handle, fmt, coo1, A1, x, y, alpha, beta)
+
+
+def test_empty_matrix_is_a_noop(ours, gpu_handle):
+    import torch
+    z = torch.full((4,), 7.0, dtype=torch.float64, device="cuda")
+    t = util.TYPES["D"]
+    ours.spgpuDhellspmv(gpu_handle, z.data_ptr(), 0, t.scalar(1.0), 0, 0, 32, 0, 0, 0, 1, 0, 0, t.scalar(0.0), 0)
+    ours.spgpuDellspmv(gpu_handle, z.data_ptr(), 0, t.scalar(1.0), 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, t.scalar(0.0), 0)
+    ours.spgpuDdiaspmv(gpu_handle, z.data_ptr(), 0, t.scalar(1.0), 0, 0, 0, 0, 0, 0, 0, t.scalar(0.0))
+    ours.spgpuDhdiaspmv(gpu_handle, z.data_ptr(), 0, t.scalar(1.0), 0, 0, 32, 0, 0, 0, 0, t.scalar(0.0))
+    torch.cuda.synchronize()
+    assert (z == 7.0).all()
+
+
+def test_custom_stream(ours, gpu_handle):
+    """spgpuSetStream / spgpuGetStream (reference core.c:62-78): work follows the stream"""
+    import ctypes
+    import torch
+    st = ctypes.c_void_p()
+    ours.spgpuStreamCreate(gpu_handle, ctypes.byref(st))
+    default = ours.spgpuGetStream(gpu_handle)
+    ours.spgpuSetStream(gpu_handle, st)
+    assert ours.spgpuGetStream(gpu_handle) == st.value
+    coo = G.laplace2d_5pt(64)
+    A = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    x = G.random_vector(coo.nrows, np.float64, 1)
+    check(ours, gpu_handle, "hell", coo, A, x, x, 1.0, 0.0)
+    ours.spgpuSetStream(gpu_handle, None)
+    assert ours.spgpuGetStream(gpu_handle) == default
+    ours.spgpuStreamDestroy(st)
