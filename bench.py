@@ -1,0 +1,502 @@
+#!/usr/bin/env python
+"""bench.py -- SpMV GFLOP/s and achieved HBM GB/s of the B200-native spGPU drop-in.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE SpMV z = A*x over the whole matrix through the C ABI
+(spgpuDhellspmv / spgpuDhdiaspmv / ...).  Default workload: BASELINE.json's
+configs[4], the configuration the metric's 1/2/4/8-GPU scaling is quoted on --
+the 512^3 7-point Laplacian (134 M rows, 938 M non-zeros, 13.95 GB of
+algorithmic traffic per SpMV) in double HELL, hackSize 32, row-sharded by
+z-slabs with a one-plane x halo per neighbour ("strong" scaling: the matrix is
+fixed, N changes).  The other configurations are selectable with --workload
+(cfg1 ELL 2-D Laplacian, cfg2 HDIA 27-point, cfg3 float power-law HELL, cfg4
+complex banded HELL) and run on one GPU.
+
+Prints ONE JSON line (rank 0).  `value`: device-resident inputs, CUDA events on
+the launching stream, max over ranks.  `e2e`: same call with x coming from
+pinned host memory and z going back to it inside the timed region.
+`--impl reference`: the CPU arm -- OpenMP port of the same format's loop
+(oracle/liboracle.so) on the box's host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+# --------------------------------------------------------------------------- #
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------- #
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- #
+# workloads
+# --------------------------------------------------------------------------- #
+
+def algorithmic_bytes_hell(nnz, rows, hacks, ncols_read, sizeof_t, beta_nonzero=False):
+    """nnz*(sizeof(T)+4) + 4R (rS) + 4*hacks + x once + z (+ y)."""
+    return nnz * (sizeof_t + 4) + 4 * rows + 4 * hacks + ncols_read * sizeof_t + rows * sizeof_t * (2 if beta_nonzero else 1)
+
+
+def build_workload(name, rank, world, device, n_override=None):
+    """Returns a dict describing this rank's share of the workload (device resident)."""
+    import torch
+    from spgpu_b200 import device_build as DB
+    w = {"name": name}
+    if name == "cfg5":
+        n = n_override or 512
+        assert n % world == 0
+        per = n // world
+        z_lo, z_hi = rank * per, (rank + 1) * per
+        plane = n * n
+        A = DB.hell_laplace3d_7pt(n, z_lo, z_hi, local_columns=(world > 1), device=device)
+        w.update(kind="hell", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=plane if world > 1 else 0,
+                 x_len=A.ncols, sizeof=8, alpha=1.0, beta=0.0, flops_per_nnz=2,
+                 label=f"3-D 7-point Laplacian {n}^3, double HELL hackSize 32 (BASELINE configs[4])",
+                 total_rows=n ** 3)
+        x_read = A.nrows + (2 * plane if world > 1 else 0)      # owned entries + the two halo planes
+        w["bytes"] = algorithmic_bytes_hell(A.nnz, A.nrows, A.hack_offsets.numel(), x_read, 8)
+    elif name == "cfg2":
+        n = n_override or 128
+        A = DB.hdia_stencil27(n, device=device)
+        hd = int(A.offsets.numel())
+        w.update(kind="hdia", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=0, x_len=A.ncols, sizeof=8,
+                 alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=A.nrows,
+                 label=f"3-D 27-point stencil {n}^3, double HDIA hackSize 32 (BASELINE configs[1])")
+        # cells_in_range*8 + 4*#hack-diagonals + 4*(hacks+1) + x + z
+        w["bytes"] = A.cells_in_range * 8 + 4 * hd + 4 * int(A.hack_offsets.numel()) + 8 * A.ncols + 8 * A.nrows
+    elif name == "cfg1":
+        from spgpu_b200 import formats as F, generators as G
+        n = n_override or 1000
+        ell = F.coo_to_ell(G.laplace2d_5pt(n))
+        A = {"values": torch.from_numpy(ell.values).to(device), "indices": torch.from_numpy(ell.indices).to(device),
+             "rs": torch.from_numpy(ell.rs).to(device), "ell": ell}
+        nnz = int(ell.rs.sum())
+        w.update(kind="ell", sym="D", A=A, rows=ell.nrows, nnz=nnz, halo=0, x_len=ell.ncols, sizeof=8,
+                 alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=ell.nrows,
+                 label=f"2-D 5-point Laplacian {n}x{n}, double ELL with rS (BASELINE configs[0])")
+        w["bytes"] = nnz * 12 + 4 * ell.nrows + 8 * ell.ncols + 8 * ell.nrows
+    elif name == "cfg3":
+        R = n_override or (1 << 22)
+        lens, cols, vals = DB.powerlaw_entries(R, device=device)
+        A = DB.hell_from_rows(lens, cols, vals, R)
+        del lens, cols, vals
+        w.update(kind="hell", sym="S", A=A, rows=R, nnz=A.nnz, halo=0, x_len=R, sizeof=4, alpha=1.0, beta=0.0,
+                 flops_per_nnz=2, total_rows=R,
+                 label=f"power-law rows {R} avg 16 max 4096, float HELL hackSize 32 (BASELINE configs[2])")
+        w["bytes"] = algorithmic_bytes_hell(A.nnz, R, A.hack_offsets.numel(), R, 4)
+        w["ell_bytes_avoided"] = int(A.rs.max().item()) * R * 8
+    elif name == "cfg4":
+        R = n_override or 2_000_000
+        lens, cols, vals = DB.banded_complex_entries(R, device=device)
+        A = DB.hell_from_rows(lens, cols, vals, R)
+        del lens, cols, vals
+        w.update(kind="hell", sym="Z", A=A, rows=R, nnz=A.nnz, halo=0, x_len=R, sizeof=16,
+                 alpha=0.7 - 0.3j, beta=-0.5 + 0.25j, flops_per_nnz=8, total_rows=R,
+                 label=f"banded complex-double {R} rows ~40 nnz/row, HELL hackSize 32 (BASELINE configs[3])")
+        w["bytes"] = algorithmic_bytes_hell(A.nnz, R, A.hack_offsets.numel(), R, 16, beta_nonzero=True)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return w
+
+
+def make_step(L, h, w, x_ext_ptr, z_ptr, y_ptr):
+    """closure(row0, row1) launching the SpMV of rows [row0,row1) through the C ABI"""
+    from spgpu_b200.capi import TYPES
+    t = TYPES[w["sym"]]
+    a, b = t.scalar(w["alpha"]), t.scalar(w["beta"])
+    A, s, sz = w["A"], w["sym"], w["sizeof"]
+    if w["kind"] == "hell":
+        fn = getattr(L, f"spgpu{s}hellspmv")
+        cM, rP, ho, rs = A.values.data_ptr(), A.indices.data_ptr(), A.hack_offsets.data_ptr(), A.rs.data_ptr()
+        hs, avg, base = A.hack_size, A.avg, A.base
+
+        def step(r0=0, r1=w["rows"]):
+            fn(h, z_ptr + sz * r0, (y_ptr + sz * r0) if y_ptr else 0, a, cM, rP, hs, ho + 4 * (r0 // hs),
+               rs + 4 * r0, 0, avg, r1 - r0, x_ext_ptr, b, base)
+    elif w["kind"] == "hdia":
+        fn = getattr(L, f"spgpu{s}hdiaspmv")
+        dM, off, ho = A.values.data_ptr(), A.offsets.data_ptr(), A.hack_offsets.data_ptr()
+
+        def step(r0=0, r1=w["rows"]):
+            fn(h, z_ptr, y_ptr or 0, a, dM, off, A.hack_size, ho, A.nrows, A.ncols, x_ext_ptr, b)
+    elif w["kind"] == "ell":
+        fn = getattr(L, f"spgpu{s}ellspmv")
+        ell = A["ell"]
+
+        def step(r0=0, r1=w["rows"]):
+            fn(h, z_ptr, y_ptr or 0, a, A["values"].data_ptr(), A["indices"].data_ptr(), ell.pitch, ell.pitch,
+               A["rs"].data_ptr(), 0, 4, ell.maxnnz, ell.nrows, x_ext_ptr, b, 0)
+    else:
+        raise ValueError(w["kind"])
+    return step
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm (OpenMP port of the same loop) -- oracle/liboracle.so
+# --------------------------------------------------------------------------- #
+
+def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
+    """Times the OpenMP host SpMV (oracle port) over the SAME format on a bounded
+    sample of the workload, all host threads.  Returns the cpu_baseline object."""
+    import torch
+    from tests import util
+    from spgpu_b200 import device_build as DB
+    O = util.oracle_lib()
+    cores = O.dll.oracle_num_threads()
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    if workload_name == "cfg5":
+        n, nz = 512, 128         # 128 planes of 512x512: 33.5 M rows, 234 M nnz (1/4 of the workload)
+        A = DB.hell_laplace3d_7pt(n, 0, nz, local_columns=False, device=dev, nz=nz)
+        sample = f"{nz} z-planes of the same 512x512-plane 7-point Laplacian ({A.nrows} rows, {A.nnz} nnz), HELL double"
+        vals, idx, ho, rs = (t.cpu().numpy() for t in (A.values, A.indices, A.hack_offsets, A.rs))
+        x = np.random.default_rng(12345).random(A.ncols)
+        z = np.zeros(A.nrows)
+        T = util.TYPES["D"]
+        call = lambda: O.Dhellspmv(util.ptr(z), None, T.scalar(1.0), util.ptr(vals), util.ptr(idx), 32,
+                                   util.ptr(ho), util.ptr(rs), None, 7, A.nrows, util.ptr(x), T.scalar(0.0), 0)
+        flops = 2 * A.nnz
+    elif workload_name == "cfg2":
+        A = DB.hdia_stencil27(128, device=dev)
+        sample = f"the full 128^3 27-point HDIA matrix ({A.nrows} rows, {A.nnz} nnz)"
+        vals, off, ho = (t.cpu().numpy() for t in (A.values, A.offsets, A.hack_offsets))
+        x = np.random.default_rng(12345).random(A.ncols)
+        z = np.zeros(A.nrows)
+        T = util.TYPES["D"]
+        call = lambda: O.Dhdiaspmv(util.ptr(z), None, T.scalar(1.0), util.ptr(vals), util.ptr(off), 32,
+                                   util.ptr(ho), A.nrows, A.ncols, util.ptr(x), T.scalar(0.0))
+        flops = 2 * A.nnz
+    else:
+        return None
+    call()                       # warm-up (page faults, thread pool)
+    best, spent = float("inf"), 0.0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        call()
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+        spent += dt
+        if spent > budget_s:
+            break
+    return {"value": flops / best / 1e9, "unit": "GFLOP/s", "cores": int(cores), "kind": "port",
+            "sample": sample + f"; OpenMP schedule(static) over rows, best of {repeats}"}, best
+
+
+# --------------------------------------------------------------------------- #
+# main
+# --------------------------------------------------------------------------- #
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--n", type=int, default=None, help="override the grid size / row count (testing)")
+    ap.add_argument("--halo", default="push", choices=["push", "nccl"], help="multi-GPU halo exchange mode")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", default="", help="key=value,... passed to spgpuSetTuning")
+    ap.add_argument("--sweep", default="", help="'k=v,k=v;k=v;...': kernel-only timing per tuning set (stderr)")
+    args = ap.parse_args()
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ---------------- reference arm: host OpenMP on rank 0 only -----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = cpu_baseline(args.workload if args.workload in ("cfg5", "cfg2") else "cfg5")
+        cb, best = res
+        # K timed steps of the bounded sample, W warm-ups (already warm after cpu_baseline)
+        out = {"impl": "reference", "metric": "spmv_gflops", "value": cb["value"], "unit": "GFLOP/s",
+               "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": best * 1e3,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": {"workload": args.workload, "arm": "host OpenMP SpMV over the same format"},
+               "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from spgpu_b200 import capi, mg
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.workload != "cfg5" and world > 1:
+        raise SystemExit("only cfg5 is row-sharded across GPUs; run the other workloads with --gpus 1")
+
+    L = capi.lib()
+    h = ctypes.c_void_p()
+    st = L.spgpuCreate(ctypes.byref(h), local_rank)
+    assert st == 0, f"spgpuCreate -> {st}"
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        assert L.spgpuSetTuning(h, k.encode(), int(v)) == 0, f"unknown tuning key {k}"
+
+    # everything (torch ops, NCCL, our kernels) is ordered on ONE stream: the handle's
+    stream = torch.cuda.ExternalStream(L.spgpuGetStream(h), device=device)
+    torch.cuda.set_stream(stream)
+
+    w = build_workload(args.workload, rank, world, device, args.n)
+    tdt = {"S": torch.float32, "D": torch.float64, "C": torch.complex64, "Z": torch.complex128}[w["sym"]]
+    rows, halo = w["rows"], w["halo"]
+    ext_len = w["x_len"]
+
+    # x_ext lives in its own cudaMalloc block so it can be IPC-exported to the neighbours
+    gen = torch.Generator(device=device)
+    gen.manual_seed(12345 + rank)
+    if w["sym"] == "D":
+        x_ptr, x_ext = mg.raw_device_vector(L, ext_len, torch.float64)
+        x_ext.copy_(torch.rand(ext_len, generator=gen, device=device, dtype=torch.float64))
+    else:
+        real = torch.float32 if w["sym"] in "SC" else torch.float64
+        if w["sym"] in "CZ":
+            x_ext = torch.complex(torch.rand(ext_len, generator=gen, device=device, dtype=real),
+                                  torch.rand(ext_len, generator=gen, device=device, dtype=real))
+        else:
+            x_ext = torch.rand(ext_len, generator=gen, device=device, dtype=real)
+        x_ptr = x_ext.data_ptr()
+    z = torch.zeros(rows, dtype=tdt, device=device)
+    y = None
+    if w["beta"] != 0:
+        y = torch.rand(rows, generator=gen, device=device, dtype=torch.float64).to(tdt)
+    step = make_step(L, h, w, x_ptr, z.data_ptr(), y.data_ptr() if y is not None else 0)
+
+    peer = None
+    ex = mg.HaloExchange(rank, world, halo, "nccl")
+    if world > 1 and args.halo == "push":
+        peer = mg.PeerHalo(L, h, rank, world, x_ptr, ext_len, halo)
+    op = mg.MgHellSpmv(rank, world, rows, halo, lambda _z, _x, r0, r1: step(r0, r1), ex, peer,
+                       overlap=not args.no_overlap)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        op.apply(z, x_ext)
+
+    # ---------------- device-resident timing ------------------------------------
+    for _ in range(W):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.spgpuGetLaunchCount(h)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        one_step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.spgpuGetLaunchCount(h) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / K
+
+    nnz_total = torch.tensor([float(w["nnz"])], dtype=torch.float64, device=device)
+    bytes_total = torch.tensor([float(w["bytes"])], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(nnz_total)
+        dist.all_reduce(bytes_total)
+    nnz_total, bytes_total = float(nnz_total.item()), float(bytes_total.item())
+    gflops = w["flops_per_nnz"] * nnz_total / (ms_step * 1e-3) / 1e9
+
+    # ---------------- the dominant kernel alone (roofline) ----------------------
+    # per-launch duration of the full-block SpMV kernel on this rank's stream
+    ker_ms = []
+    for _ in range(min(K, 10)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        step()
+        b.record(stream)
+        b.synchronize()
+        ker_ms.append(a.elapsed_time(b))
+    ker_ms = float(np.mean(ker_ms))
+    peak, peak_src = measured_peak()
+    achieved = w["bytes"] / (ker_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}_n{world}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": f"{w['kind']}_spmv_kernel<{w['sym']}>",
+                "kernel_ms": ker_ms, "algorithmic_bytes_per_launch": w["bytes"]}
+
+    # ---------------- optional tuning sweep (kernel only, stderr) ---------------
+    for setting in filter(None, args.sweep.split(";")):
+        for kv in filter(None, setting.split(",")):
+            k, v = kv.split("=")
+            assert L.spgpuSetTuning(h, k.encode(), int(v)) == 0, f"unknown tuning key {k}"
+        ts = []
+        for _ in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); step(); b.record(stream); b.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts = ts[2:]
+        print(json.dumps({"sweep": setting, "workload": args.workload, "kernel_ms": float(np.mean(ts)),
+                          "min_ms": float(np.min(ts)), "gbs": w["bytes"] / (np.mean(ts) * 1e-3) / 1e9,
+                          "frac": w["bytes"] / (np.mean(ts) * 1e-3) / 1e9 / peak}), file=sys.stderr, flush=True)
+    if args.sweep:
+        for kv in filter(None, args.tune.split(",")):          # restore the requested tuning
+            k, v = kv.split("=")
+            L.spgpuSetTuning(h, k.encode(), int(v))
+
+    # ---------------- end to end: x from pinned host, z back to pinned host -----
+    e2e = None
+    if not args.no_e2e:
+        own = x_ext[halo:halo + rows] if halo else x_ext
+        hx = torch.empty(own.shape, dtype=own.dtype, pin_memory=True)
+        hx.copy_(own)
+        hz = torch.empty(z.shape, dtype=z.dtype, pin_memory=True)
+        Ke = max(2, min(K, 5))
+        for _ in range(2):
+            own.copy_(hx, non_blocking=True); one_step(); hz.copy_(z, non_blocking=True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(Ke):
+            own.copy_(hx, non_blocking=True)
+            one_step()
+            hz.copy_(z, non_blocking=True)
+        b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item()) / Ke
+        e2e = {"value": w["flops_per_nnz"] * nnz_total / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(hx.numel() * hx.element_size()) * world,
+               "d2h_bytes_per_step": int(hz.numel() * hz.element_size()) * world,
+               "ms_per_step": ms_e2e, "steps": Ke,
+               "what": "x (owned part) H2D from pinned memory + SpMV through the C ABI + z D2H, per step; matrix resident"}
+
+    # ---------------- CPU baseline (rank 0, N=1) --------------------------------
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        res = cpu_baseline(args.workload)
+        cb = res[0] if res else None
+
+    if peer is not None:
+        peer.close()
+    if rank == 0:
+        out = {
+            "metric": "spmv_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"S": "f32", "D": "f64", "C": "c64", "Z": "c128"}[w["sym"]], "data": "synthetic",
+            "config": {"workload": w["label"], "rows": w["total_rows"], "nnz": int(nnz_total),
+                       "parallelism": f"row-sharded z-slabs x{world}, halo={args.halo if world > 1 else 'none'}"
+                                      f"{'' if args.no_overlap or world == 1 else ', interior/boundary overlap'}",
+                       "l2": "inputs larger than L2 (no flush needed)" if w["bytes"] / max(world, 1) > 4 * 126e6
+                             else "working set comparable to L2: numbers include L2 hits, see DESIGN.md",
+                       "alpha": str(w["alpha"]), "beta": str(w["beta"])},
+            "hbm_gbs": bytes_total / (ms_step * 1e-3) / 1e9,
+            "hbm_frac_of_peak": bytes_total / (ms_step * 1e-3) / 1e9 / (peak * world),
+            "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    L.spgpuDestroy(h)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

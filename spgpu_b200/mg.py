@@ -1,0 +1,295 @@
+"""Row-partitioned multi-GPU SpMV (north_star item 3; no reference counterpart:
+the reference is one handle per device with no communication, core.h:88-93).
+
+One process per GPU (torchrun), `torch.distributed` for the plumbing.  The
+matrix is split in contiguous row blocks whose boundaries are multiples of the
+hack size, so a block is a self-contained HELL matrix (its hackOffsets re-base
+by subtraction).  Each rank owns x[lo:hi) and keeps it inside
+
+    x_ext = [ lower halo (w) | owned (hi-lo) | upper halo (w) ]
+
+with the block's column indices remapped to x_ext positions, so the UNCHANGED
+single-GPU kernel (spgpu?hellspmv through the C ABI) runs on it.  Before a SpMV
+the two halo zones are filled from the neighbours' boundary entries:
+
+  * mode "nccl":  grouped ncclSend/ncclRecv (torch.distributed P2P ops);
+  * mode "push":  each rank's spgpuDhaloPush kernel stores its boundary entries
+    straight into the neighbour's halo zone through a CUDA-IPC peer pointer over
+    NVLink and release-stores a sequence number into the neighbour's flag word;
+    the consumer's stream waits on its own flag (spgpuWaitFlag).  An "ack" flag
+    in the other direction keeps a producer from overwriting a halo that is
+    still being read.
+  * mode "allgather": for unstructured columns every rank gathers the full x.
+
+Rows that reference no halo entry ("interior") are multiplied while the
+exchange is in flight; the boundary rows run after it.  Dots are local partial
+reductions + an all-reduce of one scalar.
+
+The same class runs on CPU tensors with the gloo backend and a caller-supplied
+local SpMV (the tests pass the CPU oracle) to check the partition / remap /
+exchange logic without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# --------------------------------------------------------------------------- #
+# partitioning (pure host logic)
+# --------------------------------------------------------------------------- #
+
+def row_blocks(nrows: int, world: int, align: int):
+    """Contiguous, near-equal row blocks whose boundaries are multiples of `align`."""
+    units = (nrows + align - 1) // align
+    bounds = [min(nrows, ((units * r) // world) * align) for r in range(world)] + [nrows]
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+@dataclass
+class LocalHell:
+    """One rank's block in HELL layout with columns remapped into x_ext."""
+    values: object
+    indices: object
+    hack_offsets: object
+    rs: object
+    hack_size: int
+    nrows: int
+    lo: int
+    hi: int
+    halo: int          # entries in each halo zone
+    base: int
+    nnz: int
+
+    @property
+    def ext_len(self):
+        return self.nrows + 2 * self.halo
+
+
+def split_hell(hell, world: int, rank: int, halo: int) -> LocalHell:
+    """Cut rank's block out of a global host-side formats.Hell and remap its
+    column indices to x_ext positions.  Raises if a row references a column
+    outside [lo-halo, hi+halo) (then use mode 'allgather')."""
+    hs = hell.hack_size
+    lo, hi = row_blocks(hell.nrows, world, hs)[rank]
+    h0, h1 = lo // hs, (hi + hs - 1) // hs
+    hoff = np.asarray(hell.hack_offsets)
+    e0 = int(hoff[h0]) if h0 < hoff.shape[0] else int(hell.values.shape[0])
+    e1 = int(hoff[h1]) if h1 < hoff.shape[0] else int(hell.values.shape[0])
+    values = np.array(hell.values[e0:e1], copy=True)
+    indices = np.array(hell.indices[e0:e1], copy=True)
+    rs = np.array(hell.rs[lo:hi], copy=True)
+    local_hoff = (hoff[h0:h1] - e0).astype(np.int32)
+    # remap only the slots that exist (padding is undefined and stays so)
+    nnz = 0
+    for h in range(h1 - h0):
+        rows = rs[h * hs:(h + 1) * hs]
+        if rows.size == 0:
+            continue
+        at = int(local_hoff[h])
+        for k in range(int(rows.max())):
+            live = np.nonzero(rows > k)[0]
+            sl = at + k * hs + live
+            g = indices[sl] - hell.base
+            if ((g < lo - halo) | (g >= hi + halo)).any():
+                raise ValueError("column outside the halo window; use mode='allgather'")
+            indices[sl] = g - (lo - halo) + hell.base
+            nnz += live.size
+    return LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, halo, hell.base, nnz)
+
+
+# --------------------------------------------------------------------------- #
+# communicator
+# --------------------------------------------------------------------------- #
+
+class HaloExchange:
+    """Fills the two halo zones of x_ext from the neighbours (1-D chain of ranks)."""
+
+    def __init__(self, rank, world, halo, mode="nccl", group=None):
+        self.rank, self.world, self.halo, self.mode, self.group = rank, world, halo, mode, group
+        self.seq = 0
+        self.push = None
+
+    # -- NCCL / gloo point-to-point ------------------------------------------
+    def start(self, x_ext: torch.Tensor):
+        """Begin the exchange; returns a list of work handles (may be empty)."""
+        w, n = self.halo, x_ext.numel() - 2 * self.halo
+        if self.world == 1 or w == 0:
+            return []
+        ops = []
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, x_ext[w:2 * w], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, x_ext[0:w], self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.isend, x_ext[n:n + w], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, x_ext[n + w:n + 2 * w], self.rank + 1, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def finish(works):
+        for wk in works:
+            wk.wait()
+
+
+class PeerHalo:
+    """mode 'push': NVLink peer stores + flags (CUDA IPC between the rank processes)."""
+
+    FLAG_WORDS = 16     # [0] ready-from-below  [1] ready-from-above  [2] ack-from-below  [3] ack-from-above
+
+    def __init__(self, L, handle, rank, world, x_ext_ptr, ext_len, halo, group=None):
+        self.L, self.h, self.rank, self.world, self.halo = L, handle, rank, world, halo
+        self.x_ptr, self.ext_len = x_ext_ptr, ext_len
+        self.seq = 0
+        flags = ctypes.c_void_p()
+        assert L.spgpuDeviceAlloc(ctypes.byref(flags), 4 * self.FLAG_WORDS) == 0
+        self.flags = flags.value
+        # zero the flags through a torch view of the raw allocation
+        self._flag_view = _as_tensor(self.flags, self.FLAG_WORDS, torch.int32)
+        self._flag_view.zero_()
+        torch.cuda.synchronize()
+        hx = (ctypes.c_char * 64)()
+        hf = (ctypes.c_char * 64)()
+        assert L.spgpuIpcGetHandle(x_ext_ptr, hx) == 0
+        assert L.spgpuIpcGetHandle(self.flags, hf) == 0
+        mine = (bytes(hx), bytes(hf), ext_len)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.peer = {}
+        for nb in (rank - 1, rank + 1):
+            if 0 <= nb < world:
+                px, pf = ctypes.c_void_p(), ctypes.c_void_p()
+                bx = (ctypes.c_char * 64).from_buffer_copy(everyone[nb][0])
+                bf = (ctypes.c_char * 64).from_buffer_copy(everyone[nb][1])
+                rc = L.spgpuIpcOpenHandle(bx, ctypes.byref(px))
+                assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
+                rc = L.spgpuIpcOpenHandle(bf, ctypes.byref(pf))
+                assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
+                self.peer[nb] = (px.value, pf.value, everyone[nb][2])
+        dist.barrier(group=group)
+
+    def exchange(self):
+        """push my boundary entries to both neighbours, then make my stream wait
+        until both of mine have arrived (all stream-ordered, no host sync)."""
+        L, h, w = self.L, self.h, self.halo
+        n = self.ext_len - 2 * w
+        self.seq += 1
+        seq = self.seq
+        lo_nb, hi_nb = self.rank - 1, self.rank + 1
+        # wait until the neighbours have consumed the previous halo I sent them
+        if seq > 1:
+            if lo_nb in self.peer:
+                L.spgpuWaitFlag(h, self.flags + 4 * 2, seq - 1)
+            if hi_nb in self.peer:
+                L.spgpuWaitFlag(h, self.flags + 4 * 3, seq - 1)
+        if lo_nb in self.peer:       # my first w owned entries -> their upper halo, their flag[1]
+            px, pf, plen = self.peer[lo_nb]
+            L.spgpuDhaloPush(h, px + 8 * (plen - w), self.x_ptr + 8 * w, w, pf + 4 * 1, seq)
+        if hi_nb in self.peer:       # my last w owned entries -> their lower halo, their flag[0]
+            px, pf, plen = self.peer[hi_nb]
+            L.spgpuDhaloPush(h, px, self.x_ptr + 8 * n, w, pf + 4 * 0, seq)
+
+    def wait(self):
+        L, h, seq = self.L, self.h, self.seq
+        if self.rank - 1 in self.peer:
+            L.spgpuWaitFlag(h, self.flags + 4 * 0, seq)
+        if self.rank + 1 in self.peer:
+            L.spgpuWaitFlag(h, self.flags + 4 * 1, seq)
+
+    def ack(self):
+        """tell both neighbours their halo data has been consumed (after the SpMV)."""
+        L, h, seq = self.L, self.h, self.seq
+        for nb, word in ((self.rank - 1, 3), (self.rank + 1, 2)):
+            if nb in self.peer:
+                _px, pf, _plen = self.peer[nb]
+                L.spgpuDhaloPush(h, 0, 0, 0, pf + 4 * word, seq)
+
+    def close(self):
+        torch.cuda.synchronize()
+        for px, pf, _ in self.peer.values():
+            self.L.spgpuIpcCloseHandle(px)
+            self.L.spgpuIpcCloseHandle(pf)
+        self.peer = {}
+
+
+class _RawCuda:
+    """__cuda_array_interface__ carrier so torch can view a raw cudaMalloc block."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def _as_tensor(ptr: int, n: int, dtype: torch.dtype) -> torch.Tensor:
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_RawCuda(ptr, n, typestr), device="cuda")
+
+
+def raw_device_vector(L, n: int, dtype=torch.float64):
+    """(ptr, torch view) of a dedicated cudaMalloc allocation (IPC-exportable)."""
+    p = ctypes.c_void_p()
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    rc = L.spgpuDeviceAlloc(ctypes.byref(p), nbytes)
+    assert rc == 0, f"cudaMalloc({nbytes}) -> {rc}"
+    return p.value, _as_tensor(p.value, n, dtype)
+
+
+# --------------------------------------------------------------------------- #
+# the partitioned operator
+# --------------------------------------------------------------------------- #
+
+class MgHellSpmv:
+    """z_owned = A_block * x_ext with halo exchange, one rank's view.
+
+    local_spmv(z, x_ext, row0, row1) multiplies rows [row0, row1) of the block
+    (used to split interior / boundary work); on the GPU it is a closure around
+    spgpuDhellspmv with offset pointers (same trick as the reference's
+    large-vector loop, hell_spmv_base.cuh:121-137)."""
+
+    def __init__(self, rank, world, nrows, halo, local_spmv, exchange: HaloExchange,
+                 peer: PeerHalo | None = None, overlap=True, align=32):
+        self.rank, self.world, self.nrows, self.halo = rank, world, nrows, halo
+        self.local_spmv, self.ex, self.peer = local_spmv, exchange, peer
+        # rows [0, head) and [tail, nrows) may touch a halo zone; both cuts sit on
+        # hack boundaries so each piece is a valid HELL sub-matrix
+        self.head = min(nrows, -(-halo // align) * align)
+        self.tail = max(self.head, ((nrows - halo) // align) * align)
+        self.overlap = overlap and world > 1 and halo > 0 and self.tail > self.head
+
+    def apply(self, z, x_ext):
+        w, n = self.halo, self.nrows
+        if self.world == 1 or w == 0:
+            self.local_spmv(z, x_ext, 0, n)
+            return
+        if self.peer is not None:
+            # NVLink push: everything is ordered on the handle's stream
+            self.peer.exchange()
+            if self.overlap:
+                self.local_spmv(z, x_ext, self.head, self.tail)   # interior rows need no halo
+                self.peer.wait()
+                self.local_spmv(z, x_ext, 0, self.head)
+                self.local_spmv(z, x_ext, self.tail, n)
+            else:
+                self.peer.wait()
+                self.local_spmv(z, x_ext, 0, n)
+            self.peer.ack()
+            return
+        works = self.ex.start(x_ext)
+        if self.overlap:
+            self.local_spmv(z, x_ext, self.head, self.tail)
+            HaloExchange.finish(works)
+            self.local_spmv(z, x_ext, 0, self.head)
+            self.local_spmv(z, x_ext, self.tail, n)
+        else:
+            HaloExchange.finish(works)
+            self.local_spmv(z, x_ext, 0, n)
+
+
+def global_dot(local_value: torch.Tensor, group=None) -> torch.Tensor:
+    """sum over ranks of a 1-element tensor holding the local partial dot."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(local_value, op=dist.ReduceOp.SUM, group=group)
+    return local_value

@@ -30,10 +30,11 @@ def test_axpby_scal(ours, oracle, gpu_handle, dtype, n, offset):
     x = G.random_vector(n + offset, dtype, 1, -1, 1)
     y = G.random_vector(n + offset, dtype, 2, -1, 1)
     dx, dy = util.to_dev(x)[offset:], util.to_dev(y)[offset:]
+    xs, ys = x[offset:].copy(), y[offset:].copy()      # keep the host copies alive across the calls
     dz = torch.zeros_like(dx)
     getattr(ours, f"spgpu{s}axpby")(gpu_handle, dz.data_ptr(), n, t.scalar(beta), dy.data_ptr(), t.scalar(alpha), dx.data_ptr())
     want = np.zeros(n, dtype=dtype)
-    getattr(oracle, f"{s}axpby")(util.ptr(want), n, t.scalar(beta), util.ptr(y[offset:].copy()), t.scalar(alpha), util.ptr(x[offset:].copy()))
+    getattr(oracle, f"{s}axpby")(util.ptr(want), n, t.scalar(beta), util.ptr(ys), t.scalar(alpha), util.ptr(xs))
     torch.cuda.synchronize()
     np.testing.assert_allclose(dz.cpu().numpy(), want, rtol=0, atol=util.TOL[s] * 4)
     # beta == 0: y not read
@@ -42,7 +43,7 @@ def test_axpby_scal(ours, oracle, gpu_handle, dtype, n, offset):
     getattr(ours, f"spgpu{s}scal")(gpu_handle, dy.data_ptr(), n, t.scalar(alpha), dx.data_ptr())
     torch.cuda.synchronize()
     np.testing.assert_array_equal(dz.cpu().numpy(), dy.cpu().numpy())
-    getattr(oracle, f"{s}scal")(util.ptr(want), n, t.scalar(alpha), util.ptr(x[offset:].copy()))
+    getattr(oracle, f"{s}scal")(util.ptr(want), n, t.scalar(alpha), util.ptr(xs))
     np.testing.assert_allclose(dz.cpu().numpy(), want, rtol=0, atol=util.TOL[s] * 4)
     # in place: z aliases x
     getattr(ours, f"spgpu{s}axpby")(gpu_handle, dx.data_ptr(), n, t.scalar(beta), dy.data_ptr(), t.scalar(alpha), dx.data_ptr())
