@@ -492,6 +492,11 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
+    # hand the stream back before the handle (and its stream) go away
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream(device))
+    del step, op, z, y, x_ext, w
+    torch.cuda.synchronize()
     L.spgpuDestroy(h)
     if world > 1:
         dist.destroy_process_group()

@@ -18,10 +18,10 @@
 static void default_tuning(SpgpuTuning* t)
 {
 	t->hellVariant = 0;
-	t->hellBlock = 128;
+	t->hellBlock = 0;          /* 0 = per-type default occupancy, <=64 force 32 warps, >=256 force 48 */
 	t->hellLongFactor = 4;
 	t->hdiaVariant = 0;
-	t->hdiaBlock = 128;
+	t->hdiaBlock = 0;
 	t->diaBlock = 128;
 	t->streamLoads = 1;
 	t->redBlocksPerSm = 4;

@@ -79,7 +79,7 @@ dhell_spmv_dot_kernel(double* __restrict__ z, const double* __restrict__ cM,
 		const int hack = (int)(warpRow / hackSize);
 		const long long at = (long long)__ldg(hackOffsets + hack) + (warpRow % hackSize) + lane;
 		const int len = live ? ld_stream(rS + i) : 0;
-		double acc = warp_rows_dot<double, UNROLL>(cM + at, rP + at, hackSize, hackSize, len, longCut, x, baseIndex);
+		double acc = warp_rows_dot<double, UNROLL, 0>(cM + at, rP + at, hackSize, hackSize, len, longCut, 0, x, baseIndex);
 		if (live) {
 			z[i] = acc;
 			contrib = acc * __ldg(x + xOffset + i);

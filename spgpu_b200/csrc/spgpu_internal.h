@@ -25,11 +25,11 @@ extern "C" {
 
 /* Tunables that steer kernel selection; settable with spgpuSetTuning (ext). */
 typedef struct SpgpuTuning {
-	int hellVariant;     /* 0 auto, 1 row-per-lane, 2 two-rows-per-lane (128-bit), 3 bulk-async slabs */
-	int hellBlock;       /* threads per CTA for HELL/ELL kernels                */
+	int hellVariant;     /* 0 auto, 1 direct loads predicated on rS, 2 direct loads with unpredicated slab reads, 3 bulk-async (TMA) pipeline */
+	int hellBlock;       /* occupancy knob: 0 per-type default, <=64 force 32 warps/SM, >=256 force 48 */
 	int hellLongFactor;  /* a row is "long" when rS > factor*avgNnzPerRow (min 32) */
-	int hdiaVariant;     /* 0 auto, 1 direct, 2 bulk-async slabs                */
-	int hdiaBlock;
+	int hdiaVariant;     /* reserved */
+	int hdiaBlock;       /* occupancy knob: >=256 force 48 warps/SM (default 32) */
 	int diaBlock;
 	int streamLoads;     /* 1: matrix streams use evict-first loads            */
 	int redBlocksPerSm;  /* CTAs per SM for the reductions                      */

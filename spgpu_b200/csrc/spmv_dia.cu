@@ -13,47 +13,58 @@
  * lanes of a warp and broadcast by shuffle (no shared memory, no block
  * barrier, unlike the reference's per-128-diagonal __syncthreads).
  */
+#include <climits>
 #include "launch.cuh"
 #include "numeric.cuh"
 
 template <typename T, int UNROLL>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(128, 8)
 dia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM,
 	const int* __restrict__ offsets, int dMPitch, int rows, int cols, int diags,
 	const T* __restrict__ x, T beta)
 {
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	if (i - lane >= rows)
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31;
+	if (i - lane >= (unsigned)rows)
 		return;
-	const bool live = i < rows;
+	const bool live = i < (unsigned)rows;
+	/* 0 <= row+off < cols as one unsigned compare; dead lanes get cols = 0 and
+	 * offsets past the last diagonal INT_MIN, so both fail it */
+	const unsigned colsEff = live ? (unsigned)cols : 0u;
 	const bool useBeta = Num<T>::nonzero(beta);
 	T yv = Num<T>::zero();
 	if (useBeta && live)
 		yv = y[i];
 
-	const T* cell = dM + i;
+	const long long pitch = dMPitch;
+	const T* cp = dM + i;
 	T acc = Num<T>::zero();
 
 	for (int j0 = 0; j0 < diags; j0 += 32) {
-		const int mineOff = (j0 + lane < diags) ? __ldg(offsets + j0 + lane) : 0;
+		const int mineOff = (j0 + (int)lane < diags) ? __ldg(offsets + j0 + lane) : INT_MIN;
 		const int n = min(32, diags - j0);
 		for (int u0 = 0; u0 < n; u0 += UNROLL) {
 			T a[UNROLL];
 			T xv[UNROLL];
+			bool on[UNROLL];
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u) {
-				const int jj = u0 + u;
-				const int off = __shfl_sync(SPGPU_FULL_MASK, mineOff, jj & 31);
-				const long long c = i + off;
-				const bool on = live && jj < n && c >= 0 && c < cols;
-				a[u] = on ? ld_stream(cell + (long long)(j0 + jj) * dMPitch) : Num<T>::zero();
-				xv[u] = on ? ld_keep(x + c) : Num<T>::zero();
+				const int off = __shfl_sync(SPGPU_FULL_MASK, mineOff, u0 + u);
+				const int c = (int)i + off;
+				on[u] = (unsigned)c < colsEff;
+				a[u] = Num<T>::zero();
+				xv[u] = Num<T>::zero();
+				if (on[u]) {                       /* cells outside the matrix are not read */
+					a[u] = ld_stream(cp + u * pitch);
+					xv[u] = ld_keep(x + c);
+				}
 			}
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u)
 				acc = Num<T>::fma(a[u], xv[u], acc);
+			cp += UNROLL * pitch;
 		}
+		/* cp advanced by ceil(n/UNROLL)*UNROLL diagonals; n == 32 except in the last chunk */
 	}
 
 	if (live)
@@ -67,9 +78,7 @@ static void dia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 {
 	if (rows <= 0)
 		return;
-	const SpgpuTuning* t = spgpu_tuning(handle);
-	const int block = spgpu_block(t->diaBlock);
-	dia_spmv_kernel<T, UNROLL><<<spgpu_ceil_div(rows, block), block, 0, handle->currentStream>>>(
+	dia_spmv_kernel<T, UNROLL><<<spgpu_ceil_div(rows, 128), 128, 0, handle->currentStream>>>(
 		z, y, alpha, dM, offsets, dMPitch, rows, cols, diags, x, beta);
 	spgpu_count_launch(handle);
 }

@@ -35,7 +35,7 @@ ell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
 	if (useBeta && live)
 		yv = y[out];
 
-	T acc = warp_rows_dot<T, UNROLL>(cM + i, rP + i, cMPitch, rPPitch, len, longCut, x, baseIndex);
+	T acc = warp_rows_dot<T, UNROLL, 0>(cM + i, rP + i, cMPitch, rPPitch, len, longCut, 0, x, baseIndex);
 
 	if (live)
 		z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);

@@ -14,52 +14,72 @@
  * memory with only `volatile` between writer and readers).
  * Per diagonal the warp reads 32 adjacent cells and 32 adjacent x entries.
  */
+#include <climits>
 #include "launch.cuh"
 #include "numeric.cuh"
 
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(1024)
+/*
+ * HACK > 0: hackSize known at compile time -> cell addresses are base +
+ * immediate.  All index arithmetic is 32-bit: the in-range test
+ * 0 <= row+off < cols is ONE unsigned compare; lanes past the last row get
+ * cols = 0 and offsets past a hack's last diagonal get INT_MIN, so both fail
+ * that same compare without extra predicates.  The matrix cells of a round are
+ * loaded without waiting for the offsets (they all exist in the slab); only the
+ * x gather and the FMA depend on the in-range test.
+ */
+template <typename T, int UNROLL, int HACK, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM,
-	const int* __restrict__ offsets, int hackSize,
+	const int* __restrict__ offsets, int hackSizeRt,
 	const int* __restrict__ hackOffsets, int rows, int cols,
 	const T* __restrict__ x, T beta)
 {
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	const long long warpRow = i - lane;
-	if (warpRow >= rows)
+	const int hackSize = HACK > 0 ? HACK : hackSizeRt;
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned warpRow = i - lane;
+	if (warpRow >= (unsigned)rows)
 		return;
-	const bool live = i < rows;
+	const bool live = i < (unsigned)rows;
+	const unsigned colsEff = live ? (unsigned)cols : 0u;
 	const bool useBeta = Num<T>::nonzero(beta);
 	T yv = Num<T>::zero();
 	if (useBeta && live)
 		yv = y[i];
 
-	const int hack = (int)(warpRow / hackSize);
+	const unsigned hack = warpRow / (unsigned)hackSize;
 	const int first = __ldg(hackOffsets + hack);
 	const int diags = __ldg(hackOffsets + hack + 1) - first;
-	const T* cell = dM + (long long)first * hackSize + (warpRow % hackSize) + lane;
+	const T* cell = dM + (long long)first * hackSize + (warpRow % (unsigned)hackSize) + lane;
 	const int* offs = offsets + first;
 	T acc = Num<T>::zero();
 
 	for (int j0 = 0; j0 < diags; j0 += 32) {
-		const int mineOff = (j0 + lane < diags) ? ld_stream(offs + j0 + lane) : 0;
+		const int mineOff = (j0 + (int)lane < diags) ? ld_stream(offs + j0 + lane) : INT_MIN;
 		const int n = min(32, diags - j0);
 		for (int u0 = 0; u0 < n; u0 += UNROLL) {
+			const T* cp = cell + (long long)(j0 + u0) * hackSize;
 			T a[UNROLL];
 			T xv[UNROLL];
+			bool on[UNROLL];
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u) {
-				const int jj = u0 + u;
-				const int off = __shfl_sync(SPGPU_FULL_MASK, mineOff, jj & 31);
-				const long long c = i + off;
-				const bool on = live && jj < n && c >= 0 && c < cols;
-				a[u] = on ? ld_stream(cell + (long long)(j0 + jj) * hackSize) : Num<T>::zero();
-				xv[u] = on ? ld_keep(x + c) : Num<T>::zero();
+				a[u] = Num<T>::zero();
+				if (u0 + u < n)                       /* warp-uniform: cell exists */
+					a[u] = ld_stream(cp + (long long)u * hackSize);
+			}
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u) {
+				const int off = __shfl_sync(SPGPU_FULL_MASK, mineOff, u0 + u);
+				const int c = (int)i + off;
+				on[u] = (unsigned)c < colsEff;
+				xv[u] = Num<T>::zero();
+				if (on[u])
+					xv[u] = ld_keep(x + c);
 			}
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u)
-				acc = Num<T>::fma(a[u], xv[u], acc);
+				acc = on[u] ? Num<T>::fma(a[u], xv[u], acc) : acc;
 		}
 	}
 
@@ -75,9 +95,15 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	if (rows <= 0)
 		return;
 	const SpgpuTuning* t = spgpu_tuning(handle);
-	const int block = spgpu_block(t->hdiaBlock);
-	hdia_spmv_kernel<T, UNROLL><<<spgpu_ceil_div(rows, block), block, 0, handle->currentStream>>>(
-		z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+	const unsigned grid = spgpu_ceil_div(rows, 128);
+	cudaStream_t s = handle->currentStream;
+	const bool dense = t->hdiaBlock >= 256;          /* knob: trade registers for occupancy */
+	if (hackSize == 32) {
+		if (dense) hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else       hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+	} else {
+		hdia_spmv_kernel<T, UNROLL, 0, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+	}
 	spgpu_count_launch(handle);
 }
 

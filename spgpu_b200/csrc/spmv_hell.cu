@@ -15,35 +15,86 @@
  */
 #include "launch.cuh"
 #include "spmv_slots.cuh"
+#include "spmv_hell_bulk.cuh"
 
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(1024)
+/*
+ * HACK > 0: hackSize known at compile time (32 is what the reference recommends,
+ * hell_conv.h:25) -- slot addresses become base + immediate.  MINB: CTAs of 128
+ * threads the register allocator must leave room for per SM.
+ */
+template <typename T, int UNROLL, int HACK, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 hell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
-	const T* __restrict__ cM, const int* __restrict__ rP, int hackSize,
+	const T* __restrict__ cM, const int* __restrict__ rP, int hackSizeRt,
 	const int* __restrict__ hackOffsets, const int* __restrict__ rS,
 	const int* __restrict__ rIdx, int rows, const T* __restrict__ x, T beta,
-	int baseIndex, int longCut)
+	int baseIndex, int longCut, int speculate)
 {
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	const long long warpRow = i - lane;
-	if (warpRow >= rows)
+	const int hackSize = HACK > 0 ? HACK : hackSizeRt;
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned warpRow = i - lane;
+	if (warpRow >= (unsigned)rows)
 		return;                       /* whole warp past the end */
-	const bool live = i < rows;
+	const bool live = i < (unsigned)rows;
 
-	const int hack = (int)(warpRow / hackSize);
-	const long long at = (long long)__ldg(hackOffsets + hack) + (warpRow % hackSize) + lane;
+	const unsigned hack = warpRow / (unsigned)hackSize;
+	const unsigned lastHack = ((unsigned)rows - 1u) / (unsigned)hackSize;
+	const int slab = __ldg(hackOffsets + hack);
+	/* slab height of this hack = slots that exist for all of its rows; the last
+	 * hack has no terminator entry, so it takes the predicated path */
+	int allocated = 0;
+	if (speculate && hack < lastHack)
+		allocated = (__ldg(hackOffsets + hack + 1) - slab) / hackSize;
 	const int len = live ? ld_stream(rS + i) : 0;
 	const bool useBeta = Num<T>::nonzero(beta);
-	const long long out = (live && rIdx) ? (long long)__ldg(rIdx + i) : i;
+	const unsigned out = (live && rIdx) ? (unsigned)__ldg(rIdx + i) : i;
 	T yv = Num<T>::zero();
 	if (useBeta && live)
 		yv = y[out];
 
-	T acc = warp_rows_dot<T, UNROLL>(cM + at, rP + at, hackSize, hackSize, len, longCut, x, baseIndex);
+	const long long at = (long long)slab + (warpRow % (unsigned)hackSize) + lane;
+	T acc = warp_rows_dot<T, UNROLL, HACK>(cM + at, rP + at, hackSize, hackSize, len, longCut,
+		allocated, x, baseIndex);
 
 	if (live)
 		z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
+}
+
+/* Bulk-async variant: returns false when the call is not eligible (then the
+ * direct kernel runs).  Stage capacity is sized from avgNnzPerRow. */
+template <typename T, int UNROLL, int HACK>
+static bool hell_spmv_try_bulk(spgpuHandle_t handle, T* z, const T* y, T alpha,
+	const T* cM, const int* rP, const int* hackOffsets, const int* rS,
+	const int* rIdx, int avgNnzPerRow, int rows, const T* x, T beta,
+	int baseIndex, int longCut)
+{
+	static bool configured = false;
+	const int avg = avgNnzPerRow > 0 ? avgNnzPerRow : 1;
+	const int slots = avg + (avg / 4 > 1 ? avg / 4 : 1);
+	const int cap = HB_CONSUMER_WARPS * 32 * slots;
+	const size_t stageBytes = (size_t)cap * (sizeof(T) + sizeof(int)) + HB_CONSUMER_WARPS * 32 * sizeof(int);
+	const size_t budget = 110 * 1024;                     /* two CTAs per SM */
+	int stages = (int)((budget - 256) / stageBytes);
+	if (stages > 4) stages = 4;
+	if (stages < 2)
+		return false;
+	if ((((size_t)cM | (size_t)rP | (size_t)rS) & 15) != 0)
+		return false;                                     /* bulk copies need 16-byte aligned sources */
+	const size_t smem = stages * stageBytes + 2 * stages * sizeof(uint64_t);
+	if (!configured) {
+		if (cudaFuncSetAttribute(hell_spmv_bulk_kernel<T, HACK, UNROLL>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024)) != cudaSuccess)
+			return false;
+		configured = true;
+	}
+	const int tiles = (rows + HB_CONSUMER_WARPS * 32 - 1) / (HB_CONSUMER_WARPS * 32);
+	int grid = 2 * handle->multiProcessorCount;
+	if (grid > tiles) grid = tiles;
+	hell_spmv_bulk_kernel<T, HACK, UNROLL><<<grid, HB_THREADS, smem, handle->currentStream>>>(
+		z, y, alpha, cM, rP, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, cap, stages);
+	spgpu_count_launch(handle);
+	return true;
 }
 
 template <typename T, int UNROLL>
@@ -55,11 +106,42 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	if (rows <= 0)
 		return;
 	const SpgpuTuning* t = spgpu_tuning(handle);
-	const int block = spgpu_block(t->hellBlock);
+	const int block = 128;
 	const unsigned grid = spgpu_ceil_div(rows, block);
-	hell_spmv_kernel<T, UNROLL><<<grid, block, 0, handle->currentStream>>>(
-		z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta,
-		baseIndex, spgpu_long_cut(t, avgNnzPerRow));
+	const int longCut = spgpu_long_cut(t, avgNnzPerRow);
+	/* hellVariant: 0 auto, 1 direct loads predicated on rS, 2 direct loads with
+	 * unpredicated slab reads, 3 bulk-async pipeline */
+	int variant = t->hellVariant;
+	if (variant == 0)
+		variant = 2;
+	if (variant == 3 && rows >= 8 * HB_CONSUMER_WARPS * 32) {
+		bool done = false;
+		if (hackSize == 32)
+			done = hell_spmv_try_bulk<T, UNROLL, 32>(handle, z, y, alpha, cM, rP, hackOffsets, rS, rIdx,
+				avgNnzPerRow, rows, x, beta, baseIndex, longCut);
+		else if (hackSize == 64)
+			done = hell_spmv_try_bulk<T, UNROLL, 64>(handle, z, y, alpha, cM, rP, hackOffsets, rS, rIdx,
+				avgNnzPerRow, rows, x, beta, baseIndex, longCut);
+		if (done)
+			return;
+	}
+	const int speculate = variant != 1;
+	cudaStream_t s = handle->currentStream;
+#define HELL_ARGS z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, speculate
+	/* 48 resident warps (<= 40 registers) beat 32 warps for the 4/8-byte types
+	 * (measured on B200: 2.11 ms vs 2.33 ms on the 512^3 Laplacian); the complex
+	 * types spill at 40 registers and stay at 32 warps.  hellBlock = 128 / 256
+	 * forces one or the other. */
+	bool dense = !Num<T>::is_complex;
+	if (t->hellBlock >= 256) dense = true;
+	else if (t->hellBlock > 0 && t->hellBlock <= 64) dense = false;
+	if (hackSize == 32) {
+		if (dense) hell_spmv_kernel<T, UNROLL, 32, 12><<<grid, block, 0, s>>>(HELL_ARGS);
+		else       hell_spmv_kernel<T, UNROLL, 32, 8><<<grid, block, 0, s>>>(HELL_ARGS);
+	} else {
+		hell_spmv_kernel<T, UNROLL, 0, 8><<<grid, block, 0, s>>>(HELL_ARGS);
+	}
+#undef HELL_ARGS
 	spgpu_count_launch(handle);
 }
 

@@ -13,55 +13,100 @@
  *   phase 1  slots [0, cut): each lane walks its own row, UNROLL slots per
  *            round; all index and value loads of a round are issued before the
  *            dependent x gathers, then the FMAs.  Lanes whose row is shorter
- *            are switched off by predicated loads (select, not branch), so the
- *            padding is never touched.
+ *            are switched off by predication (select, not branch).
  *   phase 2  only when some row of the warp is longer than `cut` (spike rows):
  *            those rows are finished one at a time by ALL 32 lanes striding
  *            over the remaining slots, followed by a shuffle reduction -- a
  *            4096-slot row costs 128 warp rounds instead of 4096.
- * `cut` = min(longest row of the warp, longCut); longCut is chosen by the host
- * from avgNnzPerRow, so regular matrices (stencils) never enter phase 2.
+ *
+ * STRIDE > 0 makes the slot stride a compile-time constant (HELL with the usual
+ * hackSize 32/64): every load of a round is then base + immediate, with no
+ * address arithmetic at all.
+ *
+ * `allocated` (HELL only) is the number of slots that exist in memory for every
+ * row of the warp (the hack's slab height).  Slots below it can be loaded
+ * WITHOUT waiting for rS -- their content may be padding garbage, so the lane
+ * predicate is applied to the x gather and to the FMA instead of to the load.
+ * This removes one dependent DRAM round trip (rS -> matrix) from every warp;
+ * it costs no extra DRAM traffic because a slot row is fetched as whole lines
+ * as soon as one row of the hack uses it.
  */
 #ifndef SPGPU_SPMV_SLOTS_CUH_
 #define SPGPU_SPMV_SLOTS_CUH_
 
 #include "numeric.cuh"
 
-template <typename T, int UNROLL>
+template <typename T, int UNROLL, int STRIDE>
 __device__ __forceinline__ T warp_rows_dot(
 	const T* __restrict__ vals, const int* __restrict__ idxs,   /* already at this lane's slot 0 */
-	long long valStride, long long idxStride,
+	int valStrideRt, int idxStrideRt,
 	int rowLen,              /* slots of this lane's row (0 for lanes past the end) */
 	int longCut,
+	int allocated,           /* slots guaranteed to exist for the whole warp, 0 = unknown */
 	const T* __restrict__ x, int baseIndex)
 {
 	const int lane = threadIdx.x & 31;
+	const long long valStride = STRIDE > 0 ? STRIDE : valStrideRt;
+	const long long idxStride = STRIDE > 0 ? STRIDE : idxStrideRt;
 	T acc = Num<T>::zero();
+	int cut;
 
-	const int longest = __reduce_max_sync(SPGPU_FULL_MASK, rowLen);
-	const int cut = min(longest, longCut);
-	const int mine = min(rowLen, cut);
-
-	/* ---- phase 1: one row per lane ---- */
-	for (int k0 = 0; k0 < cut; k0 += UNROLL) {
+	if (allocated > 0 && allocated <= UNROLL) {
+		/* ---- phase 1, short regular rows: unpredicated matrix loads ---- */
 		int col[UNROLL];
 		T a[UNROLL];
-		T xv[UNROLL];
 #pragma unroll
 		for (int u = 0; u < UNROLL; ++u) {
-			const int k = k0 + u;
-			const bool on = k < mine;
-			col[u] = on ? ld_stream(idxs + (long long)k * idxStride) : baseIndex;
-			a[u] = on ? ld_stream(vals + (long long)k * valStride) : Num<T>::zero();
+			if (u < allocated) {               /* warp-uniform */
+				col[u] = ld_stream(idxs + u * idxStride);
+				a[u] = ld_stream(vals + u * valStride);
+			}
 		}
 #pragma unroll
 		for (int u = 0; u < UNROLL; ++u) {
-			const bool on = (k0 + u) < mine;
-			xv[u] = on ? ld_keep(x + (col[u] - baseIndex)) : Num<T>::zero();
+			if (u < allocated) {
+				const bool on = u < rowLen;
+				T xv = Num<T>::zero();
+				if (on)
+					xv = ld_keep(x + (col[u] - baseIndex));
+				acc = on ? Num<T>::fma(a[u], xv, acc) : acc;
+			}
 		}
+		cut = allocated;
+	} else {
+		/* ---- phase 1, general: one row per lane, predicated loads ---- */
+		const int longest = __reduce_max_sync(SPGPU_FULL_MASK, rowLen);
+		cut = min(longest, longCut);
+		const int mine = min(rowLen, cut);
+		const T* vp = vals;
+		const int* ip = idxs;
+		for (int k0 = 0; k0 < cut; k0 += UNROLL) {
+			int col[UNROLL];
+			T a[UNROLL];
+			T xv[UNROLL];
 #pragma unroll
-		for (int u = 0; u < UNROLL; ++u)
-			acc = Num<T>::fma(a[u], xv[u], acc);
+			for (int u = 0; u < UNROLL; ++u) {
+				const bool on = (k0 + u) < mine;
+				col[u] = baseIndex;
+				a[u] = Num<T>::zero();
+				if (on) {
+					col[u] = ld_stream(ip + u * idxStride);
+					a[u] = ld_stream(vp + u * valStride);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u) {
+				const bool on = (k0 + u) < mine;
+				xv[u] = Num<T>::zero();
+				if (on)
+					xv[u] = ld_keep(x + (col[u] - baseIndex));
+			}
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u)
+				acc = Num<T>::fma(a[u], xv[u], acc);
+			vp += UNROLL * valStride;
+			ip += UNROLL * idxStride;
+		}
 	}
 
 	/* ---- phase 2: spike rows, all lanes on one row ---- */
@@ -81,13 +126,19 @@ __device__ __forceinline__ T warp_rows_dot(
 			for (int u = 0; u < 4; ++u) {
 				const int k = k0 + 32 * u;
 				const bool on = k < len;
-				col[u] = on ? ld_stream(ri + (long long)k * idxStride) : baseIndex;
-				a[u] = on ? ld_stream(rv + (long long)k * valStride) : Num<T>::zero();
+				col[u] = baseIndex;
+				a[u] = Num<T>::zero();
+				if (on) {
+					col[u] = ld_stream(ri + k * idxStride);
+					a[u] = ld_stream(rv + k * valStride);
+				}
 			}
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				const bool on = (k0 + 32 * u) < len;
-				T xv = on ? ld_keep(x + (col[u] - baseIndex)) : Num<T>::zero();
+				T xv = Num<T>::zero();
+				if (on)
+					xv = ld_keep(x + (col[u] - baseIndex));
 				part = Num<T>::fma(a[u], xv, part);
 			}
 		}

@@ -187,3 +187,28 @@ def test_custom_stream(ours, gpu_handle):
     ours.spgpuSetStream(gpu_handle, None)
     assert ours.spgpuGetStream(gpu_handle) == default
     ours.spgpuStreamDestroy(st)
+
+
+@pytest.mark.parametrize("variant,occ", [(1, 64), (2, 64), (2, 256), (3, 0)])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hack", [32, 64])
+def test_hell_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
+    """every HELL code path (predicated / unpredicated slab reads / 32 vs 48 warps per SM /
+    the bulk-async TMA pipeline incl. its oversize-tile and tail-tile fallbacks)
+    must give the oracle's result; padding is NaN / invalid indices"""
+    try:
+        assert ours.spgpuSetTuning(gpu_handle, b"hellVariant", variant) == 0
+        assert ours.spgpuSetTuning(gpu_handle, b"hellBlock", occ) == 0
+        mats = [G.laplace3d_7pt(20), G.random_coo(5000, 5000, (0, 13), 1, dtype, 0),
+                G.powerlaw(9000, mean=6, maxlen=900, spike_every=700, seed=5, dtype=dtype)]
+        for coo in mats:
+            coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+            A = build("hell", coo, 0, hack)
+            x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
+            y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
+            alpha, beta = scalars(dtype)
+            check(ours, gpu_handle, "hell", coo, A, x, y, alpha, beta)
+            check(ours, gpu_handle, "hell", coo, A, x, y, alpha, 0.0)
+    finally:
+        ours.spgpuSetTuning(gpu_handle, b"hellVariant", 0)
+        ours.spgpuSetTuning(gpu_handle, b"hellBlock", 0)
