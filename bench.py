@@ -268,11 +268,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--n", type=int, default=None, help="override the grid size / row count (testing)")
+    ap.add_argument("--size", type=int, default=None, help="override the grid size / row count (testing)")
     ap.add_argument("--halo", default="push", choices=["push", "nccl"], help="multi-GPU halo exchange mode")
-    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="multiply interior rows while the halos are in flight (3 SpMV launches per step); "
+                         "default: one fused exchange kernel, then one SpMV launch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cg", action="store_true", help="also time CG iterations (SpMV + 2 dots + 3 axpby), cfg5 only")
+    ap.add_argument("--verify", action="store_true",
+                    help="cfg5, N>1: check the partitioned result bit-for-bit against the same rows multiplied with global columns")
     ap.add_argument("--tune", default="", help="key=value,... passed to spgpuSetTuning")
     ap.add_argument("--sweep", default="", help="'k=v,k=v;k=v;...': kernel-only timing per tuning set (stderr)")
     args = ap.parse_args()
@@ -300,6 +305,12 @@ def main():
         print(json.dumps(out), flush=True)
         return 0
 
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version
+    # banner ...) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from spgpu_b200 import capi, mg
@@ -324,7 +335,7 @@ def main():
     stream = torch.cuda.ExternalStream(L.spgpuGetStream(h), device=device)
     torch.cuda.set_stream(stream)
 
-    w = build_workload(args.workload, rank, world, device, args.n)
+    w = build_workload(args.workload, rank, world, device, args.size)
     tdt = {"S": torch.float32, "D": torch.float64, "C": torch.complex64, "Z": torch.complex128}[w["sym"]]
     rows, halo = w["rows"], w["halo"]
     ext_len = w["x_len"]
@@ -354,7 +365,7 @@ def main():
     if world > 1 and args.halo == "push":
         peer = mg.PeerHalo(L, h, rank, world, x_ptr, ext_len, halo)
     op = mg.MgHellSpmv(rank, world, rows, halo, lambda _z, _x, r0, r1: step(r0, r1), ex, peer,
-                       overlap=not args.no_overlap)
+                       overlap=args.overlap)
 
     def barrier():
         torch.cuda.synchronize()
@@ -365,6 +376,60 @@ def main():
     def one_step():
         op.apply(z, x_ext)
 
+    # working sets that are not >> L2 (126 MB): write a 512 MB scratch between timed steps
+    flush_l2 = (w["bytes"] / max(world, 1)) < 8 * 126e6
+    scratch = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=device) if flush_l2 else None
+
+    def timed_steps(fn, count):
+        """total ms of `count` calls of fn on the handle's stream (CUDA events); with
+        flush_l2 every call is bracketed by its own event pair and the flush sits outside"""
+        if not flush_l2:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(count):
+                fn()
+            b.record(stream)
+            return a, b, None
+        pairs = []
+        for _ in range(count):
+            scratch.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            pairs.append((a, b))
+        return None, None, pairs
+
+    def elapsed(a, b, pairs):
+        if pairs is None:
+            return a.elapsed_time(b)
+        return float(sum(x.elapsed_time(y) for x, y in pairs))
+
+    # ---------------- optional multi-GPU self-check ------------------------------
+    verified = None
+    if args.verify and args.workload == "cfg5" and world > 1:
+        from spgpu_b200 import device_build as DB
+        n = args.size or 512
+        per = n // world
+        one_step()
+        barrier()
+        owned = x_ext[halo:halo + rows].contiguous()
+        x_full = torch.empty(world * rows, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(x_full, owned)
+        Ag = DB.hell_laplace3d_7pt(n, rank * per, (rank + 1) * per, local_columns=False, device=device)
+        z_ref = torch.full((rows,), float("nan"), dtype=torch.float64, device=device)
+        T = capi.TYPES["D"]
+        L.spgpuDhellspmv(h, z_ref.data_ptr(), 0, T.scalar(1.0), Ag.values.data_ptr(), Ag.indices.data_ptr(), 32,
+                         Ag.hack_offsets.data_ptr(), Ag.rs.data_ptr(), 0, Ag.avg, rows, x_full.data_ptr(),
+                         T.scalar(0.0), 0)
+        torch.cuda.synchronize()
+        ok = torch.tensor([1.0 if torch.equal(z, z_ref) else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        verified = bool(ok.item() == 1.0)
+        del Ag, z_ref, x_full
+        if rank == 0:
+            print(f"verify: partitioned SpMV == global-column SpMV on every rank: {verified}", file=sys.stderr, flush=True)
+
     # ---------------- device-resident timing ------------------------------------
     for _ in range(W):
         one_step()
@@ -374,13 +439,9 @@ def main():
         sampler.start()
     launches0 = L.spgpuGetLaunchCount(h)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        one_step()
-    e1.record(stream)
+    e0, e1, pairs = timed_steps(one_step, K)
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = elapsed(e0, e1, pairs)
     launches = L.spgpuGetLaunchCount(h) - launches0
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=device)
@@ -400,6 +461,8 @@ def main():
     # per-launch duration of the full-block SpMV kernel on this rank's stream
     ker_ms = []
     for _ in range(min(K, 10)):
+        if flush_l2:
+            scratch.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         step()
@@ -426,6 +489,8 @@ def main():
             assert L.spgpuSetTuning(h, k.encode(), int(v)) == 0, f"unknown tuning key {k}"
         ts = []
         for _ in range(8):
+            if flush_l2:
+                scratch.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream); step(); b.record(stream); b.synchronize()
             ts.append(a.elapsed_time(b))
@@ -467,6 +532,53 @@ def main():
                "ms_per_step": ms_e2e, "steps": Ke,
                "what": "x (owned part) H2D from pinned memory + SpMV through the C ABI + z D2H, per step; matrix resident"}
 
+    # ---------------- CG step: SpMV + 2 dots + 3 axpby (BASELINE configs[4]) ------
+    cg_out = None
+    if args.cg and w["kind"] == "hell" and w["sym"] == "D":
+        from spgpu_b200 import krylov
+        A = w["A"]
+        st = krylov.CgState(rows, halo, device, p_ext=x_ext)
+        step_cg = make_step(L, h, w, x_ptr, st.ap.data_ptr(), 0)
+        op_cg = mg.MgHellSpmv(rank, world, rows, halo, lambda _z, _x, r0, r1: step_cg(r0, r1), ex, peer,
+                              overlap=args.overlap)
+
+        def apply_A(_z, _x):
+            op_cg.apply(st.ap, x_ext)
+
+        def apply_A_dot(_z, _x, dres):
+            L.spgpuDhellspmvDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
+                                A.hack_offsets.data_ptr(), A.rs.data_ptr(), rows, x_ptr, A.base, 0, dres)
+
+        allred = (lambda t: dist.all_reduce(t)) if world > 1 else None
+        cg = krylov.Cg(L, h, st, apply_A, apply_A_dot, allred)
+        bvec = torch.rand(rows, generator=gen, device=device, dtype=torch.float64)
+        iters = 10
+        cg_out = {"iterations": iters}
+        for flavour, fn in (("blocking", cg.step_blocking), ("device", cg.step_device)):
+            cg.start(bvec)
+            for _ in range(2):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = L.spgpuGetLaunchCount(h)
+            a.record(stream)
+            for _ in range(iters):
+                fn()
+            b.record(stream)
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_it = float(t.item()) / iters
+            vec_bytes = krylov.CG_BYTES_PER_ROW_VECTOR_OPS[flavour] * w["total_rows"]
+            cg_out[flavour] = {"ms_per_iteration": ms_it,
+                               "algorithmic_gb_per_iteration": (bytes_total + vec_bytes) / 1e9,
+                               "hbm_gbs": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9,
+                               "frac_of_peak": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9 / (peak * world),
+                               "kernels_per_iteration": (L.spgpuGetLaunchCount(h) - l0) / iters,
+                               "residual_norm2_after": cg.residual_norm2() if flavour == "device" else st.rr_host}
+        del st, cg, bvec
+
     # ---------------- CPU baseline (rank 0, N=1) --------------------------------
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -482,25 +594,33 @@ def main():
             "dtype": {"S": "f32", "D": "f64", "C": "c64", "Z": "c128"}[w["sym"]], "data": "synthetic",
             "config": {"workload": w["label"], "rows": w["total_rows"], "nnz": int(nnz_total),
                        "parallelism": f"row-sharded z-slabs x{world}, halo={args.halo if world > 1 else 'none'}"
-                                      f"{'' if args.no_overlap or world == 1 else ', interior/boundary overlap'}",
-                       "l2": "inputs larger than L2 (no flush needed)" if w["bytes"] / max(world, 1) > 4 * 126e6
-                             else "working set comparable to L2: numbers include L2 hits, see DESIGN.md",
+                                      f"{', interior/boundary overlap' if args.overlap and world > 1 else ''}",
+                       "l2": "L2 flushed between timed steps (512 MB scratch write, outside the event pairs)" if flush_l2
+                             else "inputs larger than L2 (>= 8x 126 MB per GPU), no flush",
                        "alpha": str(w["alpha"]), "beta": str(w["beta"])},
             "hbm_gbs": bytes_total / (ms_step * 1e-3) / 1e9,
             "hbm_frac_of_peak": bytes_total / (ms_step * 1e-3) / 1e9 / (peak * world),
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        if verified is not None:
+            out["verified_vs_global_columns"] = verified
+        if cg_out is not None:
+            out["cg"] = cg_out
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     # hand the stream back before the handle (and its stream) go away
     torch.cuda.synchronize()
     torch.cuda.set_stream(torch.cuda.default_stream(device))
-    del step, op, z, y, x_ext, w
+    del step, op, z, y, x_ext, w, scratch
     torch.cuda.synchronize()
-    L.spgpuDestroy(h)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    return 0
+    L.spgpuDestroy(h)
+    # pinned buffers and cached blocks that were used on the handle's (now destroyed) stream
+    # would make torch's allocators record events on it at interpreter exit: leave directly
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -92,8 +92,24 @@ int spgpuDeviceFree(void* devPtr);
  */
 void spgpuDhaloPush(spgpuHandle_t handle, double* peerDst, const double* src,
 	int n, unsigned* peerFlag, unsigned flagValue);
-/* Stream-ordered wait until *flag >= value (bounded spin; traps on timeout). */
+/* Stream-ordered wait until *flag >= value (bounded spin, gives up after 2 s). */
 void spgpuWaitFlag(spgpuHandle_t handle, const unsigned* flag, unsigned value);
+
+/*
+ * Fused halo exchange of a 1-D chain of ranks, ONE kernel per SpMV: waits until
+ * the neighbours have acknowledged the previous halo (ackLo/ackHi, local flags,
+ * value seq-1), pushes srcLo[0..n) into the lower neighbour's upper halo zone and
+ * srcHi[0..n) into the upper neighbour's lower halo zone (peer pointers), release-
+ * stores seq into the neighbours' ready flags and returns when this rank's own
+ * ready flags (myReadyLo/myReadyHi) have reached seq.  NULL pointers = no
+ * neighbour on that side.  spgpuHaloAck (after the SpMV has consumed the halos)
+ * stores seq into the neighbours' ack flags.
+ */
+void spgpuDhaloExchange(spgpuHandle_t handle, double* peerDstLo, const double* srcLo,
+	double* peerDstHi, const double* srcHi, int n, const unsigned* ackLo,
+	const unsigned* ackHi, unsigned* peerReadyLo, unsigned* peerReadyHi,
+	const unsigned* myReadyLo, const unsigned* myReadyHi, unsigned seq);
+void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq);
 
 #ifdef __cplusplus
 }

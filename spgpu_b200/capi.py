@@ -113,7 +113,8 @@ def ext_symbols():
         names += [f"spgpu{s}dotDev", f"spgpu{s}nrm2sqDev"]
     names += ["spgpuDaxpbyDev", "spgpuDhellspmvDot",
               "spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
-              "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag"]
+              "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag",
+              "spgpuDhaloExchange", "spgpuHaloAck"]
     return names
 
 
@@ -234,6 +235,9 @@ class SpgpuLib:
             f["spgpuDhaloPush"] = _sig(d, "spgpuDhaloPush", None,
                 [H, P, P, c_int, P, ctypes.c_uint], optional=True)
             f["spgpuWaitFlag"] = _sig(d, "spgpuWaitFlag", None, [H, P, ctypes.c_uint], optional=True)
+            f["spgpuDhaloExchange"] = _sig(d, "spgpuDhaloExchange", None,
+                [H, P, P, P, P, c_int, P, P, P, P, P, P, ctypes.c_uint], optional=True)
+            f["spgpuHaloAck"] = _sig(d, "spgpuHaloAck", None, [H, P, P, ctypes.c_uint], optional=True)
 
     def __getattr__(self, name):
         try:

@@ -63,7 +63,7 @@ extern "C" void spgpuDaxpbyDev(spgpuHandle_t handle, double* z, int n,
 /* ---- HELL SpMV fused with p.Ap ---------------------------------------------- */
 
 template <int UNROLL>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(128, 8)
 dhell_spmv_dot_kernel(double* __restrict__ z, const double* __restrict__ cM,
 	const int* __restrict__ rP, int hackSize, const int* __restrict__ hackOffsets,
 	const int* __restrict__ rS, int rows, const double* __restrict__ x,
@@ -106,7 +106,7 @@ extern "C" void spgpuDhellspmvDot(spgpuHandle_t handle, double* z, const double*
 	if (rows <= 0)
 		return;
 	const SpgpuTuning* t = spgpu_tuning(handle);
-	const int block = spgpu_block(t->hellBlock);
+	const int block = 128;
 	dhell_spmv_dot_kernel<8><<<spgpu_ceil_div(rows, block), block, 0, handle->currentStream>>>(
 		z, cM, rP, hackSize, hackOffsets, rS, rows, x, baseIndex, xOffset,
 		spgpu_long_cut(t, 8), dRes);
@@ -200,6 +200,122 @@ extern "C" void spgpuDhaloPush(spgpuHandle_t handle, double* peerDst, const doub
 	/* the ticket word next to the reductions' one (offset 16 bytes) */
 	halo_push_kernel<<<(unsigned)want, 256, 0, handle->currentStream>>>(peerDst, src, n > 0 ? n : 0,
 		vec, peerFlag, flagValue, h->dTicket + 4);
+	spgpu_count_launch(handle);
+}
+
+/* ---- fused halo exchange: wait acks -> push both planes -> signal -> wait arrivals ---- */
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+/* spin until *flag >= value; gives up (with a message) after timeoutNs so a bug is a wrong
+ * answer the tests catch, never a hung GPU */
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned value, unsigned long long timeoutNs)
+{
+	unsigned long long t0, t1;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	for (;;) {
+		const unsigned v = ld_acquire_sys(flag);
+		if ((int)(v - value) >= 0)
+			return;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (t1 - t0 > timeoutNs) {
+			printf("spgpu halo: timed out waiting for flag value %u (saw %u)\n", value, v);
+			return;
+		}
+		__nanosleep(100);
+	}
+}
+
+/*
+ * One kernel per SpMV on each rank.  Even CTAs copy this rank's first n owned entries into
+ * the LOWER neighbour's upper halo zone, odd CTAs its last n owned entries into the UPPER
+ * neighbour's lower halo zone (128-bit stores through NVLink peer pointers).  Before
+ * copying, a CTA waits until that neighbour has acknowledged the previous halo (so it is
+ * not overwritten while still being read).  The last CTA to finish release-stores the
+ * sequence number into both neighbours' "ready" flags and then waits for this rank's own
+ * two "ready" flags, so the kernel completes exactly when this rank's halos have arrived.
+ */
+__global__ void __launch_bounds__(256)
+halo_exchange_kernel(double* dstLo, const double* srcLo, double* dstHi, const double* srcHi,
+	long long n, const unsigned* ackLo, const unsigned* ackHi, unsigned* peerReadyLo,
+	unsigned* peerReadyHi, const unsigned* myReadyLo, const unsigned* myReadyHi,
+	unsigned seq, unsigned* ticket, unsigned long long timeoutNs)
+{
+	__shared__ bool amLast;
+	const bool toHi = (blockIdx.x & 1) != 0;
+	double* dst = toHi ? dstHi : dstLo;
+	const double* src = toHi ? srcHi : srcLo;
+	const unsigned* ack = toHi ? ackHi : ackLo;
+	if (dst) {
+		if (threadIdx.x == 0 && ack && seq > 1)
+			spin_until(ack, seq - 1, timeoutNs);
+		__syncthreads();
+		const long long half = gridDim.x >> 1;
+		const long long tid = (long long)(blockIdx.x >> 1) * blockDim.x + threadIdx.x;
+		const long long nthreads = half * blockDim.x;
+		if ((((size_t)dst | (size_t)src) & 15) == 0) {
+			double2* d2 = reinterpret_cast<double2*>(dst);
+			const double2* s2 = reinterpret_cast<const double2*>(src);
+			for (long long p = tid; p < (n >> 1); p += nthreads)
+				d2[p] = s2[p];
+			if (tid == 0 && (n & 1))
+				dst[n - 1] = src[n - 1];
+		} else {
+			for (long long e = tid; e < n; e += nthreads)
+				dst[e] = src[e];
+		}
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0)
+		amLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (amLast && threadIdx.x == 0) {
+		*ticket = 0u;
+		__threadfence_system();
+		if (peerReadyLo) st_release_sys(peerReadyLo, seq);
+		if (peerReadyHi) st_release_sys(peerReadyHi, seq);
+		if (myReadyLo) spin_until(myReadyLo, seq, timeoutNs);
+		if (myReadyHi) spin_until(myReadyHi, seq, timeoutNs);
+	}
+}
+
+extern "C" void spgpuDhaloExchange(spgpuHandle_t handle, double* peerDstLo, const double* srcLo,
+	double* peerDstHi, const double* srcHi, int n, const unsigned* ackLo, const unsigned* ackHi,
+	unsigned* peerReadyLo, unsigned* peerReadyHi, const unsigned* myReadyLo,
+	const unsigned* myReadyHi, unsigned seq)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	long long want = 2 * (((long long)n / 2 + 255) / 256);
+	const long long cap = 2LL * (handle->multiProcessorCount / 2 > 0 ? handle->multiProcessorCount / 2 : 1);
+	if (want > cap) want = cap;
+	if (want < 2) want = 2;
+	halo_exchange_kernel<<<(unsigned)want, 256, 0, handle->currentStream>>>(peerDstLo, srcLo, peerDstHi, srcHi,
+		n > 0 ? n : 0, ackLo, ackHi, peerReadyLo, peerReadyHi, myReadyLo, myReadyHi, seq,
+		h->dTicket + 8, 2000000000ull);
+	spgpu_count_launch(handle);
+}
+
+__global__ void halo_ack_kernel(unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq)
+{
+	__threadfence_system();
+	if (peerAckLo) st_release_sys(peerAckLo, seq);
+	if (peerAckHi) st_release_sys(peerAckHi, seq);
+}
+
+extern "C" void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq)
+{
+	halo_ack_kernel<<<1, 1, 0, handle->currentStream>>>(peerAckLo, peerAckHi, seq);
 	spgpu_count_launch(handle);
 }
 

@@ -14,28 +14,28 @@
 #include "launch.cuh"
 #include "spmv_slots.cuh"
 
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(1024)
+template <typename T, int UNROLL, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 ell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
 	const T* __restrict__ cM, const int* __restrict__ rP, int cMPitch,
 	int rPPitch, const int* __restrict__ rS, const int* __restrict__ rIdx,
 	int maxNnzPerRow, int rows, const T* __restrict__ x, T beta, int baseIndex,
-	int longCut)
+	int longCut, int allocated)
 {
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	if (i - lane >= rows)
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31;
+	if (i - lane >= (unsigned)rows)
 		return;
-	const bool live = i < rows;
+	const bool live = i < (unsigned)rows;
 
 	const int len = live ? (rS ? ld_stream(rS + i) : maxNnzPerRow) : 0;
 	const bool useBeta = Num<T>::nonzero(beta);
-	const long long out = (live && rIdx) ? (long long)__ldg(rIdx + i) : i;
+	const unsigned out = (live && rIdx) ? (unsigned)__ldg(rIdx + i) : i;
 	T yv = Num<T>::zero();
 	if (useBeta && live)
 		yv = y[out];
 
-	T acc = warp_rows_dot<T, UNROLL, 0>(cM + i, rP + i, cMPitch, rPPitch, len, longCut, 0, x, baseIndex);
+	T acc = warp_rows_dot<T, UNROLL, 0>(cM + i, rP + i, cMPitch, rPPitch, len, longCut, allocated, x, baseIndex);
 
 	if (live)
 		z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
@@ -50,11 +50,26 @@ static void ell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	if (rows <= 0)
 		return;
 	const SpgpuTuning* t = spgpu_tuning(handle);
-	const int block = spgpu_block(t->hellBlock);
+	const int block = 128;
 	const unsigned grid = spgpu_ceil_div(rows, block);
-	ell_spmv_kernel<T, UNROLL><<<grid, block, 0, handle->currentStream>>>(
-		z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow, rows, x,
-		beta, baseIndex, spgpu_long_cut(t, avgNnzPerRow));
+	/* every slot below maxNnzPerRow exists in an ELL allocation, so short regular
+	 * matrices can read them without waiting for rS (spmv_slots.cuh); only worth it
+	 * when little of that is padding (avg close to max) */
+	int allocated = 0;
+	if (t->hellVariant != 1 && maxNnzPerRow > 0 && maxNnzPerRow <= UNROLL &&
+	    (rS == NULL || 4LL * avgNnzPerRow >= 3LL * maxNnzPerRow))
+		allocated = maxNnzPerRow;
+	bool dense = !Num<T>::is_complex;
+	if (t->hellBlock >= 256) dense = true;
+	else if (t->hellBlock > 0 && t->hellBlock <= 64) dense = false;
+	if (dense)
+		ell_spmv_kernel<T, UNROLL, 12><<<grid, block, 0, handle->currentStream>>>(
+			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow, rows, x,
+			beta, baseIndex, spgpu_long_cut(t, avgNnzPerRow), allocated);
+	else
+		ell_spmv_kernel<T, UNROLL, 8><<<grid, block, 0, handle->currentStream>>>(
+			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow, rows, x,
+			beta, baseIndex, spgpu_long_cut(t, avgNnzPerRow), allocated);
 	spgpu_count_launch(handle);
 }
 

@@ -1,0 +1,117 @@
+"""Conjugate-gradient iteration built on the C ABI (BASELINE configs[4]: "plus CG
+step (spmv+dot+axpby)").  Caller-side code -- the reference ships no solver, its
+users write this loop around spgpu?hellspmv / spgpu?dot / spgpu?axpby.
+
+Two flavours of the same recurrence:
+
+* `step_blocking`  what a spGPU user writes today: spgpuDhellspmv, spgpuDdot
+  (blocks the host, returns the value), spgpuDaxpby with host scalars --
+  6 kernels and 2 host synchronisations per iteration.
+* `step_device`    the additive entry points of include/spgpu_ext.h: the SpMV is
+  fused with p.Ap (spgpuDhellspmvDot), r.r goes to device memory
+  (spgpuDdotDev) and the three vector updates read alpha = rr/pAp and
+  beta = rr'/rr from device memory (spgpuDaxpbyDev) -- 5 kernels, no host
+  synchronisation, CUDA-graph capturable.  With several GPUs the two scalars are
+  all-reduced in place (NCCL) and the halo of the new p is exchanged by the
+  partitioned operator (spgpu_b200/mg.py).
+
+Vectors of a partition: p lives inside p_ext = [halo | owned | halo]; x, r, Ap
+are owned-length.
+"""
+from __future__ import annotations
+
+import torch
+
+from .capi import TYPES
+
+
+class CgState:
+    def __init__(self, n_owned, halo, device, p_ext=None):
+        f64 = torch.float64
+        self.n, self.halo = n_owned, halo
+        self.x = torch.zeros(n_owned, dtype=f64, device=device)
+        self.r = torch.zeros(n_owned, dtype=f64, device=device)
+        self.ap = torch.zeros(n_owned, dtype=f64, device=device)
+        self.p_ext = p_ext if p_ext is not None else torch.zeros(n_owned + 2 * halo, dtype=f64, device=device)
+        self.p = self.p_ext[halo:halo + n_owned]
+        # device scalars: [rr, pAp, rr_new, spare]
+        self.s = torch.zeros(4, dtype=f64, device=device)
+        self.rr_host = 0.0
+
+
+class Cg:
+    """apply_A(z_tensor, x_ext_tensor) must compute z = A * x_ext (incl. halo exchange);
+    apply_A_dot(z, x_ext, d_out_ptr) optionally the fused SpMV + p.Ap (single GPU)."""
+
+    def __init__(self, L, handle, state: CgState, apply_A, apply_A_dot=None, allreduce=None):
+        self.L, self.h, self.st = L, handle, state
+        self.apply_A, self.apply_A_dot, self.allreduce = apply_A, apply_A_dot, allreduce
+        self.T = TYPES["D"]
+
+    def start(self, b: torch.Tensor):
+        """x = 0, r = p = b, rr = b.b"""
+        st, L, h, n = self.st, self.L, self.h, self.st.n
+        st.x.zero_()
+        st.r.copy_(b)
+        st.p.copy_(b)
+        L.spgpuDdotDev(h, n, st.r.data_ptr(), st.r.data_ptr(), st.s.data_ptr())
+        if self.allreduce:
+            self.allreduce(st.s[0:1])
+        st.rr_host = float(st.s[0].item())
+        return st.rr_host
+
+    # ---- reference-style: blocking dots, host scalars -----------------------
+    def step_blocking(self):
+        st, L, h, n, T = self.st, self.L, self.h, self.st.n, self.T
+        self.apply_A(st.ap, st.p_ext)
+        pap = L.spgpuDdot(h, n, st.p.data_ptr(), st.ap.data_ptr())
+        if self.allreduce:
+            t = torch.tensor([pap], dtype=torch.float64, device=st.x.device)
+            self.allreduce(t)
+            pap = float(t.item())
+        alpha = st.rr_host / pap
+        L.spgpuDaxpby(h, st.x.data_ptr(), n, T.scalar(1.0), st.x.data_ptr(), T.scalar(alpha), st.p.data_ptr())
+        L.spgpuDaxpby(h, st.r.data_ptr(), n, T.scalar(1.0), st.r.data_ptr(), T.scalar(-alpha), st.ap.data_ptr())
+        rr_new = L.spgpuDdot(h, n, st.r.data_ptr(), st.r.data_ptr())
+        if self.allreduce:
+            t = torch.tensor([rr_new], dtype=torch.float64, device=st.x.device)
+            self.allreduce(t)
+            rr_new = float(t.item())
+        beta = rr_new / st.rr_host
+        L.spgpuDaxpby(h, st.p.data_ptr(), n, T.scalar(beta), st.p.data_ptr(), T.scalar(1.0), st.r.data_ptr())
+        st.rr_host = rr_new
+        return rr_new
+
+    # ---- device scalars: no host synchronisation ----------------------------
+    def step_device(self):
+        st, L, h, n = self.st, self.L, self.h, self.st.n
+        s = st.s.data_ptr()
+        rr, pap, rrn = s, s + 8, s + 16
+        if self.apply_A_dot is not None and self.allreduce is None:
+            self.apply_A_dot(st.ap, st.p_ext, pap)
+        else:
+            self.apply_A(st.ap, st.p_ext)
+            L.spgpuDdotDev(h, n, st.p.data_ptr(), st.ap.data_ptr(), pap)
+            if self.allreduce:
+                self.allreduce(st.s[1:2])
+        # x += (rr/pAp) p ;  r -= (rr/pAp) Ap
+        L.spgpuDaxpbyDev(h, st.x.data_ptr(), n, 0, 0, 1.0, st.x.data_ptr(), rr, pap, 1.0, st.p.data_ptr())
+        L.spgpuDaxpbyDev(h, st.r.data_ptr(), n, 0, 0, 1.0, st.r.data_ptr(), rr, pap, -1.0, st.ap.data_ptr())
+        L.spgpuDdotDev(h, n, st.r.data_ptr(), st.r.data_ptr(), rrn)
+        if self.allreduce:
+            self.allreduce(st.s[2:3])
+        # p = r + (rr'/rr) p ; then rr <- rr'
+        L.spgpuDaxpbyDev(h, st.p.data_ptr(), n, rrn, rr, 1.0, st.p.data_ptr(), 0, 0, 1.0, st.r.data_ptr())
+        st.s[0:1].copy_(st.s[2:3])
+
+    def residual_norm2(self):
+        return float(self.st.s[0].item())
+
+
+CG_BYTES_PER_ROW_VECTOR_OPS = {
+    # algorithmic bytes per row of the vector part of one iteration (double):
+    # blocking: p.Ap 16 + x update 24 + r update 24 + r.r 8 + p update 24
+    "blocking": 96,
+    # device: p.Ap fused into the SpMV epilogue (p re-read 8) + 24 + 24 + 8 + 24
+    "device": 88,
+}

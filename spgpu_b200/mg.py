@@ -207,6 +207,27 @@ class PeerHalo:
                 _px, pf, _plen = self.peer[nb]
                 L.spgpuDhaloPush(h, 0, 0, 0, pf + 4 * word, seq)
 
+    def exchange_fused(self):
+        """ONE kernel: wait acks, push both planes, signal, wait for my own halos."""
+        L, h, w = self.L, self.h, self.halo
+        n = self.ext_len - 2 * w
+        self.seq += 1
+        lo, hi = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
+        f = self.flags
+        L.spgpuDhaloExchange(
+            h,
+            (lo[0] + 8 * (lo[2] - w)) if lo else 0, self.x_ptr + 8 * w,      # -> lower neighbour's upper halo
+            hi[0] if hi else 0, self.x_ptr + 8 * n,                           # -> upper neighbour's lower halo
+            w,
+            (f + 4 * 2) if lo else 0, (f + 4 * 3) if hi else 0,               # acks I wait for
+            (lo[1] + 4 * 1) if lo else 0, (hi[1] + 4 * 0) if hi else 0,       # their ready flags
+            (f + 4 * 0) if lo else 0, (f + 4 * 1) if hi else 0,               # my ready flags
+            self.seq)
+
+    def ack_fused(self):
+        lo, hi = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
+        self.L.spgpuHaloAck(self.h, (lo[1] + 4 * 3) if lo else 0, (hi[1] + 4 * 2) if hi else 0, self.seq)
+
     def close(self):
         torch.cuda.synchronize()
         for px, pf, _ in self.peer.values():
@@ -266,16 +287,17 @@ class MgHellSpmv:
             return
         if self.peer is not None:
             # NVLink push: everything is ordered on the handle's stream
-            self.peer.exchange()
             if self.overlap:
+                self.peer.exchange()
                 self.local_spmv(z, x_ext, self.head, self.tail)   # interior rows need no halo
                 self.peer.wait()
                 self.local_spmv(z, x_ext, 0, self.head)
                 self.local_spmv(z, x_ext, self.tail, n)
+                self.peer.ack()
             else:
-                self.peer.wait()
+                self.peer.exchange_fused()          # returns when both halos are in place
                 self.local_spmv(z, x_ext, 0, n)
-            self.peer.ack()
+                self.peer.ack_fused()
             return
         works = self.ex.start(x_ext)
         if self.overlap:

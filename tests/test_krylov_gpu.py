@@ -1,0 +1,124 @@
+"""GPU tests of the additive Krylov entry points (include/spgpu_ext.h) and of the CG
+iteration built on the C ABI (BASELINE configs[4]: SpMV + dot + axpby)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from spgpu_b200 import formats as F, generators as G
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_result_reductions(ours, oracle, gpu_handle):
+    import torch
+    for s, dtype in (("S", np.float32), ("D", np.float64), ("C", np.complex64), ("Z", np.complex128)):
+        n = 300007
+        x = G.random_vector(n, dtype, 1, -1, 1)
+        y = G.random_vector(n, dtype, 2, -1, 1)
+        dx, dy = util.to_dev(x), util.to_dev(y)
+        out = torch.zeros(2, dtype=dx.dtype, device="cuda")
+        getattr(ours, f"spgpu{s}dotDev")(gpu_handle, n, dx.data_ptr(), dy.data_ptr(), out.data_ptr())
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()[0]
+        blocking = util.TYPES[s].from_c(getattr(ours, f"spgpu{s}dot")(gpu_handle, n, dx.data_ptr(), dy.data_ptr()))
+        assert got == np.asarray(blocking, dtype=dtype)            # same kernel, same order -> same bits
+        want = oracle.dot(s, x, y)
+        mag = float(np.sum(np.abs(x.astype(np.complex128)) * np.abs(y.astype(np.complex128))))
+        assert abs(got - want) <= (2e-7 if s in "SC" else 4e-16) * 64 * mag
+        rout = torch.zeros(2, dtype=torch.float32 if s in "SC" else torch.float64, device="cuda")
+        getattr(ours, f"spgpu{s}nrm2sqDev")(gpu_handle, n, dx.data_ptr(), rout.data_ptr())
+        torch.cuda.synchronize()
+        nrm = getattr(oracle, f"{s}nrm2")(n, util.ptr(x))
+        assert abs(np.sqrt(float(rout[0].item())) - nrm) <= (1e-5 if s in "SC" else 1e-13) * nrm
+
+
+def test_axpby_with_device_scalars(ours, gpu_handle):
+    import torch
+    for n in (1, 1001, 1 << 20):
+        rng = np.random.default_rng(n)
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        sc = np.array([3.0, 7.0, -2.0, 5.0])
+        dx, dy, ds = util.to_dev(x), util.to_dev(y), util.to_dev(sc)
+        dz = torch.zeros_like(dx)
+        p = ds.data_ptr()
+        # z = (sc0/sc1) * y - (sc2/sc3) * x
+        ours.spgpuDaxpbyDev(gpu_handle, dz.data_ptr(), n, p, p + 8, 1.0, dy.data_ptr(), p + 16, p + 24, -1.0, dx.data_ptr())
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dz.cpu().numpy(), (3.0 / 7.0) * y - (-2.0 / 5.0) * x, rtol=1e-14, atol=1e-15)
+        # NULL pairs mean 1; in place on y
+        ours.spgpuDaxpbyDev(gpu_handle, dy.data_ptr(), n, 0, 0, 1.0, dy.data_ptr(), p, 0, 1.0, dx.data_ptr())
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dy.cpu().numpy(), y + 3.0 * x, rtol=1e-14, atol=1e-15)
+
+
+def test_fused_spmv_dot(ours, gpu_handle):
+    import torch
+    coo = G.laplace3d_7pt(24)
+    A = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    dA = util.upload(A)
+    n = coo.nrows
+    x = G.random_vector(n, np.float64, 3)
+    dx = util.to_dev(x)
+    dz = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    dres = torch.full((1,), float("nan"), dtype=torch.float64, device="cuda")
+    ours.spgpuDhellspmvDot(gpu_handle, dz.data_ptr(), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
+                           dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), n, dx.data_ptr(), 0, 0, dres.data_ptr())
+    torch.cuda.synchronize()
+    want = util.oracle_spmv("hell", A, x, None, 1.0, 0.0)
+    util.assert_rows_close(dz.cpu().numpy(), want, util.row_scale(coo, x, None, 1.0, 0.0), "D", "fused spmv")
+    scale = float(np.sum(np.abs(x) * np.abs(want)))
+    assert abs(float(dres.item()) - float(np.dot(x, want))) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("flavour", ["blocking", "device"])
+def test_cg_converges_like_the_cpu_recurrence(ours, gpu_handle, flavour):
+    """40 CG iterations on a 3-D Laplacian: same residual history as the identical
+    recurrence run with numpy + the CPU oracle, and the final x solves the system"""
+    import torch
+    from spgpu_b200 import krylov
+    coo = G.laplace3d_7pt(16)
+    A = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    dA = util.upload(A)
+    n = coo.nrows
+    T = util.TYPES["D"]
+    b = G.random_vector(n, np.float64, 9)
+
+    def apply_A(z, x_ext):
+        ours.spgpuDhellspmv(gpu_handle, z.data_ptr(), 0, T.scalar(1.0), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
+                            dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), 0, 7, n, x_ext.data_ptr(), T.scalar(0.0), 0)
+
+    def apply_A_dot(z, x_ext, dres):
+        ours.spgpuDhellspmvDot(gpu_handle, z.data_ptr(), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
+                               dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), n, x_ext.data_ptr(), 0, 0, dres)
+
+    stream = torch.cuda.ExternalStream(ours.spgpuGetStream(gpu_handle))
+    with torch.cuda.stream(stream):
+        st = krylov.CgState(n, 0, "cuda")
+        cg = krylov.Cg(ours, gpu_handle, st, apply_A, apply_A_dot)
+        rr0 = cg.start(util.to_dev(b))
+        hist = []
+        for _ in range(40):
+            if flavour == "blocking":
+                hist.append(cg.step_blocking())
+            else:
+                cg.step_device()
+                hist.append(cg.residual_norm2())
+        torch.cuda.synchronize()
+        x_gpu = st.x.cpu().numpy()
+    # CPU recurrence with the oracle SpMV
+    x = np.zeros(n); r = b.copy(); p = b.copy(); rr = float(r @ r)
+    assert abs(rr0 - rr) <= 1e-12 * rr
+    ref = []
+    for _ in range(40):
+        ap = util.oracle_spmv("hell", A, p, None, 1.0, 0.0)
+        alpha = rr / float(p @ ap)
+        x += alpha * p; r -= alpha * ap
+        rr_new = float(r @ r)
+        p = r + (rr_new / rr) * p
+        rr = rr_new
+        ref.append(rr)
+    np.testing.assert_allclose(hist, ref, rtol=1e-8)
+    assert hist[-1] < 1e-6 * rr0
+    np.testing.assert_allclose(x_gpu, x, rtol=1e-9, atol=1e-12)
