@@ -269,7 +269,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--size", type=int, default=None, help="override the grid size / row count (testing)")
-    ap.add_argument("--halo", default="push", choices=["push", "nccl"], help="multi-GPU halo exchange mode")
+    ap.add_argument("--halo", default="fused", choices=["fused", "push", "nccl"],
+                    help="multi-GPU halo exchange: fused = inside the SpMV kernel over NVLink peer pointers; "
+                         "push = separate NVLink push kernel + flags; nccl = grouped send/recv")
     ap.add_argument("--overlap", action="store_true",
                     help="multiply interior rows while the halos are in flight (3 SpMV launches per step); "
                          "default: one fused exchange kernel, then one SpMV launch")
@@ -362,10 +364,24 @@ def main():
 
     peer = None
     ex = mg.HaloExchange(rank, world, halo, "nccl")
-    if world > 1 and args.halo == "push":
+    if world > 1 and args.halo in ("push", "fused"):
         peer = mg.PeerHalo(L, h, rank, world, x_ptr, ext_len, halo)
+
+    def make_fused(z_ptr_):
+        if peer is None or args.halo != "fused" or w["kind"] != "hell" or w["sym"] != "D":
+            return None
+        A = w["A"]
+        plo, phi, myf, pflo, pfhi = peer.fused_pointers()
+        T = capi.TYPES["D"]
+
+        def fused(seq):
+            L.spgpuDhellspmvHalo(h, z_ptr_, 0, 1.0, A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
+                                 A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, 0.0, A.base,
+                                 halo, plo, phi, myf, pflo, pfhi, seq)
+        return fused
+
     op = mg.MgHellSpmv(rank, world, rows, halo, lambda _z, _x, r0, r1: step(r0, r1), ex, peer,
-                       overlap=args.overlap)
+                       overlap=args.overlap, fused_spmv=make_fused(z.data_ptr()))
 
     def barrier():
         torch.cuda.synchronize()

@@ -111,6 +111,27 @@ void spgpuDhaloExchange(spgpuHandle_t handle, double* peerDstLo, const double* s
 	const unsigned* myReadyLo, const unsigned* myReadyHi, unsigned seq);
 void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq);
 
+/*
+ * HELL SpMV of one row block FUSED with its halo exchange -- one kernel per
+ * partitioned SpMV, transfer and multiply overlapped inside the launch.
+ * xExt = [lower halo (haloN) | owned (rows) | upper halo (haloN)], columns of the
+ * block index into it.  peerXLoUpperHalo / peerXHiLowerHalo are PEER pointers to the
+ * neighbours' halo zones this rank fills (NULL = no neighbour on that side).
+ * myFlags / peerFlagsLo / peerFlagsHi point at 4+ zero-initialised unsigned words per
+ * rank: [0] ready-from-below, [1] ready-from-above, [2] ack-from-below,
+ * [3] ack-from-above.  seq = 1, 2, 3, ... (same on every rank) numbers the exchanges.
+ * The first CTAs push the two boundary planes over NVLink (after the neighbour
+ * acknowledged the previous ones) and publish seq; interior row blocks are scheduled
+ * first, the row blocks that read a halo zone last (they wait on the local ready
+ * flag); the last CTA acknowledges the neighbours' halos.
+ */
+void spgpuDhellspmvHalo(spgpuHandle_t handle, __device double* z, const __device double* y,
+	double alpha, const __device double* cM, const __device int* rP, int hackSize,
+	const __device int* hackOffsets, const __device int* rS, int avgNnzPerRow, int rows,
+	__device double* xExt, double beta, int baseIndex, int haloN,
+	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,7 +114,7 @@ def ext_symbols():
     names += ["spgpuDaxpbyDev", "spgpuDhellspmvDot",
               "spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
               "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag",
-              "spgpuDhaloExchange", "spgpuHaloAck"]
+              "spgpuDhaloExchange", "spgpuHaloAck", "spgpuDhellspmvHalo"]
     return names
 
 
@@ -238,6 +238,9 @@ class SpgpuLib:
             f["spgpuDhaloExchange"] = _sig(d, "spgpuDhaloExchange", None,
                 [H, P, P, P, P, c_int, P, P, P, P, P, P, ctypes.c_uint], optional=True)
             f["spgpuHaloAck"] = _sig(d, "spgpuHaloAck", None, [H, P, P, ctypes.c_uint], optional=True)
+            f["spgpuDhellspmvHalo"] = _sig(d, "spgpuDhellspmvHalo", None,
+                [H, P, P, c_double, P, P, c_int, P, P, c_int, c_int, P, c_double, c_int, c_int,
+                 P, P, P, P, P, ctypes.c_uint], optional=True)
 
     def __getattr__(self, name):
         try:

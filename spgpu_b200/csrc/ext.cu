@@ -6,7 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include "launch.cuh"
-#include "spmv_slots.cuh"
+#include "spmv_hell_body.cuh"
 
 /* ---- z = b*y + a*x with a, b formed from device-resident scalars ----------- */
 
@@ -316,6 +316,143 @@ __global__ void halo_ack_kernel(unsigned* peerAckLo, unsigned* peerAckHi, unsign
 extern "C" void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq)
 {
 	halo_ack_kernel<<<1, 1, 0, handle->currentStream>>>(peerAckLo, peerAckHi, seq);
+	spgpu_count_launch(handle);
+}
+
+/* ---- HELL SpMV fused with the halo exchange: ONE kernel per partitioned SpMV ---------- */
+
+struct HaloArgs {
+	double* dstLo; const double* srcLo;      /* my first n owned entries -> lower neighbour's upper halo */
+	double* dstHi; const double* srcHi;      /* my last n owned entries  -> upper neighbour's lower halo */
+	int n;
+	const unsigned* ackLo; const unsigned* ackHi;        /* local : neighbour consumed my previous halo   */
+	unsigned* peerReadyLo; unsigned* peerReadyHi;        /* remote: my halo for `seq` is in place         */
+	const unsigned* myReadyLo; const unsigned* myReadyHi;/* local : neighbour's halo for `seq` is in place */
+	unsigned* peerAckLo; unsigned* peerAckHi;            /* remote: I have consumed their halo for `seq`   */
+	unsigned seq;
+	unsigned* pushTicket; unsigned* doneTicket;
+	int pushCtas;
+	int headBlocks, tailBlocks;              /* 128-row blocks that read the lower / upper halo zone */
+	unsigned long long timeoutNs;
+};
+
+/*
+ * grid = pushCtas + ceil(rows/128).  The first pushCtas CTAs move the two boundary planes
+ * into the neighbours' halo zones over NVLink (after the neighbours acknowledged the
+ * previous ones) and publish `seq`.  Every other CTA multiplies 128 rows; the CTAs are
+ * numbered so that the interior row blocks come first and the blocks that read a halo zone
+ * come LAST -- by the time the hardware schedules them the neighbours' planes have long
+ * arrived, and if not they spin on the local ready flag.  The last CTA to finish tells the
+ * neighbours that their halo data has been consumed.  Transfer and multiply overlap inside
+ * one launch; there is no separate pack / exchange / wait / ack kernel.
+ */
+template <int UNROLL, int HACK, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx)
+{
+	__shared__ bool amLast;
+	if (blockIdx.x < (unsigned)hx.pushCtas) {
+		const bool toHi = (blockIdx.x & 1) != 0;
+		double* dst = toHi ? hx.dstHi : hx.dstLo;
+		const double* src = toHi ? hx.srcHi : hx.srcLo;
+		const unsigned* ack = toHi ? hx.ackHi : hx.ackLo;
+		if (dst) {
+			if (threadIdx.x == 0 && ack && hx.seq > 1)
+				spin_until(ack, hx.seq - 1, hx.timeoutNs);
+			__syncthreads();
+			const long long half = hx.pushCtas >> 1;
+			const long long tid = (long long)(blockIdx.x >> 1) * blockDim.x + threadIdx.x;
+			const long long nthreads = half * blockDim.x;
+			if ((((size_t)dst | (size_t)src) & 15) == 0) {
+				double2* d2 = reinterpret_cast<double2*>(dst);
+				const double2* s2 = reinterpret_cast<const double2*>(src);
+				for (long long p = tid; p < (hx.n >> 1); p += nthreads)
+					d2[p] = s2[p];
+				if (tid == 0 && (hx.n & 1))
+					dst[hx.n - 1] = src[hx.n - 1];
+			} else {
+				for (long long e = tid; e < hx.n; e += nthreads)
+					dst[e] = src[e];
+			}
+		}
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			if (atomicAdd(hx.pushTicket, 1u) == (unsigned)hx.pushCtas - 1u) {
+				*hx.pushTicket = 0u;
+				__threadfence_system();
+				if (hx.peerReadyLo) st_release_sys(hx.peerReadyLo, hx.seq);
+				if (hx.peerReadyHi) st_release_sys(hx.peerReadyHi, hx.seq);
+			}
+		}
+	} else {
+		const unsigned b = blockIdx.x - hx.pushCtas;
+		const unsigned rowBlocks = ((unsigned)a.rows + 127u) >> 7;
+		const unsigned head = min((unsigned)hx.headBlocks, rowBlocks);
+		const unsigned tail = min((unsigned)hx.tailBlocks, rowBlocks - head);
+		const unsigned interior = rowBlocks - head - tail;
+		unsigned rb;
+		if (b < interior) rb = head + b;                       /* interior first            */
+		else if (b < interior + head) rb = b - interior;       /* then the lower boundary   */
+		else rb = b;                                           /* then the upper boundary   */
+		const bool needLo = rb < head, needHi = rb >= rowBlocks - tail;
+		if (threadIdx.x == 0) {
+			if (needLo && hx.myReadyLo) spin_until(hx.myReadyLo, hx.seq, hx.timeoutNs);
+			if (needHi && hx.myReadyHi) spin_until(hx.myReadyHi, hx.seq, hx.timeoutNs);
+		}
+		if (needLo || needHi)
+			__syncthreads();
+		hell_warp_rows<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u));
+	}
+	/* completion: the last CTA of the grid acknowledges the neighbours' halos */
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		amLast = (atomicAdd(hx.doneTicket, 1u) == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (amLast && threadIdx.x == 0) {
+		*hx.doneTicket = 0u;
+		__threadfence_system();
+		if (hx.peerAckLo) st_release_sys(hx.peerAckLo, hx.seq);
+		if (hx.peerAckHi) st_release_sys(hx.peerAckHi, hx.seq);
+	}
+}
+
+extern "C" void spgpuDhellspmvHalo(spgpuHandle_t handle, double* z, const double* y, double alpha,
+	const double* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
+	int avgNnzPerRow, int rows, double* xExt, double beta, int baseIndex, int haloN,
+	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq)
+{
+	if (rows <= 0)
+		return;
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const HellArgs<double> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
+		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1 };
+	HaloArgs hx;
+	hx.dstLo = peerXLoUpperHalo; hx.srcLo = xExt + haloN;
+	hx.dstHi = peerXHiLowerHalo; hx.srcHi = xExt + rows;        /* last haloN owned entries */
+	hx.n = haloN;
+	/* flag words (spgpu_ext.h): [0] ready-from-below [1] ready-from-above [2] ack-from-below [3] ack-from-above */
+	hx.ackLo = peerFlagsLo ? myFlags + 2 : NULL;   hx.ackHi = peerFlagsHi ? myFlags + 3 : NULL;
+	hx.peerReadyLo = peerFlagsLo ? peerFlagsLo + 1 : NULL;  hx.peerReadyHi = peerFlagsHi ? peerFlagsHi + 0 : NULL;
+	hx.myReadyLo = peerFlagsLo ? myFlags + 0 : NULL;  hx.myReadyHi = peerFlagsHi ? myFlags + 1 : NULL;
+	hx.peerAckLo = peerFlagsLo ? peerFlagsLo + 3 : NULL;  hx.peerAckHi = peerFlagsHi ? peerFlagsHi + 2 : NULL;
+	hx.seq = seq;
+	hx.pushTicket = h->dTicket + 8;
+	hx.doneTicket = h->dTicket + 12;
+	hx.pushCtas = 8;
+	hx.headBlocks = peerFlagsLo ? (haloN + 127) / 128 : 0;
+	hx.tailBlocks = peerFlagsHi ? (haloN + 127) / 128 : 0;
+	hx.timeoutNs = 2000000000ull;
+	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
+	cudaStream_t s = handle->currentStream;
+	if (hackSize == 32)
+		dhell_spmv_halo_kernel<8, 32, 10><<<grid, 128, 0, s>>>(a, hx);
+	else
+		dhell_spmv_halo_kernel<8, 0, 8><<<grid, 128, 0, s>>>(a, hx);
 	spgpu_count_launch(handle);
 }
 

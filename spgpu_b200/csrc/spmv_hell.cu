@@ -14,7 +14,7 @@
  * (SURVEY 2.2); indices are 64-bit where products can pass 2^31.
  */
 #include "launch.cuh"
-#include "spmv_slots.cuh"
+#include "spmv_hell_body.cuh"
 #include "spmv_hell_bulk.cuh"
 
 /*
@@ -24,41 +24,10 @@
  */
 template <typename T, int UNROLL, int HACK, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-hell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
-	const T* __restrict__ cM, const int* __restrict__ rP, int hackSizeRt,
-	const int* __restrict__ hackOffsets, const int* __restrict__ rS,
-	const int* __restrict__ rIdx, int rows, const T* __restrict__ x, T beta,
-	int baseIndex, int longCut, int speculate)
+hell_spmv_kernel(const HellArgs<T> a)
 {
-	const int hackSize = HACK > 0 ? HACK : hackSizeRt;
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned lane = threadIdx.x & 31;
-	const unsigned warpRow = i - lane;
-	if (warpRow >= (unsigned)rows)
-		return;                       /* whole warp past the end */
-	const bool live = i < (unsigned)rows;
-
-	const unsigned hack = warpRow / (unsigned)hackSize;
-	const unsigned lastHack = ((unsigned)rows - 1u) / (unsigned)hackSize;
-	const int slab = __ldg(hackOffsets + hack);
-	/* slab height of this hack = slots that exist for all of its rows; the last
-	 * hack has no terminator entry, so it takes the predicated path */
-	int allocated = 0;
-	if (speculate && hack < lastHack)
-		allocated = (__ldg(hackOffsets + hack + 1) - slab) / hackSize;
-	const int len = live ? ld_stream(rS + i) : 0;
-	const bool useBeta = Num<T>::nonzero(beta);
-	const unsigned out = (live && rIdx) ? (unsigned)__ldg(rIdx + i) : i;
-	T yv = Num<T>::zero();
-	if (useBeta && live)
-		yv = y[out];
-
-	const long long at = (long long)slab + (warpRow % (unsigned)hackSize) + lane;
-	T acc = warp_rows_dot<T, UNROLL, HACK>(cM + at, rP + at, hackSize, hackSize, len, longCut,
-		allocated, x, baseIndex);
-
-	if (live)
-		z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
+	hell_warp_rows<T, UNROLL, HACK>(a, i - (threadIdx.x & 31));
 }
 
 /* Bulk-async variant: returns false when the call is not eligible (then the
@@ -127,7 +96,8 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	}
 	const int speculate = variant != 1;
 	cudaStream_t s = handle->currentStream;
-#define HELL_ARGS z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, speculate
+	const HellArgs<T> args = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, speculate };
+#define HELL_ARGS args
 	/* 48 resident warps (<= 40 registers) beat 32 warps for the 4/8-byte types
 	 * (measured on B200: 2.11 ms vs 2.33 ms on the 512^3 Laplacian); the complex
 	 * types spill at 40 registers and stay at 32 warps.  hellBlock = 128 / 256

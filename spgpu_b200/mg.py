@@ -13,6 +13,12 @@ single-GPU kernel (spgpu?hellspmv through the C ABI) runs on it.  Before a SpMV
 the two halo zones are filled from the neighbours' boundary entries:
 
   * mode "nccl":  grouped ncclSend/ncclRecv (torch.distributed P2P ops);
+  * mode "fused" (default on GPUs): ONE kernel per SpMV, spgpuDhellspmvHalo: its
+    first CTAs store this rank's boundary entries straight into the neighbours' halo
+    zones through CUDA-IPC peer pointers over NVLink and publish a sequence number;
+    the interior row blocks are scheduled first and the row blocks that read a halo
+    zone last (they wait on the local ready flag); the last CTA acknowledges the
+    neighbours' halos.  Transfer and multiply overlap inside one launch.
   * mode "push":  each rank's spgpuDhaloPush kernel stores its boundary entries
     straight into the neighbour's halo zone through a CUDA-IPC peer pointer over
     NVLink and release-stores a sequence number into the neighbour's flag word;
@@ -228,6 +234,18 @@ class PeerHalo:
         lo, hi = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
         self.L.spgpuHaloAck(self.h, (lo[1] + 4 * 3) if lo else 0, (hi[1] + 4 * 2) if hi else 0, self.seq)
 
+    def fused_pointers(self):
+        """(peerXLoUpperHalo, peerXHiLowerHalo, myFlags, peerFlagsLo, peerFlagsHi) for
+        spgpuDhellspmvHalo; 0 where there is no neighbour."""
+        w = self.halo
+        lo, hi = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
+        return ((lo[0] + 8 * (lo[2] - w)) if lo else 0, hi[0] if hi else 0, self.flags,
+                lo[1] if lo else 0, hi[1] if hi else 0)
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
     def close(self):
         torch.cuda.synchronize()
         for px, pf, _ in self.peer.values():
@@ -271,7 +289,7 @@ class MgHellSpmv:
     large-vector loop, hell_spmv_base.cuh:121-137)."""
 
     def __init__(self, rank, world, nrows, halo, local_spmv, exchange: HaloExchange,
-                 peer: PeerHalo | None = None, overlap=True, align=32):
+                 peer: PeerHalo | None = None, overlap=True, align=32, fused_spmv=None):
         self.rank, self.world, self.nrows, self.halo = rank, world, nrows, halo
         self.local_spmv, self.ex, self.peer = local_spmv, exchange, peer
         # rows [0, head) and [tail, nrows) may touch a halo zone; both cuts sit on
@@ -279,11 +297,16 @@ class MgHellSpmv:
         self.head = min(nrows, -(-halo // align) * align)
         self.tail = max(self.head, ((nrows - halo) // align) * align)
         self.overlap = overlap and world > 1 and halo > 0 and self.tail > self.head
+        # fused_spmv(seq): the SpMV kernel that carries its own halo exchange (spgpuDhellspmvHalo)
+        self.fused_spmv = fused_spmv
 
     def apply(self, z, x_ext):
         w, n = self.halo, self.nrows
         if self.world == 1 or w == 0:
             self.local_spmv(z, x_ext, 0, n)
+            return
+        if self.peer is not None and self.fused_spmv is not None:
+            self.fused_spmv(self.peer.next_seq())      # ONE kernel: push + multiply + ack
             return
         if self.peer is not None:
             # NVLink push: everything is ordered on the handle's stream
