@@ -350,7 +350,6 @@ template <int UNROLL, int HACK, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx)
 {
-	__shared__ bool amLast;
 	if (blockIdx.x < (unsigned)hx.pushCtas) {
 		const bool toHi = (blockIdx.x & 1) != 0;
 		double* dst = toHi ? hx.dstHi : hx.dstLo;
@@ -396,26 +395,33 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx)
 		else if (b < interior + head) rb = b - interior;       /* then the lower boundary   */
 		else rb = b;                                           /* then the upper boundary   */
 		const bool needLo = rb < head, needHi = rb >= rowBlocks - tail;
+		if (!needLo && !needHi) {
+			/* interior: no flags, no tickets -- exactly the plain kernel */
+			hell_warp_rows<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u));
+			return;
+		}
 		if (threadIdx.x == 0) {
 			if (needLo && hx.myReadyLo) spin_until(hx.myReadyLo, hx.seq, hx.timeoutNs);
 			if (needHi && hx.myReadyHi) spin_until(hx.myReadyHi, hx.seq, hx.timeoutNs);
 		}
-		if (needLo || needHi)
-			__syncthreads();
+		__syncthreads();
 		hell_warp_rows<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u));
-	}
-	/* completion: the last CTA of the grid acknowledges the neighbours' halos */
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		amLast = (atomicAdd(hx.doneTicket, 1u) == gridDim.x - 1);
-	}
-	__syncthreads();
-	if (amLast && threadIdx.x == 0) {
-		*hx.doneTicket = 0u;
-		__threadfence_system();
-		if (hx.peerAckLo) st_release_sys(hx.peerAckLo, hx.seq);
-		if (hx.peerAckHi) st_release_sys(hx.peerAckHi, hx.seq);
+		/* the last CTA that read a halo zone tells that neighbour its data has been consumed
+		 * (only the few boundary CTAs touch these counters) */
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			__threadfence();
+			if (needLo && atomicAdd(hx.doneTicket, 1u) == head - 1u) {
+				*hx.doneTicket = 0u;
+				__threadfence_system();
+				if (hx.peerAckLo) st_release_sys(hx.peerAckLo, hx.seq);
+			}
+			if (needHi && atomicAdd(hx.doneTicket + 1, 1u) == tail - 1u) {
+				*(hx.doneTicket + 1) = 0u;
+				__threadfence_system();
+				if (hx.peerAckHi) st_release_sys(hx.peerAckHi, hx.seq);
+			}
+		}
 	}
 }
 
