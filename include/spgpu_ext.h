@@ -74,6 +74,14 @@ void spgpuDhellspmvDot(spgpuHandle_t handle, __device double* z,
 	const __device double* x, int baseIndex, int xOffset,
 	__device double* dRes);
 
+/*
+ * Fused CG update: x += a*p ; r -= a*Ap ; dRrNew[0] = r.r, with a = *dRr / *dPAp read
+ * from device memory.  One pass over four vectors instead of three kernels.
+ */
+void spgpuDcgUpdateDev(spgpuHandle_t handle, __device double* x, __device double* r,
+	const __device double* p, const __device double* ap, int n,
+	const __device double* dRr, const __device double* dPAp, __device double* dRrNew);
+
 /* ---- multi-GPU helpers ---------------------------------------------------- */
 
 /* 64-byte CUDA IPC handle of a cudaMalloc'ed pointer / open it in a peer process. */

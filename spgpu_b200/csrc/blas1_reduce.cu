@@ -20,7 +20,7 @@
  */
 #include <cstring>
 #include "launch.cuh"
-#include "numeric.cuh"
+#include "reduce_common.cuh"
 
 #define RED_BLOCK 256
 
@@ -28,9 +28,6 @@ template <typename T> struct alignas(16) RPack {
 	static constexpr int N = 16 / (int)sizeof(T);
 	T v[N];
 };
-
-/* accumulator: up to two doubles (re, im) or (value, unused) */
-struct alignas(16) Acc2 { double a, b; };
 
 /* ---- per-operation policy -------------------------------------------------- */
 /* Each op accumulates in the element's real precision per thread (short chains:
@@ -75,39 +72,6 @@ template <typename T> struct OpAbsMax {
 	__device__ __forceinline__ void take(T x, T) { s = fmax(s, Num<T>::abs(x)); }
 	__device__ __forceinline__ Acc2 result() const { return { (double)s, 0.0 }; }
 };
-
-template <bool IS_MAX>
-__device__ __forceinline__ Acc2 combine(Acc2 p, Acc2 q)
-{
-	if (IS_MAX)
-		return { fmax(p.a, q.a), 0.0 };
-	return { p.a + q.a, p.b + q.b };
-}
-
-template <bool IS_MAX>
-__device__ __forceinline__ Acc2 block_reduce(Acc2 v, Acc2* smem)
-{
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-	for (int m = 16; m > 0; m >>= 1) {
-		Acc2 o = { __shfl_xor_sync(SPGPU_FULL_MASK, v.a, m), __shfl_xor_sync(SPGPU_FULL_MASK, v.b, m) };
-		v = combine<IS_MAX>(v, o);
-	}
-	if (lane == 0)
-		smem[warp] = v;
-	__syncthreads();
-	if (warp == 0) {
-		const int nwarps = blockDim.x >> 5;
-		v = lane < nwarps ? smem[lane] : Acc2{ 0.0, 0.0 };
-#pragma unroll
-		for (int m = 16; m > 0; m >>= 1) {
-			Acc2 o = { __shfl_xor_sync(SPGPU_FULL_MASK, v.a, m), __shfl_xor_sync(SPGPU_FULL_MASK, v.b, m) };
-			v = combine<IS_MAX>(v, o);
-		}
-	}
-	__syncthreads();
-	return v;          /* valid in warp 0 */
-}
 
 /*
  * finish: 0 sum as is, 1 sqrt of the sum (nrm2).  outKind: how the final value
@@ -161,24 +125,9 @@ reduce_kernel(const T* x, const T* y, long long n, int vec, Acc2* partials,
 	Acc2 v = combine<Op::IS_MAX>(acc0.result(), acc1.result());
 	v = block_reduce<Op::IS_MAX>(v, smem);
 
-	if (threadIdx.x == 0) {
-		partials[blockIdx.x] = v;
-		__threadfence();
-		const unsigned t = atomicAdd(ticket, 1u);
-		amLast = (t == gridDim.x - 1);
-	}
-	__syncthreads();
-	if (!amLast)
+	Acc2 total;
+	if (!reduce_finish<Op::IS_MAX>(v, partials, ticket, smem, &amLast, total))
 		return;
-
-	/* last CTA: fold the partials in index order (deterministic) */
-	__threadfence();
-	Acc2 total = { 0.0, 0.0 };
-	for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-		const double2 pv = __ldcg(reinterpret_cast<const double2*>(partials) + b);
-		total = combine<Op::IS_MAX>(total, Acc2{ pv.x, pv.y });
-	}
-	total = block_reduce<Op::IS_MAX>(total, smem);
 	if (threadIdx.x == 0) {
 		double a = total.a, b = total.b;
 		if (finish == 1)
@@ -190,7 +139,6 @@ reduce_kernel(const T* x, const T* y, long long n, int vec, Acc2* partials,
 			reinterpret_cast<R*>(out)[0] = (R)a;
 			reinterpret_cast<R*>(out)[1] = (R)b;
 		}
-		*ticket = 0u;              /* ready for the next launch on this handle */
 		__threadfence_system();
 	}
 }

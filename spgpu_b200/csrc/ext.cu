@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include "launch.cuh"
+#include "reduce_common.cuh"
 #include "spmv_hell_body.cuh"
 
 /* ---- z = b*y + a*x with a, b formed from device-resident scalars ----------- */
@@ -62,54 +63,137 @@ extern "C" void spgpuDaxpbyDev(spgpuHandle_t handle, double* z, int n,
 
 /* ---- HELL SpMV fused with p.Ap ---------------------------------------------- */
 
-template <int UNROLL>
-__global__ void __launch_bounds__(128, 8)
-dhell_spmv_dot_kernel(double* __restrict__ z, const double* __restrict__ cM,
-	const int* __restrict__ rP, int hackSize, const int* __restrict__ hackOffsets,
-	const int* __restrict__ rS, int rows, const double* __restrict__ x,
-	int baseIndex, int xOffset, int longCut, double* dRes)
+/*
+ * Persistent form of the direct HELL kernel (a CTA walks row blocks blockIdx.x,
+ * blockIdx.x + gridDim.x, ...) so that the dot product needs one partial per CTA
+ * (<= SPGPU_RED_MAX_BLOCKS of them) and the deterministic last-CTA fold of
+ * reduce_common.cuh instead of a million contended atomics.
+ */
+template <int UNROLL, int HACK, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+dhell_spmv_dot_kernel(const HellArgs<double> a, int xOffset, Acc2* partials, unsigned* ticket, double* dRes)
 {
-	__shared__ double warpSums[32];
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const long long warpRow = i - lane;
+	__shared__ Acc2 smem[32];
+	__shared__ bool amLast;
+	const int hackSize = HACK > 0 ? HACK : a.hackSize;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned rowBlocks = ((unsigned)a.rows + 127u) >> 7;
+	const unsigned lastHack = ((unsigned)a.rows - 1u) / (unsigned)hackSize;
 	double contrib = 0.0;
-	if (warpRow < rows) {
-		const bool live = i < rows;
-		const int hack = (int)(warpRow / hackSize);
-		const long long at = (long long)__ldg(hackOffsets + hack) + (warpRow % hackSize) + lane;
-		const int len = live ? ld_stream(rS + i) : 0;
-		double acc = warp_rows_dot<double, UNROLL, 0>(cM + at, rP + at, hackSize, hackSize, len, longCut, 0, x, baseIndex);
+	for (unsigned rb = blockIdx.x; rb < rowBlocks; rb += gridDim.x) {
+		const unsigned warpRow = rb * 128u + (threadIdx.x & ~31u);
+		if (warpRow >= (unsigned)a.rows)
+			continue;
+		const unsigned i = warpRow + lane;
+		const bool live = i < (unsigned)a.rows;
+		const unsigned hack = warpRow / (unsigned)hackSize;
+		const int slab = __ldg(a.hackOffsets + hack);
+		int allocated = 0;
+		if (a.speculate && hack < lastHack)
+			allocated = (__ldg(a.hackOffsets + hack + 1) - slab) / hackSize;
+		const int len = live ? ld_stream(a.rS + i) : 0;
+		const long long at = (long long)slab + (warpRow % (unsigned)hackSize) + lane;
+		const double acc = warp_rows_dot<double, UNROLL, HACK>(a.cM + at, a.rP + at, hackSize, hackSize, len,
+			a.longCut, allocated, a.x, a.baseIndex);
 		if (live) {
-			z[i] = acc;
-			contrib = acc * __ldg(x + xOffset + i);
+			a.z[i] = acc;
+			contrib = fma(acc, __ldg(a.x + xOffset + i), contrib);
 		}
 	}
-	contrib = warp_sum<double>(contrib);
-	if (lane == 0)
-		warpSums[warp] = contrib;
-	__syncthreads();
-	if (warp == 0) {
-		const int nwarps = blockDim.x >> 5;
-		double v = lane < nwarps ? warpSums[lane] : 0.0;
-		v = warp_sum<double>(v);
-		if (lane == 0)
-			atomicAdd(dRes, v);
-	}
+	Acc2 v = block_reduce<false>(Acc2{ contrib, 0.0 }, smem);
+	Acc2 total;
+	if (reduce_finish<false>(v, partials, ticket, smem, &amLast, total))
+		*dRes = total.a;
 }
 
 extern "C" void spgpuDhellspmvDot(spgpuHandle_t handle, double* z, const double* cM,
 	const int* rP, int hackSize, const int* hackOffsets, const int* rS, int rows,
 	const double* x, int baseIndex, int xOffset, double* dRes)
 {
-	cudaMemsetAsync(dRes, 0, sizeof(double), handle->currentStream);
-	if (rows <= 0)
+	if (rows <= 0) {
+		cudaMemsetAsync(dRes, 0, sizeof(double), handle->currentStream);
 		return;
+	}
+	SpgpuHandlePriv* h = spgpuPriv(handle);
 	const SpgpuTuning* t = spgpu_tuning(handle);
-	const int block = 128;
-	dhell_spmv_dot_kernel<8><<<spgpu_ceil_div(rows, block), block, 0, handle->currentStream>>>(
-		z, cM, rP, hackSize, hackOffsets, rS, rows, x, baseIndex, xOffset,
-		spgpu_long_cut(t, 8), dRes);
+	const HellArgs<double> a = { z, NULL, 1.0, cM, rP, hackSize, hackOffsets, rS, NULL, rows, x, 0.0,
+		baseIndex, spgpu_long_cut(t, 8), t->hellVariant != 1 };
+	long long grid = (long long)handle->multiProcessorCount * 12;
+	const long long rowBlocks = ((long long)rows + 127) / 128;
+	if (grid > rowBlocks) grid = rowBlocks;
+	if (grid > SPGPU_RED_MAX_BLOCKS) grid = SPGPU_RED_MAX_BLOCKS;
+	Acc2* partials = reinterpret_cast<Acc2*>(h->dPartials);
+	if (hackSize == 32)
+		dhell_spmv_dot_kernel<8, 32, 12><<<(unsigned)grid, 128, 0, handle->currentStream>>>(a, xOffset, partials, h->dTicket, dRes);
+	else
+		dhell_spmv_dot_kernel<8, 0, 8><<<(unsigned)grid, 128, 0, handle->currentStream>>>(a, xOffset, partials, h->dTicket, dRes);
+	spgpu_count_launch(handle);
+}
+
+/* ---- fused CG update: x += a p ; r -= a Ap ; dRes = r.r   (a = *rr / *pAp) ---- */
+
+__global__ void __launch_bounds__(256)
+dcg_update_kernel(double* x, double* r, const double* p, const double* ap, long long n,
+	const double* rr, const double* pap, int vec, Acc2* partials, unsigned* ticket, double* dRes)
+{
+	__shared__ Acc2 smem[32];
+	__shared__ bool amLast;
+	const double alpha = __ldg(rr) / __ldg(pap);
+	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long nthreads = (long long)gridDim.x * blockDim.x;
+	double s0 = 0.0, s1 = 0.0;
+	if (vec) {
+		double2* x2 = reinterpret_cast<double2*>(x);
+		double2* r2 = reinterpret_cast<double2*>(r);
+		const double2* p2 = reinterpret_cast<const double2*>(p);
+		const double2* a2 = reinterpret_cast<const double2*>(ap);
+		const long long np = n >> 1;
+		for (long long q = tid; q < np; q += nthreads) {
+			double2 xv = x2[q], rv = r2[q];
+			const double2 pv = p2[q], av = a2[q];
+			xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+			rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+			x2[q] = xv; r2[q] = rv;
+			s0 = fma(rv.x, rv.x, s0); s1 = fma(rv.y, rv.y, s1);
+		}
+		if (tid == 0 && (n & 1)) {
+			const long long e = n - 1;
+			x[e] = fma(alpha, p[e], x[e]);
+			const double rv = fma(-alpha, ap[e], r[e]);
+			r[e] = rv;
+			s0 = fma(rv, rv, s0);
+		}
+	} else {
+		for (long long e = tid; e < n; e += nthreads) {
+			x[e] = fma(alpha, p[e], x[e]);
+			const double rv = fma(-alpha, ap[e], r[e]);
+			r[e] = rv;
+			s0 = fma(rv, rv, s0);
+		}
+	}
+	Acc2 v = block_reduce<false>(Acc2{ s0 + s1, 0.0 }, smem);
+	Acc2 total;
+	if (reduce_finish<false>(v, partials, ticket, smem, &amLast, total))
+		*dRes = total.a;
+}
+
+extern "C" void spgpuDcgUpdateDev(spgpuHandle_t handle, double* x, double* r, const double* p,
+	const double* ap, int n, const double* dRr, const double* dPAp, double* dRrNew)
+{
+	if (n <= 0) {
+		cudaMemsetAsync(dRrNew, 0, sizeof(double), handle->currentStream);
+		return;
+	}
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const int vec = (((size_t)x | (size_t)r | (size_t)p | (size_t)ap) & 15) == 0;
+	long long want = ((vec ? n / 2 : n) + 255) / 256;
+	long long cap = (long long)handle->multiProcessorCount * (t->vecBlocksPerSm > 0 ? t->vecBlocksPerSm : 8);
+	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
+	if (want > cap) want = cap;
+	if (want < 1) want = 1;
+	dcg_update_kernel<<<(unsigned)want, 256, 0, handle->currentStream>>>(x, r, p, ap, n, dRr, dPAp, vec,
+		reinterpret_cast<Acc2*>(h->dPartials), h->dTicket, dRrNew);
 	spgpu_count_launch(handle);
 }
 

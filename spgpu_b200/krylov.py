@@ -8,12 +8,12 @@ Two flavours of the same recurrence:
   (blocks the host, returns the value), spgpuDaxpby with host scalars --
   6 kernels and 2 host synchronisations per iteration.
 * `step_device`    the additive entry points of include/spgpu_ext.h: the SpMV is
-  fused with p.Ap (spgpuDhellspmvDot), r.r goes to device memory
-  (spgpuDdotDev) and the three vector updates read alpha = rr/pAp and
-  beta = rr'/rr from device memory (spgpuDaxpbyDev) -- 5 kernels, no host
-  synchronisation, CUDA-graph capturable.  With several GPUs the two scalars are
-  all-reduced in place (NCCL) and the halo of the new p is exchanged by the
-  partitioned operator (spgpu_b200/mg.py).
+  fused with p.Ap (spgpuDhellspmvDot); the x and r updates and r.r are one pass
+  over the four vectors (spgpuDcgUpdateDev); the p update reads beta = rr'/rr
+  from device memory (spgpuDaxpbyDev) -- 3 kernels, no host synchronisation,
+  CUDA-graph capturable.  With several GPUs the two scalars are all-reduced in
+  place (NCCL) and the halo of the new p travels inside the SpMV kernel
+  (spgpuDhellspmvHalo, spgpu_b200/mg.py).
 
 Vectors of a partition: p lives inside p_ext = [halo | owned | halo]; x, r, Ap
 are owned-length.
@@ -94,10 +94,8 @@ class Cg:
             L.spgpuDdotDev(h, n, st.p.data_ptr(), st.ap.data_ptr(), pap)
             if self.allreduce:
                 self.allreduce(st.s[1:2])
-        # x += (rr/pAp) p ;  r -= (rr/pAp) Ap
-        L.spgpuDaxpbyDev(h, st.x.data_ptr(), n, 0, 0, 1.0, st.x.data_ptr(), rr, pap, 1.0, st.p.data_ptr())
-        L.spgpuDaxpbyDev(h, st.r.data_ptr(), n, 0, 0, 1.0, st.r.data_ptr(), rr, pap, -1.0, st.ap.data_ptr())
-        L.spgpuDdotDev(h, n, st.r.data_ptr(), st.r.data_ptr(), rrn)
+        # x += (rr/pAp) p ;  r -= (rr/pAp) Ap ;  rr' = r.r   -- one pass (spgpuDcgUpdateDev)
+        L.spgpuDcgUpdateDev(h, st.x.data_ptr(), st.r.data_ptr(), st.p.data_ptr(), st.ap.data_ptr(), n, rr, pap, rrn)
         if self.allreduce:
             self.allreduce(st.s[2:3])
         # p = r + (rr'/rr) p ; then rr <- rr'
@@ -112,6 +110,6 @@ CG_BYTES_PER_ROW_VECTOR_OPS = {
     # algorithmic bytes per row of the vector part of one iteration (double):
     # blocking: p.Ap 16 + x update 24 + r update 24 + r.r 8 + p update 24
     "blocking": 96,
-    # device: p.Ap fused into the SpMV epilogue (p re-read 8) + 24 + 24 + 8 + 24
-    "device": 88,
+    # device: p.Ap fused into the SpMV epilogue (p re-read 8) + fused x/r update 48 + p update 24
+    "device": 80,
 }

@@ -122,3 +122,21 @@ def test_cg_converges_like_the_cpu_recurrence(ours, gpu_handle, flavour):
     np.testing.assert_allclose(hist, ref, rtol=1e-8)
     assert hist[-1] < 1e-6 * rr0
     np.testing.assert_allclose(x_gpu, x, rtol=1e-9, atol=1e-12)
+
+
+def test_fused_cg_update(ours, gpu_handle):
+    """x += a p ; r -= a Ap ; rr' = r.r in one pass, a = rr/pAp from device memory"""
+    import torch
+    for n in (1, 777, 1 << 20, (1 << 20) + 1):
+        rng = np.random.default_rng(n)
+        x, r, p, ap = (rng.standard_normal(n) for _ in range(4))
+        sc = np.array([3.5, 1.25, 0.0])
+        dx, dr, dp, dap, ds = (util.to_dev(a) for a in (x, r, p, ap, sc))
+        s = ds.data_ptr()
+        ours.spgpuDcgUpdateDev(gpu_handle, dx.data_ptr(), dr.data_ptr(), dp.data_ptr(), dap.data_ptr(), n, s, s + 8, s + 16)
+        torch.cuda.synchronize()
+        a = 3.5 / 1.25
+        np.testing.assert_allclose(dx.cpu().numpy(), x + a * p, rtol=1e-14, atol=1e-14)
+        rn = r - a * ap
+        np.testing.assert_allclose(dr.cpu().numpy(), rn, rtol=1e-14, atol=1e-14)
+        assert abs(float(ds[2].item()) - float(rn @ rn)) <= 1e-13 * float(rn @ rn)
