@@ -49,6 +49,9 @@ int spgpuGetTuning(spgpuHandle_t handle, const char* key);
 		const __device T* x, __device R* dRes);
 SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_DOT_DEV)
 
+/* dRes[0] = sum x_i, left in device memory (deterministic; folds per-CTA partials). */
+void spgpuDsumDev(spgpuHandle_t handle, int n, const __device double* x, __device double* dRes);
+
 /*
  * z = (*dBetaNum / *dBetaDen) * betaSign * y + (*dAlphaNum / *dAlphaDen) *
  * alphaSign * x with the four scalars read from DEVICE memory at kernel time
@@ -66,7 +69,8 @@ void spgpuDaxpbyDev(spgpuHandle_t handle, __device double* z, int n,
 /*
  * HELL SpMV z = A*x fused with dRes[0] = sum_i x[xOffset+i]*z[i] (the p.Ap of CG)
  * in the SpMV epilogue.  xOffset = position of row 0's own entry inside x
- * (0 on one GPU, the lower halo width on a partition).  dRes is zeroed by the call.
+ * (0 on one GPU, the lower halo width on a partition).  Two launches: the SpMV leaves one
+ * partial per CTA in handle-owned scratch, spgpuDsumDev folds them (deterministic).
  */
 void spgpuDhellspmvDot(spgpuHandle_t handle, __device double* z,
 	const __device double* cM, const __device int* rP, int hackSize,

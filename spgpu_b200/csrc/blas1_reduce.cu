@@ -55,6 +55,15 @@ template <typename T> struct OpSqSum {
 	__device__ __forceinline__ Acc2 result() const { return { (double)s, 0.0 }; }
 };
 
+template <typename T> struct OpSum {
+	static constexpr int NIN = 1;
+	static constexpr bool IS_MAX = false;
+	T s;
+	__device__ __forceinline__ void init() { s = Num<T>::zero(); }
+	__device__ __forceinline__ void take(T x, T) { s = Num<T>::add(s, x); }
+	__device__ __forceinline__ Acc2 result() const { return { (double)s, 0.0 }; }
+};
+
 template <typename T> struct OpAbsSum {
 	static constexpr int NIN = 1;
 	static constexpr bool IS_MAX = false;
@@ -232,3 +241,10 @@ SPGPU_DEFINE_REDUCE(S, float, float)
 SPGPU_DEFINE_REDUCE(D, double, double)
 SPGPU_DEFINE_REDUCE(C, cuFloatComplex, float)
 SPGPU_DEFINE_REDUCE(Z, cuDoubleComplex, double)
+
+/* dRes[0] = sum x_i, result left in device memory (used to fold per-CTA partials) */
+extern "C" void spgpuDsumDev(spgpuHandle_t h, int n, const double* x, double* dRes)
+{
+	if (n > 0) reduce_launch<double, OpSum<double> >(h, x, (const double*)0, n, dRes, 0, 1);
+	else cudaMemsetAsync(dRes, 0, sizeof(double), h->currentStream);
+}

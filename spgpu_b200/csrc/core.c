@@ -103,6 +103,7 @@ void spgpuDestroy(spgpuHandle_t pHandle)
 		if (h->dPartials) cudaFree(h->dPartials);
 		if (h->dTicket) cudaFree(h->dTicket);
 		if (h->hResult) cudaFreeHost(h->hResult);
+		if (h->dBig) cudaFree(h->dBig);
 		h->magic = 0;
 	}
 	free(h);
@@ -142,6 +143,25 @@ size_t spgpuSizeOf(spgpuType_t typeCode)
 	if (typeCode < 0 || typeCode > SPGPU_TYPE_COMPLEX_DOUBLE)
 		return 0;
 	return bytes[typeCode];
+}
+
+void* spgpuScratch(spgpuHandle_t handle, size_t bytes)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	if (!h || h->magic != SPGPU_PRIV_MAGIC)
+		return NULL;
+	if (h->bigBytes >= bytes)
+		return h->dBig;
+	/* grow: earlier work on the stream may still use the old block */
+	cudaStreamSynchronize(h->pub.currentStream);
+	if (h->dBig)
+		cudaFree(h->dBig);
+	h->dBig = NULL;
+	h->bigBytes = 0;
+	if (cudaMalloc(&h->dBig, bytes) != cudaSuccess)
+		return NULL;
+	h->bigBytes = bytes;
+	return h->dBig;
 }
 
 /* ---- additive API (include/spgpu_ext.h) ---------------------------------- */

@@ -31,8 +31,8 @@ daxpby_dev_kernel(double* z, long long n, const double* bNum, const double* bDen
 		for (long long p = tid; p < np; p += 2 * nthreads) {
 			const long long q = p + nthreads;
 			const bool two = q < np;
-			double2 y0 = y2[p], x0 = x2[p], y1 = y0, x1 = x0;
-			if (two) { y1 = y2[q]; x1 = x2[q]; }
+			const long long q2 = two ? q : p;              /* both loads always issued together */
+			double2 y0 = y2[p], x0 = x2[p], y1 = y2[q2], x1 = x2[q2];
 			zo[p] = make_double2(fma(b, y0.x, a * x0.x), fma(b, y0.y, a * x0.y));
 			if (two) zo[q] = make_double2(fma(b, y1.x, a * x1.x), fma(b, y1.y, a * x1.y));
 		}
@@ -64,47 +64,34 @@ extern "C" void spgpuDaxpbyDev(spgpuHandle_t handle, double* z, int n,
 /* ---- HELL SpMV fused with p.Ap ---------------------------------------------- */
 
 /*
- * Persistent form of the direct HELL kernel (a CTA walks row blocks blockIdx.x,
- * blockIdx.x + gridDim.x, ...) so that the dot product needs one partial per CTA
- * (<= SPGPU_RED_MAX_BLOCKS of them) and the deterministic last-CTA fold of
- * reduce_common.cuh instead of a million contended atomics.
+ * The direct HELL kernel with one extra step per row: z_i * x[xOffset+i] is summed over
+ * the CTA (shuffle + 4 shared doubles, fixed order) and stored as ONE partial per CTA
+ * into handle-owned scratch -- no atomics, no tickets (a million CTAs hammering one
+ * address cost more than the dot they save).  spgpuDsumDev then folds the partials
+ * deterministically; that second launch reads 8 MB where a separate dot would re-read
+ * two 1 GB vectors.
  */
 template <int UNROLL, int HACK, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-dhell_spmv_dot_kernel(const HellArgs<double> a, int xOffset, Acc2* partials, unsigned* ticket, double* dRes)
+dhell_spmv_dot_kernel(const HellArgs<double> a, int xOffset, double* __restrict__ ctaPartials)
 {
-	__shared__ Acc2 smem[32];
-	__shared__ bool amLast;
-	const int hackSize = HACK > 0 ? HACK : a.hackSize;
+	__shared__ double ws[4];
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned lane = threadIdx.x & 31;
-	const unsigned rowBlocks = ((unsigned)a.rows + 127u) >> 7;
-	const unsigned lastHack = ((unsigned)a.rows - 1u) / (unsigned)hackSize;
+	double zval;
+	hell_warp_rows_value<double, UNROLL, HACK>(a, i - lane, zval);
 	double contrib = 0.0;
-	for (unsigned rb = blockIdx.x; rb < rowBlocks; rb += gridDim.x) {
-		const unsigned warpRow = rb * 128u + (threadIdx.x & ~31u);
-		if (warpRow >= (unsigned)a.rows)
-			continue;
-		const unsigned i = warpRow + lane;
-		const bool live = i < (unsigned)a.rows;
-		const unsigned hack = warpRow / (unsigned)hackSize;
-		const int slab = __ldg(a.hackOffsets + hack);
-		int allocated = 0;
-		if (a.speculate && hack < lastHack)
-			allocated = (__ldg(a.hackOffsets + hack + 1) - slab) / hackSize;
-		const int len = live ? ld_stream(a.rS + i) : 0;
-		const long long at = (long long)slab + (warpRow % (unsigned)hackSize) + lane;
-		const double acc = warp_rows_dot<double, UNROLL, HACK>(a.cM + at, a.rP + at, hackSize, hackSize, len,
-			a.longCut, allocated, a.x, a.baseIndex);
-		if (live) {
-			a.z[i] = acc;
-			contrib = fma(acc, __ldg(a.x + xOffset + i), contrib);
-		}
-	}
-	Acc2 v = block_reduce<false>(Acc2{ contrib, 0.0 }, smem);
-	Acc2 total;
-	if (reduce_finish<false>(v, partials, ticket, smem, &amLast, total))
-		*dRes = total.a;
+	if (i < (unsigned)a.rows)
+		contrib = zval * __ldg(a.x + xOffset + i);
+	contrib = warp_sum<double>(contrib);
+	if (lane == 0)
+		ws[threadIdx.x >> 5] = contrib;
+	__syncthreads();
+	if (threadIdx.x == 0)
+		ctaPartials[blockIdx.x] = (ws[0] + ws[1]) + (ws[2] + ws[3]);
 }
+
+extern "C" void spgpuDsumDev(spgpuHandle_t h, int n, const double* x, double* dRes);
 
 extern "C" void spgpuDhellspmvDot(spgpuHandle_t handle, double* z, const double* cM,
 	const int* rP, int hackSize, const int* hackOffsets, const int* rS, int rows,
@@ -114,20 +101,19 @@ extern "C" void spgpuDhellspmvDot(spgpuHandle_t handle, double* z, const double*
 		cudaMemsetAsync(dRes, 0, sizeof(double), handle->currentStream);
 		return;
 	}
-	SpgpuHandlePriv* h = spgpuPriv(handle);
 	const SpgpuTuning* t = spgpu_tuning(handle);
+	const unsigned grid = spgpu_ceil_div(rows, 128);
+	double* partials = (double*)spgpuScratch(handle, (size_t)grid * sizeof(double));
+	if (!partials)
+		return;
 	const HellArgs<double> a = { z, NULL, 1.0, cM, rP, hackSize, hackOffsets, rS, NULL, rows, x, 0.0,
 		baseIndex, spgpu_long_cut(t, 8), t->hellVariant != 1 };
-	long long grid = (long long)handle->multiProcessorCount * 12;
-	const long long rowBlocks = ((long long)rows + 127) / 128;
-	if (grid > rowBlocks) grid = rowBlocks;
-	if (grid > SPGPU_RED_MAX_BLOCKS) grid = SPGPU_RED_MAX_BLOCKS;
-	Acc2* partials = reinterpret_cast<Acc2*>(h->dPartials);
 	if (hackSize == 32)
-		dhell_spmv_dot_kernel<8, 32, 12><<<(unsigned)grid, 128, 0, handle->currentStream>>>(a, xOffset, partials, h->dTicket, dRes);
+		dhell_spmv_dot_kernel<8, 32, 10><<<grid, 128, 0, handle->currentStream>>>(a, xOffset, partials);
 	else
-		dhell_spmv_dot_kernel<8, 0, 8><<<(unsigned)grid, 128, 0, handle->currentStream>>>(a, xOffset, partials, h->dTicket, dRes);
+		dhell_spmv_dot_kernel<8, 0, 8><<<grid, 128, 0, handle->currentStream>>>(a, xOffset, partials);
 	spgpu_count_launch(handle);
+	spgpuDsumDev(handle, (int)grid, partials, dRes);
 }
 
 /* ---- fused CG update: x += a p ; r -= a Ap ; dRes = r.r   (a = *rr / *pAp) ---- */

@@ -46,8 +46,13 @@ typedef struct SpgpuHandlePriv {
 	int l2Bytes;
 	int smemPerBlockOptin;
 	unsigned long long launches;   /* kernels launched through this handle        */
+	void* dBig;                    /* device: grow-only scratch (per-CTA partials of fused kernels) */
+	size_t bigBytes;
 	SpgpuTuning tune;
 } SpgpuHandlePriv;
+
+/* grow-only device scratch owned by the handle; NULL on failure (core.c) */
+void* spgpuScratch(spgpuHandle_t handle, size_t bytes);
 
 static inline SpgpuHandlePriv* spgpuPriv(spgpuHandle_t h)
 {

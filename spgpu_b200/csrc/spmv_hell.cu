@@ -106,7 +106,8 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	if (t->hellBlock >= 256) dense = true;
 	else if (t->hellBlock > 0 && t->hellBlock <= 64) dense = false;
 	if (hackSize == 32) {
-		if (dense) hell_spmv_kernel<T, UNROLL, 32, 12><<<grid, block, 0, s>>>(HELL_ARGS);
+		if (t->hellBlock == 192) hell_spmv_kernel<T, UNROLL, 32, 10><<<grid, block, 0, s>>>(HELL_ARGS);   /* 40 warps */
+		else if (dense) hell_spmv_kernel<T, UNROLL, 32, 12><<<grid, block, 0, s>>>(HELL_ARGS);
 		else       hell_spmv_kernel<T, UNROLL, 32, 8><<<grid, block, 0, s>>>(HELL_ARGS);
 	} else {
 		hell_spmv_kernel<T, UNROLL, 0, 8><<<grid, block, 0, s>>>(HELL_ARGS);

@@ -28,9 +28,11 @@ struct HellArgs {
 	int speculate;
 };
 
+/* returns the value stored for this lane's row in `zval` (zero for lanes without a row) */
 template <typename T, int UNROLL, int HACK>
-__device__ __forceinline__ void hell_warp_rows(const HellArgs<T>& a, unsigned warpRow)
+__device__ __forceinline__ void hell_warp_rows_value(const HellArgs<T>& a, unsigned warpRow, T& zval)
 {
+	zval = Num<T>::zero();
 	const int hackSize = HACK > 0 ? HACK : a.hackSize;
 	const unsigned lane = threadIdx.x & 31;
 	if (warpRow >= (unsigned)a.rows)
@@ -57,8 +59,17 @@ __device__ __forceinline__ void hell_warp_rows(const HellArgs<T>& a, unsigned wa
 	T acc = warp_rows_dot<T, UNROLL, HACK>(a.cM + at, a.rP + at, hackSize, hackSize, len, a.longCut,
 		allocated, a.x, a.baseIndex);
 
-	if (live)
-		a.z[out] = spmv_epilogue<T>(acc, a.alpha, a.beta, useBeta, yv);
+	if (live) {
+		zval = spmv_epilogue<T>(acc, a.alpha, a.beta, useBeta, yv);
+		a.z[out] = zval;
+	}
+}
+
+template <typename T, int UNROLL, int HACK>
+__device__ __forceinline__ void hell_warp_rows(const HellArgs<T>& a, unsigned warpRow)
+{
+	T unused;
+	hell_warp_rows_value<T, UNROLL, HACK>(a, warpRow, unused);
 }
 
 #endif

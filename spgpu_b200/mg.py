@@ -108,6 +108,57 @@ def split_hell(hell, world: int, rank: int, halo: int) -> LocalHell:
     return LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, halo, hell.base, nnz)
 
 
+def split_hell_allgather(hell, world: int, rank: int) -> LocalHell:
+    """Cut rank's block out of a global HELL matrix for the ALL-GATHER mode (unstructured
+    columns): every rank gathers the whole x into x_full = [block 0 | block 1 | ...], each
+    block padded to the largest block, and the column indices are remapped to that padded
+    layout.  Works for any sparsity pattern; costs an all-gather of x per SpMV."""
+    hs = hell.hack_size
+    blocks = row_blocks(hell.nrows, world, hs)
+    lo, hi = blocks[rank]
+    h0, h1 = lo // hs, (hi + hs - 1) // hs
+    hoff = np.asarray(hell.hack_offsets)
+    end = int(hell.values.shape[0])
+    e0 = int(hoff[h0]) if h0 < hoff.shape[0] else end
+    e1 = int(hoff[h1]) if h1 < hoff.shape[0] else end
+    values = np.array(hell.values[e0:e1], copy=True)
+    indices = np.array(hell.indices[e0:e1], copy=True)
+    rs = np.array(hell.rs[lo:hi], copy=True)
+    local_hoff = (hoff[h0:h1] - e0).astype(np.int32)
+    starts = np.array([b[0] for b in blocks], dtype=np.int64)
+    widest = max(b[1] - b[0] for b in blocks)
+    nnz = 0
+    for h in range(h1 - h0):
+        rows = rs[h * hs:(h + 1) * hs]
+        if rows.size == 0:
+            continue
+        at = int(local_hoff[h])
+        for k in range(int(rows.max())):
+            live = np.nonzero(rows > k)[0]
+            sl = at + k * hs + live
+            g = indices[sl].astype(np.int64) - hell.base
+            owner = np.searchsorted(starts, g, side="right") - 1
+            indices[sl] = (owner * widest + (g - starts[owner]) + hell.base).astype(np.int32)
+            nnz += live.size
+    out = LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, 0, hell.base, nnz)
+    out.widest = widest
+    return out
+
+
+class MgAllGatherSpmv:
+    """z_owned = A_block * x with x all-gathered from every rank's (padded) owned slice."""
+
+    def __init__(self, world, widest, local_spmv, group=None):
+        self.world, self.widest, self.local_spmv, self.group = world, widest, local_spmv, group
+
+    def apply(self, z, x_owned_padded, x_full):
+        if self.world > 1:
+            dist.all_gather_into_tensor(x_full, x_owned_padded, group=self.group)
+        else:
+            x_full.copy_(x_owned_padded)
+        self.local_spmv(z, x_full)
+
+
 # --------------------------------------------------------------------------- #
 # communicator
 # --------------------------------------------------------------------------- #

@@ -102,3 +102,41 @@ def test_partitioned_spmv_over_gloo(tmp_path, world, overlap):
     dots = [float(np.load(tmp_path / f"dot{r}.npy")[0]) for r in range(world)]
     assert all(d == dots[0] for d in dots)
     assert abs(dots[0] - float(np.dot(want, want))) <= 1e-12 * float(np.dot(want, want))
+
+
+def _ag_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        coo = G.random_coo(1000, 1000, (0, 12), 77, np.float64, 1)      # unstructured, base 1
+        hell = F.ell_to_hell(F.coo_to_ell(coo, 1), 32)
+        loc = mg.split_hell_allgather(hell, world, rank)
+        x = G.random_vector(1000, np.float64, 5)
+        own = torch.zeros(loc.widest, dtype=torch.float64)
+        own[:loc.nrows] = torch.from_numpy(x[loc.lo:loc.hi])
+        x_full = torch.zeros(world * loc.widest, dtype=torch.float64)
+        z = torch.full((loc.nrows,), float("nan"), dtype=torch.float64)
+        O = util.oracle_lib()
+        T = util.TYPES["D"]
+
+        def local_spmv(zt, xt):
+            O.Dhellspmv(util.ptr(zt.numpy()), None, T.scalar(1.0), util.ptr(loc.values), util.ptr(loc.indices), 32,
+                        util.ptr(loc.hack_offsets), util.ptr(loc.rs), None, 6, loc.nrows, util.ptr(xt.numpy()),
+                        T.scalar(0.0), 1)
+
+        mg.MgAllGatherSpmv(world, loc.widest, local_spmv).apply(z, own, x_full)
+        np.save(os.path.join(out_dir, f"z{rank}.npy"), z.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_mode_for_unstructured_columns(tmp_path):
+    world = 3
+    mp.spawn(_ag_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    coo = G.random_coo(1000, 1000, (0, 12), 77, np.float64, 1)
+    hell = F.ell_to_hell(F.coo_to_ell(coo, 1), 32)
+    x = G.random_vector(1000, np.float64, 5)
+    want = util.oracle_spmv("hell", hell, x, None, 1.0, 0.0)
+    got = np.concatenate([np.load(tmp_path / f"z{r}.npy") for r in range(world)])
+    np.testing.assert_array_equal(got, want)

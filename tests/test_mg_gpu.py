@@ -1,0 +1,98 @@
+"""Single-GPU checks of the multi-GPU device code (include/spgpu_ext.h).  Kernels of
+different ranks must never wait on each other on ONE GPU, so the neighbours are emulated:
+their "pushes" are pre-filled halo zones + pre-set ready flags, and this rank's pushes land
+in scratch buffers standing in for the neighbours' memory.  The real multi-rank runs are
+bench.py --verify under torchrun (bit-exact against global columns) and the gloo tests."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from spgpu_b200 import formats as F, generators as G, mg
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _middle_block(n=24, world=3, rank=1):
+    coo = G.laplace3d_7pt(n)
+    plane = n * n
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    loc = mg.split_hell(hell, world, rank, plane)
+    x = G.random_vector(coo.nrows, np.float64, 12345)
+    x_ext = x[loc.lo - plane: loc.hi + plane].copy()
+    want = util.oracle_spmv("hell", hell, x, None, 1.0, 0.0)[loc.lo:loc.hi]
+    return coo, loc, plane, x, x_ext, want
+
+
+@pytest.mark.parametrize("seq", [1, 5])
+def test_spmv_fused_with_halo_exchange(ours, gpu_handle, seq):
+    import torch
+    coo, loc, plane, x, x_ext, want = _middle_block()
+    dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
+    dx = util.to_dev(x_ext)
+    dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+    my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    my_flags[0] = seq; my_flags[1] = seq          # both neighbours' halos "have arrived"
+    my_flags[2] = seq - 1; my_flags[3] = seq - 1  # and they acknowledged my previous pushes
+    peer_lo_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    peer_hi_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    peer_lo_halo = torch.full((plane,), float("nan"), dtype=torch.float64, device="cuda")
+    peer_hi_halo = torch.full((plane,), float("nan"), dtype=torch.float64, device="cuda")
+    ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), 0, 1.0, dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
+                            drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0.0, 0, plane,
+                            peer_lo_halo.data_ptr(), peer_hi_halo.data_ptr(), my_flags.data_ptr(),
+                            peer_lo_flags.data_ptr(), peer_hi_flags.data_ptr(), seq)
+    torch.cuda.synchronize()
+    util.assert_rows_close(dz.cpu().numpy(), want, np.full(loc.nrows, 12.0), "D", "fused spmv+halo")
+    # my first / last owned plane landed in the neighbours' halo zones
+    np.testing.assert_array_equal(peer_lo_halo.cpu().numpy(), x_ext[plane:2 * plane])
+    np.testing.assert_array_equal(peer_hi_halo.cpu().numpy(), x_ext[loc.nrows:loc.nrows + plane])
+    lo_f, hi_f = peer_lo_flags.cpu().numpy(), peer_hi_flags.cpu().numpy()
+    assert lo_f[1] == seq and lo_f[3] == seq       # lower neighbour: ready-from-above, ack-from-above
+    assert hi_f[0] == seq and hi_f[2] == seq       # upper neighbour: ready-from-below, ack-from-below
+    assert lo_f[0] == 0 and hi_f[1] == 0
+
+
+def test_spmv_fused_without_neighbours_is_the_plain_kernel(ours, gpu_handle):
+    import torch
+    coo = G.laplace3d_7pt(20)
+    A = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    dA = util.upload(A)
+    x = G.random_vector(coo.nrows, np.float64, 3)
+    y = G.random_vector(coo.nrows, np.float64, 4)
+    plain = util.dev_spmv(ours, gpu_handle, "hell", A, dA, x, y, 1.5, -0.5)
+    dx, dy = util.to_dev(x), util.to_dev(y)
+    dz = torch.full((coo.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+    flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), dy.data_ptr(), 1.5, dA["values"].data_ptr(), dA["indices"].data_ptr(),
+                            32, dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), 7, coo.nrows, dx.data_ptr(), -0.5, 0, 0,
+                            0, 0, flags.data_ptr(), 0, 0, 1)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dz.cpu().numpy(), plain)
+
+
+def test_halo_exchange_kernel_and_ack(ours, gpu_handle):
+    """spgpuDhaloExchange / spgpuHaloAck / spgpuDhaloPush / spgpuWaitFlag with emulated neighbours"""
+    import torch
+    n = 5000
+    src = torch.arange(3 * n, dtype=torch.float64, device="cuda")
+    dst_lo = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dst_hi = torch.zeros(n, dtype=torch.float64, device="cuda")
+    mine = torch.zeros(16, dtype=torch.int32, device="cuda")
+    peer = torch.zeros(16, dtype=torch.int32, device="cuda")
+    mine[0] = 1; mine[1] = 1                       # neighbours already signalled seq 1
+    m, p = mine.data_ptr(), peer.data_ptr()
+    ours.spgpuDhaloExchange(gpu_handle, dst_lo.data_ptr(), src.data_ptr(), dst_hi.data_ptr(), src.data_ptr() + 8 * 2 * n, n,
+                            m + 8, m + 12, p + 4, p + 0, m + 0, m + 4, 1)
+    ours.spgpuHaloAck(gpu_handle, p + 12, p + 8, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(dst_lo, src[:n]) and torch.equal(dst_hi, src[2 * n:])
+    assert peer.cpu().numpy()[:4].tolist() == [1, 1, 1, 1]
+    # the two-kernel form
+    dst = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
+    flag = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ours.spgpuDhaloPush(gpu_handle, dst.data_ptr() + 8, src.data_ptr() + 8, n, flag.data_ptr(), 7)   # unaligned -> scalar path
+    ours.spgpuWaitFlag(gpu_handle, flag.data_ptr(), 7)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[1:], src[1:n + 1]) and int(flag[0].item()) == 7
