@@ -189,6 +189,35 @@ static Ret reduce_blocking(spgpuHandle_t handle, const T* x, const T* y, int n, 
 	return r;
 }
 
+/*
+ * Multi-vector forms: `count` reductions over vectors `pitch` elements apart.  The
+ * reference loops the blocking scalar routine (count host synchronisations, e.g.
+ * reference ddot.cu:152-160); here all `count` kernels are queued first, their results
+ * land in handle-owned device scratch, and ONE copy + ONE synchronisation returns them.
+ */
+template <typename T, typename Op, typename Ret>
+static void reduce_many(spgpuHandle_t handle, Ret* hostOut, const T* x, const T* y, int n,
+	int count, int pitch, int finish, int outKind)
+{
+	if (count <= 0)
+		return;
+	if (n <= 0) {
+		memset(hostOut, 0, sizeof(Ret) * (size_t)count);
+		return;
+	}
+	/* results live behind the per-CTA partial area other fused kernels use: keep them apart */
+	char* base = (char*)spgpuScratch(handle, 4096 + sizeof(Ret) * (size_t)count);
+	if (!base)
+		return;
+	Ret* dOut = reinterpret_cast<Ret*>(base);
+	for (int v = 0; v < count; ++v) {
+		const long long o = (long long)v * pitch;
+		reduce_launch<T, Op>(handle, x + o, y ? y + o : (const T*)0, n, dOut + v, finish, outKind);
+	}
+	cudaMemcpyAsync(hostOut, dOut, sizeof(Ret) * (size_t)count, cudaMemcpyDeviceToHost, handle->currentStream);
+	cudaStreamSynchronize(handle->currentStream);
+}
+
 /* ---- C entry points -------------------------------------------------------- */
 
 #define SPGPU_DEFINE_REDUCE(S, T, R)                                           \
@@ -196,34 +225,22 @@ static Ret reduce_blocking(spgpuHandle_t handle, const T* x, const T* y, int n, 
 	{ return reduce_blocking<T, OpDot<T>, T>(h, a, b, n, 0, 0); }               \
 	extern "C" void spgpu##S##mdot(spgpuHandle_t h, T* y, int n, T* a, T* b,    \
 		int count, int pitch)                                                   \
-	{                                                                           \
-		for (int v = 0; v < count; ++v)                                         \
-			y[v] = spgpu##S##dot(h, n, a + (long long)v * pitch, b + (long long)v * pitch); \
-	}                                                                           \
+	{ reduce_many<T, OpDot<T>, T>(h, y, a, b, n, count, pitch, 0, 0); }                                                                           \
 	extern "C" R spgpu##S##nrm2(spgpuHandle_t h, int n, T* x)                   \
 	{ return reduce_blocking<T, OpSqSum<T>, R>(h, x, (const T*)0, n, 1, 1); }   \
 	extern "C" void spgpu##S##mnrm2(spgpuHandle_t h, R* y, int n, T* x,         \
 		int count, int pitch)                                                   \
-	{                                                                           \
-		for (int v = 0; v < count; ++v)                                         \
-			y[v] = spgpu##S##nrm2(h, n, x + (long long)v * pitch);              \
-	}                                                                           \
+	{ reduce_many<T, OpSqSum<T>, R>(h, y, x, (const T*)0, n, count, pitch, 1, 1); }                                                                           \
 	extern "C" R spgpu##S##asum(spgpuHandle_t h, int n, T* x)                   \
 	{ return reduce_blocking<T, OpAbsSum<T>, R>(h, x, (const T*)0, n, 0, 1); }  \
 	extern "C" R spgpu##S##amax(spgpuHandle_t h, int n, T* x)                   \
 	{ return reduce_blocking<T, OpAbsMax<T>, R>(h, x, (const T*)0, n, 0, 1); }  \
 	extern "C" void spgpu##S##masum(spgpuHandle_t h, R* y, int n, T* x,         \
 		int count, int pitch)                                                   \
-	{                                                                           \
-		for (int v = 0; v < count; ++v)                                         \
-			y[v] = spgpu##S##asum(h, n, x + (long long)v * pitch);              \
-	}                                                                           \
+	{ reduce_many<T, OpAbsSum<T>, R>(h, y, x, (const T*)0, n, count, pitch, 0, 1); }                                                                           \
 	extern "C" void spgpu##S##mamax(spgpuHandle_t h, R* y, int n, T* x,         \
 		int count, int pitch)                                                   \
-	{                                                                           \
-		for (int v = 0; v < count; ++v)                                         \
-			y[v] = spgpu##S##amax(h, n, x + (long long)v * pitch);              \
-	}                                                                           \
+	{ reduce_many<T, OpAbsMax<T>, R>(h, y, x, (const T*)0, n, count, pitch, 0, 1); }                                                                           \
 	extern "C" void spgpu##S##dotDev(spgpuHandle_t h, int n, const T* a,        \
 		const T* b, T* dRes)                                                    \
 	{                                                                           \

@@ -98,17 +98,21 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	cudaStream_t s = handle->currentStream;
 	const HellArgs<T> args = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, speculate };
 #define HELL_ARGS args
-	/* 48 resident warps (<= 40 registers) beat 32 warps for the 4/8-byte types
-	 * (measured on B200: 2.11 ms vs 2.33 ms on the 512^3 Laplacian); the complex
-	 * types spill at 40 registers and stay at 32 warps.  hellBlock = 128 / 256
-	 * forces one or the other. */
-	bool dense = !Num<T>::is_complex;
-	if (t->hellBlock >= 256) dense = true;
-	else if (t->hellBlock > 0 && t->hellBlock <= 64) dense = false;
+	/* Resident warps per SM are set by the register budget (__launch_bounds__ minimum
+	 * CTAs): more warps = more loads in flight, until the allocator starts spilling.
+	 * Measured on B200 (512^3 Laplacian, double): 32 warps 2.33 ms, 40 warps (48 regs, no
+	 * spill) 2.15 ms, 48 warps (40 regs, 20 B spill) 2.11-2.21 ms.  Defaults: float 48
+	 * warps (39 regs, no spill), double 40, complex 32 (they spill below 64 registers and
+	 * are already at the HBM peak).  hellBlock forces a level: <=64 -> 32 warps, 192 -> 40,
+	 * >=256 -> 48. */
+	int level = Num<T>::is_complex ? 8 : (sizeof(T) == 4 ? 12 : 10);
+	if (t->hellBlock >= 256) level = 12;
+	else if (t->hellBlock == 192) level = 10;
+	else if (t->hellBlock > 0 && t->hellBlock <= 64) level = 8;
 	if (hackSize == 32) {
-		if (t->hellBlock == 192) hell_spmv_kernel<T, UNROLL, 32, 10><<<grid, block, 0, s>>>(HELL_ARGS);   /* 40 warps */
-		else if (dense) hell_spmv_kernel<T, UNROLL, 32, 12><<<grid, block, 0, s>>>(HELL_ARGS);
-		else       hell_spmv_kernel<T, UNROLL, 32, 8><<<grid, block, 0, s>>>(HELL_ARGS);
+		if (level == 10)      hell_spmv_kernel<T, UNROLL, 32, 10><<<grid, block, 0, s>>>(HELL_ARGS);
+		else if (level == 12) hell_spmv_kernel<T, UNROLL, 32, 12><<<grid, block, 0, s>>>(HELL_ARGS);
+		else                  hell_spmv_kernel<T, UNROLL, 32, 8><<<grid, block, 0, s>>>(HELL_ARGS);
 	} else {
 		hell_spmv_kernel<T, UNROLL, 0, 8><<<grid, block, 0, s>>>(HELL_ARGS);
 	}
