@@ -161,6 +161,19 @@ def build_workload(name, rank, world, device, n_override=None):
                  label=f"power-law rows {R} avg 16 max 4096, float HELL hackSize 32 (BASELINE configs[2])")
         w["bytes"] = algorithmic_bytes_hell(A.nnz, R, A.hack_offsets.numel(), R, 4)
         w["ell_bytes_avoided"] = int(A.rs.max().item()) * R * 8
+    elif name == "cfg3o":
+        # cfg3's matrix stored as OHELL: rows sorted by length (the reference's ellToOell order) with
+        # rIdx sending results home -- hacks become homogeneous, so HELL's padding sectors disappear
+        R = n_override or (1 << 22)
+        lens, cols, vals = DB.powerlaw_entries(R, device=device)
+        lens, cols, vals, ridx = DB.sort_rows_by_length(lens, cols, vals)
+        A = DB.hell_from_rows(lens, cols, vals, R)
+        A.ridx = ridx
+        del lens, cols, vals
+        w.update(kind="hell", sym="S", A=A, rows=R, nnz=A.nnz, halo=0, x_len=R, sizeof=4, alpha=1.0, beta=0.0,
+                 flops_per_nnz=2, total_rows=R,
+                 label=f"power-law rows {R} avg 16 max 4096, float OHELL (rows sorted by length + rIdx) hackSize 32")
+        w["bytes"] = algorithmic_bytes_hell(A.nnz, R, A.hack_offsets.numel(), R, 4) + 4 * R
     elif name == "cfg4":
         R = n_override or 2_000_000
         lens, cols, vals = DB.banded_complex_entries(R, device=device)
@@ -185,10 +198,15 @@ def make_step(L, h, w, x_ext_ptr, z_ptr, y_ptr):
         fn = getattr(L, f"spgpu{s}hellspmv")
         cM, rP, ho, rs = A.values.data_ptr(), A.indices.data_ptr(), A.hack_offsets.data_ptr(), A.rs.data_ptr()
         hs, avg, base = A.hack_size, A.avg, A.base
+        ridx = A.ridx.data_ptr() if getattr(A, "ridx", None) is not None else 0
 
         def step(r0=0, r1=w["rows"]):
-            fn(h, z_ptr + sz * r0, (y_ptr + sz * r0) if y_ptr else 0, a, cM, rP, hs, ho + 4 * (r0 // hs),
-               rs + 4 * r0, 0, avg, r1 - r0, x_ext_ptr, b, base)
+            if ridx:             # rIdx addresses z/y absolutely: no pointer offset for a sub-range
+                fn(h, z_ptr, y_ptr or 0, a, cM, rP, hs, ho + 4 * (r0 // hs), rs + 4 * r0, ridx + 4 * r0, avg,
+                   r1 - r0, x_ext_ptr, b, base)
+            else:
+                fn(h, z_ptr + sz * r0, (y_ptr + sz * r0) if y_ptr else 0, a, cM, rP, hs, ho + 4 * (r0 // hs),
+                   rs + 4 * r0, 0, avg, r1 - r0, x_ext_ptr, b, base)
     elif w["kind"] == "hdia":
         fn = getattr(L, f"spgpu{s}hdiaspmv")
         dM, off, ho = A.values.data_ptr(), A.offsets.data_ptr(), A.hack_offsets.data_ptr()
@@ -267,7 +285,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg3o", "cfg4", "cfg5"])
     ap.add_argument("--size", type=int, default=None, help="override the grid size / row count (testing)")
     ap.add_argument("--halo", default="fused", choices=["fused", "push", "nccl"],
                     help="multi-GPU halo exchange: fused = inside the SpMV kernel over NVLink peer pointers; "

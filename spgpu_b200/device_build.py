@@ -34,6 +34,7 @@ class DevHell:
     nnz: int
     base: int = 0
     avg: int = 1
+    ridx: torch.Tensor | None = None   # int32 output-row permutation (OHELL), or None
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.values, self.indices, self.hack_offsets, self.rs))
@@ -175,6 +176,23 @@ def hell_from_rows(lens: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n
     indices[dest] = (cols + base).to(torch.int32)
     nnz = int(cols.numel())
     return DevHell(values, indices, hoff, rs, hack, R, ncols, nnz, base, max(1, int(round(nnz / max(R, 1)))))
+
+
+def sort_rows_by_length(lens: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor):
+    """Device twin of ellToOell's ordering (reference ell.c:161-202): rows by descending
+    length, ties by descending row index.  Returns (lens', cols', vals', rIdx) with
+    rIdx[i] = original row now stored as row i."""
+    R = lens.numel()
+    idx = torch.arange(R, dtype=torch.int64, device=lens.device)
+    key = lens.to(torch.int64) * R + idx                 # descending key = length desc, index desc
+    perm = torch.argsort(key, descending=True)
+    new_lens = lens[perm]
+    old_start = torch.cumsum(lens.to(torch.int64), 0) - lens.to(torch.int64)
+    new_start = torch.cumsum(new_lens.to(torch.int64), 0) - new_lens.to(torch.int64)
+    new_rows = torch.repeat_interleave(idx, new_lens.to(torch.int64))
+    k = torch.arange(cols.numel(), dtype=torch.int64, device=lens.device) - new_start[new_rows]
+    src = old_start[perm[new_rows]] + k
+    return new_lens, cols[src], vals[src], perm.to(torch.int32)
 
 
 def _strided_columns(lens, lo, hi, gen):

@@ -104,3 +104,20 @@ def test_entry_builders_match_host_route(which):
     coo = F.Coo((rows + base).astype(np.int32), (c + base).astype(np.int32), vals.cpu().numpy(), R, R, base)
     host = F.ell_to_hell(F.coo_to_ell(coo, base), 32)
     _same_hell(dev, host)
+
+
+def test_sort_rows_by_length_matches_ell_to_oell():
+    """device OHELL ordering == the reference's ellToOell permutation (ties: higher row first)"""
+    import torch
+    from spgpu_b200 import device_build as DB
+    R = 3000
+    lens, cols, vals = DB.powerlaw_entries(R, mean=5, maxlen=300, spike_every=512)
+    slens, scols, svals, ridx = DB.sort_rows_by_length(lens, cols, vals)
+    rows = torch.repeat_interleave(torch.arange(R, device=cols.device), lens).cpu().numpy()
+    coo = F.Coo(rows.astype(np.int32), cols.cpu().numpy().astype(np.int32), vals.cpu().numpy(), R, R, 0)
+    ell = F.coo_to_ell(coo)
+    oell = F.ell_to_oell(ell)
+    np.testing.assert_array_equal(ridx.cpu().numpy(), oell.ridx)
+    np.testing.assert_array_equal(slens.cpu().numpy().astype(np.int32), oell.rs)
+    dev = DB.hell_from_rows(slens, scols, svals, R, 32, 0)
+    _same_hell(dev, F.ell_to_hell(oell, 32))
