@@ -296,6 +296,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cg", action="store_true", help="also time CG iterations (SpMV + 2 dots + 3 axpby), cfg5 only")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="CG scalars across GPUs: peer = one-double all-reduce over NVLink peer memory; nccl")
     ap.add_argument("--verify", action="store_true",
                     help="cfg5, N>1: check the partitioned result bit-for-bit against the same rows multiplied with global columns")
     ap.add_argument("--tune", default="", help="key=value,... passed to spgpuSetTuning")
@@ -627,11 +629,26 @@ def main():
         def apply_A(_z, _x):
             op_cg.apply(st.ap, x_ext)
 
-        def apply_A_dot(_z, _x, dres):
-            L.spgpuDhellspmvDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
-                                A.hack_offsets.data_ptr(), A.rs.data_ptr(), rows, x_ptr, A.base, 0, dres)
+        if world == 1:
+            def apply_A_dot(_z, _x, dres):
+                L.spgpuDhellspmvDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
+                                    A.hack_offsets.data_ptr(), A.rs.data_ptr(), rows, x_ptr, A.base, 0, dres)
+        elif peer is not None and args.halo == "fused":
+            plo, phi, myf, pflo, pfhi = peer.fused_pointers()
 
-        allred = (lambda t: dist.all_reduce(t)) if world > 1 else None
+            def apply_A_dot(_z, _x, dres):      # halo exchange + SpMV + this rank's p.Ap in one kernel (+ fold)
+                L.spgpuDhellspmvHaloDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
+                                        A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, A.base, halo,
+                                        plo, phi, myf, pflo, pfhi, peer.next_seq(), dres)
+        else:
+            apply_A_dot = None
+
+        peer_ar = None
+        if world > 1 and args.allreduce == "peer":
+            peer_ar = mg.PeerAllreduce(L, h, rank, world)
+            allred = peer_ar
+        else:
+            allred = (lambda t: dist.all_reduce(t)) if world > 1 else None
         cg = krylov.Cg(L, h, st, apply_A, apply_A_dot, allred)
         bvec = torch.rand(rows, generator=gen, device=device, dtype=torch.float64)
         iters = 10
@@ -653,12 +670,17 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_it = float(t.item()) / iters
             vec_bytes = krylov.CG_BYTES_PER_ROW_VECTOR_OPS[flavour] * w["total_rows"]
+            if flavour == "device" and apply_A_dot is None:
+                vec_bytes += 8 * w["total_rows"]          # separate p.Ap pass re-reads Ap
             cg_out[flavour] = {"ms_per_iteration": ms_it,
                                "algorithmic_gb_per_iteration": (bytes_total + vec_bytes) / 1e9,
                                "hbm_gbs": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9,
                                "frac_of_peak": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9 / (peak * world),
                                "kernels_per_iteration": (L.spgpuGetLaunchCount(h) - l0) / iters,
                                "residual_norm2_after": cg.residual_norm2() if flavour == "device" else st.rr_host}
+        cg_out["allreduce"] = args.allreduce if world > 1 else "none"
+        if peer_ar is not None:
+            peer_ar.close()
         del st, cg, bvec
 
     # ---------------- CPU baseline (rank 0, N=1) --------------------------------

@@ -144,6 +144,24 @@ void spgpuDhellspmvHalo(spgpuHandle_t handle, __device double* z, const __device
 	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
 	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq);
 
+/* The same kernel with this rank's share of p.Ap = sum_i xExt[haloN+i]*z[i] left in dRes
+ * (alpha = 1, beta = 0); partials per row block in handle scratch, folded by spgpuDsumDev. */
+void spgpuDhellspmvHaloDot(spgpuHandle_t handle, __device double* z, const __device double* cM,
+	const __device int* rP, int hackSize, const __device int* hackOffsets, const __device int* rS,
+	int avgNnzPerRow, int rows, __device double* xExt, int baseIndex, int haloN,
+	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, __device double* dRes);
+
+/*
+ * In-place sum all-reduce of ONE double over NVLink peer memory (latency-bound payload:
+ * one round of remote 16-byte stores + local polling instead of an NCCL launch).
+ * tables[r] = pointer (peer pointer for r != myRank) to rank r's zero-initialised table of
+ * 2 * world 16-byte slots; world <= 16; seq = 1, 2, 3, ... identical on every rank.  All
+ * ranks obtain the same bits (values are added in rank order).
+ */
+void spgpuAllreduceSumDev(spgpuHandle_t handle, __device double* dValue, int world, int myRank,
+	void* const* tables, unsigned seq);
+
 #ifdef __cplusplus
 }
 #endif

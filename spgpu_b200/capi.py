@@ -114,7 +114,8 @@ def ext_symbols():
     names += ["spgpuDaxpbyDev", "spgpuDhellspmvDot", "spgpuDcgUpdateDev", "spgpuDsumDev",
               "spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
               "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag",
-              "spgpuDhaloExchange", "spgpuHaloAck", "spgpuDhellspmvHalo"]
+              "spgpuDhaloExchange", "spgpuHaloAck", "spgpuDhellspmvHalo",
+              "spgpuDhellspmvHaloDot", "spgpuAllreduceSumDev"]
     return names
 
 
@@ -240,6 +241,10 @@ class SpgpuLib:
             f["spgpuDhaloExchange"] = _sig(d, "spgpuDhaloExchange", None,
                 [H, P, P, P, P, c_int, P, P, P, P, P, P, ctypes.c_uint], optional=True)
             f["spgpuHaloAck"] = _sig(d, "spgpuHaloAck", None, [H, P, P, ctypes.c_uint], optional=True)
+            f["spgpuDhellspmvHaloDot"] = _sig(d, "spgpuDhellspmvHaloDot", None,
+                [H, P, P, P, c_int, P, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, ctypes.c_uint, P], optional=True)
+            f["spgpuAllreduceSumDev"] = _sig(d, "spgpuAllreduceSumDev", None,
+                [H, P, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.c_uint], optional=True)
             f["spgpuDhellspmvHalo"] = _sig(d, "spgpuDhellspmvHalo", None,
                 [H, P, P, c_double, P, P, c_int, P, P, c_int, c_int, P, c_double, c_int, c_int,
                  P, P, P, P, P, ctypes.c_uint], optional=True)

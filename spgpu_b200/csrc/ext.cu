@@ -416,9 +416,21 @@ struct HaloArgs {
  * neighbours that their halo data has been consumed.  Transfer and multiply overlap inside
  * one launch; there is no separate pack / exchange / wait / ack kernel.
  */
-template <int UNROLL, int HACK, int MINB>
+/* z_i * x[xOffset+i] summed over the CTA, one partial per ROW BLOCK (fixed order) */
+__device__ __forceinline__ void cta_dot_partial(double contrib, double* ctaPartials, unsigned slot)
+{
+	__shared__ double ws[4];
+	contrib = warp_sum<double>(contrib);
+	if ((threadIdx.x & 31) == 0)
+		ws[threadIdx.x >> 5] = contrib;
+	__syncthreads();
+	if (threadIdx.x == 0)
+		ctaPartials[slot] = (ws[0] + ws[1]) + (ws[2] + ws[3]);
+}
+
+template <int UNROLL, int HACK, int MINB, bool DOT>
 __global__ void __launch_bounds__(128, MINB)
-dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx)
+dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx, int xOffset, double* __restrict__ ctaPartials)
 {
 	if (blockIdx.x < (unsigned)hx.pushCtas) {
 		const bool toHi = (blockIdx.x & 1) != 0;
@@ -465,9 +477,13 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx)
 		else if (b < interior + head) rb = b - interior;       /* then the lower boundary   */
 		else rb = b;                                           /* then the upper boundary   */
 		const bool needLo = rb < head, needHi = rb >= rowBlocks - tail;
+		const unsigned myRow = rb * 128u + threadIdx.x;
 		if (!needLo && !needHi) {
 			/* interior: no flags, no tickets -- exactly the plain kernel */
-			hell_warp_rows<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u));
+			double zval;
+			hell_warp_rows_value<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u), zval);
+			if (DOT)
+				cta_dot_partial(myRow < (unsigned)a.rows ? zval * __ldg(a.x + xOffset + myRow) : 0.0, ctaPartials, rb);
 			return;
 		}
 		if (threadIdx.x == 0) {
@@ -475,7 +491,10 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx)
 			if (needHi && hx.myReadyHi) spin_until(hx.myReadyHi, hx.seq, hx.timeoutNs);
 		}
 		__syncthreads();
-		hell_warp_rows<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u));
+		double zval;
+		hell_warp_rows_value<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u), zval);
+		if (DOT)
+			cta_dot_partial(myRow < (unsigned)a.rows ? zval * __ldg(a.x + xOffset + myRow) : 0.0, ctaPartials, rb);
 		/* the last CTA that read a halo zone tells that neighbour its data has been consumed
 		 * (only the few boundary CTAs touch these counters) */
 		__syncthreads();
@@ -495,14 +514,12 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx)
 	}
 }
 
-extern "C" void spgpuDhellspmvHalo(spgpuHandle_t handle, double* z, const double* y, double alpha,
+static void dhell_spmv_halo_launch(spgpuHandle_t handle, double* z, const double* y, double alpha,
 	const double* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
 	int avgNnzPerRow, int rows, double* xExt, double beta, int baseIndex, int haloN,
 	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
-	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq)
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, double* ctaPartials)
 {
-	if (rows <= 0)
-		return;
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const HellArgs<double> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
@@ -525,10 +542,98 @@ extern "C" void spgpuDhellspmvHalo(spgpuHandle_t handle, double* z, const double
 	hx.timeoutNs = 2000000000ull;
 	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
-	if (hackSize == 32)
-		dhell_spmv_halo_kernel<8, 32, 10><<<grid, 128, 0, s>>>(a, hx);
-	else
-		dhell_spmv_halo_kernel<8, 0, 8><<<grid, 128, 0, s>>>(a, hx);
+	if (ctaPartials) {
+		if (hackSize == 32)
+			dhell_spmv_halo_kernel<8, 32, 10, true><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+		else
+			dhell_spmv_halo_kernel<8, 0, 8, true><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+	} else {
+		if (hackSize == 32)
+			dhell_spmv_halo_kernel<8, 32, 10, false><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+		else
+			dhell_spmv_halo_kernel<8, 0, 8, false><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+	}
+	spgpu_count_launch(handle);
+}
+
+extern "C" void spgpuDhellspmvHalo(spgpuHandle_t handle, double* z, const double* y, double alpha,
+	const double* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
+	int avgNnzPerRow, int rows, double* xExt, double beta, int baseIndex, int haloN,
+	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq)
+{
+	if (rows <= 0)
+		return;
+	dhell_spmv_halo_launch(handle, z, y, alpha, cM, rP, hackSize, hackOffsets, rS, avgNnzPerRow, rows, xExt,
+		beta, baseIndex, haloN, peerXLoUpperHalo, peerXHiLowerHalo, myFlags, peerFlagsLo, peerFlagsHi, seq, NULL);
+}
+
+/* z = A*xExt with the halo exchange inside, plus dRes[0] = sum_i xExt[haloN+i]*z[i] (this rank's
+ * share of p.Ap): per-row-block partials in handle scratch, folded by spgpuDsumDev. */
+extern "C" void spgpuDhellspmvHaloDot(spgpuHandle_t handle, double* z, const double* cM, const int* rP,
+	int hackSize, const int* hackOffsets, const int* rS, int avgNnzPerRow, int rows, double* xExt,
+	int baseIndex, int haloN, double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, double* dRes)
+{
+	if (rows <= 0) {
+		cudaMemsetAsync(dRes, 0, sizeof(double), handle->currentStream);
+		return;
+	}
+	const unsigned rowBlocks = spgpu_ceil_div(rows, 128);
+	double* partials = (double*)spgpuScratch(handle, (size_t)rowBlocks * sizeof(double));
+	if (!partials)
+		return;
+	dhell_spmv_halo_launch(handle, z, NULL, 1.0, cM, rP, hackSize, hackOffsets, rS, avgNnzPerRow, rows, xExt,
+		0.0, baseIndex, haloN, peerXLoUpperHalo, peerXHiLowerHalo, myFlags, peerFlagsLo, peerFlagsHi, seq, partials);
+	spgpuDsumDev(handle, (int)rowBlocks, partials, dRes);
+}
+
+/* ---- one-double sum all-reduce over NVLink peer memory ------------------------------- */
+
+#define SPGPU_MAX_RANKS 16
+struct PeerTables { unsigned char* t[SPGPU_MAX_RANKS]; };
+struct alignas(16) ArSlot { double value; unsigned seq; unsigned pad; };
+
+/*
+ * Every rank stores (value, seq) into slot [parity][myRank] of EVERY rank's table (remote
+ * 16-byte stores over NVLink, value first, then a release store of seq), then polls its own
+ * table until all `world` slots of this parity carry seq and adds the values in rank order --
+ * the same order on every rank, so all ranks get the same bits.  Payload is 8 bytes, so this
+ * is pure latency: one NVLink round instead of an NCCL launch + ring.  Two parities because
+ * a fast rank can be at most one all-reduce ahead of the slowest.
+ */
+__global__ void allreduce_sum_kernel(double* dValue, int world, int myRank, PeerTables tables,
+	unsigned seq, unsigned long long timeoutNs)
+{
+	const int r = threadIdx.x;
+	const unsigned parity = seq & 1u;
+	double v = 0.0;
+	if (r < world) {
+		const double mine = *dValue;
+		ArSlot* dst = reinterpret_cast<ArSlot*>(tables.t[r]) + parity * world + myRank;
+		dst->value = mine;
+		__threadfence_system();
+		st_release_sys(&dst->seq, seq);
+		const ArSlot* src = reinterpret_cast<const ArSlot*>(tables.t[myRank]) + parity * world + r;
+		spin_until(&src->seq, seq, timeoutNs);
+		v = *reinterpret_cast<const volatile double*>(&src->value);
+	}
+	double total = 0.0;
+	for (int k = 0; k < world; ++k)
+		total += __shfl_sync(SPGPU_FULL_MASK, v, k);
+	if (r == 0)
+		*dValue = total;
+}
+
+extern "C" void spgpuAllreduceSumDev(spgpuHandle_t handle, double* dValue, int world, int myRank,
+	void* const* tables, unsigned seq)
+{
+	if (world <= 1)
+		return;
+	PeerTables pt;
+	for (int r = 0; r < SPGPU_MAX_RANKS; ++r)
+		pt.t[r] = r < world ? (unsigned char*)tables[r] : NULL;
+	allreduce_sum_kernel<<<1, 32, 0, handle->currentStream>>>(dValue, world, myRank, pt, seq, 2000000000ull);
 	spgpu_count_launch(handle);
 }
 

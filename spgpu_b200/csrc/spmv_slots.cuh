@@ -14,10 +14,12 @@
  *            round; all index and value loads of a round are issued before the
  *            dependent x gathers, then the FMAs.  Lanes whose row is shorter
  *            are switched off by predication (select, not branch).
- *   phase 2  only when some row of the warp is longer than `cut` (spike rows):
- *            those rows are finished one at a time by ALL 32 lanes striding
- *            over the remaining slots, followed by a shuffle reduction -- a
- *            4096-slot row costs 128 warp rounds instead of 4096.
+ *   phase 2  only when a few rows of the warp are much longer than the rest
+ *            (spike rows): those rows are finished one at a time by ALL 32
+ *            lanes striding over the remaining slots, followed by a shuffle
+ *            reduction -- a 4096-slot row costs 128 warp rounds instead of 4096.
+ *            `cut` adapts per warp (see below), so hacks whose rows are all
+ *            long (length-sorted OHELL) stay in phase 1.
  *
  * STRIDE > 0 makes the slot stride a compile-time constant (HELL with the usual
  * hackSize 32/64): every load of a round is then base + immediate, with no
@@ -41,7 +43,7 @@ __device__ __forceinline__ T warp_rows_dot(
 	const T* __restrict__ vals, const int* __restrict__ idxs,   /* already at this lane's slot 0 */
 	int valStrideRt, int idxStrideRt,
 	int rowLen,              /* slots of this lane's row (0 for lanes past the end) */
-	int longCut,
+	int longCut,             /* "longRows": phase 1 goes on while at least this many rows are active */
 	int allocated,           /* slots guaranteed to exist for the whole warp, 0 = unknown */
 	const T* __restrict__ x, int baseIndex)
 {
@@ -76,7 +78,25 @@ __device__ __forceinline__ T warp_rows_dot(
 	} else {
 		/* ---- phase 1, general: one row per lane, predicated loads ---- */
 		const int longest = __reduce_max_sync(SPGPU_FULL_MASK, rowLen);
-		cut = min(longest, longCut);
+		cut = longest;
+		if (longest > 2 * UNROLL) {
+			/* Where to stop walking row-per-lane: a slot row costs one warp round however
+			 * few lanes still have a row that long, while a leftover row finished by all 32
+			 * lanes costs (len-cut)/32 rounds of uncoalesced loads (~4x dearer each).  So go
+			 * on while at least longRows (default 8 = 32/4) rows are still active: cut = the
+			 * smallest depth with fewer than longRows longer rows (binary search on ballots).
+			 * Homogeneous hacks (regular or length-sorted matrices) never leave phase 1;
+			 * a few spike rows in a short hack are peeled off early. */
+			int lo = 0, hi = longest;
+			while (lo < hi) {
+				const int mid = (lo + hi) >> 1;
+				if (__popc(__ballot_sync(SPGPU_FULL_MASK, rowLen > mid)) < longCut)
+					hi = mid;
+				else
+					lo = mid + 1;
+			}
+			cut = lo;
+		}
 		const int mine = min(rowLen, cut);
 		const T* vp = vals;
 		const int* ip = idxs;

@@ -87,8 +87,10 @@ class Cg:
         st, L, h, n = self.st, self.L, self.h, self.st.n
         s = st.s.data_ptr()
         rr, pap, rrn = s, s + 8, s + 16
-        if self.apply_A_dot is not None and self.allreduce is None:
-            self.apply_A_dot(st.ap, st.p_ext, pap)
+        if self.apply_A_dot is not None:
+            self.apply_A_dot(st.ap, st.p_ext, pap)          # SpMV (+ halo exchange) fused with p.Ap
+            if self.allreduce:
+                self.allreduce(st.s[1:2])
         else:
             self.apply_A(st.ap, st.p_ext)
             L.spgpuDdotDev(h, n, st.p.data_ptr(), st.ap.data_ptr(), pap)

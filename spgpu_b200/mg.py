@@ -305,6 +305,50 @@ class PeerHalo:
         self.peer = {}
 
 
+class PeerAllreduce:
+    """Sum all-reduce of one double over NVLink peer memory (spgpuAllreduceSumDev): every
+    rank's 2*world-slot table is CUDA-IPC mapped into every other rank."""
+
+    def __init__(self, L, handle, rank, world, group=None):
+        assert world <= 16
+        self.L, self.h, self.rank, self.world = L, handle, rank, world
+        self.seq = 0
+        nbytes = 2 * world * 16
+        p = ctypes.c_void_p()
+        assert L.spgpuDeviceAlloc(ctypes.byref(p), nbytes) == 0
+        self.table = p.value
+        _as_tensor(self.table, nbytes // 4, torch.int32).zero_()
+        torch.cuda.synchronize()
+        hb = (ctypes.c_char * 64)()
+        assert L.spgpuIpcGetHandle(self.table, hb) == 0
+        everyone = [None] * world
+        dist.all_gather_object(everyone, bytes(hb), group=group)
+        self.tables = (ctypes.c_void_p * world)()
+        self.opened = []
+        for r in range(world):
+            if r == rank:
+                self.tables[r] = self.table
+            else:
+                q = ctypes.c_void_p()
+                buf = (ctypes.c_char * 64).from_buffer_copy(everyone[r])
+                rc = L.spgpuIpcOpenHandle(buf, ctypes.byref(q))
+                assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
+                self.tables[r] = q.value
+                self.opened.append(q.value)
+        dist.barrier(group=group)
+
+    def __call__(self, t: torch.Tensor):
+        """in-place sum of a 1-element float64 device tensor across the ranks (stream-ordered)"""
+        self.seq += 1
+        self.L.spgpuAllreduceSumDev(self.h, t.data_ptr(), self.world, self.rank, self.tables, self.seq)
+
+    def close(self):
+        torch.cuda.synchronize()
+        for q in self.opened:
+            self.L.spgpuIpcCloseHandle(q)
+        self.opened = []
+
+
 class _RawCuda:
     """__cuda_array_interface__ carrier so torch can view a raw cudaMalloc block."""
 
