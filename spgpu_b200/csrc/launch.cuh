@@ -14,7 +14,7 @@ static inline void spgpu_count_launch(spgpuHandle_t handle)
 
 static inline const SpgpuTuning* spgpu_tuning(spgpuHandle_t handle)
 {
-	static const SpgpuTuning fallback = { 0, 0, 8, 0, 0, 128, 1, 4, 8 };
+	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 128, 1, 4, 8 };
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	return h->magic == SPGPU_PRIV_MAGIC ? &h->tune : &fallback;
 }
@@ -31,13 +31,13 @@ static inline unsigned spgpu_ceil_div(long long a, long long b)
 	return (unsigned)((a + b - 1) / b);
 }
 
-/* phase 1 of spmv_slots.cuh continues while at least this many rows of the warp are active */
+/* rows deeper than this many slots count as spikes (spmv_slots.cuh decides per warp what to do with them) */
 static inline int spgpu_long_cut(const SpgpuTuning* t, int avgNnzPerRow)
 {
-	(void)avgNnzPerRow;
-	int k = t->hellLongFactor > 0 ? t->hellLongFactor : 8;
-	if (k > 32) k = 32;
-	return k;
+	long long cut = (long long)(t->hellLongFactor > 0 ? t->hellLongFactor : 4) * (avgNnzPerRow > 0 ? avgNnzPerRow : 1);
+	if (cut < 32) cut = 32;
+	if (cut > (1 << 30)) cut = 1 << 30;
+	return (int)cut;
 }
 
 #endif

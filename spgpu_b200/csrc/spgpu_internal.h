@@ -27,7 +27,7 @@ extern "C" {
 typedef struct SpgpuTuning {
 	int hellVariant;     /* 0 auto, 1 direct loads predicated on rS, 2 direct loads with unpredicated slab reads, 3 bulk-async (TMA) pipeline */
 	int hellBlock;       /* occupancy knob: 0 per-type default, <=64 force 32 warps/SM, >=256 force 48 */
-	int hellLongFactor;  /* "longRows": rows of a warp that must still be active for the row-per-lane walk to continue (default 8) */
+	int hellLongFactor;  /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike (default 4) */
 	int hdiaVariant;     /* reserved */
 	int hdiaBlock;       /* occupancy knob: >=256 force 48 warps/SM (default 32) */
 	int diaBlock;

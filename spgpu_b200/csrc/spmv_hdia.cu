@@ -97,10 +97,12 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const unsigned grid = spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
-	const bool dense = t->hdiaBlock >= 256;          /* knob: trade registers for occupancy */
+	/* occupancy knob (registers vs resident warps): hdiaBlock >=256 -> 48 warps, 192 -> 40, else 32 */
 	if (hackSize == 32) {
-		if (dense) hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else       hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		if (t->hdiaBlock >= 256)      hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else if (t->hdiaBlock == 224) hdia_spmv_kernel<T, 4, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else if (t->hdiaBlock == 192) hdia_spmv_kernel<T, UNROLL, 32, 10><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else                          hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 	} else {
 		hdia_spmv_kernel<T, UNROLL, 0, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 	}

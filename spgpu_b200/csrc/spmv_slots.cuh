@@ -43,7 +43,7 @@ __device__ __forceinline__ T warp_rows_dot(
 	const T* __restrict__ vals, const int* __restrict__ idxs,   /* already at this lane's slot 0 */
 	int valStrideRt, int idxStrideRt,
 	int rowLen,              /* slots of this lane's row (0 for lanes past the end) */
-	int longCut,             /* "longRows": phase 1 goes on while at least this many rows are active */
+	int longCut,             /* depth beyond which a row counts as a spike (host: 4 x avgNnzPerRow, >= 32) */
 	int allocated,           /* slots guaranteed to exist for the whole warp, 0 = unknown */
 	const T* __restrict__ x, int baseIndex)
 {
@@ -78,19 +78,21 @@ __device__ __forceinline__ T warp_rows_dot(
 	} else {
 		/* ---- phase 1, general: one row per lane, predicated loads ---- */
 		const int longest = __reduce_max_sync(SPGPU_FULL_MASK, rowLen);
-		cut = longest;
-		if (longest > 2 * UNROLL) {
-			/* Where to stop walking row-per-lane: a slot row costs one warp round however
-			 * few lanes still have a row that long, while a leftover row finished by all 32
-			 * lanes costs (len-cut)/32 rounds of uncoalesced loads (~4x dearer each).  So go
-			 * on while at least longRows (default 8 = 32/4) rows are still active: cut = the
-			 * smallest depth with fewer than longRows longer rows (binary search on ballots).
-			 * Homogeneous hacks (regular or length-sorted matrices) never leave phase 1;
-			 * a few spike rows in a short hack are peeled off early. */
-			int lo = 0, hi = longest;
+		cut = min(longest, longCut);
+		if (longest > longCut) {
+			/* Some row is much longer than the matrix average (longCut = 4 x avgNnzPerRow,
+			 * at least 32).  If only a FEW rows are (spikes in an otherwise short hack), stop
+			 * the row-per-lane walk at longCut and finish those rows cooperatively (phase 2).
+			 * If MANY rows of the warp are that long (homogeneous long hacks: length-sorted
+			 * OHELL, dense blocks), the row-per-lane walk is the efficient one -- it stays
+			 * coalesced -- so it continues while at least SPIKE_ROWS rows are still active:
+			 * cut = the smallest depth with fewer than SPIKE_ROWS longer rows (binary search
+			 * on ballots). */
+			constexpr int SPIKE_ROWS = 8;
+			int lo = longCut, hi = longest;
 			while (lo < hi) {
 				const int mid = (lo + hi) >> 1;
-				if (__popc(__ballot_sync(SPGPU_FULL_MASK, rowLen > mid)) < longCut)
+				if (__popc(__ballot_sync(SPGPU_FULL_MASK, rowLen > mid)) < SPIKE_ROWS)
 					hi = mid;
 				else
 					lo = mid + 1;

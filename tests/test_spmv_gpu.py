@@ -119,14 +119,13 @@ def test_spike_rows_take_the_cooperative_path(ours, gpu_handle, dtype, fmt):
     x = G.random_vector(6000, dtype, 1, -1, 1)
     y = G.random_vector(6000, dtype, 2, -1, 1)
     alpha, beta = scalars(dtype)
-    try:
-        # longRows = 1: the row-per-lane walk runs to the longest row (no cooperative phase);
-        # 32: it stops as soon as one row ends (almost everything is finished cooperatively)
-        for long_rows in (1, 8, 32):
-            assert ours.spgpuSetTuning(gpu_handle, b"hellLongFactor", long_rows) == 0
-            check(ours, gpu_handle, fmt, coo, A, x, y, alpha, beta)
-    finally:
-        ours.spgpuSetTuning(gpu_handle, b"hellLongFactor", 8)
+    for avg in (1, 8, 4000):          # spike threshold 32 / 32 / 16000 slots: cooperative phase on .. off
+        check(ours, gpu_handle, fmt, coo, A, x, y, alpha, beta, avg=avg)
+    # length-sorted rows (OHELL): homogeneous long hacks must stay in the row-per-lane walk
+    ell = F.coo_to_ell(coo)
+    oell = F.ell_to_oell(ell)
+    B = oell if fmt == "ell" else F.ell_to_hell(oell, 32)
+    check(ours, gpu_handle, fmt, coo, B, x, y, alpha, beta, ridx=oell.ridx, avg=8)
 
 
 @pytest.mark.parametrize("hack", [32, 64, 128])
