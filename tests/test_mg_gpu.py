@@ -96,3 +96,53 @@ def test_halo_exchange_kernel_and_ack(ours, gpu_handle):
     ours.spgpuWaitFlag(gpu_handle, flag.data_ptr(), 7)
     torch.cuda.synchronize()
     assert torch.equal(dst[1:], src[1:n + 1]) and int(flag[0].item()) == 7
+
+
+def test_peer_allreduce_kernel_with_emulated_peer(ours, gpu_handle):
+    """spgpuAllreduceSumDev, world = 3, this rank = 1: the two peers' contributions are pre-filled in
+    this rank's table; this rank's (value, seq) must land in slot 1 of every table and the sum must
+    be taken in rank order"""
+    import ctypes
+    import struct
+    import torch
+    world, me = 3, 1
+    for seq in (1, 2, 7):
+        tabs = [torch.zeros(2 * world * 4, dtype=torch.int32, device="cuda") for _ in range(world)]
+        parity = seq & 1
+        vals = {0: 0.125, 2: -3.5}
+        host = np.zeros(2 * world * 4, dtype=np.int32)
+        for r, v in vals.items():
+            lo, hi = struct.unpack("<ii", struct.pack("<d", v))
+            base = (parity * world + r) * 4
+            host[base:base + 4] = [lo, hi, seq, 0]
+        tabs[me].copy_(torch.from_numpy(host))
+        value = torch.tensor([10.0], dtype=torch.float64, device="cuda")
+        ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in tabs])
+        ours.spgpuAllreduceSumDev(gpu_handle, value.data_ptr(), world, me, ptrs, seq)
+        torch.cuda.synchronize()
+        assert float(value.item()) == (0.125 + 10.0) + -3.5
+        for t in tabs:
+            got = t.cpu().numpy()[(parity * world + me) * 4:(parity * world + me) * 4 + 3]
+            assert struct.unpack("<d", struct.pack("<ii", int(got[0]), int(got[1])))[0] == 10.0 and got[2] == seq
+
+
+def test_spmv_halo_dot(ours, gpu_handle):
+    """spgpuDhellspmvHaloDot: fused exchange + SpMV + this rank's share of p.Ap"""
+    import torch
+    coo, loc, plane, x, x_ext, want = _middle_block()
+    dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
+    dx = util.to_dev(x_ext)
+    dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+    my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    my_flags[0] = 1; my_flags[1] = 1
+    pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
+    ph = [torch.zeros(plane, dtype=torch.float64, device="cuda") for _ in range(2)]
+    dres = torch.full((1,), float("nan"), dtype=torch.float64, device="cuda")
+    ours.spgpuDhellspmvHaloDot(gpu_handle, dz.data_ptr(), dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(), drs.data_ptr(),
+                               7, loc.nrows, dx.data_ptr(), 0, plane, ph[0].data_ptr(), ph[1].data_ptr(),
+                               my_flags.data_ptr(), pf[0].data_ptr(), pf[1].data_ptr(), 1, dres.data_ptr())
+    torch.cuda.synchronize()
+    util.assert_rows_close(dz.cpu().numpy(), want, np.full(loc.nrows, 12.0), "D", "fused spmv+halo+dot")
+    own = x_ext[plane:plane + loc.nrows]
+    ref = float(np.dot(own, want))
+    assert abs(float(dres.item()) - ref) <= 1e-12 * float(np.sum(np.abs(own) * np.abs(want)))
