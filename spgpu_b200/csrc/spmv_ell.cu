@@ -13,6 +13,7 @@
  */
 #include "launch.cuh"
 #include "spmv_slots.cuh"
+#include "spmv_ell_bulk.cuh"
 
 template <typename T, int UNROLL, int MINB>
 __global__ void __launch_bounds__(128, MINB)
@@ -41,6 +42,35 @@ ell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
 		z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
 }
 
+/* bulk-async variant (hellVariant = 3): short regular rows, aligned arrays */
+template <typename T, int UNROLL>
+static bool ell_spmv_try_bulk(spgpuHandle_t handle, T* z, const T* y, T alpha,
+	const T* cM, const int* rP, int cMPitch, int rPPitch, const int* rS,
+	const int* rIdx, int maxNnzPerRow, int rows, const T* x, T beta,
+	int baseIndex, int longCut)
+{
+	const int tileRows = HB_CONSUMER_WARPS * 32;
+	const size_t stageBytes = (size_t)maxNnzPerRow * tileRows * (sizeof(T) + sizeof(int)) + tileRows * sizeof(int);
+	int stages = (int)((110 * 1024 - 256) / stageBytes);
+	if (stages > 4) stages = 4;
+	if (stages < 2 || maxNnzPerRow <= 0 || rows < 8 * tileRows)
+		return false;
+	if ((((size_t)cM | (size_t)rP | (size_t)rS) & 15) != 0 ||
+	    ((size_t)cMPitch * sizeof(T)) % 16 != 0 || ((size_t)rPPitch * sizeof(int)) % 16 != 0)
+		return false;
+	if (cudaFuncSetAttribute(ell_spmv_bulk_kernel<T, UNROLL>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024)) != cudaSuccess)
+		return false;
+	const size_t smem = stages * stageBytes + 2 * stages * sizeof(uint64_t);
+	const int tiles = (rows + tileRows - 1) / tileRows;
+	int grid = 2 * handle->multiProcessorCount;
+	if (grid > tiles) grid = tiles;
+	ell_spmv_bulk_kernel<T, UNROLL><<<grid, HB_THREADS, smem, handle->currentStream>>>(
+		z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow, rows, x, beta, baseIndex, longCut, stages);
+	spgpu_count_launch(handle);
+	return true;
+}
+
 template <typename T, int UNROLL>
 static void ell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const T* cM, const int* rP, int cMPitch, int rPPitch, const int* rS,
@@ -52,6 +82,10 @@ static void ell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const int block = 128;
 	const unsigned grid = spgpu_ceil_div(rows, block);
+	if (t->hellVariant == 3 &&
+	    ell_spmv_try_bulk<T, UNROLL>(handle, z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow,
+			rows, x, beta, baseIndex, spgpu_long_cut(t, avgNnzPerRow)))
+		return;
 	/* every slot below maxNnzPerRow exists in an ELL allocation, so short regular
 	 * matrices can read them without waiting for rS (spmv_slots.cuh); only worth it
 	 * when little of that is padding (avg close to max) */

@@ -103,6 +103,8 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		else if (t->hdiaBlock == 224) hdia_spmv_kernel<T, 4, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else if (t->hdiaBlock == 192) hdia_spmv_kernel<T, UNROLL, 32, 10><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else                          hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+	} else if (hackSize == 64) {
+		hdia_spmv_kernel<T, UNROLL, 64, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 	} else {
 		hdia_spmv_kernel<T, UNROLL, 0, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 	}

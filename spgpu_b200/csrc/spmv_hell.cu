@@ -38,7 +38,6 @@ static bool hell_spmv_try_bulk(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const int* rIdx, int avgNnzPerRow, int rows, const T* x, T beta,
 	int baseIndex, int longCut)
 {
-	static bool configured = false;
 	const int avg = avgNnzPerRow > 0 ? avgNnzPerRow : 1;
 	const int slots = avg + (avg / 4 > 1 ? avg / 4 : 1);
 	const int cap = HB_CONSUMER_WARPS * 32 * slots;
@@ -51,12 +50,10 @@ static bool hell_spmv_try_bulk(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	if ((((size_t)cM | (size_t)rP | (size_t)rS) & 15) != 0)
 		return false;                                     /* bulk copies need 16-byte aligned sources */
 	const size_t smem = stages * stageBytes + 2 * stages * sizeof(uint64_t);
-	if (!configured) {
-		if (cudaFuncSetAttribute(hell_spmv_bulk_kernel<T, HACK, UNROLL>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024)) != cudaSuccess)
-			return false;
-		configured = true;
-	}
+	/* function attributes are per device: set on every call (a process may drive several GPUs) */
+	if (cudaFuncSetAttribute(hell_spmv_bulk_kernel<T, HACK, UNROLL>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024)) != cudaSuccess)
+		return false;
 	const int tiles = (rows + HB_CONSUMER_WARPS * 32 - 1) / (HB_CONSUMER_WARPS * 32);
 	int grid = 2 * handle->multiProcessorCount;
 	if (grid > tiles) grid = tiles;
@@ -113,6 +110,9 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		if (level == 10)      hell_spmv_kernel<T, UNROLL, 32, 10><<<grid, block, 0, s>>>(HELL_ARGS);
 		else if (level == 12) hell_spmv_kernel<T, UNROLL, 32, 12><<<grid, block, 0, s>>>(HELL_ARGS);
 		else                  hell_spmv_kernel<T, UNROLL, 32, 8><<<grid, block, 0, s>>>(HELL_ARGS);
+	} else if (hackSize == 64) {
+		if (level >= 10) hell_spmv_kernel<T, UNROLL, 64, 10><<<grid, block, 0, s>>>(HELL_ARGS);
+		else             hell_spmv_kernel<T, UNROLL, 64, 8><<<grid, block, 0, s>>>(HELL_ARGS);
 	} else {
 		hell_spmv_kernel<T, UNROLL, 0, 8><<<grid, block, 0, s>>>(HELL_ARGS);
 	}

@@ -217,3 +217,24 @@ def test_hell_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
     finally:
         ours.spgpuSetTuning(gpu_handle, b"hellVariant", 0)
         ours.spgpuSetTuning(gpu_handle, b"hellBlock", 0)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ell_kernel_variants(ours, gpu_handle, variant, dtype):
+    """ELL code paths: predicated / unpredicated slab reads / bulk-async pipeline (incl. ragged tail
+    tile, rS == NULL and rIdx)"""
+    try:
+        assert ours.spgpuSetTuning(gpu_handle, b"hellVariant", variant) == 0
+        for coo in (G.laplace3d_7pt(20), G.random_coo(5000, 5000, (0, 5), 1, dtype, 0), G.laplace2d_5pt(70, 53)):
+            coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+            A = build("ell", coo, 0, 32)
+            x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
+            y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
+            alpha, beta = scalars(dtype)
+            check(ours, gpu_handle, "ell", coo, A, x, y, alpha, beta)
+            check(ours, gpu_handle, "ell", coo, A, x, y, alpha, 0.0, rs_null=True)
+            oell = F.ell_to_oell(A)
+            check(ours, gpu_handle, "ell", coo, oell, x, y, alpha, beta, ridx=oell.ridx)
+    finally:
+        ours.spgpuSetTuning(gpu_handle, b"hellVariant", 0)
