@@ -86,6 +86,23 @@ void spgpuDcgUpdateDev(spgpuHandle_t handle, __device double* x, __device double
 	const __device double* p, const __device double* ap, int n,
 	const __device double* dRr, const __device double* dPAp, __device double* dRrNew);
 
+/* ---- device-side format construction -------------------- */
+
+/*
+ * CSR (device, rowPtr with rows+1 entries, csrBase-based) -> HELL (device), bit-identical
+ * to the host route cooToEll + ellToHell on the same entries.  Step 1 (blocking) fills
+ * dRs and dHackOffsets and returns the number of elements to allocate for the HELL value
+ * and index arrays; step 2 (asynchronous) places the entries (padding slots untouched).
+ */
+int spgpuCsrToHellLayoutDevice(spgpuHandle_t handle, int rows, const __device int* dRowPtr,
+	int hackSize, __device int* dRs, __device int* dHackOffsets, long long* totalElements);
+#define SPGPU_DECL_CSR2HELL(S, T, R)                                                 \
+	void spgpu##S##csrToHellDevice(spgpuHandle_t handle, int rows,                    \
+		const __device int* dRowPtr, const __device int* dCols, const __device T* dVals, \
+		int csrBase, int hackSize, const __device int* dHackOffsets, int hellBase,    \
+		__device T* dHellValues, __device int* dHellIndices);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_CSR2HELL)
+
 /* ---- multi-GPU helpers ---------------------------------------------------- */
 
 /* 64-byte CUDA IPC handle of a cudaMalloc'ed pointer / open it in a peer process. */

@@ -111,6 +111,7 @@ def ext_symbols():
     names = ["spgpuB200Version", "spgpuGetLaunchCount", "spgpuSetTuning", "spgpuGetTuning"]
     for s in FLOAT_SYMS:
         names += [f"spgpu{s}dotDev", f"spgpu{s}nrm2sqDev"]
+    names += ["spgpuCsrToHellLayoutDevice"] + [f"spgpu{s}csrToHellDevice" for s in FLOAT_SYMS]
     names += ["spgpuDaxpbyDev", "spgpuDhellspmvDot", "spgpuDcgUpdateDev", "spgpuDsumDev",
               "spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
               "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag",
@@ -226,6 +227,11 @@ class SpgpuLib:
                 [H, P, c_int, P, P, c_double, P, P, P, c_double, P], optional=True)
             f["spgpuDhellspmvDot"] = _sig(d, "spgpuDhellspmvDot", None,
                 [H, P, P, P, c_int, P, P, c_int, P, c_int, c_int, P], optional=True)
+            f["spgpuCsrToHellLayoutDevice"] = _sig(d, "spgpuCsrToHellLayoutDevice", c_int,
+                [H, c_int, P, c_int, P, P, ctypes.POINTER(ctypes.c_longlong)], optional=True)
+            for s in FLOAT_SYMS:
+                f[f"spgpu{s}csrToHellDevice"] = _sig(d, f"spgpu{s}csrToHellDevice", None,
+                    [H, c_int, P, P, P, c_int, c_int, P, c_int, P, P], optional=True)
             f["spgpuDsumDev"] = _sig(d, "spgpuDsumDev", None, [H, c_int, P, P], optional=True)
             f["spgpuDcgUpdateDev"] = _sig(d, "spgpuDcgUpdateDev", None, [H, P, P, P, P, c_int, P, P, P], optional=True)
             f["spgpuIpcGetHandle"] = _sig(d, "spgpuIpcGetHandle", c_int, [P, P], optional=True)

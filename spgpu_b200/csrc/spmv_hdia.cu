@@ -87,6 +87,96 @@ hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ d
 		z[i] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
 }
 
+/*
+ * Variant with shared-memory staging of the x windows (hdiaVariant = 2).  Stencil matrices
+ * have runs of consecutive offsets (.., o-1, o, o+1, ..): the 32 rows of a warp then need
+ * the 32+L-1 consecutive x entries x[row0+o .. row0+o+31+L-1] for the L diagonals of a
+ * run.  The warp loads that window ONCE into its slice of shared memory (two coalesced
+ * loads) and every diagonal of the run reads its operand at lane+d -- conflict-free --
+ * instead of issuing L overlapping, mostly misaligned global loads.  Runs are found with
+ * one shuffle + ballot per 32 diagonals.  Matrix cells are still loaded 8 diagonals at a
+ * time before they are consumed.
+ */
+template <typename T, int HACK>
+__global__ void __launch_bounds__(128, 8)
+hdia_spmv_staged_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM,
+	const int* __restrict__ offsets, int hackSizeRt,
+	const int* __restrict__ hackOffsets, int rows, int cols,
+	const T* __restrict__ x, T beta)
+{
+	constexpr int U = 8;
+	__shared__ T win[4][64];
+	const int hackSize = HACK > 0 ? HACK : hackSizeRt;
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned warpRow = i - lane;
+	if (warpRow >= (unsigned)rows)
+		return;
+	T* w = win[threadIdx.x >> 5];
+	const bool live = i < (unsigned)rows;
+	const bool useBeta = Num<T>::nonzero(beta);
+	T yv = Num<T>::zero();
+	if (useBeta && live)
+		yv = y[i];
+
+	const unsigned hack = warpRow / (unsigned)hackSize;
+	const int first = __ldg(hackOffsets + hack);
+	const int diags = __ldg(hackOffsets + hack + 1) - first;
+	const T* cell = dM + (long long)first * hackSize + (warpRow % (unsigned)hackSize) + lane;
+	const int* offs = offsets + first;
+	T acc = Num<T>::zero();
+
+	for (int j0 = 0; j0 < diags; j0 += 32) {
+		const int n = min(32, diags - j0);
+		const int mineOff = ((int)lane < n) ? ld_stream(offs + j0 + lane) : INT_MIN;
+		const int prevOff = __shfl_up_sync(SPGPU_FULL_MASK, mineOff, 1);
+		/* bit j set: diagonal j starts a run (its offset is not the previous one + 1) */
+		const unsigned starts = __ballot_sync(SPGPU_FULL_MASK, (int)lane < n && (lane == 0 || mineOff != prevOff + 1));
+		for (int u0 = 0; u0 < n; u0 += U) {
+			const T* cp = cell + (long long)(j0 + u0) * hackSize;
+			T a[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				a[u] = Num<T>::zero();
+				if (u0 + u < n)
+					a[u] = ld_stream(cp + (long long)u * hackSize);
+			}
+			/* walk the runs that intersect diagonals [u0, u0+U) */
+			int d = u0;
+			const int dEnd = min(u0 + U, n);
+			while (d < dEnd) {
+				/* run containing d ends at the next start bit after d (or at dEnd) */
+				const unsigned later = starts & ~((2u << d) - 1u);
+				const int runEnd = min(later ? (__ffs(later) - 1) : n, dEnd);
+				const int L = runEnd - d;
+				const int o = __shfl_sync(SPGPU_FULL_MASK, mineOff, d);
+				const int c0 = (int)warpRow + o + (int)lane;
+				__syncwarp();
+				w[lane] = ((unsigned)c0 < (unsigned)cols) ? ld_keep(x + c0) : Num<T>::zero();
+				if ((int)lane < L - 1) {
+					const int c1 = c0 + 32;
+					w[32 + lane] = ((unsigned)c1 < (unsigned)cols) ? ld_keep(x + c1) : Num<T>::zero();
+				}
+				__syncwarp();
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int dd = u0 + u;
+					if (dd >= d && dd < runEnd) {            /* warp-uniform */
+						const int c = (int)i + o + (dd - d);
+						const bool on = live && (unsigned)c < (unsigned)cols;
+						const T xv = w[lane + (dd - d)];
+						acc = on ? Num<T>::fma(a[u], xv, acc) : acc;
+					}
+				}
+				d = runEnd;
+			}
+		}
+	}
+
+	if (live)
+		z[i] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
+}
+
 template <typename T, int UNROLL>
 static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const T* dM, const int* offsets, int hackSize, const int* hackOffsets,
@@ -97,6 +187,12 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const unsigned grid = spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
+	if (t->hdiaVariant == 2) {
+		if (hackSize == 32) hdia_spmv_staged_kernel<T, 32><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else                hdia_spmv_staged_kernel<T, 0><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		spgpu_count_launch(handle);
+		return;
+	}
 	/* occupancy knob (registers vs resident warps): hdiaBlock >=256 -> 48 warps, 192 -> 40, else 32 */
 	if (hackSize == 32) {
 		if (t->hdiaBlock >= 256)      hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);

@@ -238,3 +238,27 @@ def test_ell_kernel_variants(ours, gpu_handle, variant, dtype):
             check(ours, gpu_handle, "ell", coo, oell, x, y, alpha, beta, ridx=oell.ridx)
     finally:
         ours.spgpuSetTuning(gpu_handle, b"hellVariant", 0)
+
+
+@pytest.mark.parametrize("variant,occ", [(0, 0), (2, 0), (0, 192), (0, 224), (0, 256)])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hack", [32, 64])
+def test_hdia_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
+    """HDIA code paths: direct x loads at three occupancy levels, and the variant that stages the
+    x windows of runs of consecutive offsets in shared memory (stencils have such runs, the random
+    matrix has none, the rectangular one exercises the column range test)"""
+    try:
+        assert ours.spgpuSetTuning(gpu_handle, b"hdiaVariant", variant) == 0
+        assert ours.spgpuSetTuning(gpu_handle, b"hdiaBlock", occ) == 0
+        for coo in (G.stencil3d_27pt(12), G.laplace2d_5pt(61, 47), G.random_coo(700, 900, (0, 9), 4, dtype, 0),
+                    G.banded_complex(3000, 45, 30, 5)):
+            coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+            A = build("hdia", coo, 0, hack)
+            x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
+            y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
+            alpha, beta = scalars(dtype)
+            check(ours, gpu_handle, "hdia", coo, A, x, y, alpha, beta)
+            check(ours, gpu_handle, "hdia", coo, A, x, y, alpha, 0.0)
+    finally:
+        ours.spgpuSetTuning(gpu_handle, b"hdiaVariant", 0)
+        ours.spgpuSetTuning(gpu_handle, b"hdiaBlock", 0)
