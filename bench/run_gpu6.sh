@@ -4,7 +4,7 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 --cg > gpurun_out/bench_r1_cfg5_n1.json 2> gpurun_out/bench_r1_cfg5_n1.err; echo "cfg5 rc=$?"; cat gpurun_out/bench_r1_cfg5_n1.json
-for c in cfg2 cfg1 cfg3 cfg4; do
+for c in cfg2 cfg1 cfg3 cfg3o cfg4; do
   timeout 600 python bench.py --workload $c --steps 20 --warmup 3 > gpurun_out/bench_r1_${c}_n1.json 2> gpurun_out/bench_r1_${c}_n1.err; echo "$c rc=$?"; cat gpurun_out/bench_r1_${c}_n1.json
 done
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_r1_reference_arm.json 2>/dev/null; cat gpurun_out/bench_r1_reference_arm.json

@@ -207,7 +207,7 @@ def test_hell_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
         mats = [G.laplace3d_7pt(20), G.random_coo(5000, 5000, (0, 13), 1, dtype, 0),
                 G.powerlaw(9000, mean=6, maxlen=900, spike_every=700, seed=5, dtype=dtype)]
         for coo in mats:
-            coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+            coo = F.Coo(coo.rows, coo.cols, (coo.vals if np.dtype(dtype).kind == "c" or coo.vals.dtype.kind != "c" else coo.vals.real).astype(dtype), coo.nrows, coo.ncols, coo.base)
             A = build("hell", coo, 0, hack)
             x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
             y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
@@ -227,7 +227,7 @@ def test_ell_kernel_variants(ours, gpu_handle, variant, dtype):
     try:
         assert ours.spgpuSetTuning(gpu_handle, b"hellVariant", variant) == 0
         for coo in (G.laplace3d_7pt(20), G.random_coo(5000, 5000, (0, 5), 1, dtype, 0), G.laplace2d_5pt(70, 53)):
-            coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+            coo = F.Coo(coo.rows, coo.cols, (coo.vals if np.dtype(dtype).kind == "c" or coo.vals.dtype.kind != "c" else coo.vals.real).astype(dtype), coo.nrows, coo.ncols, coo.base)
             A = build("ell", coo, 0, 32)
             x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
             y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
@@ -252,7 +252,7 @@ def test_hdia_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
         assert ours.spgpuSetTuning(gpu_handle, b"hdiaBlock", occ) == 0
         for coo in (G.stencil3d_27pt(12), G.laplace2d_5pt(61, 47), G.random_coo(700, 900, (0, 9), 4, dtype, 0),
                     G.banded_complex(3000, 45, 30, 5)):
-            coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+            coo = F.Coo(coo.rows, coo.cols, (coo.vals if np.dtype(dtype).kind == "c" or coo.vals.dtype.kind != "c" else coo.vals.real).astype(dtype), coo.nrows, coo.ncols, coo.base)
             A = build("hdia", coo, 0, hack)
             x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
             y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
