@@ -140,6 +140,13 @@ def build_workload(name, rank, world, device, n_override=None):
                  label=f"3-D 27-point stencil {n}^3, double HDIA hackSize 32 (BASELINE configs[1])")
         # cells_in_range*8 + 4*#hack-diagonals + 4*(hacks+1) + x + z
         w["bytes"] = A.cells_in_range * 8 + 4 * hd + 4 * int(A.hack_offsets.numel()) + 8 * A.ncols + 8 * A.nrows
+    elif name == "cfg2dia":
+        n = n_override or 128
+        A = DB.dia_stencil27(n, device=device)
+        w.update(kind="dia", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=0, x_len=A.ncols, sizeof=8,
+                 alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=A.nrows,
+                 label=f"3-D 27-point stencil {n}^3, double DIA (27 diagonals; BASELINE configs[1] stored as plain DIA)")
+        w["bytes"] = A.cells_in_range * 8 + 4 * 27 + 8 * A.ncols + 8 * A.nrows
     elif name == "cfg1":
         from spgpu_b200 import formats as F, generators as G
         n = n_override or 1000
@@ -213,6 +220,12 @@ def make_step(L, h, w, x_ext_ptr, z_ptr, y_ptr):
 
         def step(r0=0, r1=w["rows"]):
             fn(h, z_ptr, y_ptr or 0, a, dM, off, A.hack_size, ho, A.nrows, A.ncols, x_ext_ptr, b)
+    elif w["kind"] == "dia":
+        fn = getattr(L, f"spgpu{s}diaspmv")
+
+        def step(r0=0, r1=w["rows"]):
+            fn(h, z_ptr, y_ptr or 0, a, A.values.data_ptr(), A.offsets.data_ptr(), A.pitch, A.nrows, A.ncols, A.diags,
+               x_ext_ptr, b)
     elif w["kind"] == "ell":
         fn = getattr(L, f"spgpu{s}ellspmv")
         ell = A["ell"]
@@ -285,7 +298,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg3o", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg2dia", "cfg3", "cfg3o", "cfg4", "cfg5"])
     ap.add_argument("--size", type=int, default=None, help="override the grid size / row count (testing)")
     ap.add_argument("--halo", default="fused", choices=["fused", "push", "nccl"],
                     help="multi-GPU halo exchange: fused = inside the SpMV kernel over NVLink peer pointers; "

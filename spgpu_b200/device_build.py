@@ -290,6 +290,41 @@ def hdia_stencil27(n, dtype=torch.float64, hack=32, device="cuda") -> DevHdia:
     return DevHdia(values.view(-1), offsets, hoff, hack, n ** 3, n ** 3, nnz, in_range)
 
 
+@dataclass
+class DevDia:
+    values: torch.Tensor        # diags * pitch
+    offsets: torch.Tensor       # int32 ascending
+    pitch: int
+    diags: int
+    nrows: int
+    ncols: int
+    nnz: int
+    cells_in_range: int
+
+
+def dia_stencil27(n, dtype=torch.float64, device="cuda") -> DevDia:
+    """cfg2 as plain DIA: 27 diagonals of the 27-point stencil (26 / -1) on n^3; same output
+    as coo2dia on the row-major COO (zero where the neighbour falls outside the grid)."""
+    dev = torch.device(device)
+    N = n ** 3
+    pitch = (N + 31) // 32 * 32
+    r = torch.arange(N, dtype=torch.int64, device=dev)
+    x, y, z = r % n, (r // n) % n, r // (n * n)
+    dirs = [(dz, dy, dx) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    values = torch.zeros(27 * pitch, dtype=dtype, device=dev).view(27, pitch)
+    offs, nnz, in_range = [], 0, 0
+    for j, (dz, dy, dx) in enumerate(dirs):
+        ok = ((z + dz >= 0) & (z + dz < n) & (y + dy >= 0) & (y + dy < n) & (x + dx >= 0) & (x + dx < n))
+        v = 26.0 if (dz, dy, dx) == (0, 0, 0) else -1.0
+        values[j, :N] = torch.where(ok, torch.full((), v, dtype=dtype, device=dev), torch.zeros((), dtype=dtype, device=dev))
+        off = (dz * n + dy) * n + dx
+        offs.append(off)
+        nnz += int(ok.sum().item())
+        c = r + off
+        in_range += int(((c >= 0) & (c < N)).sum().item())
+    return DevDia(values.view(-1), torch.tensor(offs, dtype=torch.int32, device=dev), pitch, 27, N, N, nnz, in_range)
+
+
 def to_host_hell(d: DevHell):
     """numpy copies, for the bit-exactness tests"""
     return (d.values.cpu().numpy(), d.indices.cpu().numpy(), d.hack_offsets.cpu().numpy(), d.rs.cpu().numpy())
