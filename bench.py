@@ -248,6 +248,9 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
     import torch
     from tests import util
     from spgpu_b200 import device_build as DB
+    if not os.path.exists(util.ORACLE_PATH):       # normally prebuilt by __graft_entry__.build()
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     O = util.oracle_lib()
     cores = O.dll.oracle_num_threads()
     dev = "cuda" if torch.cuda.is_available() else "cpu"
@@ -704,8 +707,12 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1) --------------------------------
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        res = cpu_baseline(args.workload)
-        cb = res[0] if res else None
+        try:
+            res = cpu_baseline(args.workload)
+            cb = res[0] if res else None
+        except Exception as exc:          # a missing checker must not void the GPU measurement
+            print(f"cpu_baseline leg failed: {exc!r}", file=sys.stderr, flush=True)
+            cb = None
 
     if peer is not None:
         peer.close()
