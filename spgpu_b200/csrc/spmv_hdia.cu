@@ -27,7 +27,7 @@
  * loaded without waiting for the offsets (they all exist in the slab); only the
  * x gather and the FMA depend on the in-range test.
  */
-template <typename T, int UNROLL, int HACK, int MINB>
+template <typename T, int UNROLL, int HACK, int MINB, bool PREDICATED = false>
 __global__ void __launch_bounds__(128, MINB)
 hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM,
 	const int* __restrict__ offsets, int hackSizeRt,
@@ -62,11 +62,13 @@ hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ d
 			T a[UNROLL];
 			T xv[UNROLL];
 			bool on[UNROLL];
+			if (!PREDICATED) {
 #pragma unroll
-			for (int u = 0; u < UNROLL; ++u) {
-				a[u] = Num<T>::zero();
-				if (u0 + u < n)                       /* warp-uniform: cell exists */
-					a[u] = ld_stream(cp + (long long)u * hackSize);
+				for (int u = 0; u < UNROLL; ++u) {
+					a[u] = Num<T>::zero();
+					if (u0 + u < n)                       /* warp-uniform: cell exists */
+						a[u] = ld_stream(cp + (long long)u * hackSize);
+				}
 			}
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u) {
@@ -74,12 +76,18 @@ hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ d
 				const int c = (int)i + off;
 				on[u] = (unsigned)c < colsEff;
 				xv[u] = Num<T>::zero();
-				if (on[u])
+				if (PREDICATED)
+					a[u] = Num<T>::zero();
+				if (on[u]) {
 					xv[u] = ld_keep(x + c);
+					if (PREDICATED)                       /* cells outside the matrix are not read */
+						a[u] = ld_stream(cp + (long long)u * hackSize);
+				}
 			}
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u)
-				acc = on[u] ? Num<T>::fma(a[u], xv[u], acc) : acc;
+				acc = PREDICATED ? Num<T>::fma(a[u], xv[u], acc)
+				                 : (on[u] ? Num<T>::fma(a[u], xv[u], acc) : acc);
 		}
 	}
 
@@ -194,7 +202,9 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		return;
 	}
 	/* occupancy knob (registers vs resident warps): hdiaBlock >=256 -> 48 warps, 192 -> 40, else 32 */
-	if (hackSize == 32) {
+	if (hackSize == 32 && t->hdiaVariant == 3) {
+		hdia_spmv_kernel<T, UNROLL, 32, 8, true><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+	} else if (hackSize == 32) {
 		if (t->hdiaBlock >= 256)      hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else if (t->hdiaBlock == 224) hdia_spmv_kernel<T, 4, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else if (t->hdiaBlock == 192) hdia_spmv_kernel<T, UNROLL, 32, 10><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
