@@ -17,6 +17,7 @@
 #include <climits>
 #include "launch.cuh"
 #include "numeric.cuh"
+#include "spmv_hdia_bulk.cuh"
 
 /*
  * HACK > 0: hackSize known at compile time -> cell addresses are base +
@@ -185,6 +186,32 @@ hdia_spmv_staged_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restr
 		z[i] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
 }
 
+template <typename T, int UNROLL, int HACK>
+static bool hdia_spmv_try_bulk(spgpuHandle_t handle, T* z, const T* y, T alpha, const T* dM,
+	const int* offsets, const int* hackOffsets, int rows, int cols, const T* x, T beta)
+{
+	const int stages = 3;
+	const size_t budget = 110 * 1024 - 256;
+	const size_t perDiag = (size_t)HACK * sizeof(T) + sizeof(int);
+	const int capD = (int)((budget / stages - 8 * sizeof(int)) / perDiag) & ~3;
+	if (capD < 8 || rows < 8 * HDB_WARPS * 32)
+		return false;
+	if ((((size_t)dM | (size_t)offsets) & 15) != 0)
+		return false;
+	if (cudaFuncSetAttribute(hdia_spmv_bulk_kernel<T, HACK, UNROLL>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024)) != cudaSuccess)
+		return false;
+	const size_t stageBytes = (size_t)capD * HACK * sizeof(T) + (size_t)(capD + 8) * sizeof(int);
+	const size_t smem = stages * stageBytes + 2 * stages * sizeof(uint64_t);
+	const int tiles = (rows + HDB_WARPS * 32 - 1) / (HDB_WARPS * 32);
+	int grid = 2 * handle->multiProcessorCount;
+	if (grid > tiles) grid = tiles;
+	hdia_spmv_bulk_kernel<T, HACK, UNROLL><<<grid, HDB_THREADS, smem, handle->currentStream>>>(
+		z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta, capD, stages);
+	spgpu_count_launch(handle);
+	return true;
+}
+
 template <typename T, int UNROLL>
 static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const T* dM, const int* offsets, int hackSize, const int* hackOffsets,
@@ -195,6 +222,13 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const unsigned grid = spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
+	if (t->hdiaVariant == 4) {
+		bool done = false;
+		if (hackSize == 32)      done = hdia_spmv_try_bulk<T, UNROLL, 32>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta);
+		else if (hackSize == 64) done = hdia_spmv_try_bulk<T, UNROLL, 64>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta);
+		if (done)
+			return;
+	}
 	if (t->hdiaVariant == 2) {
 		if (hackSize == 32) hdia_spmv_staged_kernel<T, 32><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else                hdia_spmv_staged_kernel<T, 0><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);

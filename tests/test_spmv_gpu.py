@@ -240,7 +240,7 @@ def test_ell_kernel_variants(ours, gpu_handle, variant, dtype):
         ours.spgpuSetTuning(gpu_handle, b"hellVariant", 0)
 
 
-@pytest.mark.parametrize("variant,occ", [(0, 0), (2, 0), (3, 0), (0, 192), (0, 224), (0, 256)])
+@pytest.mark.parametrize("variant,occ", [(0, 0), (2, 0), (3, 0), (4, 0), (0, 192), (0, 224), (0, 256)])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("hack", [32, 64])
 def test_hdia_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
@@ -250,7 +250,7 @@ def test_hdia_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
     try:
         assert ours.spgpuSetTuning(gpu_handle, b"hdiaVariant", variant) == 0
         assert ours.spgpuSetTuning(gpu_handle, b"hdiaBlock", occ) == 0
-        for coo in (G.stencil3d_27pt(12), G.laplace2d_5pt(61, 47), G.random_coo(700, 900, (0, 9), 4, dtype, 0),
+        for coo in (G.stencil3d_27pt(12), G.stencil3d_27pt(20), G.laplace2d_5pt(61, 47), G.random_coo(700, 900, (0, 9), 4, dtype, 0),
                     G.banded_complex(3000, 45, 30, 5)):
             coo = F.Coo(coo.rows, coo.cols, (coo.vals if np.dtype(dtype).kind == "c" or coo.vals.dtype.kind != "c" else coo.vals.real).astype(dtype), coo.nrows, coo.ncols, coo.base)
             A = build("hdia", coo, 0, hack)
