@@ -186,6 +186,100 @@ hdia_spmv_staged_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restr
 		z[i] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
 }
 
+/*
+ * Persistent variant with software prefetch of the per-hack metadata (hdiaVariant = 5).
+ * The direct kernel's warps each walk the dependent chain hackOffsets -> offsets -> x once
+ * and stall on it (ncu: 37 % of the stall samples sit on the first use of the x gather).
+ * Here a warp walks 32-row units u, u + W, u + 2W, ... (W = warps in the grid) and, while
+ * it multiplies unit u, already holds the hackOffsets pair and the first 32 offsets of unit
+ * u + W and has the hackOffsets pair of unit u + 2W in flight.
+ */
+template <typename T, int UNROLL, int HACK>
+__global__ void __launch_bounds__(128, 8)
+hdia_spmv_persistent_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM,
+	const int* __restrict__ offsets, int hackSizeRt,
+	const int* __restrict__ hackOffsets, int rows, int cols,
+	const T* __restrict__ x, T beta)
+{
+	const int hackSize = HACK > 0 ? HACK : hackSizeRt;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned units = ((unsigned)rows + 31u) >> 5;
+	const unsigned W = (gridDim.x * blockDim.x) >> 5;
+	const unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const bool useBeta = Num<T>::nonzero(beta);
+
+	/* pipeline registers: metadata of the current unit, the next one, and the pair after that */
+	int first0 = 0, cnt0 = 0, off0 = INT_MIN;
+	int first1 = 0, cnt1 = 0;
+	unsigned u = g;
+	if (u < units) {
+		const unsigned hk = (u * 32u) / (unsigned)hackSize;
+		first0 = __ldg(hackOffsets + hk);
+		cnt0 = __ldg(hackOffsets + hk + 1) - first0;
+		off0 = ((int)lane < cnt0) ? ld_stream(offsets + first0 + lane) : INT_MIN;
+	}
+	if (u + W < units) {
+		const unsigned hk = ((u + W) * 32u) / (unsigned)hackSize;
+		first1 = __ldg(hackOffsets + hk);
+		cnt1 = __ldg(hackOffsets + hk + 1) - first1;
+	}
+
+	for (; u < units; u += W) {
+		/* prefetch: offsets of the next unit (its pair is already here), pair of the one after */
+		int off1 = INT_MIN, first2 = 0, cnt2 = 0;
+		if (u + W < units)
+			off1 = ((int)lane < cnt1) ? ld_stream(offsets + first1 + lane) : INT_MIN;
+		if (u + 2 * W < units) {
+			const unsigned hk = ((u + 2 * W) * 32u) / (unsigned)hackSize;
+			first2 = __ldg(hackOffsets + hk);
+			cnt2 = __ldg(hackOffsets + hk + 1) - first2;
+		}
+
+		const unsigned warpRow = u * 32u;
+		const unsigned i = warpRow + lane;
+		const bool live = i < (unsigned)rows;
+		const unsigned colsEff = live ? (unsigned)cols : 0u;
+		T yv = Num<T>::zero();
+		if (useBeta && live)
+			yv = y[i];
+		const T* cell = dM + (long long)first0 * hackSize + (warpRow % (unsigned)hackSize) + lane;
+		T acc = Num<T>::zero();
+		for (int j0 = 0; j0 < cnt0; j0 += 32) {
+			const int mineOff = j0 == 0 ? off0
+				: ((j0 + (int)lane < cnt0) ? ld_stream(offsets + first0 + j0 + lane) : INT_MIN);
+			const int n = min(32, cnt0 - j0);
+			for (int u0 = 0; u0 < n; u0 += UNROLL) {
+				const T* cp = cell + (long long)(j0 + u0) * hackSize;
+				T a[UNROLL];
+				T xv[UNROLL];
+				bool on[UNROLL];
+#pragma unroll
+				for (int k = 0; k < UNROLL; ++k) {
+					a[k] = Num<T>::zero();
+					if (u0 + k < n)
+						a[k] = ld_stream(cp + (long long)k * hackSize);
+				}
+#pragma unroll
+				for (int k = 0; k < UNROLL; ++k) {
+					const int c = (int)i + __shfl_sync(SPGPU_FULL_MASK, mineOff, u0 + k);
+					on[k] = (unsigned)c < colsEff;
+					xv[k] = Num<T>::zero();
+					if (on[k])
+						xv[k] = ld_keep(x + c);
+				}
+#pragma unroll
+				for (int k = 0; k < UNROLL; ++k)
+					acc = on[k] ? Num<T>::fma(a[k], xv[k], acc) : acc;
+			}
+		}
+		if (live)
+			z[i] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
+
+		first0 = first1; cnt0 = cnt1; off0 = off1;
+		first1 = first2; cnt1 = cnt2;
+	}
+}
+
 template <typename T, int UNROLL, int HACK>
 static bool hdia_spmv_try_bulk(spgpuHandle_t handle, T* z, const T* y, T alpha, const T* dM,
 	const int* offsets, const int* hackOffsets, int rows, int cols, const T* x, T beta)
@@ -228,6 +322,14 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		else if (hackSize == 64) done = hdia_spmv_try_bulk<T, UNROLL, 64>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta);
 		if (done)
 			return;
+	}
+	if (t->hdiaVariant == 5) {
+		long long want = (long long)handle->multiProcessorCount * 8;
+		if (want > (long long)grid) want = grid;
+		if (hackSize == 32) hdia_spmv_persistent_kernel<T, UNROLL, 32><<<(unsigned)want, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else                hdia_spmv_persistent_kernel<T, UNROLL, 0><<<(unsigned)want, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		spgpu_count_launch(handle);
+		return;
 	}
 	if (t->hdiaVariant == 2) {
 		if (hackSize == 32) hdia_spmv_staged_kernel<T, 32><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);

@@ -240,7 +240,7 @@ def test_ell_kernel_variants(ours, gpu_handle, variant, dtype):
         ours.spgpuSetTuning(gpu_handle, b"hellVariant", 0)
 
 
-@pytest.mark.parametrize("variant,occ", [(0, 0), (2, 0), (3, 0), (4, 0), (0, 192), (0, 224), (0, 256)])
+@pytest.mark.parametrize("variant,occ", [(0, 0), (2, 0), (3, 0), (4, 0), (5, 0), (0, 192), (0, 224), (0, 256)])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("hack", [32, 64])
 def test_hdia_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
