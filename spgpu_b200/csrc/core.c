@@ -42,6 +42,10 @@ spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
 	}
 	h->magic = SPGPU_PRIV_MAGIC;
 	default_tuning(&h->tune);
+	{
+		const char* dbg = getenv("SPGPU_DEBUG");
+		h->debug = dbg && dbg[0] && dbg[0] != '0';
+	}
 
 	cudaGetDevice(&previous);
 	cudaSetDevice(device);

@@ -2,14 +2,27 @@
 #ifndef SPGPU_LAUNCH_CUH_
 #define SPGPU_LAUNCH_CUH_
 
+#include <cstdio>
 #include <cuda_runtime.h>
 #include "spgpu_internal.h"
 
+/* Called after every kernel launch.  With SPGPU_DEBUG set in the environment (read once per
+ * handle) the stream is synchronised and any CUDA error is reported on stderr -- the
+ * reference's -DDEBUG build prints and calls exit(0) (reference kernels/cudadebug.h:12-25);
+ * here the process keeps running and the error stays queryable with cudaGetLastError. */
 static inline void spgpu_count_launch(spgpuHandle_t handle)
 {
 	SpgpuHandlePriv* h = spgpuPriv(handle);
-	if (h->magic == SPGPU_PRIV_MAGIC)
-		++h->launches;
+	if (h->magic != SPGPU_PRIV_MAGIC)
+		return;
+	++h->launches;
+	if (h->debug) {
+		cudaError_t e = cudaStreamSynchronize(handle->currentStream);
+		if (e == cudaSuccess)
+			e = cudaPeekAtLastError();
+		if (e != cudaSuccess)
+			fprintf(stderr, "spgpu: CUDA error after launch %llu: %s\n", h->launches, cudaGetErrorString(e));
+	}
 }
 
 static inline const SpgpuTuning* spgpu_tuning(spgpuHandle_t handle)

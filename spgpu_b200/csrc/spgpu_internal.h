@@ -46,6 +46,7 @@ typedef struct SpgpuHandlePriv {
 	int l2Bytes;
 	int smemPerBlockOptin;
 	unsigned long long launches;   /* kernels launched through this handle        */
+	int debug;                     /* SPGPU_DEBUG set: check for CUDA errors after every launch */
 	void* dBig;                    /* device: grow-only scratch (per-CTA partials of fused kernels) */
 	size_t bigBytes;
 	SpgpuTuning tune;
