@@ -113,7 +113,7 @@ def algorithmic_bytes_hell(nnz, rows, hacks, ncols_read, sizeof_t, beta_nonzero=
     return nnz * (sizeof_t + 4) + 4 * rows + 4 * hacks + ncols_read * sizeof_t + rows * sizeof_t * (2 if beta_nonzero else 1)
 
 
-def build_workload(name, rank, world, device, n_override=None):
+def build_workload(name, rank, world, device, n_override=None, global_columns=False):
     """Returns a dict describing this rank's share of the workload (device resident)."""
     import torch
     from spgpu_b200 import device_build as DB
@@ -124,12 +124,14 @@ def build_workload(name, rank, world, device, n_override=None):
         per = n // world
         z_lo, z_hi = rank * per, (rank + 1) * per
         plane = n * n
-        A = DB.hell_laplace3d_7pt(n, z_lo, z_hi, local_columns=(world > 1), device=device)
-        w.update(kind="hell", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=plane if world > 1 else 0,
+        local = world > 1 and not global_columns
+        A = DB.hell_laplace3d_7pt(n, z_lo, z_hi, local_columns=local, device=device)
+        w.update(kind="hell", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=plane if local else 0,
                  x_len=A.ncols, sizeof=8, alpha=1.0, beta=0.0, flops_per_nnz=2,
                  label=f"3-D 7-point Laplacian {n}^3, double HELL hackSize 32 (BASELINE configs[4])",
                  total_rows=n ** 3, bandwidth=plane)
         x_read = A.nrows + (2 * plane if world > 1 else 0)      # owned entries + the two halo planes
+        w["allgather"] = world > 1 and global_columns
         w["bytes"] = algorithmic_bytes_hell(A.nnz, A.nrows, A.hack_offsets.numel(), x_read, 8)
     elif name == "cfg2":
         n = n_override or 128
@@ -303,9 +305,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg2dia", "cfg3", "cfg3o", "cfg4", "cfg5"])
     ap.add_argument("--size", type=int, default=None, help="override the grid size / row count (testing)")
-    ap.add_argument("--halo", default="fused", choices=["fused", "push", "nccl"],
+    ap.add_argument("--halo", default="fused", choices=["fused", "push", "nccl", "allgather"],
                     help="multi-GPU halo exchange: fused = inside the SpMV kernel over NVLink peer pointers; "
-                         "push = separate NVLink push kernel + flags; nccl = grouped send/recv")
+                         "push = separate NVLink push kernel + flags; nccl = grouped send/recv; "
+                         "allgather = global columns + NCCL all-gather of x (the mode for unstructured matrices)")
     ap.add_argument("--overlap", action="store_true",
                     help="multiply interior rows while the halos are in flight (3 SpMV launches per step); "
                          "default: one fused exchange kernel, then one SpMV launch")
@@ -373,7 +376,7 @@ def main():
     stream = torch.cuda.ExternalStream(L.spgpuGetStream(h), device=device)
     torch.cuda.set_stream(stream)
 
-    w = build_workload(args.workload, rank, world, device, args.size)
+    w = build_workload(args.workload, rank, world, device, args.size, global_columns=(args.halo == "allgather"))
     tdt = {"S": torch.float32, "D": torch.float64, "C": torch.complex64, "Z": torch.complex128}[w["sym"]]
     rows, halo = w["rows"], w["halo"]
     ext_len = w["x_len"]
@@ -425,8 +428,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step():
-        op.apply(z, x_ext)
+    if w.get("allgather"):
+        # unstructured-matrix mode: columns are global, every rank gathers the whole x per SpMV
+        x_owned = x_ext[rank * rows:(rank + 1) * rows].clone()
+        ag = mg.MgAllGatherSpmv(world, rows, lambda _z, _x: step(0, rows))
+
+        def one_step():
+            ag.apply(z, x_owned, x_ext)
+    else:
+        def one_step():
+            op.apply(z, x_ext)
 
     # working sets that are not >> L2 (126 MB): evict it between timed steps by READING a 512 MB
     # scratch (a write-flush would leave 126 MB of dirty lines whose write-back lands inside the
@@ -464,7 +475,7 @@ def main():
 
     # ---------------- optional multi-GPU self-check ------------------------------
     verified = None
-    if args.verify and args.workload == "cfg5" and world > 1:
+    if args.verify and args.workload == "cfg5" and world > 1 and not w.get("allgather"):
         from spgpu_b200 import device_build as DB
         n = args.size or 512
         per = n // world
@@ -568,7 +579,7 @@ def main():
     # loop uses (hell_spmv_base.cuh:121-137) -- so PCIe runs in both directions at once.
     e2e = None
     if not args.no_e2e:
-        own = x_ext[halo:halo + rows] if halo else x_ext
+        own = x_owned if w.get("allgather") else (x_ext[halo:halo + rows] if halo else x_ext)
         hx = torch.empty(own.shape, dtype=own.dtype, pin_memory=True)
         hx.copy_(own)
         hz = torch.empty(z.shape, dtype=z.dtype, pin_memory=True)
