@@ -254,6 +254,12 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     O = util.oracle_lib()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    O.dll.oracle_set_num_threads(avail)
     cores = O.dll.oracle_num_threads()
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     if workload_name == "cfg5":
