@@ -593,7 +593,7 @@ def main():
         bw = w.get("bandwidth")
         pipelined = world == 1 and w["kind"] == "hell" and bw is not None and rows >= (1 << 22)
         if pipelined:
-            nchunk = 16
+            nchunk = 32
             unit = 32 * 1024                                   # chunk boundaries on hack boundaries
             csz = -(-rows // nchunk // unit) * unit
             assert csz >= bw
@@ -649,7 +649,7 @@ def main():
                "d2h_bytes_per_step": int(hz.numel() * hz.element_size()) * world,
                "ms_per_step": ms_e2e, "steps": Ke,
                "what": ("x H2D from pinned memory, SpMV through the C ABI, z D2H to pinned memory, every step; matrix "
-                        "resident" + ("; the three stages pipelined over 16 row chunks on three streams "
+                        "resident" + ("; the three stages pipelined over 32 row chunks on three streams "
                                       "(banded matrix), result checked equal to the one-shot SpMV" if pipelined else ""))}
         if e2e_ok is not None:
             e2e["pipelined_result_equals_one_shot"] = e2e_ok
