@@ -20,6 +20,7 @@ static void default_tuning(SpgpuTuning* t)
 	t->hellVariant = 0;
 	t->hellBlock = 0;          /* 0 = per-type default occupancy, <=64 force 32 warps, >=256 force 48 */
 	t->hellLongFactor = 4;     /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike */
+	t->hellSplit = 0;
 	t->hdiaVariant = 0;
 	t->hdiaBlock = 0;
 	t->diaBlock = 128;
@@ -174,6 +175,7 @@ void* spgpuScratch(spgpuHandle_t handle, size_t bytes)
 	X(hellVariant)            \
 	X(hellBlock)              \
 	X(hellLongFactor)         \
+	X(hellSplit)              \
 	X(hdiaVariant)            \
 	X(hdiaBlock)              \
 	X(diaBlock)               \

@@ -107,7 +107,7 @@ extern "C" void spgpuDhellspmvDot(spgpuHandle_t handle, double* z, const double*
 	if (!partials)
 		return;
 	const HellArgs<double> a = { z, NULL, 1.0, cM, rP, hackSize, hackOffsets, rS, NULL, rows, x, 0.0,
-		baseIndex, spgpu_long_cut(t, 8), t->hellVariant != 1 };
+		baseIndex, spgpu_long_cut(t, 8), t->hellVariant != 1, 0, NULL, NULL, 0 };
 	if (hackSize == 32)
 		dhell_spmv_dot_kernel<8, 32, 10><<<grid, 128, 0, handle->currentStream>>>(a, xOffset, partials);
 	else
@@ -523,7 +523,7 @@ static void dhell_spmv_halo_launch(spgpuHandle_t handle, double* z, const double
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const HellArgs<double> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
-		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1 };
+		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1, 0, NULL, NULL, 0 };
 	HaloArgs hx;
 	hx.dstLo = peerXLoUpperHalo; hx.srcLo = xExt + haloN;
 	hx.dstHi = peerXHiLowerHalo; hx.srcHi = xExt + rows;        /* last haloN owned entries */

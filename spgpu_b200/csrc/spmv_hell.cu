@@ -30,6 +30,87 @@ hell_spmv_kernel(const HellArgs<T> a)
 	hell_warp_rows<T, UNROLL, HACK>(a, i - (threadIdx.x & 31));
 }
 
+/*
+ * Tail kernel of the split mode: persistent warps take (unit, chunk) items off the queue the
+ * main kernel filled and walk slots [(c+1)T, (c+2)T) of the unit's 32 rows (row per lane,
+ * coalesced), then add alpha * partial to z with an atomic (several chunks of one row finish
+ * in any order; the main kernel has already stored beta*y + alpha*(first T slots)).
+ */
+template <typename T> __device__ __forceinline__ void atomic_add_value(T* p, T v);
+template <> __device__ __forceinline__ void atomic_add_value<float>(float* p, float v) { atomicAdd(p, v); }
+template <> __device__ __forceinline__ void atomic_add_value<double>(double* p, double v) { atomicAdd(p, v); }
+template <> __device__ __forceinline__ void atomic_add_value<cuFloatComplex>(cuFloatComplex* p, cuFloatComplex v)
+{
+	atomicAdd(&p->x, v.x);
+	atomicAdd(&p->y, v.y);
+}
+template <> __device__ __forceinline__ void atomic_add_value<cuDoubleComplex>(cuDoubleComplex* p, cuDoubleComplex v)
+{
+	atomicAdd(&p->x, v.x);
+	atomicAdd(&p->y, v.y);
+}
+
+template <typename T, int UNROLL, int HACK>
+__global__ void __launch_bounds__(128, 8)
+hell_tail_kernel(const HellArgs<T> a)
+{
+	const int hackSize = HACK > 0 ? HACK : a.hackSize;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned queued = min(__ldg(a.workHeader), (unsigned)a.workCap);
+	for (;;) {
+		unsigned idx = 0;
+		if (lane == 0)
+			idx = atomicAdd(a.workHeader + 1, 1u);
+		idx = __shfl_sync(SPGPU_FULL_MASK, idx, 0);
+		if (idx >= queued)
+			return;
+		const uint2 item = a.workItems[idx];
+		if (item.x == SPGPU_WORK_INVALID)
+			continue;
+		const unsigned warpRow = item.x << 5;
+		const unsigned i = warpRow + lane;
+		const bool live = i < (unsigned)a.rows;
+		const int len = live ? __ldg(a.rS + i) : 0;
+		const int kBeg = (int)(item.y + 1u) * a.splitT;
+		const int kEnd = min(len, kBeg + a.splitT);
+		const unsigned hack = warpRow / (unsigned)hackSize;
+		const long long at = (long long)__ldg(a.hackOffsets + hack) + (warpRow % (unsigned)hackSize) + lane;
+		const T* vp = a.cM + at;
+		const int* ip = a.rP + at;
+		T acc = Num<T>::zero();
+		const int top = __reduce_max_sync(SPGPU_FULL_MASK, kEnd);
+		for (int k0 = kBeg; k0 < top; k0 += UNROLL) {
+			int col[UNROLL];
+			T v[UNROLL];
+			T xv[UNROLL];
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u) {
+				const bool on = (k0 + u) < kEnd;
+				col[u] = a.baseIndex;
+				v[u] = Num<T>::zero();
+				if (on) {
+					col[u] = ld_stream(ip + (long long)(k0 + u) * hackSize);
+					v[u] = ld_stream(vp + (long long)(k0 + u) * hackSize);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u) {
+				const bool on = (k0 + u) < kEnd;
+				xv[u] = Num<T>::zero();
+				if (on)
+					xv[u] = ld_keep(a.x + (col[u] - a.baseIndex));
+			}
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u)
+				acc = Num<T>::fma(v[u], xv[u], acc);
+		}
+		if (live && kEnd > kBeg) {
+			const unsigned out = a.rIdx ? (unsigned)__ldg(a.rIdx + i) : i;
+			atomic_add_value<T>(a.z + out, Num<T>::mul(a.alpha, acc));
+		}
+	}
+}
+
 /* Bulk-async variant: returns false when the call is not eligible (then the
  * direct kernel runs).  Stage capacity is sized from avgNnzPerRow. */
 template <typename T, int UNROLL, int HACK>
@@ -93,7 +174,23 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	}
 	const int speculate = variant != 1;
 	cudaStream_t s = handle->currentStream;
-	const HellArgs<T> args = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, speculate };
+	HellArgs<T> args = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, speculate,
+		0, NULL, NULL, 0 };
+	/* Split mode: on for length-sorted matrices (rIdx given: their long rows sit together in a
+	 * few hacks whose warps would be the critical path), or forced with hellSplit = 1; off with
+	 * hellSplit = -1.  Costs one 8-byte memset and one small extra launch per call. */
+	const bool split = t->hellSplit > 0 || (t->hellSplit == 0 && rIdx != NULL);
+	if (split) {
+		const int cap = t->hellSplit > 1 ? t->hellSplit : (1 << 16);     /* hellSplit > 1: queue capacity (tests) */
+		unsigned* hdr = (unsigned*)spgpuScratch(handle, 16 + (size_t)cap * sizeof(uint2));
+		if (hdr) {
+			args.splitT = longCut > 64 ? longCut : 64;
+			args.workHeader = hdr;
+			args.workItems = reinterpret_cast<uint2*>(hdr + 4);
+			args.workCap = cap;
+			cudaMemsetAsync(hdr, 0, 16, s);
+		}
+	}
 #define HELL_ARGS args
 	/* Resident warps per SM are set by the register budget (__launch_bounds__ minimum
 	 * CTAs): more warps = more loads in flight, until the allocator starts spilling.
@@ -118,6 +215,13 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	}
 #undef HELL_ARGS
 	spgpu_count_launch(handle);
+	if (args.splitT > 0) {
+		const unsigned tg = (unsigned)handle->multiProcessorCount * 4u;
+		if (hackSize == 32)      hell_tail_kernel<T, UNROLL, 32><<<tg, 128, 0, s>>>(args);
+		else if (hackSize == 64) hell_tail_kernel<T, UNROLL, 64><<<tg, 128, 0, s>>>(args);
+		else                     hell_tail_kernel<T, UNROLL, 0><<<tg, 128, 0, s>>>(args);
+		spgpu_count_launch(handle);
+	}
 }
 
 #define SPGPU_DEFINE_HELLSPMV(S, T, U)                                        \

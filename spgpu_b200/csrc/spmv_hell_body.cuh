@@ -26,7 +26,15 @@ struct HellArgs {
 	int baseIndex;
 	int longCut;
 	int speculate;
+	/* split mode (0 = off): rows are walked by their own warp only up to splitT slots; deeper
+	 * slots are cut into chunks of splitT and queued for hell_tail_kernel (spmv_hell.cu) */
+	int splitT;
+	unsigned* workHeader;        /* [0] items queued, [1] items taken */
+	uint2* workItems;            /* (32-row unit, chunk) */
+	int workCap;
 };
+
+#define SPGPU_WORK_INVALID 0xffffffffu
 
 /* returns the value stored for this lane's row in `zval` (zero for lanes without a row) */
 template <typename T, int UNROLL, int HACK>
@@ -48,7 +56,26 @@ __device__ __forceinline__ void hell_warp_rows_value(const HellArgs<T>& a, unsig
 	int allocated = 0;
 	if (a.speculate && hack < lastHack)
 		allocated = (__ldg(a.hackOffsets + hack + 1) - slab) / hackSize;
-	const int len = live ? ld_stream(a.rS + i) : 0;
+	int len = live ? ld_stream(a.rS + i) : 0;
+	if (a.splitT > 0) {
+		/* long hack: queue the slots beyond splitT as independent chunks so that other warps
+		 * of the grid (the tail kernel) share a walk that would otherwise be this warp's
+		 * serial critical path */
+		const int longest = __reduce_max_sync(SPGPU_FULL_MASK, len);
+		if (longest > a.splitT) {
+			const int nchunks = (longest - 1) / a.splitT;            /* chunks c = 0.. cover [ (c+1)T, (c+2)T ) */
+			unsigned base = 0;
+			if (lane == 0)
+				base = atomicAdd(a.workHeader, (unsigned)nchunks);
+			base = __shfl_sync(SPGPU_FULL_MASK, base, 0);
+			const bool fits = base + (unsigned)nchunks <= (unsigned)a.workCap;
+			for (unsigned c = lane; c < (unsigned)nchunks; c += 32)
+				if (base + c < (unsigned)a.workCap)
+					a.workItems[base + c] = fits ? make_uint2(warpRow >> 5, c) : make_uint2(SPGPU_WORK_INVALID, 0u);
+			if (fits)
+				len = min(len, a.splitT);                            /* else: queue full, walk it all here */
+		}
+	}
 	const bool useBeta = Num<T>::nonzero(a.beta);
 	const unsigned out = (live && a.rIdx) ? (unsigned)__ldg(a.rIdx + i) : i;
 	T yv = Num<T>::zero();

@@ -262,3 +262,28 @@ def test_hdia_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
     finally:
         ours.spgpuSetTuning(gpu_handle, b"hdiaVariant", 0)
         ours.spgpuSetTuning(gpu_handle, b"hdiaBlock", 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("split", [-1, 1, 8])
+def test_hell_long_hack_split_mode(ours, gpu_handle, dtype, split):
+    """split mode: slots beyond 64 of a long hack are queued as chunks for the tail kernel (atomic
+    adds into z); -1 = off, 1 = on, 8 = on with a queue of 8 items (overflow: the warp that cannot
+    queue walks its rows itself).  Sorted (rIdx) and unsorted matrices, beta != 0, in place."""
+    try:
+        assert ours.spgpuSetTuning(gpu_handle, b"hellSplit", split) == 0
+        coo = G.powerlaw(6000, mean=8, maxlen=1500, spike_every=256, seed=4, dtype=np.float32)
+        coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+        x = G.random_vector(6000, dtype, 1, -1, 1)
+        y = G.random_vector(6000, dtype, 2, -1, 1)
+        alpha, beta = scalars(dtype)
+        ell = F.coo_to_ell(coo)
+        A = F.ell_to_hell(ell, 32)
+        check(ours, gpu_handle, "hell", coo, A, x, y, alpha, beta, avg=8)
+        check(ours, gpu_handle, "hell", coo, A, x, y, alpha, beta, avg=8, inplace=True)
+        oell = F.ell_to_oell(ell)
+        B = F.ell_to_hell(oell, 32)
+        check(ours, gpu_handle, "hell", coo, B, x, y, alpha, beta, ridx=oell.ridx, avg=8)
+        check(ours, gpu_handle, "hell", coo, B, x, y, alpha, 0.0, ridx=oell.ridx, avg=8)
+    finally:
+        ours.spgpuSetTuning(gpu_handle, b"hellSplit", 0)
