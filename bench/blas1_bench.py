@@ -39,6 +39,7 @@ def main():
     x = torch.rand(n, dtype=torch.float64, device="cuda")
     y = torch.rand(n, dtype=torch.float64, device="cuda")
     z = torch.empty(n, dtype=torch.float64, device="cuda")
+    w = torch.rand(n, dtype=torch.float64, device="cuda")
     m = n // 16
     idx = torch.randperm(n, device="cuda")[:m].to(torch.int32)
     xv = torch.rand(m, dtype=torch.float64, device="cuda")
@@ -53,7 +54,7 @@ def main():
         "spgpuDamax (blocking)": (lambda: L.spgpuDamax(h, n, X), 8 * n),
         "spgpuDasum (blocking)": (lambda: L.spgpuDasum(h, n, X), 8 * n),
         "spgpuDdotDev (device result)": (lambda: L.spgpuDdotDev(h, n, X, Y, dres.data_ptr()), 16 * n),
-        "spgpuDcgUpdateDev": (lambda: L.spgpuDcgUpdateDev(h, Z, Y, X, X, n, dres.data_ptr() + 8, dres.data_ptr() + 16,
+        "spgpuDcgUpdateDev": (lambda: L.spgpuDcgUpdateDev(h, Z, Y, X, w.data_ptr(), n, dres.data_ptr() + 8, dres.data_ptr() + 16,
                                                           dres.data_ptr()), 48 * n),
         "spgpuDgath (n/16 random indices)": (lambda: L.spgpuDgath(h, xv.data_ptr(), m, idx.data_ptr(), 0, X), 20 * m),
         "spgpuDscat (n/16 random indices, beta=2)": (lambda: L.spgpuDscat(h, Z, m, xv.data_ptr(), idx.data_ptr(), 0,

@@ -7,6 +7,7 @@ timeout 600 python bench.py --steps 20 --warmup 3 --cg > gpurun_out/bench_r1_cfg
 for c in cfg2 cfg1 cfg3 cfg3o cfg4; do
   timeout 600 python bench.py --workload $c --steps 20 --warmup 3 > gpurun_out/bench_r1_${c}_n1.json 2> gpurun_out/bench_r1_${c}_n1.err; echo "$c rc=$?"; cat gpurun_out/bench_r1_${c}_n1.json
 done
+timeout 600 python bench/blas1_bench.py > gpurun_out/r1_blas1.json 2>/dev/null; echo "blas1 rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_r1_reference_arm.json 2>/dev/null; cat gpurun_out/bench_r1_reference_arm.json
 CMD5="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e"
 CMD2="python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu --no-e2e"
