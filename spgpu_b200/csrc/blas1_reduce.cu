@@ -163,7 +163,7 @@ static void reduce_launch(spgpuHandle_t handle, const T* x, const T* y, long lon
 	const int vec = r_aligned16(x) && (Op::NIN < 2 || r_aligned16(y));
 	const long long items = vec ? (n / RPack<T>::N + 1) / 2 + 1 : n;
 	long long want = (items + RED_BLOCK - 1) / RED_BLOCK;
-	long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 8);
+	long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 4);
 	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
 	if (cap < 1) cap = 1;
 	if (want > cap) want = cap;

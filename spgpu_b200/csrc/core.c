@@ -25,7 +25,7 @@ static void default_tuning(SpgpuTuning* t)
 	t->hdiaBlock = 0;
 	t->diaBlock = 128;
 	t->streamLoads = 1;
-	t->redBlocksPerSm = 8;
+	t->redBlocksPerSm = 4;
 	t->vecBlocksPerSm = 8;
 }
 
