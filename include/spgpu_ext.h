@@ -30,8 +30,9 @@ unsigned long long spgpuGetLaunchCount(spgpuHandle_t handle);
 
 /*
  * Kernel-selection knobs (per handle).  Keys: hellVariant, hellBlock,
- * hellLongFactor, hdiaVariant, hdiaBlock, diaBlock, streamLoads,
- * redBlocksPerSm, vecBlocksPerSm.  Returns 0, or -1 for an unknown key.
+ * hellLongFactor, hellSplit, hdiaVariant, hdiaBlock, redBlocksPerSm,
+ * vecBlocksPerSm (meanings: csrc/spgpu_internal.h).  Returns 0, or -1 for an
+ * unknown key.
  */
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value);
 int spgpuGetTuning(spgpuHandle_t handle, const char* key);

@@ -23,8 +23,6 @@ static void default_tuning(SpgpuTuning* t)
 	t->hellSplit = 0;
 	t->hdiaVariant = 0;
 	t->hdiaBlock = 0;
-	t->diaBlock = 128;
-	t->streamLoads = 1;
 	t->redBlocksPerSm = 4;
 	t->vecBlocksPerSm = 8;
 }
@@ -178,8 +176,6 @@ void* spgpuScratch(spgpuHandle_t handle, size_t bytes)
 	X(hellSplit)              \
 	X(hdiaVariant)            \
 	X(hdiaBlock)              \
-	X(diaBlock)               \
-	X(streamLoads)            \
 	X(redBlocksPerSm)         \
 	X(vecBlocksPerSm)
 

@@ -27,16 +27,9 @@ static inline void spgpu_count_launch(spgpuHandle_t handle)
 
 static inline const SpgpuTuning* spgpu_tuning(spgpuHandle_t handle)
 {
-	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 0, 128, 1, 4, 8 };
+	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 0, 4, 8 };
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	return h->magic == SPGPU_PRIV_MAGIC ? &h->tune : &fallback;
-}
-
-static inline int spgpu_block(int requested)
-{
-	if (requested < 32) return 32;
-	if (requested > 1024) return 1024;
-	return requested & ~31;
 }
 
 static inline unsigned spgpu_ceil_div(long long a, long long b)

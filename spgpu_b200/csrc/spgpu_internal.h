@@ -31,8 +31,6 @@ typedef struct SpgpuTuning {
 	int hellSplit;       /* long-hack split mode: 0 auto (on when rIdx is given), 1 on, -1 off, >1 on with that queue capacity */
 	int hdiaVariant;     /* 0/1 direct (unpredicated cell loads), 2 x windows staged in shared memory, 3 direct with predicated cell loads, 4 bulk-async (TMA) pipeline */
 	int hdiaBlock;       /* occupancy knob: >=256 force 48 warps/SM (default 32) */
-	int diaBlock;
-	int streamLoads;     /* 1: matrix streams use evict-first loads            */
 	int redBlocksPerSm;  /* CTAs per SM for the reductions                      */
 	int vecBlocksPerSm;  /* CTAs per SM for grid-stride vector kernels          */
 } SpgpuTuning;
