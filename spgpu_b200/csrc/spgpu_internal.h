@@ -26,11 +26,11 @@ extern "C" {
 /* Tunables that steer kernel selection; settable with spgpuSetTuning (ext). */
 typedef struct SpgpuTuning {
 	int hellVariant;     /* 0 auto, 1 direct loads predicated on rS, 2 direct loads with unpredicated slab reads, 3 bulk-async (TMA) pipeline */
-	int hellBlock;       /* occupancy knob: 0 per-type default, <=64 force 32 warps/SM, >=256 force 48 */
+	int hellBlock;       /* occupancy knob: 0 per-type default, <=64 force 32 warps/SM, 192 force 40, >=256 force 48 */
 	int hellLongFactor;  /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike (default 4) */
 	int hellSplit;       /* long-hack split mode: 0 auto (on when rIdx is given), 1 on, -1 off, >1 on with that queue capacity */
-	int hdiaVariant;     /* 0/1 direct (unpredicated cell loads), 2 x windows staged in shared memory, 3 direct with predicated cell loads, 4 bulk-async (TMA) pipeline */
-	int hdiaBlock;       /* occupancy knob: >=256 force 48 warps/SM (default 32) */
+	int hdiaVariant;     /* 0/1 direct (unpredicated cell loads), 2 x windows staged in shared memory, 3 direct with predicated cell loads, 4 bulk-async (TMA) pipeline, 5 persistent with metadata prefetch */
+	int hdiaBlock;       /* occupancy knob: 192 -> 40 warps/SM, 224 -> 48 warps with UNROLL 4, >=256 -> 48 (default 32) */
 	int redBlocksPerSm;  /* CTAs per SM for the reductions                      */
 	int vecBlocksPerSm;  /* CTAs per SM for grid-stride vector kernels          */
 } SpgpuTuning;
