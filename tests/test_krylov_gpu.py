@@ -140,3 +140,56 @@ def test_fused_cg_update(ours, gpu_handle):
         rn = r - a * ap
         np.testing.assert_allclose(dr.cpu().numpy(), rn, rtol=1e-14, atol=1e-14)
         assert abs(float(ds[2].item()) - float(rn @ rn)) <= 1e-13 * float(rn @ rn)
+
+
+def test_cuda_graph_capture_of_a_device_cg_iteration(ours, gpu_handle):
+    """the non-blocking entry points neither allocate nor synchronise, so a whole device-scalar CG
+    iteration can be captured in a CUDA graph and replayed (B200 guidance: graphs for launch-bound
+    inner loops); the replayed iterations must follow the eagerly launched ones bit for bit"""
+    import torch
+    from spgpu_b200 import krylov
+    coo = G.laplace3d_7pt(12)
+    A = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    dA = util.upload(A)
+    n = coo.nrows
+    T = util.TYPES["D"]
+    b = util.to_dev(G.random_vector(n, np.float64, 21))
+
+    def apply_A(z, x_ext):
+        ours.spgpuDhellspmv(gpu_handle, z.data_ptr(), 0, T.scalar(1.0), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
+                            dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), 0, 7, n, x_ext.data_ptr(), T.scalar(0.0), 0)
+
+    def apply_A_dot(z, x_ext, dres):
+        ours.spgpuDhellspmvDot(gpu_handle, z.data_ptr(), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
+                               dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), n, x_ext.data_ptr(), 0, 0, dres)
+
+    def run(iterations, graph):
+        st = krylov.CgState(n, 0, "cuda")
+        cg = krylov.Cg(ours, gpu_handle, st, apply_A, apply_A_dot)
+        cg.start(b)
+        cg.step_device()                                  # warm-up: sizes the handle's scratch
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream()
+            default = ours.spgpuGetStream(gpu_handle)
+            torch.cuda.synchronize()
+            ours.spgpuSetStream(gpu_handle, cap.cuda_stream)
+            with torch.cuda.graph(g, stream=cap):
+                cg.step_device()
+            ours.spgpuSetStream(gpu_handle, None)
+            assert ours.spgpuGetStream(gpu_handle) == default
+            torch.cuda.synchronize()
+            for _ in range(iterations):
+                g.replay()
+        else:
+            for _ in range(iterations):
+                cg.step_device()
+        torch.cuda.synchronize()
+        return st.x.cpu().numpy(), float(st.s[0].item())
+
+    stream = torch.cuda.ExternalStream(ours.spgpuGetStream(gpu_handle))
+    with torch.cuda.stream(stream):
+        x_eager, rr_eager = run(6, graph=False)
+    x_graph, rr_graph = run(6, graph=True)
+    np.testing.assert_array_equal(x_graph, x_eager)
+    assert rr_graph == rr_eager
