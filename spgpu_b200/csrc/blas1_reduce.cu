@@ -105,28 +105,22 @@ reduce_kernel(const T* x, const T* y, long long n, int vec, Acc2* partials,
 		const long long npacks = n / N;
 		const RPack<T>* px = reinterpret_cast<const RPack<T>*>(x);
 		const RPack<T>* py = reinterpret_cast<const RPack<T>*>(y);
-		/* four packs (64 bytes per input) in flight per thread: the single-input reductions move
-		 * only 8 bytes per element and need the extra memory-level parallelism */
-		for (long long p = tid; p < npacks; p += 4 * nthreads) {
-			RPack<T> a[4], b[4];
-			bool have[4];
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const long long q = p + k * nthreads;
-				have[k] = q < npacks;
-				const long long qq = have[k] ? q : p;
-				a[k] = px[qq];
-				if (Op::NIN > 1) b[k] = py[qq];
+		for (long long p = tid; p < npacks; p += 2 * nthreads) {
+			const long long q = p + nthreads;
+			const bool two = q < npacks;
+			RPack<T> a0 = px[p], b0, a1, b1;
+			if (Op::NIN > 1) b0 = py[p];
+			if (two) {
+				a1 = px[q];
+				if (Op::NIN > 1) b1 = py[q];
 			}
 #pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				if (have[k]) {
+			for (int e = 0; e < N; ++e)
+				acc0.take(a0.v[e], b0.v[e]);
+			if (two) {
 #pragma unroll
-					for (int e = 0; e < N; ++e) {
-						if (k & 1) acc1.take(a[k].v[e], b[k].v[e]);
-						else       acc0.take(a[k].v[e], b[k].v[e]);
-					}
-				}
+				for (int e = 0; e < N; ++e)
+					acc1.take(a1.v[e], b1.v[e]);
 			}
 		}
 		const long long done = npacks * N;
@@ -167,7 +161,7 @@ static void reduce_launch(spgpuHandle_t handle, const T* x, const T* y, long lon
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const int vec = r_aligned16(x) && (Op::NIN < 2 || r_aligned16(y));
-	const long long items = vec ? (n / RPack<T>::N + 3) / 4 + 1 : n;
+	const long long items = vec ? (n / RPack<T>::N + 1) / 2 + 1 : n;
 	long long want = (items + RED_BLOCK - 1) / RED_BLOCK;
 	long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 4);
 	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
