@@ -505,12 +505,12 @@ def main():
             print(f"verify: partitioned SpMV == global-column SpMV on every rank: {verified}", file=sys.stderr, flush=True)
 
     # ---------------- device-resident timing ------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~0.1 s to start printing: begin before the warm-up
     for _ in range(W):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = L.spgpuGetLaunchCount(h)
     barrier()
     e0, e1, pairs = timed_steps(one_step, K)
