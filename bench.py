@@ -158,7 +158,8 @@ def build_workload(name, rank, world, device, n_override=None, global_columns=Fa
         nnz = int(ell.rs.sum())
         w.update(kind="ell", sym="D", A=A, rows=ell.nrows, nnz=nnz, halo=0, x_len=ell.ncols, sizeof=8,
                  alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=ell.nrows,
-                 label=f"2-D 5-point Laplacian {n}x{n}, double ELL with rS (BASELINE configs[0])")
+                 label=f"2-D 5-point Laplacian {n}x{n}, double ELL with rS (BASELINE configs[0])",
+                 kernel="ell_spmv_short_kernel<D, 5 slots>")
         w["bytes"] = nnz * 12 + 4 * ell.nrows + 8 * ell.ncols + 8 * ell.nrows
     elif name == "cfg3":
         R = n_override or (1 << 22)
@@ -283,6 +284,41 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
         call = lambda: O.Dhdiaspmv(util.ptr(z), None, T.scalar(1.0), util.ptr(vals), util.ptr(off), 32,
                                    util.ptr(ho), A.nrows, A.ncols, util.ptr(x), T.scalar(0.0))
         flops = 2 * A.nnz
+    elif workload_name == "cfg1":
+        from spgpu_b200 import formats as F, generators as G
+        ell = F.coo_to_ell(G.laplace2d_5pt(1000))
+        nnz = int(ell.rs.sum())
+        sample = f"the full 1000x1000 5-point ELL matrix ({ell.nrows} rows, {nnz} nnz)"
+        x = np.random.default_rng(12345).random(ell.ncols)
+        z = np.zeros(ell.nrows)
+        T = util.TYPES["D"]
+        call = lambda: O.Dellspmv(util.ptr(z), None, T.scalar(1.0), util.ptr(ell.values), util.ptr(ell.indices), ell.pitch,
+                                  ell.pitch, util.ptr(ell.rs), None, 4, ell.maxnnz, ell.nrows, util.ptr(x), T.scalar(0.0), 0)
+        flops = 2 * nnz
+    elif workload_name in ("cfg3", "cfg4"):
+        # a quarter of the rows, generated by the same builders (device when there is one) and copied to the host
+        if workload_name == "cfg3":
+            R, sym, dt, fl = 1 << 20, "S", np.float32, 2
+            lens, cols, vals = DB.powerlaw_entries(R, device=dev)
+            alpha, beta = 1.0, 0.0
+        else:
+            R, sym, dt, fl = 500_000, "Z", np.complex128, 8
+            lens, cols, vals = DB.banded_complex_entries(R, device=dev)
+            alpha, beta = 0.7 - 0.3j, -0.5 + 0.25j
+        A = DB.hell_from_rows(lens, cols, vals, R)
+        del lens, cols, vals
+        sample = f"{R} rows generated like the workload's ({A.nnz} nnz), HELL {sym}"
+        hv, hi, ho, rs = (t.cpu().numpy() for t in (A.values, A.indices, A.hack_offsets, A.rs))
+        hi = np.where(hi < 0, 0, hi).astype(np.int32)            # builders poison the padding indices; never read
+        rng = np.random.default_rng(12345)
+        x = rng.random(R).astype(dt) if sym == "S" else (rng.random(R) + 1j * rng.random(R))
+        y = x.copy()
+        z = np.zeros(R, dtype=dt)
+        T = util.TYPES[sym]
+        call = lambda: getattr(O, f"{sym}hellspmv")(util.ptr(z), util.ptr(y) if beta != 0 else None, T.scalar(alpha),
+                                                   util.ptr(hv), util.ptr(hi), 32, util.ptr(ho), util.ptr(rs), None,
+                                                   A.avg, R, util.ptr(x), T.scalar(beta), 0)
+        flops = fl * A.nnz
     else:
         return None
     call()                       # warm-up (page faults, thread pool)
@@ -339,13 +375,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res = cpu_baseline(args.workload if args.workload in ("cfg5", "cfg2") else "cfg5")
+        arm = args.workload if args.workload in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5") else "cfg5"
+        res = cpu_baseline(arm)
         cb, best = res
         # K timed steps of the bounded sample, W warm-ups (already warm after cpu_baseline)
         out = {"impl": "reference", "metric": "spmv_gflops", "value": cb["value"], "unit": "GFLOP/s",
                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": best * 1e3,
-               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic", "config": {"workload": args.workload, "arm": "host OpenMP SpMV over the same format"},
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": {"cfg3": "f32", "cfg4": "c128"}.get(arm, "f64"),
+               "data": "synthetic", "config": {"workload": arm, "arm": "host OpenMP SpMV over the same format"},
                "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
@@ -553,7 +591,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": f"{w['kind']}_spmv_kernel<{w['sym']}>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": w.get("kernel", f"{w['kind']}_spmv_kernel<{w['sym']}>"),
                 "kernel_ms": ker_ms, "algorithmic_bytes_per_launch": w["bytes"]}
 
     # ---------------- optional tuning sweep (kernel only, stderr) ---------------

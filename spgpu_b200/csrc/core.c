@@ -23,6 +23,7 @@ static void default_tuning(SpgpuTuning* t)
 	t->hellSplit = 0;
 	t->hdiaVariant = 0;
 	t->hdiaBlock = 0;
+	t->ellRows = 0;
 	t->redBlocksPerSm = 4;
 	t->vecBlocksPerSm = 8;
 }
@@ -176,6 +177,7 @@ void* spgpuScratch(spgpuHandle_t handle, size_t bytes)
 	X(hellSplit)              \
 	X(hdiaVariant)            \
 	X(hdiaBlock)              \
+	X(ellRows)                \
 	X(redBlocksPerSm)         \
 	X(vecBlocksPerSm)
 

@@ -29,8 +29,9 @@ typedef struct SpgpuTuning {
 	int hellBlock;       /* occupancy knob: 0 per-type default, <=64 force 32 warps/SM, 192 force 40, >=256 force 48 */
 	int hellLongFactor;  /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike (default 4) */
 	int hellSplit;       /* long-hack split mode: 0 auto (on when rIdx is given), 1 on, -1 off, >1 on with that queue capacity */
-	int hdiaVariant;     /* 0/1 direct (unpredicated cell loads), 2 x windows staged in shared memory, 3 direct with predicated cell loads, 4 bulk-async (TMA) pipeline, 5 persistent with metadata prefetch */
-	int hdiaBlock;       /* occupancy knob: 192 -> 40 warps/SM, 224 -> 48 warps with UNROLL 4, >=256 -> 48 (default 32) */
+	int hdiaVariant;     /* 0/1 direct (unpredicated cell loads), 2 x windows staged in shared memory, 3 direct with predicated cell loads, 4 bulk-async (TMA) pipeline, 5 persistent with metadata prefetch, 6/7 per-warp slab by bulk copy with 16/32 x gathers in flight (hackSize 32) */
+	int hdiaBlock;       /* occupancy knob: 8 -> rounds of 8 diagonals instead of 9, 64 -> 64-thread CTAs, 160 -> 24 warps/SM with twice the unroll, 176 -> 36, 192 -> 40, 224 -> 48 warps with UNROLL 4, >=256 -> 48 (default 32); variants 6/7: 1..32 = diagonals per warp slice */
+	int ellRows;         /* ELL, short regular rows: 0/1 = exact-slot-count kernel (default), 2 = the same with 2 rows per lane, -1 = general kernel */
 	int redBlocksPerSm;  /* CTAs per SM for the reductions                      */
 	int vecBlocksPerSm;  /* CTAs per SM for grid-stride vector kernels          */
 } SpgpuTuning;

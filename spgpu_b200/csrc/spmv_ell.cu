@@ -42,6 +42,87 @@ ell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
 		z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
 }
 
+/*
+ * Short regular rows (every row fits one round: maxNnzPerRow <= UNROLL, little padding) with the
+ * slot count NS as a compile-time constant and ROWS rows per lane (ellRows = 1 or 2).  With 4-5
+ * slots a row is ~80 bytes and a warp's whole memory phase is two dependent round trips
+ * (indices -> x); what limits a matrix like the 2-D 5-point Laplacian is the bytes the SM has in
+ * flight during that phase, i.e. resident warps x rows per lane.  An exact NS keeps only NS
+ * (index, value) pairs in registers instead of UNROLL, which buys the occupancy: ROWS = 1 runs at
+ * 64 warps per SM, ROWS = 2 (a CTA covers 256 consecutive rows; lane t owns rows t and t+128, so
+ * every warp-level load stays one coalesced run) at 32-40 with twice the loads per lane.
+ */
+template <typename T, int NS, int ROWS, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+ell_spmv_short_kernel(T* __restrict__ z, const T* y, T alpha,
+	const T* __restrict__ cM, const int* __restrict__ rP, int cMPitch,
+	int rPPitch, const int* __restrict__ rS, const int* __restrict__ rIdx,
+	int rows, const T* __restrict__ x, T beta, int baseIndex)
+{
+	const unsigned first = blockIdx.x * (128u * ROWS) + threadIdx.x;
+	const bool useBeta = Num<T>::nonzero(beta);
+	int col[ROWS][NS];
+	T a[ROWS][NS];
+	int len[ROWS];
+#pragma unroll
+	for (int r = 0; r < ROWS; ++r) {
+		const unsigned i = first + 128u * r;
+		const bool live = i < (unsigned)rows;
+		len[r] = live ? (rS ? ld_stream(rS + i) : NS) : 0;
+#pragma unroll
+		for (int u = 0; u < NS; ++u) {
+			col[r][u] = baseIndex;
+			a[r][u] = Num<T>::zero();
+			if (live) {
+				col[r][u] = ld_stream(rP + i + (long long)u * rPPitch);
+				a[r][u] = ld_stream(cM + i + (long long)u * cMPitch);
+			}
+		}
+	}
+#pragma unroll
+	for (int r = 0; r < ROWS; ++r) {
+		const unsigned i = first + 128u * r;
+		const bool live = i < (unsigned)rows;
+		const unsigned out = (live && rIdx) ? (unsigned)__ldg(rIdx + i) : i;
+		T yv = Num<T>::zero();
+		if (useBeta && live)
+			yv = y[out];
+		T xv[NS];
+#pragma unroll
+		for (int u = 0; u < NS; ++u) {
+			xv[u] = Num<T>::zero();
+			if (u < len[r])
+				xv[u] = ld_keep(x + (col[r][u] - baseIndex));
+		}
+		T acc = Num<T>::zero();
+#pragma unroll
+		for (int u = 0; u < NS; ++u)
+			if (u < len[r])
+				acc = Num<T>::fma(a[r][u], xv[u], acc);
+		if (live)
+			z[out] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
+	}
+}
+
+template <typename T, int NS>
+static void ell_spmv_short_launch(spgpuHandle_t handle, int rowsPerLane, T* z, const T* y, T alpha,
+	const T* cM, const int* rP, int cMPitch, int rPPitch, const int* rS, const int* rIdx,
+	int rows, const T* x, T beta, int baseIndex)
+{
+	cudaStream_t s = handle->currentStream;
+	/* registers ~ 20 + ROWS*NS*(1 + words per value) (ptxas -v): the CTA count that fits without spills */
+	constexpr int W = sizeof(T) / 4;
+	constexpr int MINB1 = NS * (1 + W) <= 16 ? 16 : NS * (1 + W) <= 24 ? 12 : 8;
+	constexpr int MINB2 = 2 * NS * (1 + W) <= 32 ? 10 : 2 * NS * (1 + W) <= 48 ? 8 : 5;
+	if (rowsPerLane >= 2)
+		ell_spmv_short_kernel<T, NS, 2, MINB2><<<spgpu_ceil_div(rows, 256), 128, 0, s>>>(
+			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
+	else
+		ell_spmv_short_kernel<T, NS, 1, MINB1><<<spgpu_ceil_div(rows, 128), 128, 0, s>>>(
+			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
+	spgpu_count_launch(handle);
+}
+
 /* bulk-async variant (hellVariant = 3): short regular rows, aligned arrays */
 template <typename T, int UNROLL>
 static bool ell_spmv_try_bulk(spgpuHandle_t handle, T* z, const T* y, T alpha,
@@ -91,8 +172,19 @@ static void ell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	 * when little of that is padding (avg close to max) */
 	int allocated = 0;
 	if (t->hellVariant != 1 && maxNnzPerRow > 0 && maxNnzPerRow <= UNROLL &&
-	    (rS == NULL || 4LL * avgNnzPerRow >= 3LL * maxNnzPerRow))
+	    (rS == NULL || 4LL * avgNnzPerRow >= 3LL * maxNnzPerRow) &&
+	    /* the lanes past the last row read too: the pitches must cover the last warp */
+	    (long long)cMPitch >= (((long long)rows + 31) & ~31LL) && (long long)rPPitch >= (((long long)rows + 31) & ~31LL))
 		allocated = maxNnzPerRow;
+	if (allocated > 0 && t->ellRows >= 0) {
+#define SPGPU_ELL_SHORT(NS) case NS: ell_spmv_short_launch<T, NS>(handle, t->ellRows, z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex); return;
+		switch (allocated) {
+			SPGPU_ELL_SHORT(1) SPGPU_ELL_SHORT(2) SPGPU_ELL_SHORT(3) SPGPU_ELL_SHORT(4)
+			SPGPU_ELL_SHORT(5) SPGPU_ELL_SHORT(6) SPGPU_ELL_SHORT(7) SPGPU_ELL_SHORT(8)
+		default: break;
+		}
+#undef SPGPU_ELL_SHORT
+	}
 	bool dense = !Num<T>::is_complex;
 	if (t->hellBlock >= 256) dense = true;
 	else if (t->hellBlock > 0 && t->hellBlock <= 64) dense = false;

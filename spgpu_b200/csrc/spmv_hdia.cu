@@ -18,6 +18,7 @@
 #include "launch.cuh"
 #include "numeric.cuh"
 #include "spmv_hdia_bulk.cuh"
+#include "spmv_hdia_slab.cuh"
 
 /*
  * HACK > 0: hackSize known at compile time -> cell addresses are base +
@@ -28,15 +29,53 @@
  * loaded without waiting for the offsets (they all exist in the slab); only the
  * x gather and the FMA depend on the in-range test.
  */
-template <typename T, int UNROLL, int HACK, int MINB, bool PREDICATED = false>
-__global__ void __launch_bounds__(128, MINB)
+/* one round of the direct kernel: UNROLL diagonals starting at diagonal u0 of the 32 whose offsets
+ * the warp holds in mineOff; GUARD = the round may run past the hack's last diagonal (n) */
+template <typename T, int UNROLL, bool GUARD, bool PREDICATED>
+__device__ __forceinline__ T hdia_round(T acc, const T* __restrict__ cp, long long hackSize, int mineOff,
+	int u0, int n, unsigned i, unsigned colsEff, const T* __restrict__ x)
+{
+	T a[UNROLL];
+	T xv[UNROLL];
+	bool on[UNROLL];
+	if (!PREDICATED) {
+#pragma unroll
+		for (int u = 0; u < UNROLL; ++u) {
+			a[u] = Num<T>::zero();
+			if (!GUARD || u0 + u < n)                 /* warp-uniform: cell exists */
+				a[u] = ld_stream(cp + u * hackSize);
+		}
+	}
+#pragma unroll
+	for (int u = 0; u < UNROLL; ++u) {
+		const int off = __shfl_sync(SPGPU_FULL_MASK, mineOff, u0 + u);
+		const int c = (int)i + off;
+		on[u] = (unsigned)c < colsEff && (!GUARD || u0 + u < n);   /* u0+u may pass lane 31 when UNROLL does not divide 32 */
+		xv[u] = Num<T>::zero();
+		if (PREDICATED)
+			a[u] = Num<T>::zero();
+		if (on[u]) {
+			xv[u] = ld_keep(x + c);
+			if (PREDICATED)                           /* cells outside the matrix are not read */
+				a[u] = ld_stream(cp + u * hackSize);
+		}
+	}
+#pragma unroll
+	for (int u = 0; u < UNROLL; ++u)
+		acc = PREDICATED ? Num<T>::fma(a[u], xv[u], acc)
+		                 : (on[u] ? Num<T>::fma(a[u], xv[u], acc) : acc);
+	return acc;
+}
+
+template <typename T, int UNROLL, int HACK, int MINB, bool PREDICATED = false, int BLOCK = 128>
+__global__ void __launch_bounds__(BLOCK, MINB)
 hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM,
 	const int* __restrict__ offsets, int hackSizeRt,
 	const int* __restrict__ hackOffsets, int rows, int cols,
 	const T* __restrict__ x, T beta)
 {
 	const int hackSize = HACK > 0 ? HACK : hackSizeRt;
-	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned i = blockIdx.x * BLOCK + threadIdx.x;
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned warpRow = i - lane;
 	if (warpRow >= (unsigned)rows)
@@ -58,38 +97,12 @@ hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ d
 	for (int j0 = 0; j0 < diags; j0 += 32) {
 		const int mineOff = (j0 + (int)lane < diags) ? ld_stream(offs + j0 + lane) : INT_MIN;
 		const int n = min(32, diags - j0);
-		for (int u0 = 0; u0 < n; u0 += UNROLL) {
-			const T* cp = cell + (long long)(j0 + u0) * hackSize;
-			T a[UNROLL];
-			T xv[UNROLL];
-			bool on[UNROLL];
-			if (!PREDICATED) {
-#pragma unroll
-				for (int u = 0; u < UNROLL; ++u) {
-					a[u] = Num<T>::zero();
-					if (u0 + u < n)                       /* warp-uniform: cell exists */
-						a[u] = ld_stream(cp + (long long)u * hackSize);
-				}
-			}
-#pragma unroll
-			for (int u = 0; u < UNROLL; ++u) {
-				const int off = __shfl_sync(SPGPU_FULL_MASK, mineOff, u0 + u);
-				const int c = (int)i + off;
-				on[u] = (unsigned)c < colsEff;
-				xv[u] = Num<T>::zero();
-				if (PREDICATED)
-					a[u] = Num<T>::zero();
-				if (on[u]) {
-					xv[u] = ld_keep(x + c);
-					if (PREDICATED)                       /* cells outside the matrix are not read */
-						a[u] = ld_stream(cp + (long long)u * hackSize);
-				}
-			}
-#pragma unroll
-			for (int u = 0; u < UNROLL; ++u)
-				acc = PREDICATED ? Num<T>::fma(a[u], xv[u], acc)
-				                 : (on[u] ? Num<T>::fma(a[u], xv[u], acc) : acc);
-		}
+		int u0 = 0;
+		/* full rounds need no per-diagonal guard; the last, partial round does */
+		for (; u0 + UNROLL <= n; u0 += UNROLL)
+			acc = hdia_round<T, UNROLL, false, PREDICATED>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, x);
+		if (u0 < n)
+			acc = hdia_round<T, UNROLL, true, PREDICATED>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, x);
 	}
 
 	if (live)
@@ -316,18 +329,30 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const unsigned grid = spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
+	/* the side variants index the 32 offsets a warp holds without a wrap guard: their rounds must divide 32 */
+	constexpr int U8 = UNROLL == 9 ? 8 : UNROLL;
 	if (t->hdiaVariant == 4) {
 		bool done = false;
-		if (hackSize == 32)      done = hdia_spmv_try_bulk<T, UNROLL, 32>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta);
-		else if (hackSize == 64) done = hdia_spmv_try_bulk<T, UNROLL, 64>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta);
+		if (hackSize == 32)      done = hdia_spmv_try_bulk<T, U8, 32>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta);
+		else if (hackSize == 64) done = hdia_spmv_try_bulk<T, U8, 64>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta);
+		if (done)
+			return;
+	}
+	if ((t->hdiaVariant == 6 || t->hdiaVariant == 7) && hackSize == 32) {
+		/* per-warp slab through the bulk-copy engine; hdiaBlock (1..32) caps the diagonals per slice */
+		const int cap = (t->hdiaBlock > 0 && t->hdiaBlock <= 32) ? t->hdiaBlock : 0;
+		constexpr int UX = sizeof(T) > 8 ? 8 : 16;               /* x gathers a lane keeps in flight */
+		const bool done = t->hdiaVariant == 6
+			? hdia_spmv_try_slab<T, UX, 6>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta, cap)
+			: hdia_spmv_try_slab<T, 2 * UX, 4>(handle, z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta, cap);
 		if (done)
 			return;
 	}
 	if (t->hdiaVariant == 5) {
 		long long want = (long long)handle->multiProcessorCount * 8;
 		if (want > (long long)grid) want = grid;
-		if (hackSize == 32) hdia_spmv_persistent_kernel<T, UNROLL, 32><<<(unsigned)want, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else                hdia_spmv_persistent_kernel<T, UNROLL, 0><<<(unsigned)want, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		if (hackSize == 32) hdia_spmv_persistent_kernel<T, U8, 32><<<(unsigned)want, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else                hdia_spmv_persistent_kernel<T, U8, 0><<<(unsigned)want, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		spgpu_count_launch(handle);
 		return;
 	}
@@ -337,12 +362,17 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		spgpu_count_launch(handle);
 		return;
 	}
-	/* occupancy knob (registers vs resident warps): hdiaBlock >=256 -> 48 warps, 192 -> 40, else 32 */
+	/* occupancy / round-size knob (registers vs resident warps): hdiaBlock >=256 -> 48 warps, 192 -> 40, 176 -> 36,
+	 * 160 -> 24 with twice the unroll, 64 -> 64-thread CTAs, 8 -> rounds of 8 diagonals, else 32 warps, rounds of 9 */
 	if (hackSize == 32 && t->hdiaVariant == 3) {
 		hdia_spmv_kernel<T, UNROLL, 32, 8, true><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 	} else if (hackSize == 32) {
 		if (t->hdiaBlock >= 256)      hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else if (t->hdiaBlock == 224) hdia_spmv_kernel<T, 4, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else if (t->hdiaBlock == 8)   hdia_spmv_kernel<T, U8, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else if (t->hdiaBlock == 64)  hdia_spmv_kernel<T, UNROLL, 32, 16, false, 64><<<spgpu_ceil_div(rows, 64), 64, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else if (t->hdiaBlock == 176) hdia_spmv_kernel<T, UNROLL, 32, 9><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		else if (t->hdiaBlock == 160) hdia_spmv_kernel<T, 2 * U8, 32, 6><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else if (t->hdiaBlock == 192) hdia_spmv_kernel<T, UNROLL, 32, 10><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 		else                          hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
 	} else if (hackSize == 64) {
@@ -362,7 +392,12 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 			hackOffsets, rows, cols, x, beta);                                 \
 	}
 
-SPGPU_DEFINE_HDIASPMV(S, float, 8)
-SPGPU_DEFINE_HDIASPMV(D, double, 8)
-SPGPU_DEFINE_HDIASPMV(C, cuFloatComplex, 8)
+/* Diagonals per round.  9, not 8: a warp walks ceil(diags/UNROLL) dependent rounds (cells + x
+ * gathers of a round are in flight together), and stencils come with 5, 7, 9, 19 or 27 diagonals
+ * -- 27 is three rounds of 9 but four of 8 (77.8 us vs 86.0 us on the 128^3 27-point stencil,
+ * i.e. 0.96 vs 0.87 of the measured HBM peak); 9 is never more rounds than 8 and still fits 64
+ * registers for double. */
+SPGPU_DEFINE_HDIASPMV(S, float, 9)
+SPGPU_DEFINE_HDIASPMV(D, double, 9)
+SPGPU_DEFINE_HDIASPMV(C, cuFloatComplex, 9)
 SPGPU_DEFINE_HDIASPMV(Z, cuDoubleComplex, 4)

@@ -240,13 +240,36 @@ def test_ell_kernel_variants(ours, gpu_handle, variant, dtype):
         ours.spgpuSetTuning(gpu_handle, b"hellVariant", 0)
 
 
-@pytest.mark.parametrize("variant,occ", [(0, 0), (2, 0), (3, 0), (4, 0), (5, 0), (0, 192), (0, 224), (0, 256)])
+@pytest.mark.parametrize("rows_per_lane", [-1, 0, 2])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ell_short_rows_several_rows_per_lane(ours, gpu_handle, dtype, rows_per_lane):
+    """ELL, short regular rows, general kernel (-1), exact-slot-count kernel with 1 (default) / 2 rows per lane (ellRows): ragged last CTA, rS == NULL, rIdx,
+    in-place beta; the random matrix (avg far below max) must fall back to the general kernel"""
+    try:
+        assert ours.spgpuSetTuning(gpu_handle, b"ellRows", rows_per_lane) == 0
+        for coo in (G.laplace2d_5pt(70, 53), G.laplace3d_7pt(17), G.random_coo(3000, 3000, (0, 5), 1, dtype, 0)):
+            coo = F.Coo(coo.rows, coo.cols, (coo.vals if np.dtype(dtype).kind == "c" or coo.vals.dtype.kind != "c" else coo.vals.real).astype(dtype), coo.nrows, coo.ncols, coo.base)
+            A = build("ell", coo, 0, 32)
+            x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
+            y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
+            alpha, beta = scalars(dtype)
+            check(ours, gpu_handle, "ell", coo, A, x, y, alpha, beta)
+            check(ours, gpu_handle, "ell", coo, A, x, y, alpha, 0.0, rs_null=True)
+            oell = F.ell_to_oell(A)
+            check(ours, gpu_handle, "ell", coo, oell, x, y, alpha, beta, ridx=oell.ridx)
+    finally:
+        ours.spgpuSetTuning(gpu_handle, b"ellRows", 0)
+
+
+@pytest.mark.parametrize("variant,occ", [(0, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (6, 5), (7, 0), (7, 3), (0, 8), (0, 64), (0, 160), (0, 176), (0, 192), (0, 224), (0, 256)])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("hack", [32, 64])
 def test_hdia_kernel_variants(ours, gpu_handle, variant, occ, dtype, hack):
-    """HDIA code paths: direct x loads at three occupancy levels, and the variant that stages the
+    """HDIA code paths: direct x loads at four occupancy levels, the variant that stages the
     x windows of runs of consecutive offsets in shared memory (stencils have such runs, the random
-    matrix has none, the rectangular one exercises the column range test)"""
+    matrix has none, the rectangular one exercises the column range test), the bulk-async pipeline,
+    the persistent one, and the per-warp slab variants (6/7; occ = diagonals per slice there, so 5
+    and 3 force hacks to be walked in several bulk copies)"""
     try:
         assert ours.spgpuSetTuning(gpu_handle, b"hdiaVariant", variant) == 0
         assert ours.spgpuSetTuning(gpu_handle, b"hdiaBlock", occ) == 0
