@@ -104,6 +104,46 @@ int spgpuCsrToHellLayoutDevice(spgpuHandle_t handle, int rows, const __device in
 		__device T* dHellValues, __device int* dHellIndices);
 SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_CSR2HELL)
 
+/*
+ * CSR -> OHELL on the device: rows stored by descending length in exactly the order the
+ * reference's ellToOell produces (reference ell.c:84-202: its mergesort takes the right run
+ * on ties, i.e. equal lengths end up by descending original row index).  Step 1 (blocking)
+ * fills dRidx (dRidx[i] = CSR row stored as HELL row i -- the rIdx argument of
+ * spgpu?hellspmv), dRs (lengths in the new order) and dHackOffsets; step 2 (asynchronous)
+ * places the entries.
+ */
+int spgpuCsrToOhellLayoutDevice(spgpuHandle_t handle, int rows, const __device int* dRowPtr,
+	int hackSize, __device int* dRidx, __device int* dRs, __device int* dHackOffsets,
+	long long* totalElements);
+#define SPGPU_DECL_CSR2OHELL(S, T, R)                                                \
+	void spgpu##S##csrToOhellDevice(spgpuHandle_t handle, int rows,                   \
+		const __device int* dRowPtr, const __device int* dCols, const __device T* dVals, \
+		int csrBase, int hackSize, const __device int* dHackOffsets,                  \
+		const __device int* dRidx, int hellBase, __device T* dHellValues,             \
+		__device int* dHellIndices);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_CSR2OHELL)
+
+/*
+ * COO -> HDIA on the device: the twins of computeHdiaHackOffsetsFromCoo and cooToHdia
+ * (reference hdia_conv.h:52-70, hdia.cpp:161-349) with the same argument order, device
+ * pointers instead of host pointers, and a status return.  Same results bit for bit
+ * (hackOffsets, offsets in ascending order per hack, cell placement); the COO entries may
+ * be in any order; duplicate (row, col) entries are unspecified (the reference keeps the
+ * last).  spgpuHdiaHackOffsetsFromCooDevice blocks (it returns the allocation height);
+ * spgpu?cooToHdiaDevice is asynchronous and, like the reference, expects dHdiaValues
+ * zero-filled by the caller.
+ */
+int spgpuHdiaHackOffsetsFromCooDevice(spgpuHandle_t handle, int* allocationHeight,
+	__device int* dHackOffsets, int hackSize, int rowsCount, int columnsCount, int nonZerosCount,
+	const __device int* dCooRowIndices, const __device int* dCooColsIndices, int cooBaseIndex);
+#define SPGPU_DECL_COO2HDIA(S, T, R)                                                 \
+	int spgpu##S##cooToHdiaDevice(spgpuHandle_t handle, __device T* dHdiaValues,      \
+		__device int* dHdiaOffsets, const __device int* dHackOffsets, int hackSize,   \
+		int rowsCount, int columnsCount, int nonZerosCount,                           \
+		const __device int* dCooRowIndices, const __device int* dCooColsIndices,      \
+		const __device T* dCooValues, int cooBaseIndex);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_COO2HDIA)
+
 /* ---- multi-GPU helpers ---------------------------------------------------- */
 
 /* 64-byte CUDA IPC handle of a cudaMalloc'ed pointer / open it in a peer process. */

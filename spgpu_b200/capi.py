@@ -112,6 +112,8 @@ def ext_symbols():
     for s in FLOAT_SYMS:
         names += [f"spgpu{s}dotDev", f"spgpu{s}nrm2sqDev"]
     names += ["spgpuCsrToHellLayoutDevice"] + [f"spgpu{s}csrToHellDevice" for s in FLOAT_SYMS]
+    names += ["spgpuCsrToOhellLayoutDevice"] + [f"spgpu{s}csrToOhellDevice" for s in FLOAT_SYMS]
+    names += ["spgpuHdiaHackOffsetsFromCooDevice"] + [f"spgpu{s}cooToHdiaDevice" for s in FLOAT_SYMS]
     names += ["spgpuDaxpbyDev", "spgpuDhellspmvDot", "spgpuDcgUpdateDev", "spgpuDsumDev",
               "spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
               "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag",
@@ -232,6 +234,15 @@ class SpgpuLib:
             for s in FLOAT_SYMS:
                 f[f"spgpu{s}csrToHellDevice"] = _sig(d, f"spgpu{s}csrToHellDevice", None,
                     [H, c_int, P, P, P, c_int, c_int, P, c_int, P, P], optional=True)
+            f["spgpuCsrToOhellLayoutDevice"] = _sig(d, "spgpuCsrToOhellLayoutDevice", c_int,
+                [H, c_int, P, c_int, P, P, P, ctypes.POINTER(ctypes.c_longlong)], optional=True)
+            f["spgpuHdiaHackOffsetsFromCooDevice"] = _sig(d, "spgpuHdiaHackOffsetsFromCooDevice", c_int,
+                [H, ctypes.POINTER(c_int), P, c_int, c_int, c_int, c_int, P, P, c_int], optional=True)
+            for s in FLOAT_SYMS:
+                f[f"spgpu{s}csrToOhellDevice"] = _sig(d, f"spgpu{s}csrToOhellDevice", None,
+                    [H, c_int, P, P, P, c_int, c_int, P, P, c_int, P, P], optional=True)
+                f[f"spgpu{s}cooToHdiaDevice"] = _sig(d, f"spgpu{s}cooToHdiaDevice", c_int,
+                    [H, P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int], optional=True)
             f["spgpuDsumDev"] = _sig(d, "spgpuDsumDev", None, [H, c_int, P, P], optional=True)
             f["spgpuDcgUpdateDev"] = _sig(d, "spgpuDcgUpdateDev", None, [H, P, P, P, P, c_int, P, P, P], optional=True)
             f["spgpuIpcGetHandle"] = _sig(d, "spgpuIpcGetHandle", c_int, [P, P], optional=True)

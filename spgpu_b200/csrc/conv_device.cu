@@ -6,8 +6,14 @@
  * hackOffsets[h] + k*hackSize + row%hackSize.  The host route is serial O(nnz) and needs
  * an ELL intermediate of maxRowLength x rows; this one is three small kernels and a
  * prefix sum (CUB DeviceScan, toolkit header library -- not on the SpMV path).
+ *
+ * Also here: the OHELL row order (ellToOell's mergesort, reference ell.c:84-157) as one radix
+ * sort, and COO -> HDIA (computeHdiaHackOffsetsFromCoo + cooToHdia, reference
+ * hdia.cpp:161-349) as sort + unique + binary searches.
  */
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "launch.cuh"
 #include "numeric.cuh"
@@ -39,6 +45,28 @@ hack_sizes_kernel(const int* __restrict__ rS, int rows, int hackSize, int hacks,
 	longest = __reduce_max_sync(SPGPU_FULL_MASK, longest);
 	if (lane == 0)
 		sizes[warp] = longest * hackSize;
+}
+
+/* hack sizes -> hackOffsets (exclusive prefix sum) and the allocation size; blocks on the stream.
+ * `scratch` holds sizesBytes for the per-hack sizes followed by tempBytes of CUB workspace. */
+static int hack_layout_from_rs(spgpuHandle_t handle, int rows, int hackSize, const int* dRs,
+	int* dHackOffsets, char* scratch, size_t sizesBytes, size_t tempBytes, long long* totalElements)
+{
+	cudaStream_t s = handle->currentStream;
+	const int hacks = (rows + hackSize - 1) / hackSize;
+	int* sizes = reinterpret_cast<int*>(scratch);
+	hack_sizes_kernel<<<spgpu_ceil_div((long long)hacks * 32, 256), 256, 0, s>>>(dRs, rows, hackSize, hacks, sizes);
+	spgpu_count_launch(handle);
+	cub::DeviceScan::ExclusiveSum(scratch + sizesBytes, tempBytes, sizes, dHackOffsets, hacks, s);
+	int lastOffset = 0, lastSize = 0;
+	cudaMemcpyAsync(&lastOffset, dHackOffsets + hacks - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+	cudaMemcpyAsync(&lastSize, sizes + hacks - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+	if (cudaStreamSynchronize(s) != cudaSuccess)
+		return SPGPU_UNSPECIFIED;
+	*totalElements = (long long)lastOffset + lastSize;
+	if (lastOffset < 0 || *totalElements > 2147483647LL)
+		return SPGPU_UNSUPPORTED;
+	return SPGPU_SUCCESS;
 }
 
 /* one warp per row: the row's entries are read coalesced and written to their HELL slots */
@@ -85,21 +113,8 @@ extern "C" int spgpuCsrToHellLayoutDevice(spgpuHandle_t handle, int rows, const 
 	char* scratch = (char*)spgpuScratch(handle, sizesBytes + tempBytes + 256);
 	if (!scratch)
 		return SPGPU_OUTOFMEMORY;
-	int* sizes = reinterpret_cast<int*>(scratch);
-	hack_sizes_kernel<<<spgpu_ceil_div((long long)hacks * 32, 256), 256, 0, s>>>(dRs, rows, hackSize, hacks, sizes);
-	spgpu_count_launch(handle);
-	cub::DeviceScan::ExclusiveSum(scratch + sizesBytes, tempBytes, sizes, dHackOffsets, hacks, s);
-
-	int lastOffset = 0, lastSize = 0;
-	cudaMemcpyAsync(&lastOffset, dHackOffsets + hacks - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
-	cudaMemcpyAsync(&lastSize, sizes + hacks - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
-	if (cudaStreamSynchronize(s) != cudaSuccess)
-		return SPGPU_UNSPECIFIED;
-	*totalElements = (long long)lastOffset + lastSize;
-	/* the reference ABI stores element offsets as int: refuse matrices that do not fit */
-	if (lastOffset < 0 || *totalElements > 2147483647LL)
-		return SPGPU_UNSUPPORTED;
-	return SPGPU_SUCCESS;
+	/* the reference ABI stores element offsets as int: matrices that do not fit are refused */
+	return hack_layout_from_rs(handle, rows, hackSize, dRs, dHackOffsets, scratch, sizesBytes, tempBytes, totalElements);
 }
 
 template <typename T>
@@ -129,3 +144,288 @@ SPGPU_DEFINE_CSR2HELL(S, float)
 SPGPU_DEFINE_CSR2HELL(D, double)
 SPGPU_DEFINE_CSR2HELL(C, cuFloatComplex)
 SPGPU_DEFINE_CSR2HELL(Z, cuDoubleComplex)
+
+
+/* ======================================================================================
+ * OHELL: rows ordered by length (reference ellToOell, ell.c:161-202).
+ *
+ * The reference's bottom-up mergesort takes the RIGHT run on ties (ell.c:93: strict `>`), so
+ * its result is a total order: length descending, and among equal lengths ORIGINAL ROW INDEX
+ * DESCENDING.  One descending radix sort of the 64-bit key (length << 32 | row) gives exactly
+ * that; rIdx is the key's low word.
+ * ====================================================================================== */
+
+__global__ void __launch_bounds__(256)
+ohell_keys_kernel(const int* __restrict__ rowPtr, int rows, unsigned long long* __restrict__ keys)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < rows)
+		keys[i] = ((unsigned long long)(unsigned)(rowPtr[i + 1] - rowPtr[i]) << 32) | (unsigned)i;
+}
+
+__global__ void __launch_bounds__(256)
+ohell_unpack_kernel(const unsigned long long* __restrict__ keys, int rows, int* __restrict__ rIdx, int* __restrict__ rS)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < rows) {
+		const unsigned long long k = keys[i];
+		rIdx[i] = (int)(unsigned)(k & 0xffffffffull);
+		rS[i] = (int)(unsigned)(k >> 32);
+	}
+}
+
+/* as csr_to_hell_scatter_kernel, but HELL row `row` takes CSR row rIdx[row] */
+template <typename T>
+__global__ void __launch_bounds__(256)
+csr_to_ohell_scatter_kernel(const int* __restrict__ rowPtr, const int* __restrict__ cols,
+	const T* __restrict__ vals, int rows, int csrBase, int hellBase, int hackSize,
+	const int* __restrict__ hackOffsets, const int* __restrict__ rIdx,
+	T* __restrict__ hellValues, int* __restrict__ hellIndices)
+{
+	const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (row >= rows)
+		return;
+	const int src = rIdx[row];
+	const int begin = rowPtr[src] - csrBase, end = rowPtr[src + 1] - csrBase;
+	const long long at = (long long)hackOffsets[row / hackSize] + row % hackSize;
+	for (int e = begin + lane; e < end; e += 32) {
+		const long long to = at + (long long)(e - begin) * hackSize;
+		hellValues[to] = vals[e];
+		hellIndices[to] = cols[e] - csrBase + hellBase;
+	}
+}
+
+/*
+ * Step 1 of CSR -> OHELL (blocking): dRidx[i] = CSR row stored as HELL row i (ellToOell's
+ * order), dRs[i] = its length, dHackOffsets / *totalElements as for plain HELL.
+ */
+extern "C" int spgpuCsrToOhellLayoutDevice(spgpuHandle_t handle, int rows, const int* dRowPtr,
+	int hackSize, int* dRidx, int* dRs, int* dHackOffsets, long long* totalElements)
+{
+	*totalElements = 0;
+	if (rows <= 0)
+		return 0;
+	if (hackSize <= 0 || hackSize % 32)
+		return SPGPU_UNSUPPORTED;
+	cudaStream_t s = handle->currentStream;
+	const int hacks = (rows + hackSize - 1) / hackSize;
+	size_t sortBytes = 0, scanBytes = 0;
+	cub::DeviceRadixSort::SortKeysDescending(NULL, sortBytes, (const unsigned long long*)NULL,
+		(unsigned long long*)NULL, rows, 0, 64, s);
+	cub::DeviceScan::ExclusiveSum(NULL, scanBytes, (const int*)NULL, (int*)NULL, hacks, s);
+	const size_t keyBytes = ((size_t)rows * sizeof(unsigned long long) + 255) & ~(size_t)255;
+	const size_t sizesBytes = ((size_t)hacks * sizeof(int) + 255) & ~(size_t)255;
+	const size_t tempBytes = sortBytes > scanBytes ? sortBytes : scanBytes;
+	char* scratch = (char*)spgpuScratch(handle, 2 * keyBytes + sizesBytes + tempBytes + 256);
+	if (!scratch)
+		return SPGPU_OUTOFMEMORY;
+	unsigned long long* keysIn = reinterpret_cast<unsigned long long*>(scratch);
+	unsigned long long* keysOut = reinterpret_cast<unsigned long long*>(scratch + keyBytes);
+	char* rest = scratch + 2 * keyBytes;
+	ohell_keys_kernel<<<spgpu_ceil_div(rows, 256), 256, 0, s>>>(dRowPtr, rows, keysIn);
+	spgpu_count_launch(handle);
+	size_t tb = tempBytes;
+	cub::DeviceRadixSort::SortKeysDescending(rest + sizesBytes, tb, keysIn, keysOut, rows, 0, 64, s);
+	ohell_unpack_kernel<<<spgpu_ceil_div(rows, 256), 256, 0, s>>>(keysOut, rows, dRidx, dRs);
+	spgpu_count_launch(handle);
+	return hack_layout_from_rs(handle, rows, hackSize, dRs, dHackOffsets, rest, sizesBytes, tempBytes, totalElements);
+}
+
+#define SPGPU_DEFINE_CSR2OHELL(S, T)                                                     \
+	extern "C" void spgpu##S##csrToOhellDevice(spgpuHandle_t handle, int rows,            \
+		const int* dRowPtr, const int* dCols, const T* dVals, int csrBase, int hackSize,  \
+		const int* dHackOffsets, const int* dRidx, int hellBase, T* dHellValues,          \
+		int* dHellIndices)                                                                \
+	{                                                                                     \
+		if (rows <= 0)                                                                    \
+			return;                                                                       \
+		csr_to_ohell_scatter_kernel<T><<<spgpu_ceil_div((long long)rows * 32, 256), 256, 0, \
+			handle->currentStream>>>(dRowPtr, dCols, dVals, rows, csrBase, hellBase,      \
+			hackSize, dHackOffsets, dRidx, dHellValues, dHellIndices);                    \
+		spgpu_count_launch(handle);                                                       \
+	}
+
+SPGPU_DEFINE_CSR2OHELL(S, float)
+SPGPU_DEFINE_CSR2OHELL(D, double)
+SPGPU_DEFINE_CSR2OHELL(C, cuFloatComplex)
+SPGPU_DEFINE_CSR2OHELL(Z, cuDoubleComplex)
+
+/* ======================================================================================
+ * COO -> HDIA (reference computeHdiaHackOffsetsFromCoo + cooToHdia, hdia.cpp:161-349).
+ *
+ * The reference collects, per hack, the set of diagonals its entries lie on in a std::map
+ * (ascending), stores col-row of each as the hack's offsets and copies every value to
+ * cell (hackOffsets[h] + position of its diagonal, row % hackSize).  Equivalent, in
+ * parallel: the sorted, de-duplicated list of 64-bit keys (hack << 32 | biased diagonal) IS
+ * the offsets array (low words) in storage order, hackOffsets[h] is the lower bound of
+ * (h << 32) in that list, and an entry's diagonal slot is found by binary search inside its
+ * hack's segment.  Entries are independent, so the COO order does not matter; duplicates of
+ * one (row, col) race (the reference keeps the last one in COO order).
+ * ====================================================================================== */
+
+#define HDIA_DIAG_BIAS 0x80000000u
+
+__global__ void __launch_bounds__(256)
+hdia_keys_kernel(const int* __restrict__ cooRows, const int* __restrict__ cooCols, int nnz, int base,
+	int hackSize, unsigned long long* __restrict__ keys)
+{
+	const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < nnz) {
+		const int r = cooRows[e] - base, c = cooCols[e] - base;
+		keys[e] = ((unsigned long long)(unsigned)(r / hackSize) << 32) | ((unsigned)(c - r) + HDIA_DIAG_BIAS);
+	}
+}
+
+/* hackOffsets[h] = number of unique keys below (h << 32), h = 0..hacks */
+__global__ void __launch_bounds__(256)
+hdia_hack_offsets_kernel(const unsigned long long* __restrict__ uniq, const int* __restrict__ count,
+	int hacks, int* __restrict__ hackOffsets)
+{
+	const int h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h > hacks)
+		return;
+	const unsigned long long want = (unsigned long long)(unsigned)h << 32;
+	int lo = 0, hi = *count;
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (uniq[mid] < want) lo = mid + 1; else hi = mid;
+	}
+	hackOffsets[h] = lo;
+}
+
+__global__ void __launch_bounds__(256)
+hdia_offsets_kernel(const unsigned long long* __restrict__ uniq, const int* __restrict__ count, int* __restrict__ offsets)
+{
+	const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (d < *count)
+		offsets[d] = (int)((unsigned)(uniq[d] & 0xffffffffull) - HDIA_DIAG_BIAS);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+coo_to_hdia_scatter_kernel(const int* __restrict__ cooRows, const int* __restrict__ cooCols,
+	const T* __restrict__ cooVals, int nnz, int base, int hackSize, const int* __restrict__ hackOffsets,
+	const int* __restrict__ offsets, T* __restrict__ hdiaValues)
+{
+	const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= nnz)
+		return;
+	const int r = cooRows[e] - base, c = cooCols[e] - base;
+	const int h = r / hackSize, diag = c - r;
+	int lo = hackOffsets[h], hi = hackOffsets[h + 1];
+	while (lo < hi) {                                  /* the hack's offsets are ascending */
+		const int mid = (lo + hi) >> 1;
+		if (offsets[mid] < diag) lo = mid + 1; else hi = mid;
+	}
+	hdiaValues[(long long)lo * hackSize + r % hackSize] = cooVals[e];
+}
+
+/* sorted unique (hack, diagonal) keys of the COO entries into handle scratch; returns the
+ * device pointers (valid until the next scratch user) or NULL on allocation failure */
+static bool hdia_unique_keys(spgpuHandle_t handle, int hackSize, int nnz, const int* dCooRows,
+	const int* dCooCols, int base, unsigned long long** uniq, int** dCount)
+{
+	cudaStream_t s = handle->currentStream;
+	size_t sortBytes = 0, selBytes = 0;
+	cub::DeviceRadixSort::SortKeys(NULL, sortBytes, (const unsigned long long*)NULL, (unsigned long long*)NULL, nnz, 0, 64, s);
+	cub::DeviceSelect::Unique(NULL, selBytes, (const unsigned long long*)NULL, (unsigned long long*)NULL, (int*)NULL, nnz, s);
+	const size_t keyBytes = ((size_t)nnz * sizeof(unsigned long long) + 255) & ~(size_t)255;
+	size_t tempBytes = sortBytes > selBytes ? sortBytes : selBytes;
+	char* scratch = (char*)spgpuScratch(handle, 2 * keyBytes + 256 + tempBytes + 256);
+	if (!scratch)
+		return false;
+	unsigned long long* a = reinterpret_cast<unsigned long long*>(scratch);
+	unsigned long long* b = reinterpret_cast<unsigned long long*>(scratch + keyBytes);
+	int* count = reinterpret_cast<int*>(scratch + 2 * keyBytes);
+	void* temp = scratch + 2 * keyBytes + 256;
+	hdia_keys_kernel<<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(dCooRows, dCooCols, nnz, base, hackSize, a);
+	spgpu_count_launch(handle);
+	size_t tb = tempBytes;
+	cub::DeviceRadixSort::SortKeys(temp, tb, a, b, nnz, 0, 64, s);
+	tb = tempBytes;
+	cub::DeviceSelect::Unique(temp, tb, b, a, count, nnz, s);
+	*uniq = a;
+	*dCount = count;
+	return true;
+}
+
+/*
+ * Device twin of computeHdiaHackOffsetsFromCoo (blocking): fills dHackOffsets (hacks+1
+ * entries, unit: diagonals) and *allocationHeight = total number of hack-diagonals.
+ */
+extern "C" int spgpuHdiaHackOffsetsFromCooDevice(spgpuHandle_t handle, int* allocationHeight,
+	int* dHackOffsets, int hackSize, int rowsCount, int columnsCount, int nonZerosCount,
+	const int* dCooRowIndices, const int* dCooColsIndices, int cooBaseIndex)
+{
+	(void)columnsCount;
+	*allocationHeight = 0;
+	if (hackSize <= 0 || hackSize % 32)
+		return SPGPU_UNSUPPORTED;
+	cudaStream_t s = handle->currentStream;
+	const int hacks = (rowsCount + hackSize - 1) / hackSize;
+	if (nonZerosCount <= 0) {
+		if (cudaMemsetAsync(dHackOffsets, 0, (size_t)(hacks + 1) * sizeof(int), s) != cudaSuccess)
+			return SPGPU_UNSPECIFIED;
+		return cudaStreamSynchronize(s) == cudaSuccess ? SPGPU_SUCCESS : SPGPU_UNSPECIFIED;
+	}
+	unsigned long long* uniq;
+	int* dCount;
+	if (!hdia_unique_keys(handle, hackSize, nonZerosCount, dCooRowIndices, dCooColsIndices, cooBaseIndex, &uniq, &dCount))
+		return SPGPU_OUTOFMEMORY;
+	hdia_hack_offsets_kernel<<<spgpu_ceil_div(hacks + 1, 256), 256, 0, s>>>(uniq, dCount, hacks, dHackOffsets);
+	spgpu_count_launch(handle);
+	int count = 0;
+	cudaMemcpyAsync(&count, dCount, sizeof(int), cudaMemcpyDeviceToHost, s);
+	if (cudaStreamSynchronize(s) != cudaSuccess)
+		return SPGPU_UNSPECIFIED;
+	*allocationHeight = count;
+	/* dM has count*hackSize cells: refuse what the int-based ABI cannot address */
+	if ((long long)count * hackSize > 2147483647LL)
+		return SPGPU_UNSUPPORTED;
+	return SPGPU_SUCCESS;
+}
+
+template <typename T>
+static int coo_to_hdia_fill(spgpuHandle_t handle, T* dHdiaValues, int* dHdiaOffsets, const int* dHackOffsets,
+	int hackSize, int nnz, const int* dCooRows, const int* dCooCols, const T* dCooVals, int base)
+{
+	if (nnz <= 0)
+		return SPGPU_SUCCESS;
+	if (hackSize <= 0 || hackSize % 32)
+		return SPGPU_UNSUPPORTED;
+	cudaStream_t s = handle->currentStream;
+	unsigned long long* uniq;
+	int* dCount;
+	if (!hdia_unique_keys(handle, hackSize, nnz, dCooRows, dCooCols, base, &uniq, &dCount))
+		return SPGPU_OUTOFMEMORY;
+	/* at most nnz unique keys; the kernel stops at *dCount */
+	hdia_offsets_kernel<<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(uniq, dCount, dHdiaOffsets);
+	spgpu_count_launch(handle);
+	coo_to_hdia_scatter_kernel<T><<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(dCooRows, dCooCols, dCooVals, nnz, base,
+		hackSize, dHackOffsets, dHdiaOffsets, dHdiaValues);
+	spgpu_count_launch(handle);
+	return SPGPU_SUCCESS;
+}
+
+/*
+ * Device twin of cooToHdia (asynchronous): fills dHdiaOffsets (allocationHeight entries) and
+ * places the values; like the reference it leaves all other cells untouched, so the caller
+ * zero-fills dHdiaValues first (reference diaPerf.cpp:195-196).
+ */
+#define SPGPU_DEFINE_COO2HDIA(S, T)                                                      \
+	extern "C" int spgpu##S##cooToHdiaDevice(spgpuHandle_t handle, T* dHdiaValues,        \
+		int* dHdiaOffsets, const int* dHackOffsets, int hackSize, int rowsCount,          \
+		int columnsCount, int nonZerosCount, const int* dCooRowIndices,                   \
+		const int* dCooColsIndices, const T* dCooValues, int cooBaseIndex)                \
+	{                                                                                     \
+		(void)rowsCount; (void)columnsCount;                                              \
+		return coo_to_hdia_fill<T>(handle, dHdiaValues, dHdiaOffsets, dHackOffsets,       \
+			hackSize, nonZerosCount, dCooRowIndices, dCooColsIndices, dCooValues,         \
+			cooBaseIndex);                                                                \
+	}
+
+SPGPU_DEFINE_COO2HDIA(S, float)
+SPGPU_DEFINE_COO2HDIA(D, double)
+SPGPU_DEFINE_COO2HDIA(C, cuFloatComplex)
+SPGPU_DEFINE_COO2HDIA(Z, cuDoubleComplex)
