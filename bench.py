@@ -136,11 +136,21 @@ def build_workload(name, rank, world, device, n_override=None, global_columns=Fa
     elif name == "cfg2":
         n = n_override or 128
         A = DB.hdia_stencil27(n, device=device)
+        total_rows, halo = A.nrows, 0
+        if world > 1:
+            # row block of z-planes on x_ext = [halo | owned | halo]; the 27-point stencil reaches
+            # n*n + n + 1 entries, rounded up to whole hacks (mg.split_hdia's rules, on the device)
+            from spgpu_b200 import mg
+            halo = -(-(n * n + n + 1) // 32) * 32
+            lo, hi = mg.row_blocks(A.nrows, world, 32)[rank]
+            w["full"] = A
+            w["lo"], w["hi"] = lo, hi
+            A = DB.hdia_row_block(A, lo, hi, halo)
         hd = int(A.offsets.numel())
-        w.update(kind="hdia", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=0, x_len=A.ncols, sizeof=8,
-                 alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=A.nrows,
+        w.update(kind="hdia", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=halo, x_len=A.ncols, sizeof=8,
+                 alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=total_rows,
                  label=f"3-D 27-point stencil {n}^3, double HDIA hackSize 32 (BASELINE configs[1])")
-        # cells_in_range*8 + 4*#hack-diagonals + 4*(hacks+1) + x + z
+        # cells_in_range*8 + 4*#hack-diagonals + 4*(hacks+1) + x (owned + the two halo windows) + z
         w["bytes"] = A.cells_in_range * 8 + 4 * hd + 4 * int(A.hack_offsets.numel()) + 8 * A.ncols + 8 * A.nrows
     elif name == "cfg2dia":
         n = n_override or 128
@@ -222,7 +232,9 @@ def make_step(L, h, w, x_ext_ptr, z_ptr, y_ptr):
         dM, off, ho = A.values.data_ptr(), A.offsets.data_ptr(), A.hack_offsets.data_ptr()
 
         def step(r0=0, r1=w["rows"]):
-            fn(h, z_ptr, y_ptr or 0, a, dM, off, A.hack_size, ho, A.nrows, A.ncols, x_ext_ptr, b)
+            # rows [r0, r1): hacks from r0/hackSize on; column = row + offset, so x moves with the rows
+            fn(h, z_ptr + sz * r0, (y_ptr + sz * r0) if y_ptr else 0, a, dM, off, A.hack_size,
+               ho + 4 * (r0 // A.hack_size), r1 - r0, A.ncols - r0, x_ext_ptr + sz * r0, b)
     elif w["kind"] == "dia":
         fn = getattr(L, f"spgpu{s}diaspmv")
 
@@ -405,8 +417,10 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    if args.workload != "cfg5" and world > 1:
-        raise SystemExit("only cfg5 is row-sharded across GPUs; run the other workloads with --gpus 1")
+    if args.workload not in ("cfg5", "cfg2") and world > 1:
+        raise SystemExit("only cfg5 (HELL) and cfg2 (HDIA) are row-sharded across GPUs; run the other workloads with --gpus 1")
+    if args.workload == "cfg2" and world > 1 and args.halo == "allgather":
+        args.halo = "fused"             # HDIA addresses x relative to the row: there is no global-column mode
 
     L = capi.lib()
     h = ctypes.c_void_p()
@@ -451,11 +465,16 @@ def main():
         peer = mg.PeerHalo(L, h, rank, world, x_ptr, ext_len, halo)
 
     def make_fused(z_ptr_):
-        if peer is None or args.halo != "fused" or w["kind"] != "hell" or w["sym"] != "D":
+        if peer is None or args.halo != "fused" or w["kind"] not in ("hell", "hdia") or w["sym"] != "D":
             return None
         A = w["A"]
         plo, phi, myf, pflo, pfhi = peer.fused_pointers()
-        T = capi.TYPES["D"]
+        if w["kind"] == "hdia":
+            def fused_hdia(seq):
+                L.spgpuDhdiaspmvHalo(h, z_ptr_, 0, 1.0, A.values.data_ptr(), A.offsets.data_ptr(), A.hack_size,
+                                     A.hack_offsets.data_ptr(), rows, A.ncols, x_ptr, 0.0, halo,
+                                     plo, phi, myf, pflo, pfhi, seq)
+            return fused_hdia
 
         def fused(seq):
             L.spgpuDhellspmvHalo(h, z_ptr_, 0, 1.0, A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
@@ -541,6 +560,28 @@ def main():
         del Ag, z_ref, x_full
         if rank == 0:
             print(f"verify: partitioned SpMV == global-column SpMV on every rank: {verified}", file=sys.stderr, flush=True)
+
+    if args.verify and args.workload == "cfg2" and world > 1:
+        # each rank multiplies the FULL matrix by the all-gathered x and compares its own rows
+        Af = w["full"]
+        one_step()
+        barrier()
+        own = x_ext[halo:halo + rows].contiguous()
+        parts = [torch.empty(hi_ - lo_, dtype=torch.float64, device=device) for lo_, hi_ in mg.row_blocks(Af.nrows, world, 32)]
+        dist.all_gather(parts, own)
+        x_full = torch.cat(parts)
+        z_ref = torch.full((Af.nrows,), float("nan"), dtype=torch.float64, device=device)
+        T = capi.TYPES["D"]
+        L.spgpuDhdiaspmv(h, z_ref.data_ptr(), 0, T.scalar(1.0), Af.values.data_ptr(), Af.offsets.data_ptr(), 32,
+                         Af.hack_offsets.data_ptr(), Af.nrows, Af.ncols, x_full.data_ptr(), T.scalar(0.0))
+        torch.cuda.synchronize()
+        ok = torch.tensor([1.0 if torch.equal(z, z_ref[w["lo"]:w["hi"]]) else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        verified = bool(ok.item() == 1.0)
+        del z_ref, x_full, parts
+        if rank == 0:
+            print(f"verify: partitioned HDIA SpMV == full-matrix SpMV rows on every rank: {verified}", file=sys.stderr, flush=True)
+    w.pop("full", None)
 
     # ---------------- device-resident timing ------------------------------------
     sampler = ClockSampler(local_rank)

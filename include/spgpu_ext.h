@@ -211,6 +211,18 @@ void spgpuDhellspmvHaloDot(spgpuHandle_t handle, __device double* z, const __dev
 	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, __device double* dRes);
 
 /*
+ * HDIA twin of spgpuDhellspmvHalo (same halo protocol, same flag words): the row block is in
+ * HDIA layout with its diagonal offsets addressing xExt = [halo | owned | halo], i.e. global
+ * offset + haloN, and cols = rows + 2*haloN (what mg.split_hdia / device_build.hdia_row_block
+ * produce).  Arguments up to beta as spgpuDhdiaspmv (reference hdia.h:38-142).
+ */
+void spgpuDhdiaspmvHalo(spgpuHandle_t handle, __device double* z, const __device double* y, double alpha,
+	const __device double* dM, const __device int* offsets, int hackSize, const __device int* hackOffsets,
+	int rows, int cols, __device double* xExt, double beta, int haloN,
+	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq);
+
+/*
  * In-place sum all-reduce of ONE double over NVLink peer memory (latency-bound payload:
  * one round of remote 16-byte stores + local polling instead of an NCCL launch).
  * tables[r] = pointer (peer pointer for r != myRank) to rank r's zero-initialised table of

@@ -8,6 +8,7 @@
 #include "launch.cuh"
 #include "reduce_common.cuh"
 #include "spmv_hell_body.cuh"
+#include "spmv_hdia_body.cuh"
 
 /* ---- z = b*y + a*x with a, b formed from device-resident scalars ----------- */
 
@@ -389,7 +390,7 @@ extern "C" void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned
 	spgpu_count_launch(handle);
 }
 
-/* ---- HELL SpMV fused with the halo exchange: ONE kernel per partitioned SpMV ---------- */
+/* ---- HELL / HDIA SpMV fused with the halo exchange: ONE kernel per partitioned SpMV ---- */
 
 struct HaloArgs {
 	double* dstLo; const double* srcLo;      /* my first n owned entries -> lower neighbour's upper halo */
@@ -428,9 +429,36 @@ __device__ __forceinline__ void cta_dot_partial(double contrib, double* ctaParti
 		ctaPartials[slot] = (ws[0] + ws[1]) + (ws[2] + ws[3]);
 }
 
-template <int UNROLL, int HACK, int MINB, bool DOT>
+/* what a row block of the fused kernel multiplies: the HELL or the HDIA warp body */
+template <int UNROLL, int HACK>
+struct HellRowBody {
+	HellArgs<double> a;
+	__device__ __forceinline__ int rows() const { return a.rows; }
+	__device__ __forceinline__ const double* x() const { return a.x; }
+	__device__ __forceinline__ double run(unsigned warpRow) const
+	{
+		double zval;
+		hell_warp_rows_value<double, UNROLL, HACK>(a, warpRow, zval);
+		return zval;
+	}
+};
+
+template <int UNROLL, int HACK>
+struct HdiaRowBody {
+	HdiaArgs<double> a;
+	__device__ __forceinline__ int rows() const { return a.rows; }
+	__device__ __forceinline__ const double* x() const { return a.x; }
+	__device__ __forceinline__ double run(unsigned warpRow) const
+	{
+		double zval;
+		hdia_warp_rows_value<double, UNROLL, HACK, false>(a, warpRow, zval);
+		return zval;
+	}
+};
+
+template <typename Body, int MINB, bool DOT>
 __global__ void __launch_bounds__(128, MINB)
-dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx, int xOffset, double* __restrict__ ctaPartials)
+spmv_halo_kernel(const Body body, const HaloArgs hx, int xOffset, double* __restrict__ ctaPartials)
 {
 	if (blockIdx.x < (unsigned)hx.pushCtas) {
 		const bool toHi = (blockIdx.x & 1) != 0;
@@ -468,7 +496,7 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx, int xOffset,
 		}
 	} else {
 		const unsigned b = blockIdx.x - hx.pushCtas;
-		const unsigned rowBlocks = ((unsigned)a.rows + 127u) >> 7;
+		const unsigned rowBlocks = ((unsigned)body.rows() + 127u) >> 7;
 		const unsigned head = min((unsigned)hx.headBlocks, rowBlocks);
 		const unsigned tail = min((unsigned)hx.tailBlocks, rowBlocks - head);
 		const unsigned interior = rowBlocks - head - tail;
@@ -480,10 +508,9 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx, int xOffset,
 		const unsigned myRow = rb * 128u + threadIdx.x;
 		if (!needLo && !needHi) {
 			/* interior: no flags, no tickets -- exactly the plain kernel */
-			double zval;
-			hell_warp_rows_value<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u), zval);
+			const double zval = body.run(rb * 128u + (threadIdx.x & ~31u));
 			if (DOT)
-				cta_dot_partial(myRow < (unsigned)a.rows ? zval * __ldg(a.x + xOffset + myRow) : 0.0, ctaPartials, rb);
+				cta_dot_partial(myRow < (unsigned)body.rows() ? zval * __ldg(body.x() + xOffset + myRow) : 0.0, ctaPartials, rb);
 			return;
 		}
 		if (threadIdx.x == 0) {
@@ -491,10 +518,9 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx, int xOffset,
 			if (needHi && hx.myReadyHi) spin_until(hx.myReadyHi, hx.seq, hx.timeoutNs);
 		}
 		__syncthreads();
-		double zval;
-		hell_warp_rows_value<double, UNROLL, HACK>(a, rb * 128u + (threadIdx.x & ~31u), zval);
+		const double zval = body.run(rb * 128u + (threadIdx.x & ~31u));
 		if (DOT)
-			cta_dot_partial(myRow < (unsigned)a.rows ? zval * __ldg(a.x + xOffset + myRow) : 0.0, ctaPartials, rb);
+			cta_dot_partial(myRow < (unsigned)body.rows() ? zval * __ldg(body.x() + xOffset + myRow) : 0.0, ctaPartials, rb);
 		/* the last CTA that read a halo zone tells that neighbour its data has been consumed
 		 * (only the few boundary CTAs touch these counters) */
 		__syncthreads();
@@ -514,21 +540,15 @@ dhell_spmv_halo_kernel(const HellArgs<double> a, const HaloArgs hx, int xOffset,
 	}
 }
 
-static void dhell_spmv_halo_launch(spgpuHandle_t handle, double* z, const double* y, double alpha,
-	const double* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
-	int avgNnzPerRow, int rows, double* xExt, double beta, int baseIndex, int haloN,
-	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
-	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, double* ctaPartials)
+/* flag words (spgpu_ext.h): [0] ready-from-below [1] ready-from-above [2] ack-from-below [3] ack-from-above */
+static HaloArgs halo_args(spgpuHandle_t handle, double* xExt, int rows, int haloN, double* peerXLoUpperHalo,
+	double* peerXHiLowerHalo, unsigned* myFlags, unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq)
 {
 	SpgpuHandlePriv* h = spgpuPriv(handle);
-	const SpgpuTuning* t = spgpu_tuning(handle);
-	const HellArgs<double> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
-		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1, 0, NULL, NULL, 0 };
 	HaloArgs hx;
 	hx.dstLo = peerXLoUpperHalo; hx.srcLo = xExt + haloN;
 	hx.dstHi = peerXHiLowerHalo; hx.srcHi = xExt + rows;        /* last haloN owned entries */
 	hx.n = haloN;
-	/* flag words (spgpu_ext.h): [0] ready-from-below [1] ready-from-above [2] ack-from-below [3] ack-from-above */
 	hx.ackLo = peerFlagsLo ? myFlags + 2 : NULL;   hx.ackHi = peerFlagsHi ? myFlags + 3 : NULL;
 	hx.peerReadyLo = peerFlagsLo ? peerFlagsLo + 1 : NULL;  hx.peerReadyHi = peerFlagsHi ? peerFlagsHi + 0 : NULL;
 	hx.myReadyLo = peerFlagsLo ? myFlags + 0 : NULL;  hx.myReadyHi = peerFlagsHi ? myFlags + 1 : NULL;
@@ -540,18 +560,34 @@ static void dhell_spmv_halo_launch(spgpuHandle_t handle, double* z, const double
 	hx.headBlocks = peerFlagsLo ? (haloN + 127) / 128 : 0;
 	hx.tailBlocks = peerFlagsHi ? (haloN + 127) / 128 : 0;
 	hx.timeoutNs = 2000000000ull;
+	return hx;
+}
+
+static void dhell_spmv_halo_launch(spgpuHandle_t handle, double* z, const double* y, double alpha,
+	const double* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
+	int avgNnzPerRow, int rows, double* xExt, double beta, int baseIndex, int haloN,
+	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, double* ctaPartials)
+{
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const HellArgs<double> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
+		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1, 0, NULL, NULL, 0 };
+	const HaloArgs hx = halo_args(handle, xExt, rows, haloN, peerXLoUpperHalo, peerXHiLowerHalo, myFlags,
+		peerFlagsLo, peerFlagsHi, seq);
 	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
+	const HellRowBody<8, 32> b32 = { a };
+	const HellRowBody<8, 0> b0 = { a };
 	if (ctaPartials) {
 		if (hackSize == 32)
-			dhell_spmv_halo_kernel<8, 32, 10, true><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+			spmv_halo_kernel<HellRowBody<8, 32>, 10, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
 		else
-			dhell_spmv_halo_kernel<8, 0, 8, true><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+			spmv_halo_kernel<HellRowBody<8, 0>, 8, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
 	} else {
 		if (hackSize == 32)
-			dhell_spmv_halo_kernel<8, 32, 10, false><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+			spmv_halo_kernel<HellRowBody<8, 32>, 10, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
 		else
-			dhell_spmv_halo_kernel<8, 0, 8, false><<<grid, 128, 0, s>>>(a, hx, haloN, ctaPartials);
+			spmv_halo_kernel<HellRowBody<8, 0>, 8, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
 	}
 	spgpu_count_launch(handle);
 }
@@ -586,6 +622,33 @@ extern "C" void spgpuDhellspmvHaloDot(spgpuHandle_t handle, double* z, const dou
 	dhell_spmv_halo_launch(handle, z, NULL, 1.0, cM, rP, hackSize, hackOffsets, rS, avgNnzPerRow, rows, xExt,
 		0.0, baseIndex, haloN, peerXLoUpperHalo, peerXHiLowerHalo, myFlags, peerFlagsLo, peerFlagsHi, seq, partials);
 	spgpuDsumDev(handle, (int)rowBlocks, partials, dRes);
+}
+
+/*
+ * HDIA twin of spgpuDhellspmvHalo: z = alpha*A*xExt + beta*y for a row block in HDIA layout whose
+ * offsets address xExt = [halo | owned | halo] (mg.split_hdia: global offset + haloN, cols = the
+ * length of xExt), with the same halo protocol inside the launch.
+ */
+extern "C" void spgpuDhdiaspmvHalo(spgpuHandle_t handle, double* z, const double* y, double alpha,
+	const double* dM, const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols,
+	double* xExt, double beta, int haloN, double* peerXLoUpperHalo, double* peerXHiLowerHalo,
+	unsigned* myFlags, unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq)
+{
+	if (rows <= 0)
+		return;
+	const HdiaArgs<double> a = { z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta };
+	const HaloArgs hx = halo_args(handle, xExt, rows, haloN, peerXLoUpperHalo, peerXHiLowerHalo, myFlags,
+		peerFlagsLo, peerFlagsHi, seq);
+	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
+	cudaStream_t s = handle->currentStream;
+	if (hackSize == 32) {
+		const HdiaRowBody<9, 32> b = { a };
+		spmv_halo_kernel<HdiaRowBody<9, 32>, 8, false><<<grid, 128, 0, s>>>(b, hx, haloN, NULL);
+	} else {
+		const HdiaRowBody<9, 0> b = { a };
+		spmv_halo_kernel<HdiaRowBody<9, 0>, 8, false><<<grid, 128, 0, s>>>(b, hx, haloN, NULL);
+	}
+	spgpu_count_launch(handle);
 }
 
 /* ---- one-double sum all-reduce over NVLink peer memory ------------------------------- */

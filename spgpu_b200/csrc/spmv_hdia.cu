@@ -17,55 +17,9 @@
 #include <climits>
 #include "launch.cuh"
 #include "numeric.cuh"
+#include "spmv_hdia_body.cuh"
 #include "spmv_hdia_bulk.cuh"
 #include "spmv_hdia_slab.cuh"
-
-/*
- * HACK > 0: hackSize known at compile time -> cell addresses are base +
- * immediate.  All index arithmetic is 32-bit: the in-range test
- * 0 <= row+off < cols is ONE unsigned compare; lanes past the last row get
- * cols = 0 and offsets past a hack's last diagonal get INT_MIN, so both fail
- * that same compare without extra predicates.  The matrix cells of a round are
- * loaded without waiting for the offsets (they all exist in the slab); only the
- * x gather and the FMA depend on the in-range test.
- */
-/* one round of the direct kernel: UNROLL diagonals starting at diagonal u0 of the 32 whose offsets
- * the warp holds in mineOff; GUARD = the round may run past the hack's last diagonal (n) */
-template <typename T, int UNROLL, bool GUARD, bool PREDICATED>
-__device__ __forceinline__ T hdia_round(T acc, const T* __restrict__ cp, long long hackSize, int mineOff,
-	int u0, int n, unsigned i, unsigned colsEff, const T* __restrict__ x)
-{
-	T a[UNROLL];
-	T xv[UNROLL];
-	bool on[UNROLL];
-	if (!PREDICATED) {
-#pragma unroll
-		for (int u = 0; u < UNROLL; ++u) {
-			a[u] = Num<T>::zero();
-			if (!GUARD || u0 + u < n)                 /* warp-uniform: cell exists */
-				a[u] = ld_stream(cp + u * hackSize);
-		}
-	}
-#pragma unroll
-	for (int u = 0; u < UNROLL; ++u) {
-		const int off = __shfl_sync(SPGPU_FULL_MASK, mineOff, u0 + u);
-		const int c = (int)i + off;
-		on[u] = (unsigned)c < colsEff && (!GUARD || u0 + u < n);   /* u0+u may pass lane 31 when UNROLL does not divide 32 */
-		xv[u] = Num<T>::zero();
-		if (PREDICATED)
-			a[u] = Num<T>::zero();
-		if (on[u]) {
-			xv[u] = ld_keep(x + c);
-			if (PREDICATED)                           /* cells outside the matrix are not read */
-				a[u] = ld_stream(cp + u * hackSize);
-		}
-	}
-#pragma unroll
-	for (int u = 0; u < UNROLL; ++u)
-		acc = PREDICATED ? Num<T>::fma(a[u], xv[u], acc)
-		                 : (on[u] ? Num<T>::fma(a[u], xv[u], acc) : acc);
-	return acc;
-}
 
 template <typename T, int UNROLL, int HACK, int MINB, bool PREDICATED = false, int BLOCK = 128>
 __global__ void __launch_bounds__(BLOCK, MINB)
@@ -74,39 +28,9 @@ hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ d
 	const int* __restrict__ hackOffsets, int rows, int cols,
 	const T* __restrict__ x, T beta)
 {
-	const int hackSize = HACK > 0 ? HACK : hackSizeRt;
-	const unsigned i = blockIdx.x * BLOCK + threadIdx.x;
-	const unsigned lane = threadIdx.x & 31;
-	const unsigned warpRow = i - lane;
-	if (warpRow >= (unsigned)rows)
-		return;
-	const bool live = i < (unsigned)rows;
-	const unsigned colsEff = live ? (unsigned)cols : 0u;
-	const bool useBeta = Num<T>::nonzero(beta);
-	T yv = Num<T>::zero();
-	if (useBeta && live)
-		yv = y[i];
-
-	const unsigned hack = warpRow / (unsigned)hackSize;
-	const int first = __ldg(hackOffsets + hack);
-	const int diags = __ldg(hackOffsets + hack + 1) - first;
-	const T* cell = dM + (long long)first * hackSize + (warpRow % (unsigned)hackSize) + lane;
-	const int* offs = offsets + first;
-	T acc = Num<T>::zero();
-
-	for (int j0 = 0; j0 < diags; j0 += 32) {
-		const int mineOff = (j0 + (int)lane < diags) ? ld_stream(offs + j0 + lane) : INT_MIN;
-		const int n = min(32, diags - j0);
-		int u0 = 0;
-		/* full rounds need no per-diagonal guard; the last, partial round does */
-		for (; u0 + UNROLL <= n; u0 += UNROLL)
-			acc = hdia_round<T, UNROLL, false, PREDICATED>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, x);
-		if (u0 < n)
-			acc = hdia_round<T, UNROLL, true, PREDICATED>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, x);
-	}
-
-	if (live)
-		z[i] = spmv_epilogue<T>(acc, alpha, beta, useBeta, yv);
+	const HdiaArgs<T> a = { z, y, alpha, dM, offsets, hackSizeRt, hackOffsets, rows, cols, x, beta };
+	T unused;
+	hdia_warp_rows_value<T, UNROLL, HACK, PREDICATED>(a, (blockIdx.x * BLOCK + threadIdx.x) & ~31u, unused);
 }
 
 /*

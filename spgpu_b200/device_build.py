@@ -290,6 +290,36 @@ def hdia_stencil27(n, dtype=torch.float64, hack=32, device="cuda") -> DevHdia:
     return DevHdia(values.view(-1), offsets, hoff, hack, n ** 3, n ** 3, nnz, in_range)
 
 
+def hdia_row_block(A: DevHdia, lo: int, hi: int, halo: int) -> DevHdia:
+    """Rows [lo, hi) of A (lo a multiple of the hack size) as a self-contained HDIA block on
+    x_ext = [halo | owned | halo]: torch twin of mg.split_hdia (same rules: hackOffsets re-based,
+    offsets + halo, cells whose global column is outside the matrix zeroed, non-zero cells outside
+    the window refused).  ncols of the result is the length of x_ext."""
+    hs = A.hack_size
+    assert lo % hs == 0 and 0 <= lo < hi <= A.nrows
+    h0, h1 = lo // hs, (hi + hs - 1) // hs
+    hoff = A.hack_offsets.to(torch.int64)
+    d0, d1 = int(hoff[h0].item()), int(hoff[h1].item())
+    values = A.values[d0 * hs:d1 * hs].clone().view(d1 - d0, hs)
+    offs = A.offsets[d0:d1].to(torch.int64)
+    local_hoff = (hoff[h0:h1 + 1] - d0).to(torch.int32)
+    dev = values.device
+    hack_of_diag = torch.repeat_interleave(torch.arange(h1 - h0, dtype=torch.int64, device=dev),
+                                           (hoff[h0 + 1:h1 + 1] - hoff[h0:h1]))
+    rows = hack_of_diag[:, None] * hs + torch.arange(hs, dtype=torch.int64, device=dev)[None, :]
+    cols = lo + rows + offs[:, None]
+    outside_matrix = (cols < 0) | (cols >= A.ncols) | (rows >= hi - lo)
+    values[outside_matrix] = 0
+    outside_window = ~outside_matrix & ((cols < lo - halo) | (cols >= hi + halo))
+    if bool((values[outside_window] != 0).any().item()):
+        raise ValueError("diagonal reaches outside the halo window")
+    values[outside_window] = 0
+    in_range = int((~outside_matrix).sum().item())
+    nnz = int((values != 0).sum().item())
+    return DevHdia(values.view(-1), (offs + halo).to(torch.int32), local_hoff, hs, hi - lo, hi - lo + 2 * halo,
+                   nnz, in_range)
+
+
 @dataclass
 class DevDia:
     values: torch.Tensor        # diags * pitch

@@ -145,6 +145,55 @@ def split_hell_allgather(hell, world: int, rank: int) -> LocalHell:
     return out
 
 
+@dataclass
+class LocalHdia:
+    """One rank's block in HDIA layout, diagonal offsets shifted so that row r of the
+    block reads x_ext[r + offset] (x_ext = [halo | owned | halo])."""
+    values: object
+    offsets: object
+    hack_offsets: object
+    hack_size: int
+    nrows: int
+    lo: int
+    hi: int
+    halo: int
+
+    @property
+    def ext_len(self):
+        return self.nrows + 2 * self.halo
+
+
+def split_hdia(hdia, world: int, rank: int, halo: int) -> LocalHdia:
+    """Cut rank's block out of a global host-side formats.Hdia.
+
+    HDIA addresses x relative to the row (column = row + offset), so a row block is the
+    same hacks with hackOffsets re-based by subtraction; adding `halo` to every offset
+    makes local row r read x_ext[r + offset + halo], and spgpu?hdiaspmv's own range test
+    0 <= r + offset' < cols with cols = ext_len then guards the window instead of the
+    matrix.  Cells whose GLOBAL column is outside [0, ncols) are zeroed in the copy (the
+    kernel would now see them inside the window; the conversions store 0 there anyway).
+    Raises if a non-zero cell needs a column outside [lo-halo, hi+halo)."""
+    hs = hdia.hack_size
+    lo, hi = row_blocks(hdia.nrows, world, hs)[rank]
+    h0, h1 = lo // hs, (hi + hs - 1) // hs
+    hoff = np.asarray(hdia.hack_offsets)
+    d0, d1 = int(hoff[h0]), int(hoff[h1])
+    values = np.array(hdia.values[d0 * hs:d1 * hs], copy=True).reshape(d1 - d0, hs)
+    offs = np.asarray(hdia.offsets[d0:d1]).astype(np.int64)
+    local_hoff = (hoff[h0:h1 + 1] - d0).astype(np.int32)
+    # local row of cell (d, j): first row of d's hack + j
+    hack_of_diag = np.repeat(np.arange(h1 - h0, dtype=np.int64), np.diff(local_hoff))
+    rows = hack_of_diag[:, None] * hs + np.arange(hs, dtype=np.int64)[None, :]
+    cols = lo + rows + offs[:, None]                              # global column of every cell
+    outside_matrix = (cols < 0) | (cols >= hdia.ncols) | (rows >= hi - lo)
+    values[outside_matrix] = 0
+    outside_window = ~outside_matrix & ((cols < lo - halo) | (cols >= hi + halo))
+    if (values[outside_window] != 0).any():
+        raise ValueError("diagonal reaches outside the halo window")
+    values[outside_window] = 0
+    return LocalHdia(values.reshape(-1), (offs + halo).astype(np.int32), local_hoff, hs, hi - lo, lo, hi, halo)
+
+
 class MgAllGatherSpmv:
     """z_owned = A_block * x with x all-gathered from every rank's (padded) owned slice."""
 
@@ -376,7 +425,8 @@ def raw_device_vector(L, n: int, dtype=torch.float64):
 # --------------------------------------------------------------------------- #
 
 class MgHellSpmv:
-    """z_owned = A_block * x_ext with halo exchange, one rank's view.
+    """z_owned = A_block * x_ext with halo exchange, one rank's view (HELL or HDIA blocks:
+    the format only lives inside local_spmv).
 
     local_spmv(z, x_ext, row0, row1) multiplies rows [row0, row1) of the block
     (used to split interior / boundary work); on the GPU it is a closure around

@@ -44,6 +44,90 @@ def test_split_hell_remaps_into_x_ext():
         mg.split_hell(hell, 2, 0, 8)             # halo narrower than the stencil reach
 
 
+def test_split_hdia_shifts_offsets_into_x_ext():
+    """each rank's HDIA block on x_ext = [halo | owned | halo] gives the rows of the global product,
+    including the first / last rank (window cells outside the matrix) and a rectangular matrix"""
+    for coo, halo in ((G.stencil3d_27pt(8), 64 + 8 + 1), (G.laplace2d_5pt(40, 23), 40),
+                      (G.random_coo(300, 340, (0, 6), 3, np.float64, 0), 340)):
+        hdia = F.coo_to_hdia(coo, 32)
+        x = G.random_vector(coo.ncols, np.float64, 1, -1, 1)
+        want = util.oracle_spmv("hdia", hdia, x, None, 1.0, 0.0)
+        for world in (1, 2, 3):
+            got = np.zeros(coo.nrows)
+            for r in range(world):
+                loc = mg.split_hdia(hdia, world, r, halo)
+                x_ext = np.zeros(loc.ext_len)                      # window entries outside the matrix stay 0
+                a, b = max(0, loc.lo - halo), min(coo.ncols, loc.hi + halo)
+                x_ext[a - (loc.lo - halo): b - (loc.lo - halo)] = x[a:b]
+                A = F.Hdia(loc.values, loc.offsets, loc.hack_offsets, 32, 0, loc.nrows, loc.ext_len)
+                got[loc.lo:loc.hi] = util.oracle_spmv("hdia", A, x_ext, None, 1.0, 0.0)
+            np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError):
+        mg.split_hdia(F.coo_to_hdia(G.stencil3d_27pt(8), 32), 2, 0, 8)
+
+
+def test_device_builder_row_block_equals_split_hdia():
+    """device_build.hdia_row_block (torch; what bench.py uses on the GPU) == mg.split_hdia (numpy)"""
+    from spgpu_b200 import device_build as DB
+    full = DB.hdia_stencil27(32, device="cpu")
+    host = F.Hdia(full.values.numpy(), full.offsets.numpy(), full.hack_offsets.numpy(), 32, int(full.offsets.numel()),
+                  full.nrows, full.ncols)
+    halo = 32 * 32 + 32 + 32
+    for world in (2, 4):
+        for r in range(world):
+            want = mg.split_hdia(host, world, r, halo)
+            got = DB.hdia_row_block(full, want.lo, want.hi, halo)
+            np.testing.assert_array_equal(got.values.numpy(), want.values)
+            np.testing.assert_array_equal(got.offsets.numpy(), want.offsets)
+            np.testing.assert_array_equal(got.hack_offsets.numpy(), want.hack_offsets)
+            assert got.nrows == want.nrows and got.ncols == want.ext_len
+
+
+def _hdia_worker(rank, world, port, n, overlap, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        halo = n * n + n + 1                                       # reach of the 27-point stencil
+        halo = -(-halo // 32) * 32
+        coo = G.stencil3d_27pt(n)
+        hdia = F.coo_to_hdia(coo, 32)
+        loc = mg.split_hdia(hdia, world, rank, halo)
+        x = G.random_vector(coo.nrows, np.float64, 12345)
+        x_ext = torch.zeros(loc.ext_len, dtype=torch.float64)
+        x_ext[halo:halo + loc.nrows] = torch.from_numpy(x[loc.lo:loc.hi])
+        z = torch.full((loc.nrows,), float("nan"), dtype=torch.float64)
+        O = util.oracle_lib()
+        T = util.TYPES["D"]
+
+        def local_spmv(zt, xt, r0, r1):
+            # rows [r0, r1) of the block: hacks from r0/32 on, x shifted by r0 (column = row + offset)
+            zz, xx = zt.numpy(), xt.numpy()
+            O.Dhdiaspmv(zz.ctypes.data + 8 * r0, None, T.scalar(1.0), util.ptr(loc.values), util.ptr(loc.offsets), 32,
+                        loc.hack_offsets.ctypes.data + 4 * (r0 // 32), r1 - r0, loc.ext_len - r0,
+                        xx.ctypes.data + 8 * r0, T.scalar(0.0))
+
+        op = mg.MgHellSpmv(rank, world, loc.nrows, halo, local_spmv,
+                           mg.HaloExchange(rank, world, halo, "gloo"), None, overlap=overlap)
+        for _ in range(2):
+            op.apply(z, x_ext)
+        np.save(os.path.join(out_dir, f"z{rank}.npy"), z.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,overlap", [(2, False), (2, True)])
+def test_partitioned_hdia_spmv_over_gloo(tmp_path, world, overlap):
+    n = 12
+    mp.spawn(_hdia_worker, args=(world, _free_port(), n, overlap, str(tmp_path)), nprocs=world, join=True)
+    coo = G.stencil3d_27pt(n)
+    hdia = F.coo_to_hdia(coo, 32)
+    x = G.random_vector(coo.nrows, np.float64, 12345)
+    want = util.oracle_spmv("hdia", hdia, x, None, 1.0, 0.0)
+    got = np.concatenate([np.load(tmp_path / f"z{r}.npy") for r in range(world)])
+    np.testing.assert_array_equal(got, want)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

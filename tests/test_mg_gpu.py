@@ -54,6 +54,56 @@ def test_spmv_fused_with_halo_exchange(ours, gpu_handle, seq):
     assert lo_f[0] == 0 and hi_f[1] == 0
 
 
+@pytest.mark.parametrize("seq", [1, 4])
+@pytest.mark.parametrize("rank", [0, 1, 2])
+def test_hdia_spmv_fused_with_halo_exchange(ours, gpu_handle, seq, rank):
+    """spgpuDhdiaspmvHalo on the first / a middle / the last block of a 27-point stencil split in three
+    (emulated neighbours): rows equal the global product, boundary entries land in the neighbours'
+    halo zones, flags carry seq; also equal to the plain spgpuDhdiaspmv on the same block bit for bit"""
+    import torch
+    n, world = 16, 3
+    coo = G.stencil3d_27pt(n)
+    hdia = F.coo_to_hdia(coo, 32)
+    halo = -(-(n * n + n + 1) // 32) * 32
+    loc = mg.split_hdia(hdia, world, rank, halo)
+    x = G.random_vector(coo.nrows, np.float64, 12345, -1, 1)
+    y = G.random_vector(coo.nrows, np.float64, 777, -1, 1)
+    x_ext = np.zeros(loc.ext_len)
+    a, b = max(0, loc.lo - halo), min(coo.nrows, loc.hi + halo)
+    x_ext[a - (loc.lo - halo): b - (loc.lo - halo)] = x[a:b]
+    want = util.oracle_spmv("hdia", hdia, x, y, 1.5, -0.5)[loc.lo:loc.hi]
+    dv, doff, dho = (util.to_dev(t) for t in (loc.values, loc.offsets, loc.hack_offsets))
+    dx, dy = util.to_dev(x_ext), util.to_dev(y[loc.lo:loc.hi])
+    dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+    has_lo, has_hi = rank > 0, rank < world - 1
+    my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    my_flags[0] = seq; my_flags[1] = seq
+    my_flags[2] = seq - 1; my_flags[3] = seq - 1
+    pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
+    ph = [torch.full((halo,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(2)]
+    ours.spgpuDhdiaspmvHalo(gpu_handle, dz.data_ptr(), dy.data_ptr(), 1.5, dv.data_ptr(), doff.data_ptr(), 32, dho.data_ptr(),
+                            loc.nrows, loc.ext_len, dx.data_ptr(), -0.5, halo,
+                            ph[0].data_ptr() if has_lo else 0, ph[1].data_ptr() if has_hi else 0, my_flags.data_ptr(),
+                            pf[0].data_ptr() if has_lo else 0, pf[1].data_ptr() if has_hi else 0, seq)
+    torch.cuda.synchronize()
+    scale = util.row_scale(coo, x, y, 1.5, -0.5)[loc.lo:loc.hi]
+    util.assert_rows_close(dz.cpu().numpy(), want, scale, "D", "fused hdia spmv+halo")
+    if has_lo:
+        np.testing.assert_array_equal(ph[0].cpu().numpy(), x_ext[halo:2 * halo])
+        f = pf[0].cpu().numpy()
+        assert f[1] == seq and f[3] == seq and f[0] == 0
+    if has_hi:
+        np.testing.assert_array_equal(ph[1].cpu().numpy(), x_ext[loc.nrows:loc.nrows + halo])
+        f = pf[1].cpu().numpy()
+        assert f[0] == seq and f[2] == seq and f[1] == 0
+    dz2 = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+    T = util.TYPES["D"]
+    ours.spgpuDhdiaspmv(gpu_handle, dz2.data_ptr(), dy.data_ptr(), T.scalar(1.5), dv.data_ptr(), doff.data_ptr(), 32,
+                        dho.data_ptr(), loc.nrows, loc.ext_len, dx.data_ptr(), T.scalar(-0.5))
+    torch.cuda.synchronize()
+    assert torch.equal(dz, dz2)
+
+
 def test_spmv_fused_without_neighbours_is_the_plain_kernel(ours, gpu_handle):
     import torch
     coo = G.laplace3d_7pt(20)
