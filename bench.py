@@ -208,6 +208,90 @@ def build_workload(name, rank, world, device, n_override=None, global_columns=Fa
     return w
 
 
+def build_mtx_workload(path, fmt, L, h, device, dtype_sym="D"):
+    """A MatrixMarket file run through the same harness: read with the C reader
+    (spgpuMm*, symmetric files unfolded like the reference's drivers), laid out ON THE DEVICE with the
+    ext builders (hell / ohell: CSR -> HELL, hdia: COO -> HDIA) or on the host (ell, dia: the
+    reference's own conversions).  Needs a handle: the builders are library calls."""
+    import torch
+    from spgpu_b200 import device_build as DB, formats as F, mmio
+    np_dt, t_dt, sz = {"S": (np.float32, torch.float32, 4), "D": (np.float64, torch.float64, 8)}[dtype_sym]
+    coo = mmio.read_coo(path, np_dt, L)
+    order = np.lexsort((coo.cols, coo.rows))                  # row-major, ascending columns
+    coo = F.Coo(coo.rows[order], coo.cols[order], coo.vals[order], coo.nrows, coo.ncols, 0)
+    R, C, nnz = coo.nrows, coo.ncols, coo.nnz
+    w = {"name": "mtx", "sym": dtype_sym, "rows": R, "nnz": nnz, "halo": 0, "x_len": C, "sizeof": sz, "alpha": 1.0,
+         "beta": 0.0, "flops_per_nnz": 2, "total_rows": R, "coo": coo,
+         "label": f"{os.path.basename(path)} ({R}x{C}, {nnz} nnz after unfolding) as {fmt.upper()} {'float' if dtype_sym == 'S' else 'double'}"}
+    d_cols = torch.from_numpy(coo.cols).to(device)
+    d_vals = torch.from_numpy(coo.vals).to(device)
+    avg = max(1, int(round(nnz / max(R, 1))))
+    if fmt in ("hell", "ohell"):
+        counts = np.bincount(coo.rows, minlength=R)
+        d_rowptr = torch.from_numpy(np.concatenate(([0], np.cumsum(counts))).astype(np.int32)).to(device)
+        hacks = (R + 31) // 32
+        rs = torch.zeros(R, dtype=torch.int32, device=device)
+        hoff = torch.zeros(hacks, dtype=torch.int32, device=device)
+        ridx = torch.zeros(R, dtype=torch.int32, device=device) if fmt == "ohell" else None
+        total = ctypes.c_longlong(0)
+        if fmt == "ohell":
+            rc = L.spgpuCsrToOhellLayoutDevice(h, R, d_rowptr.data_ptr(), 32, ridx.data_ptr(), rs.data_ptr(), hoff.data_ptr(),
+                                               ctypes.byref(total))
+        else:
+            rc = L.spgpuCsrToHellLayoutDevice(h, R, d_rowptr.data_ptr(), 32, rs.data_ptr(), hoff.data_ptr(), ctypes.byref(total))
+        assert rc == 0, f"HELL layout -> {rc}"
+        values = torch.full((max(total.value, 1),), float("nan"), dtype=t_dt, device=device)
+        indices = torch.full((max(total.value, 1),), DB.POISON_INDEX, dtype=torch.int32, device=device)
+        if fmt == "ohell":
+            getattr(L, f"spgpu{dtype_sym}csrToOhellDevice")(h, R, d_rowptr.data_ptr(), d_cols.data_ptr(), d_vals.data_ptr(), 0, 32,
+                                                            hoff.data_ptr(), ridx.data_ptr(), 0, values.data_ptr(), indices.data_ptr())
+        else:
+            getattr(L, f"spgpu{dtype_sym}csrToHellDevice")(h, R, d_rowptr.data_ptr(), d_cols.data_ptr(), d_vals.data_ptr(), 0, 32,
+                                                           hoff.data_ptr(), 0, values.data_ptr(), indices.data_ptr())
+        torch.cuda.synchronize()
+        A = DB.DevHell(values, indices, hoff, rs, 32, R, C, nnz, 0, avg, ridx)
+        w.update(kind="hell", A=A, stored_bytes=int(total.value) * (sz + 4),
+                 bytes=algorithmic_bytes_hell(nnz, R, hacks, C, sz) + (4 * R if fmt == "ohell" else 0))
+    elif fmt == "hdia":
+        d_rows = torch.from_numpy(coo.rows).to(device)
+        hacks = (R + 31) // 32
+        hoff = torch.zeros(hacks + 1, dtype=torch.int32, device=device)
+        height = ctypes.c_int(0)
+        rc = L.spgpuHdiaHackOffsetsFromCooDevice(h, ctypes.byref(height), hoff.data_ptr(), 32, R, C, nnz, d_rows.data_ptr(),
+                                                 d_cols.data_ptr(), 0)
+        assert rc == 0, f"HDIA layout -> {rc}"
+        values = torch.zeros(max(height.value * 32, 1), dtype=t_dt, device=device)
+        offsets = torch.zeros(max(height.value, 1), dtype=torch.int32, device=device)
+        rc = getattr(L, f"spgpu{dtype_sym}cooToHdiaDevice")(h, values.data_ptr(), offsets.data_ptr(), hoff.data_ptr(), 32, R, C, nnz,
+                                                            d_rows.data_ptr(), d_cols.data_ptr(), d_vals.data_ptr(), 0)
+        assert rc == 0
+        torch.cuda.synchronize()
+        # cells whose column is inside the matrix: per hack-diagonal, rows [row0, row0+32) cut by 0 <= row+off < C
+        off64 = offsets[:height.value].to(torch.int64)
+        row0 = torch.repeat_interleave(torch.arange(hacks, dtype=torch.int64, device=device), (hoff[1:] - hoff[:-1]).to(torch.int64)) * 32
+        lo = torch.maximum(row0, -off64)
+        hi = torch.minimum(torch.minimum(row0 + 32, torch.full_like(row0, R)), C - off64)
+        in_range = int(torch.clamp(hi - lo, min=0).sum().item())
+        A = DB.DevHdia(values, offsets, hoff, 32, R, C, nnz, in_range)
+        w.update(kind="hdia", A=A, stored_bytes=height.value * 32 * sz,
+                 bytes=in_range * sz + 4 * height.value + 4 * (hacks + 1) + sz * C + sz * R)
+    elif fmt == "ell":
+        ell = F.coo_to_ell(coo)
+        A = {"values": torch.from_numpy(ell.values).to(device), "indices": torch.from_numpy(ell.indices).to(device),
+             "rs": torch.from_numpy(ell.rs).to(device), "ell": ell, "avg": avg}
+        w.update(kind="ell", A=A, stored_bytes=ell.values.nbytes + ell.indices.nbytes, bytes=nnz * (sz + 4) + 4 * R + sz * C + sz * R)
+    elif fmt == "dia":
+        dia = F.coo_to_dia(coo)
+        r = np.arange(R, dtype=np.int64)[None, :] + dia.offsets.astype(np.int64)[:, None]
+        in_range = int(((r >= 0) & (r < C)).sum())
+        A = DB.DevDia(torch.from_numpy(dia.values).to(device), torch.from_numpy(dia.offsets).to(device), dia.pitch, dia.diags,
+                      R, C, nnz, in_range)
+        w.update(kind="dia", A=A, stored_bytes=dia.values.nbytes, bytes=in_range * sz + 4 * dia.diags + sz * C + sz * R)
+    else:
+        raise SystemExit(f"unknown format {fmt}")
+    return w
+
+
 def make_step(L, h, w, x_ext_ptr, z_ptr, y_ptr):
     """closure(row0, row1) launching the SpMV of rows [row0,row1) through the C ABI"""
     from spgpu_b200.capi import TYPES
@@ -247,7 +331,7 @@ def make_step(L, h, w, x_ext_ptr, z_ptr, y_ptr):
 
         def step(r0=0, r1=w["rows"]):
             fn(h, z_ptr, y_ptr or 0, a, A["values"].data_ptr(), A["indices"].data_ptr(), ell.pitch, ell.pitch,
-               A["rs"].data_ptr(), 0, 4, ell.maxnnz, ell.nrows, x_ext_ptr, b, 0)
+               A["rs"].data_ptr(), 0, A.get("avg", 4), ell.maxnnz, ell.nrows, x_ext_ptr, b, 0)
     else:
         raise ValueError(w["kind"])
     return step
@@ -347,6 +431,48 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
             "sample": sample + f"; OpenMP schedule(static) over rows, best of {repeats}"}, best
 
 
+def cpu_baseline_mtx(w, budget_s=20.0, repeats=5):
+    """The same OpenMP loops over the arrays of a --matrix workload (copied back to the host)."""
+    from tests import util
+    from spgpu_b200 import formats as F
+    O = util.oracle_lib()
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    O.dll.oracle_set_num_threads(avail)
+    A, kind = w["A"], w["kind"]
+    np_dt = np.float32 if w["sym"] == "S" else np.float64
+    host = lambda t: t.cpu().numpy()
+    ridx = None
+    if kind == "hell":
+        idx = host(A.indices)
+        M = F.Hell(host(A.values), np.where(idx < 0, 0, idx).astype(np.int32), host(A.hack_offsets), host(A.rs), 32, 0,
+                   A.nrows, A.ncols, 0)
+        ridx = host(A.ridx) if A.ridx is not None else None
+    elif kind == "hdia":
+        M = F.Hdia(host(A.values), host(A.offsets), host(A.hack_offsets), 32, int(A.offsets.numel()), A.nrows, A.ncols)
+    elif kind == "dia":
+        M = F.Dia(host(A.values), host(A.offsets), A.pitch, A.diags, A.nrows, A.ncols)
+    else:
+        M = A["ell"]
+    x = np.random.default_rng(12345).random(w["x_len"]).astype(np_dt)
+    kw = {"ridx": ridx} if ridx is not None else {}
+    call = lambda: util.oracle_spmv(kind, M, x, None, 1.0, 0.0, **kw)
+    call()
+    best, spent = float("inf"), 0.0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        call()
+        dt = time.perf_counter() - t0
+        best, spent = min(best, dt), spent + dt
+        if spent > budget_s:
+            break
+    return {"value": 2 * w["nnz"] / best / 1e9, "unit": "GFLOP/s", "cores": int(O.dll.oracle_num_threads()), "kind": "port",
+            "sample": f"the whole matrix ({w['rows']} rows, {w['nnz']} nnz), same {kind.upper()} arrays; OpenMP schedule(static) over rows, "
+                      f"best of {repeats}"}
+
+
 # --------------------------------------------------------------------------- #
 # main
 # --------------------------------------------------------------------------- #
@@ -359,6 +485,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg2dia", "cfg3", "cfg3o", "cfg4", "cfg5"])
     ap.add_argument("--size", type=int, default=None, help="override the grid size / row count (testing)")
+    ap.add_argument("--matrix", default=None, help="a MatrixMarket coordinate file to run instead of a synthetic workload (1 GPU)")
+    ap.add_argument("--format", default="hell", choices=["ell", "hell", "ohell", "dia", "hdia"], help="storage format for --matrix")
+    ap.add_argument("--precision", default="D", choices=["S", "D"], help="value type for --matrix")
     ap.add_argument("--halo", default="fused", choices=["fused", "push", "nccl", "allgather"],
                     help="multi-GPU halo exchange: fused = inside the SpMV kernel over NVLink peer pointers; "
                          "push = separate NVLink push kernel + flags; nccl = grouped send/recv; "
@@ -434,7 +563,12 @@ def main():
     stream = torch.cuda.ExternalStream(L.spgpuGetStream(h), device=device)
     torch.cuda.set_stream(stream)
 
-    w = build_workload(args.workload, rank, world, device, args.size, global_columns=(args.halo == "allgather"))
+    if args.matrix:
+        assert world == 1, "--matrix runs on one GPU"
+        w = build_mtx_workload(args.matrix, args.format, L, h, device, args.precision)
+        args.workload = "mtx"
+    else:
+        w = build_workload(args.workload, rank, world, device, args.size, global_columns=(args.halo == "allgather"))
     tdt = {"S": torch.float32, "D": torch.float64, "C": torch.complex64, "Z": torch.complex128}[w["sym"]]
     rows, halo = w["rows"], w["halo"]
     ext_len = w["x_len"]
@@ -848,8 +982,11 @@ def main():
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            res = cpu_baseline(args.workload)
-            cb = res[0] if res else None
+            if args.matrix:
+                cb = cpu_baseline_mtx(w)
+            else:
+                res = cpu_baseline(args.workload)
+                cb = res[0] if res else None
         except Exception as exc:          # a missing checker must not void the GPU measurement
             print(f"cpu_baseline leg failed: {exc!r}", file=sys.stderr, flush=True)
             cb = None

@@ -31,6 +31,13 @@ def test_library_exports_every_declared_symbol(ours):
         assert set(listed) >= declared - {"spgpuHandleStruct"}, sorted(declared - set(listed))
 
 
+def test_library_exports_the_matrixmarket_reader(ours):
+    declared = declared_symbols("spgpu_mm.h") - declared_symbols("spgpu.h")
+    assert declared == {"spgpuMmLoadProperties", "spgpuMmLoadMatrixToCoo", "spgpuMmUnfoldedSymmetricSize",
+                        "spgpuMmUnfoldSymmetric", "spgpuMmLoadDenseVector"}
+    assert not [n for n in declared if not ours.has(n)]
+
+
 def test_handle_struct_layout_is_the_reference_abi():
     """reference core.h:60-82: two pointers then nine ints, in this order"""
     S = capi.SpgpuHandleStruct

@@ -80,6 +80,33 @@ def ref_lib():
     return _ref
 
 
+MM_REF_PATH = os.path.join(os.path.dirname(REF_PATH), "libmm_ref.so")
+_mm_ref = False
+
+
+def mm_ref_lib():
+    """The reference's own MatrixMarket reader behind oracle/mm_ref_shim.cpp, if it was built."""
+    global _mm_ref
+    if _mm_ref is False:
+        _mm_ref = None
+        if os.path.exists(MM_REF_PATH):
+            d = ctypes.CDLL(MM_REF_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+            P, c_int, s = ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p
+            d.ref_mm_properties.restype, d.ref_mm_properties.argtypes = c_int, [s, ctypes.POINTER(c_int)]
+            for n in ("float", "double", "int"):
+                f = getattr(d, f"ref_mm_load_{n}")
+                f.restype, f.argtypes = c_int, [s, P, P, P]
+            d.ref_mm_load_pattern.restype, d.ref_mm_load_pattern.argtypes = c_int, [s, P, P]
+            for n in ("float", "double"):
+                f = getattr(d, f"ref_mm_unfolded_size_{n}")
+                f.restype, f.argtypes = c_int, [P, P, P, c_int]
+                f = getattr(d, f"ref_mm_unfold_{n}")
+                f.restype, f.argtypes = None, [P, P, P, P, P, P, c_int]
+            d.ref_mm_load_vector_double.restype, d.ref_mm_load_vector_double.argtypes = c_int, [s, P, c_int]
+            _mm_ref = d
+    return _mm_ref
+
+
 # ---------------------------------------------------------------- numpy side
 
 def sym_of(dtype):
