@@ -2,9 +2,9 @@
  * HDIA SpMV, per-warp slab variant for sm_100a (hdiaVariant = 6 / 7), hackSize 32.
  *
  * With hackSize 32 a warp owns one whole hack, and the cells of a hack are ONE contiguous
- * run of diags*32 elements at dM + hackOffsets[h]*32.  The direct kernel fetches that run 8
- * diagonals at a time into registers, so a warp walks ceil(diags/8) dependent rounds after
- * the hackOffsets -> offsets head of the chain (6 DRAM round trips for a 27-point stencil)
+ * run of diags*32 elements at dM + hackOffsets[h]*32.  The direct kernel fetches that run 8-9
+ * diagonals at a time into registers, so a warp walks ceil(diags/9) dependent rounds after
+ * the hackOffsets -> offsets head of the chain (5-6 DRAM round trips for a 27-point stencil)
  * and 32 resident warps only just cover the HBM latency.  Here lane 0 hands the whole run
  * to the bulk-copy engine (cp.async.bulk, SASS UBLKCP) as soon as hackOffsets[h] is known:
  * one instruction puts the warp's complete slab in flight (6.9 KB for 27 double diagonals),
@@ -17,6 +17,11 @@
  * Hacks with more than capD diagonals are walked capD diagonals at a time through the same
  * slice.  A slab always exists in full (HDIA allocates whole hacks), also for the last,
  * ragged hack.
+ *
+ * Measured on cfg2 (profiles/README.md): 98 us (16 gathers) / 114 us (32) against 78 us for
+ * the direct kernel with rounds of 9 -- 8 KB of shared memory per warp caps the SM at 24 warps
+ * and the carve-out leaves little L1 for the overlapping x windows, which costs more than
+ * the shorter chain wins.  Not the default; kept selectable (and tested) as the record of it.
  */
 #ifndef SPGPU_SPMV_HDIA_SLAB_CUH_
 #define SPGPU_SPMV_HDIA_SLAB_CUH_
@@ -120,13 +125,10 @@ static bool hdia_spmv_try_slab(spgpuHandle_t handle, T* z, const T* y, T alpha, 
 	if (capOverride > 0 && capOverride < capD)
 		capD = capOverride;
 	const size_t smem = (size_t)HDS_WARPS * capD * 32 * sizeof(T) + HDS_WARPS * sizeof(uint64_t);
-	static bool configured = false;
-	if (!configured) {
-		if (cudaFuncSetAttribute(hdia_spmv_slab_kernel<T, UX, MINB>,
-				cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess)
-			return false;
-		configured = true;
-	}
+	/* function attributes are per device: set on every call (a process may drive several GPUs) */
+	if (cudaFuncSetAttribute(hdia_spmv_slab_kernel<T, UX, MINB>,
+			cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+		return false;
 	hdia_spmv_slab_kernel<T, UX, MINB><<<spgpu_ceil_div(rows, HDS_WARPS * 32), HDS_WARPS * 32, smem, handle->currentStream>>>(
 		z, y, alpha, dM, offsets, hackOffsets, rows, cols, x, beta, capD);
 	spgpu_count_launch(handle);
