@@ -391,11 +391,25 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
         call = lambda: O.Dellspmv(util.ptr(z), None, T.scalar(1.0), util.ptr(ell.values), util.ptr(ell.indices), ell.pitch,
                                   ell.pitch, util.ptr(ell.rs), None, 4, ell.maxnnz, ell.nrows, util.ptr(x), T.scalar(0.0), 0)
         flops = 2 * nnz
-    elif workload_name in ("cfg3", "cfg4"):
+    elif workload_name == "cfg2dia":
+        A = DB.dia_stencil27(128, device=dev)
+        sample = f"the full 128^3 27-point DIA matrix ({A.nrows} rows, {A.nnz} nnz)"
+        vals, off = A.values.cpu().numpy(), A.offsets.cpu().numpy()
+        x = np.random.default_rng(12345).random(A.ncols)
+        z = np.zeros(A.nrows)
+        T = util.TYPES["D"]
+        call = lambda: O.Ddiaspmv(util.ptr(z), None, T.scalar(1.0), util.ptr(vals), util.ptr(off), A.pitch, A.nrows, A.ncols,
+                                  A.diags, util.ptr(x), T.scalar(0.0))
+        flops = 2 * A.nnz
+    elif workload_name in ("cfg3", "cfg3o", "cfg4"):
         # a quarter of the rows, generated by the same builders (device when there is one) and copied to the host
-        if workload_name == "cfg3":
+        ridx = None
+        if workload_name in ("cfg3", "cfg3o"):
             R, sym, dt, fl = 1 << 20, "S", np.float32, 2
             lens, cols, vals = DB.powerlaw_entries(R, device=dev)
+            if workload_name == "cfg3o":
+                lens, cols, vals, ridx = DB.sort_rows_by_length(lens, cols, vals)
+                ridx = ridx.cpu().numpy()
             alpha, beta = 1.0, 0.0
         else:
             R, sym, dt, fl = 500_000, "Z", np.complex128, 8
@@ -403,7 +417,7 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
             alpha, beta = 0.7 - 0.3j, -0.5 + 0.25j
         A = DB.hell_from_rows(lens, cols, vals, R)
         del lens, cols, vals
-        sample = f"{R} rows generated like the workload's ({A.nnz} nnz), HELL {sym}"
+        sample = f"{R} rows generated like the workload's ({A.nnz} nnz), {'OHELL' if ridx is not None else 'HELL'} {sym}"
         hv, hi, ho, rs = (t.cpu().numpy() for t in (A.values, A.indices, A.hack_offsets, A.rs))
         hi = np.where(hi < 0, 0, hi).astype(np.int32)            # builders poison the padding indices; never read
         rng = np.random.default_rng(12345)
@@ -412,7 +426,8 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
         z = np.zeros(R, dtype=dt)
         T = util.TYPES[sym]
         call = lambda: getattr(O, f"{sym}hellspmv")(util.ptr(z), util.ptr(y) if beta != 0 else None, T.scalar(alpha),
-                                                   util.ptr(hv), util.ptr(hi), 32, util.ptr(ho), util.ptr(rs), None,
+                                                   util.ptr(hv), util.ptr(hi), 32, util.ptr(ho), util.ptr(rs),
+                                                   util.ptr(ridx) if ridx is not None else None,
                                                    A.avg, R, util.ptr(x), T.scalar(beta), 0)
         flops = fl * A.nnz
     else:
@@ -516,14 +531,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        arm = args.workload if args.workload in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5") else "cfg5"
+        arm = args.workload if args.workload in ("cfg1", "cfg2", "cfg2dia", "cfg3", "cfg3o", "cfg4", "cfg5") else "cfg5"
         res = cpu_baseline(arm)
         cb, best = res
         # K timed steps of the bounded sample, W warm-ups (already warm after cpu_baseline)
         out = {"impl": "reference", "metric": "spmv_gflops", "value": cb["value"], "unit": "GFLOP/s",
                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": best * 1e3,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": {"cfg3": "f32", "cfg4": "c128"}.get(arm, "f64"),
+               "dtype": {"cfg3": "f32", "cfg3o": "f32", "cfg4": "c128"}.get(arm, "f64"),
                "data": "synthetic", "config": {"workload": arm, "arm": "host OpenMP SpMV over the same format"},
                "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

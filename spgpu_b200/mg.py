@@ -483,3 +483,15 @@ def global_dot(local_value: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(local_value, op=dist.ReduceOp.SUM, group=group)
     return local_value
+
+
+def global_amax(local_value: torch.Tensor, group=None) -> torch.Tensor:
+    """max over ranks of a 1-element tensor holding the local amax (amax reduces with max)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(local_value, op=dist.ReduceOp.MAX, group=group)
+    return local_value
+
+
+def global_nrm2(local_sum_of_squares: torch.Tensor, group=None) -> torch.Tensor:
+    """sqrt of the sum over ranks of the local sums of squares (spgpu?nrm2sqDev leaves them on the device)."""
+    return torch.sqrt(global_dot(local_sum_of_squares, group))

@@ -166,8 +166,10 @@ def _worker(rank, world, port, n, overlap, out_dir):
         # partitioned dot: z.z summed over ranks
         part = torch.tensor([float(np.dot(z.numpy(), z.numpy()))], dtype=torch.float64)
         mg.global_dot(part)
+        amax = mg.global_amax(torch.tensor([float(np.abs(z.numpy()).max())], dtype=torch.float64))
+        nrm2 = mg.global_nrm2(torch.tensor([float(np.dot(z.numpy(), z.numpy()))], dtype=torch.float64))
         np.save(os.path.join(out_dir, f"z{rank}.npy"), z.numpy())
-        np.save(os.path.join(out_dir, f"dot{rank}.npy"), part.numpy())
+        np.save(os.path.join(out_dir, f"dot{rank}.npy"), np.array([part.item(), amax.item(), nrm2.item()]))
     finally:
         dist.destroy_process_group()
 
@@ -183,9 +185,12 @@ def test_partitioned_spmv_over_gloo(tmp_path, world, overlap):
     want = util.oracle_spmv("hell", hell, x, None, 1.0, 0.0)
     got = np.concatenate([np.load(tmp_path / f"z{r}.npy") for r in range(world)])
     np.testing.assert_array_equal(got, want)
-    dots = [float(np.load(tmp_path / f"dot{r}.npy")[0]) for r in range(world)]
+    red = [np.load(tmp_path / f"dot{r}.npy") for r in range(world)]
+    dots = [float(r[0]) for r in red]
     assert all(d == dots[0] for d in dots)
     assert abs(dots[0] - float(np.dot(want, want))) <= 1e-12 * float(np.dot(want, want))
+    assert all(float(r[1]) == float(np.abs(want).max()) for r in red)                   # amax: max over ranks
+    assert all(abs(float(r[2]) - float(np.linalg.norm(want))) <= 1e-12 * float(np.linalg.norm(want)) for r in red)
 
 
 def _ag_worker(rank, world, port, out_dir):
