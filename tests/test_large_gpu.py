@@ -167,3 +167,115 @@ def test_cfg4_full_size_linearity(ours, gpu_handle):
     # |a| <= sqrt(2), |x| <= sqrt(2), 40 entries per row, coefficients (|0.5+2j| + 1.25) * |alpha|, plus |beta||w|
     bound = 1e-12 * (40 * 2 * (2.07 + 1.25) * abs(alpha) + abs(beta) * 1.5)
     assert float((z - want).abs().max().item()) <= bound
+
+
+def test_cfg2_full_size_device_coo_to_hdia_equals_the_analytic_builder(ours, gpu_handle):
+    """the 55.7 M entries of the 128^3 27-point stencil as shuffled COO -> spgpuHdiaHackOffsetsFromCooDevice +
+    spgpuDcooToHdiaDevice must give, bit for bit, the arrays of device_build.hdia_stencil27 (itself proven
+    equal to the reference's cooToHdia at sizes the host route can run)"""
+    import ctypes
+    import torch
+    from spgpu_b200 import device_build as DB
+    n, hack = 128, 32
+    A = DB.hdia_stencil27(n)
+    N = n ** 3
+    r = torch.arange(N, device="cuda", dtype=torch.int64)
+    x, y, z = r % n, (r // n) % n, r // (n * n)
+    rows, cols, vals = [], [], []
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                ok = (z + dz >= 0) & (z + dz < n) & (y + dy >= 0) & (y + dy < n) & (x + dx >= 0) & (x + dx < n)
+                rr = r[ok]
+                rows.append(rr.to(torch.int32))
+                cols.append((rr + (dz * n + dy) * n + dx).to(torch.int32))
+                vals.append(torch.full((rr.numel(),), 26.0 if (dz, dy, dx) == (0, 0, 0) else -1.0, dtype=torch.float64, device="cuda"))
+    rows, cols, vals = torch.cat(rows), torch.cat(cols), torch.cat(vals)
+    assert rows.numel() == A.nnz == 55742968                     # SURVEY 8: nnz of cfg2
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    perm = torch.randperm(rows.numel(), generator=g, device="cuda")
+    rows, cols, vals = rows[perm].contiguous(), cols[perm].contiguous(), vals[perm].contiguous()
+    del perm, r, x, y, z
+    hacks = N // hack
+    hoff = torch.full((hacks + 1,), -1, dtype=torch.int32, device="cuda")
+    height = ctypes.c_int(-1)
+    rc = ours.spgpuHdiaHackOffsetsFromCooDevice(gpu_handle, ctypes.byref(height), hoff.data_ptr(), hack, N, N, rows.numel(),
+                                                rows.data_ptr(), cols.data_ptr(), 0)
+    assert rc == 0
+    assert height.value == A.offsets.numel() == 1751088          # SURVEY 8: hack-diagonals of cfg2
+    assert torch.equal(hoff, A.hack_offsets)
+    hv = torch.zeros(height.value * hack, dtype=torch.float64, device="cuda")
+    off = torch.full((height.value,), 123456789, dtype=torch.int32, device="cuda")
+    rc = ours.spgpuDcooToHdiaDevice(gpu_handle, hv.data_ptr(), off.data_ptr(), hoff.data_ptr(), hack, N, N, rows.numel(),
+                                    rows.data_ptr(), cols.data_ptr(), vals.data_ptr(), 0)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(off, A.offsets)
+    assert torch.equal(hv, A.values)
+
+
+def test_cfg5_full_size_device_csr_to_hell_roundtrip(ours, gpu_handle):
+    """the 938 M entries of the 512^3 Laplacian as CSR -> spgpuCsrToHellLayoutDevice + spgpuDcsrToHellDevice must
+    reproduce rS, hackOffsets and every live slot of device_build.hell_laplace3d_7pt; the OHELL layout of the same
+    CSR multiplies to the same vector"""
+    import ctypes
+    import torch
+    from spgpu_b200 import device_build as DB
+    n = 512
+    A = DB.hell_laplace3d_7pt(n)
+    N = A.nrows
+    # CSR of the same matrix, read back out of the HELL arrays: entry k of row i sits at hackOffsets[i/32] + 32k + i%32
+    rs64 = A.rs.to(torch.int64)
+    rowptr64 = torch.zeros(N + 1, dtype=torch.int64, device="cuda")
+    torch.cumsum(rs64, 0, out=rowptr64[1:])
+    nnz = int(rowptr64[-1].item())
+    assert nnz == A.nnz == 937951232
+    csr_cols = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    csr_vals = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    rows = torch.arange(N, device="cuda", dtype=torch.int64)
+    at = A.hack_offsets.to(torch.int64)[rows // 32] + rows % 32
+    for k in range(7):
+        live = rs64 > k
+        src = (at + 32 * k)[live]
+        dst = (rowptr64[:-1] + k)[live]
+        csr_cols[dst] = A.indices[src]
+        csr_vals[dst] = A.values[src]
+        del src, dst, live
+    del rows, at
+    rowptr = rowptr64.to(torch.int32)
+    del rowptr64, rs64
+    hacks = N // 32
+    rs = torch.full((N,), -1, dtype=torch.int32, device="cuda")
+    hoff = torch.full((hacks,), -1, dtype=torch.int32, device="cuda")
+    total = ctypes.c_longlong(0)
+    rc = ours.spgpuCsrToHellLayoutDevice(gpu_handle, N, rowptr.data_ptr(), 32, rs.data_ptr(), hoff.data_ptr(), ctypes.byref(total))
+    assert rc == 0
+    assert torch.equal(rs, A.rs) and torch.equal(hoff, A.hack_offsets) and total.value == A.values.numel()
+    hv = torch.full((total.value,), float("nan"), dtype=torch.float64, device="cuda")
+    hi = torch.full((total.value,), DB.POISON_INDEX, dtype=torch.int32, device="cuda")
+    ours.spgpuDcsrToHellDevice(gpu_handle, N, rowptr.data_ptr(), csr_cols.data_ptr(), csr_vals.data_ptr(), 0, 32, hoff.data_ptr(), 0,
+                               hv.data_ptr(), hi.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(hi, A.indices)                            # padding poisoned the same way by both builders
+    assert torch.equal(hv.view(torch.int64), A.values.view(torch.int64))
+    del hv, hi
+    # OHELL of the same CSR: same product through rIdx
+    ridx = torch.empty(N, dtype=torch.int32, device="cuda")
+    rc = ours.spgpuCsrToOhellLayoutDevice(gpu_handle, N, rowptr.data_ptr(), 32, ridx.data_ptr(), rs.data_ptr(), hoff.data_ptr(),
+                                          ctypes.byref(total))
+    assert rc == 0 and int(rs[0].item()) == 7 and int(rs[-1].item()) == 4      # longest rows first, corners last
+    ov = torch.full((total.value,), float("nan"), dtype=torch.float64, device="cuda")
+    oi = torch.full((total.value,), DB.POISON_INDEX, dtype=torch.int32, device="cuda")
+    ours.spgpuDcsrToOhellDevice(gpu_handle, N, rowptr.data_ptr(), csr_cols.data_ptr(), csr_vals.data_ptr(), 0, 32, hoff.data_ptr(),
+                                ridx.data_ptr(), 0, ov.data_ptr(), oi.data_ptr())
+    del csr_cols, csr_vals
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    x = torch.rand(N, generator=g, device="cuda", dtype=torch.float64)
+    z0 = torch.empty(N, dtype=torch.float64, device="cuda")
+    z1 = torch.full((N,), float("nan"), dtype=torch.float64, device="cuda")
+    _hell(ours, gpu_handle, "D", A, x, z0)
+    O = DB.DevHell(ov, oi, hoff, rs, 32, N, N, nnz, 0, 7, ridx)
+    _hell(ours, gpu_handle, "D", O, x, z1, ridx=ridx)
+    torch.cuda.synchronize()
+    # same 7 products per row, possibly summed in another order: |dz| <= 1e-12 * sum|a||x| <= 1e-12 * 12
+    assert float((z1 - z0).abs().max().item()) <= 1e-12 * 12
