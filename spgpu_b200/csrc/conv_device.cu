@@ -69,23 +69,72 @@ static int hack_layout_from_rs(spgpuHandle_t handle, int rows, int hackSize, con
 	return SPGPU_SUCCESS;
 }
 
-/* one warp per row: the row's entries are read coalesced and written to their HELL slots */
+/*
+ * CSR -> HELL placement.  One LANE per HELL row (HELL row `row` takes CSR row rIdx[row], or row
+ * itself when rIdx is NULL): for a given slot k the 32 lanes of a warp write 32 consecutive
+ * elements of the slot row -- whole 128/256-byte runs -- and each lane walks its own CSR row
+ * front to back, so its reads stay in the lines it already pulled into L1.  (One warp per row
+ * with the lanes across the entries, the obvious mapping, leaves 25 of 32 lanes idle on a
+ * 7-entry row and writes 8 bytes per 32-byte sector: 31 ms for the 512^3 Laplacian against
+ * what this kernel takes, profiles/README.md.)  Rows longer than LANE_DEPTH entries are finished
+ * by the whole warp striding over the rest, so a 4096-entry spike row does not serialise.
+ */
+#define CSR2HELL_LANE_DEPTH 64
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-csr_to_hell_scatter_kernel(const int* __restrict__ rowPtr, const int* __restrict__ cols,
+csr_to_hell_place_kernel(const int* __restrict__ rowPtr, const int* __restrict__ cols,
 	const T* __restrict__ vals, int rows, int csrBase, int hellBase, int hackSize,
-	const int* __restrict__ hackOffsets, T* __restrict__ hellValues, int* __restrict__ hellIndices)
+	const int* __restrict__ hackOffsets, const int* __restrict__ rIdx,
+	T* __restrict__ hellValues, int* __restrict__ hellIndices)
 {
-	const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	if (row >= rows)
+	if (row - lane >= rows)
 		return;
-	const int begin = rowPtr[row] - csrBase, end = rowPtr[row + 1] - csrBase;
-	const long long at = (long long)hackOffsets[row / hackSize] + row % hackSize;
-	for (int e = begin + lane; e < end; e += 32) {
-		const long long to = at + (long long)(e - begin) * hackSize;
-		hellValues[to] = vals[e];
-		hellIndices[to] = cols[e] - csrBase + hellBase;
+	const bool live = row < rows;
+	int begin = 0, n = 0;
+	long long at = 0;
+	if (live) {
+		const int src = rIdx ? rIdx[row] : (int)row;
+		begin = rowPtr[src] - csrBase;
+		n = rowPtr[src + 1] - csrBase - begin;
+		at = (long long)hackOffsets[row / hackSize] + row % hackSize;
+	}
+	const int mine = min(n, CSR2HELL_LANE_DEPTH);
+	const int deepest = __reduce_max_sync(SPGPU_FULL_MASK, mine);
+	for (int k0 = 0; k0 < deepest; k0 += 4) {
+		T v[4];
+		int c[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			if (k0 + u < mine) {
+				v[u] = vals[begin + k0 + u];
+				c[u] = cols[begin + k0 + u];
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			if (k0 + u < mine) {
+				const long long to = at + (long long)(k0 + u) * hackSize;
+				hellValues[to] = v[u];
+				hellIndices[to] = c[u] - csrBase + hellBase;
+			}
+		}
+	}
+	/* long rows: all 32 lanes on one row */
+	unsigned todo = __ballot_sync(SPGPU_FULL_MASK, n > CSR2HELL_LANE_DEPTH);
+	while (todo) {
+		const int r = __ffs(todo) - 1;
+		todo &= todo - 1;
+		const int rb = __shfl_sync(SPGPU_FULL_MASK, begin, r);
+		const int rn = __shfl_sync(SPGPU_FULL_MASK, n, r);
+		const long long rat = (long long)__shfl_sync(SPGPU_FULL_MASK, (unsigned long long)at, r);
+		for (int k = CSR2HELL_LANE_DEPTH + lane; k < rn; k += 32) {
+			const long long to = rat + (long long)k * hackSize;
+			hellValues[to] = vals[rb + k];
+			hellIndices[to] = cols[rb + k] - csrBase + hellBase;
+		}
 	}
 }
 
@@ -124,8 +173,8 @@ static void csr_to_hell_fill(spgpuHandle_t handle, int rows, const int* dRowPtr,
 {
 	if (rows <= 0)
 		return;
-	csr_to_hell_scatter_kernel<T><<<spgpu_ceil_div((long long)rows * 32, 256), 256, 0, handle->currentStream>>>(
-		dRowPtr, dCols, dVals, rows, csrBase, hellBase, hackSize, dHackOffsets, dHellValues, dHellIndices);
+	csr_to_hell_place_kernel<T><<<spgpu_ceil_div(rows, 256), 256, 0, handle->currentStream>>>(
+		dRowPtr, dCols, dVals, rows, csrBase, hellBase, hackSize, dHackOffsets, NULL, dHellValues, dHellIndices);
 	spgpu_count_launch(handle);
 }
 
@@ -174,28 +223,6 @@ ohell_unpack_kernel(const unsigned long long* __restrict__ keys, int rows, int* 
 	}
 }
 
-/* as csr_to_hell_scatter_kernel, but HELL row `row` takes CSR row rIdx[row] */
-template <typename T>
-__global__ void __launch_bounds__(256)
-csr_to_ohell_scatter_kernel(const int* __restrict__ rowPtr, const int* __restrict__ cols,
-	const T* __restrict__ vals, int rows, int csrBase, int hellBase, int hackSize,
-	const int* __restrict__ hackOffsets, const int* __restrict__ rIdx,
-	T* __restrict__ hellValues, int* __restrict__ hellIndices)
-{
-	const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int lane = threadIdx.x & 31;
-	if (row >= rows)
-		return;
-	const int src = rIdx[row];
-	const int begin = rowPtr[src] - csrBase, end = rowPtr[src + 1] - csrBase;
-	const long long at = (long long)hackOffsets[row / hackSize] + row % hackSize;
-	for (int e = begin + lane; e < end; e += 32) {
-		const long long to = at + (long long)(e - begin) * hackSize;
-		hellValues[to] = vals[e];
-		hellIndices[to] = cols[e] - csrBase + hellBase;
-	}
-}
-
 /*
  * Step 1 of CSR -> OHELL (blocking): dRidx[i] = CSR row stored as HELL row i (ellToOell's
  * order), dRs[i] = its length, dHackOffsets / *totalElements as for plain HELL.
@@ -240,7 +267,7 @@ extern "C" int spgpuCsrToOhellLayoutDevice(spgpuHandle_t handle, int rows, const
 	{                                                                                     \
 		if (rows <= 0)                                                                    \
 			return;                                                                       \
-		csr_to_ohell_scatter_kernel<T><<<spgpu_ceil_div((long long)rows * 32, 256), 256, 0, \
+		csr_to_hell_place_kernel<T><<<spgpu_ceil_div(rows, 256), 256, 0,                  \
 			handle->currentStream>>>(dRowPtr, dCols, dVals, rows, csrBase, hellBase,      \
 			hackSize, dHackOffsets, dRidx, dHellValues, dHellIndices);                    \
 		spgpu_count_launch(handle);                                                       \
