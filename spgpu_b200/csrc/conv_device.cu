@@ -284,35 +284,57 @@ SPGPU_DEFINE_CSR2OHELL(Z, cuDoubleComplex)
  * The reference collects, per hack, the set of diagonals its entries lie on in a std::map
  * (ascending), stores col-row of each as the hack's offsets and copies every value to
  * cell (hackOffsets[h] + position of its diagonal, row % hackSize).  Equivalent, in
- * parallel: the sorted, de-duplicated list of 64-bit keys (hack << 32 | biased diagonal) IS
- * the offsets array (low words) in storage order, hackOffsets[h] is the lower bound of
- * (h << 32) in that list, and an entry's diagonal slot is found by binary search inside its
+ * parallel: the sorted, de-duplicated list of keys (hack << diagBits | diagonal + rows - 1) IS
+ * the offsets array (low bits) in storage order, hackOffsets[h] is the lower bound of
+ * (h << diagBits) in that list, and an entry's diagonal slot is found by binary search inside its
  * hack's segment.  Entries are independent, so the COO order does not matter; duplicates of
  * one (row, col) race (the reference keeps the last one in COO order).
  * ====================================================================================== */
 
-#define HDIA_DIAG_BIAS 0x80000000u
+/* key layout: the diagonal col-row lies in (-rows, cols), so diagonal + rows - 1 needs
+ * bit_width(rows + cols) bits; the radix sort then only visits the bits that can differ */
+struct HdiaKeyCode {
+	int diagBits;
+	int bias;          /* rows - 1 */
+	int keyBits;       /* diagBits + bit_width(hacks) */
+};
+
+static int bit_width_ll(long long v)
+{
+	int b = 0;
+	while (v > 0) { ++b; v >>= 1; }
+	return b > 0 ? b : 1;
+}
+
+static HdiaKeyCode hdia_key_code(int rows, int cols, int hackSize)
+{
+	HdiaKeyCode kc;
+	kc.diagBits = bit_width_ll((long long)rows + cols);
+	kc.bias = rows - 1;
+	kc.keyBits = kc.diagBits + bit_width_ll((rows + hackSize - 1) / hackSize);
+	return kc;
+}
 
 __global__ void __launch_bounds__(256)
 hdia_keys_kernel(const int* __restrict__ cooRows, const int* __restrict__ cooCols, int nnz, int base,
-	int hackSize, unsigned long long* __restrict__ keys)
+	int hackSize, HdiaKeyCode kc, unsigned long long* __restrict__ keys)
 {
 	const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (e < nnz) {
 		const int r = cooRows[e] - base, c = cooCols[e] - base;
-		keys[e] = ((unsigned long long)(unsigned)(r / hackSize) << 32) | ((unsigned)(c - r) + HDIA_DIAG_BIAS);
+		keys[e] = ((unsigned long long)(unsigned)(r / hackSize) << kc.diagBits) | (unsigned long long)(unsigned)(c - r + kc.bias);
 	}
 }
 
-/* hackOffsets[h] = number of unique keys below (h << 32), h = 0..hacks */
+/* hackOffsets[h] = number of unique keys below (h << diagBits), h = 0..hacks */
 __global__ void __launch_bounds__(256)
 hdia_hack_offsets_kernel(const unsigned long long* __restrict__ uniq, const int* __restrict__ count,
-	int hacks, int* __restrict__ hackOffsets)
+	int hacks, HdiaKeyCode kc, int* __restrict__ hackOffsets)
 {
 	const int h = blockIdx.x * blockDim.x + threadIdx.x;
 	if (h > hacks)
 		return;
-	const unsigned long long want = (unsigned long long)(unsigned)h << 32;
+	const unsigned long long want = (unsigned long long)(unsigned)h << kc.diagBits;
 	int lo = 0, hi = *count;
 	while (lo < hi) {
 		const int mid = (lo + hi) >> 1;
@@ -322,11 +344,12 @@ hdia_hack_offsets_kernel(const unsigned long long* __restrict__ uniq, const int*
 }
 
 __global__ void __launch_bounds__(256)
-hdia_offsets_kernel(const unsigned long long* __restrict__ uniq, const int* __restrict__ count, int* __restrict__ offsets)
+hdia_offsets_kernel(const unsigned long long* __restrict__ uniq, const int* __restrict__ count, HdiaKeyCode kc,
+	int* __restrict__ offsets)
 {
 	const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (d < *count)
-		offsets[d] = (int)((unsigned)(uniq[d] & 0xffffffffull) - HDIA_DIAG_BIAS);
+		offsets[d] = (int)(uniq[d] & ((1ull << kc.diagBits) - 1ull)) - kc.bias;
 }
 
 template <typename T>
@@ -350,12 +373,12 @@ coo_to_hdia_scatter_kernel(const int* __restrict__ cooRows, const int* __restric
 
 /* sorted unique (hack, diagonal) keys of the COO entries into handle scratch; returns the
  * device pointers (valid until the next scratch user) or NULL on allocation failure */
-static bool hdia_unique_keys(spgpuHandle_t handle, int hackSize, int nnz, const int* dCooRows,
+static bool hdia_unique_keys(spgpuHandle_t handle, int hackSize, HdiaKeyCode kc, int nnz, const int* dCooRows,
 	const int* dCooCols, int base, unsigned long long** uniq, int** dCount)
 {
 	cudaStream_t s = handle->currentStream;
 	size_t sortBytes = 0, selBytes = 0;
-	cub::DeviceRadixSort::SortKeys(NULL, sortBytes, (const unsigned long long*)NULL, (unsigned long long*)NULL, nnz, 0, 64, s);
+	cub::DeviceRadixSort::SortKeys(NULL, sortBytes, (const unsigned long long*)NULL, (unsigned long long*)NULL, nnz, 0, kc.keyBits, s);
 	cub::DeviceSelect::Unique(NULL, selBytes, (const unsigned long long*)NULL, (unsigned long long*)NULL, (int*)NULL, nnz, s);
 	const size_t keyBytes = ((size_t)nnz * sizeof(unsigned long long) + 255) & ~(size_t)255;
 	size_t tempBytes = sortBytes > selBytes ? sortBytes : selBytes;
@@ -366,10 +389,10 @@ static bool hdia_unique_keys(spgpuHandle_t handle, int hackSize, int nnz, const 
 	unsigned long long* b = reinterpret_cast<unsigned long long*>(scratch + keyBytes);
 	int* count = reinterpret_cast<int*>(scratch + 2 * keyBytes);
 	void* temp = scratch + 2 * keyBytes + 256;
-	hdia_keys_kernel<<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(dCooRows, dCooCols, nnz, base, hackSize, a);
+	hdia_keys_kernel<<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(dCooRows, dCooCols, nnz, base, hackSize, kc, a);
 	spgpu_count_launch(handle);
 	size_t tb = tempBytes;
-	cub::DeviceRadixSort::SortKeys(temp, tb, a, b, nnz, 0, 64, s);
+	cub::DeviceRadixSort::SortKeys(temp, tb, a, b, nnz, 0, kc.keyBits, s);
 	tb = tempBytes;
 	cub::DeviceSelect::Unique(temp, tb, b, a, count, nnz, s);
 	*uniq = a;
@@ -385,7 +408,6 @@ extern "C" int spgpuHdiaHackOffsetsFromCooDevice(spgpuHandle_t handle, int* allo
 	int* dHackOffsets, int hackSize, int rowsCount, int columnsCount, int nonZerosCount,
 	const int* dCooRowIndices, const int* dCooColsIndices, int cooBaseIndex)
 {
-	(void)columnsCount;
 	*allocationHeight = 0;
 	if (hackSize <= 0 || hackSize % 32)
 		return SPGPU_UNSUPPORTED;
@@ -398,9 +420,10 @@ extern "C" int spgpuHdiaHackOffsetsFromCooDevice(spgpuHandle_t handle, int* allo
 	}
 	unsigned long long* uniq;
 	int* dCount;
-	if (!hdia_unique_keys(handle, hackSize, nonZerosCount, dCooRowIndices, dCooColsIndices, cooBaseIndex, &uniq, &dCount))
+	const HdiaKeyCode kc = hdia_key_code(rowsCount, columnsCount, hackSize);
+	if (!hdia_unique_keys(handle, hackSize, kc, nonZerosCount, dCooRowIndices, dCooColsIndices, cooBaseIndex, &uniq, &dCount))
 		return SPGPU_OUTOFMEMORY;
-	hdia_hack_offsets_kernel<<<spgpu_ceil_div(hacks + 1, 256), 256, 0, s>>>(uniq, dCount, hacks, dHackOffsets);
+	hdia_hack_offsets_kernel<<<spgpu_ceil_div(hacks + 1, 256), 256, 0, s>>>(uniq, dCount, hacks, kc, dHackOffsets);
 	spgpu_count_launch(handle);
 	int count = 0;
 	cudaMemcpyAsync(&count, dCount, sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -415,7 +438,7 @@ extern "C" int spgpuHdiaHackOffsetsFromCooDevice(spgpuHandle_t handle, int* allo
 
 template <typename T>
 static int coo_to_hdia_fill(spgpuHandle_t handle, T* dHdiaValues, int* dHdiaOffsets, const int* dHackOffsets,
-	int hackSize, int nnz, const int* dCooRows, const int* dCooCols, const T* dCooVals, int base)
+	int hackSize, int rows, int cols, int nnz, const int* dCooRows, const int* dCooCols, const T* dCooVals, int base)
 {
 	if (nnz <= 0)
 		return SPGPU_SUCCESS;
@@ -424,10 +447,11 @@ static int coo_to_hdia_fill(spgpuHandle_t handle, T* dHdiaValues, int* dHdiaOffs
 	cudaStream_t s = handle->currentStream;
 	unsigned long long* uniq;
 	int* dCount;
-	if (!hdia_unique_keys(handle, hackSize, nnz, dCooRows, dCooCols, base, &uniq, &dCount))
+	const HdiaKeyCode kc = hdia_key_code(rows, cols, hackSize);
+	if (!hdia_unique_keys(handle, hackSize, kc, nnz, dCooRows, dCooCols, base, &uniq, &dCount))
 		return SPGPU_OUTOFMEMORY;
 	/* at most nnz unique keys; the kernel stops at *dCount */
-	hdia_offsets_kernel<<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(uniq, dCount, dHdiaOffsets);
+	hdia_offsets_kernel<<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(uniq, dCount, kc, dHdiaOffsets);
 	spgpu_count_launch(handle);
 	coo_to_hdia_scatter_kernel<T><<<spgpu_ceil_div(nnz, 256), 256, 0, s>>>(dCooRows, dCooCols, dCooVals, nnz, base,
 		hackSize, dHackOffsets, dHdiaOffsets, dHdiaValues);
@@ -446,10 +470,9 @@ static int coo_to_hdia_fill(spgpuHandle_t handle, T* dHdiaValues, int* dHdiaOffs
 		int columnsCount, int nonZerosCount, const int* dCooRowIndices,                   \
 		const int* dCooColsIndices, const T* dCooValues, int cooBaseIndex)                \
 	{                                                                                     \
-		(void)rowsCount; (void)columnsCount;                                              \
 		return coo_to_hdia_fill<T>(handle, dHdiaValues, dHdiaOffsets, dHackOffsets,       \
-			hackSize, nonZerosCount, dCooRowIndices, dCooColsIndices, dCooValues,         \
-			cooBaseIndex);                                                                \
+			hackSize, rowsCount, columnsCount, nonZerosCount, dCooRowIndices,             \
+			dCooColsIndices, dCooValues, cooBaseIndex);                                   \
 	}
 
 SPGPU_DEFINE_COO2HDIA(S, float)
