@@ -909,6 +909,31 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item()) / Ke
+        # the floor of this step: the same two transfers with no SpMV in between, both directions at once
+        t_in, t_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        xfer_ms = None
+        try:
+            def xfer():
+                t_in.wait_stream(stream); t_out.wait_stream(stream)
+                with torch.cuda.stream(t_in):
+                    own.copy_(hx, non_blocking=True)
+                with torch.cuda.stream(t_out):
+                    hz.copy_(z, non_blocking=True)
+                stream.wait_stream(t_in); stream.wait_stream(t_out)
+            xfer()
+            barrier()
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2.record(stream)
+            for _ in range(Ke):
+                xfer()
+            b2.record(stream)
+            barrier()
+            t2 = torch.tensor([a2.elapsed_time(b2)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            xfer_ms = float(t2.item()) / Ke
+        except Exception as exc:
+            print(f"transfer-only leg failed: {exc!r}", file=sys.stderr, flush=True)
         e2e_ok = None
         if pipelined:                                          # the pipelined result must be the plain one
             one_step()
@@ -918,6 +943,7 @@ def main():
                "h2d_bytes_per_step": int(hx.numel() * hx.element_size()) * world,
                "d2h_bytes_per_step": int(hz.numel() * hz.element_size()) * world,
                "ms_per_step": ms_e2e, "steps": Ke,
+               "transfers_only_ms": xfer_ms,     # the same H2D + D2H copies, concurrently, without the SpMV: the PCIe floor
                "what": ("x H2D from pinned memory, SpMV through the C ABI, z D2H to pinned memory, every step; matrix "
                         "resident" + ("; the three stages pipelined over 32 row chunks on three streams "
                                       "(banded matrix; on a partition the boundary chunks go first and the halo "
