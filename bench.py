@@ -683,7 +683,10 @@ def main():
     def elapsed(a, b, pairs):
         if pairs is None:
             return a.elapsed_time(b)
-        return float(sum(x.elapsed_time(y) for x, y in pairs))
+        per_step = [x.elapsed_time(y) for x, y in pairs]
+        if os.environ.get("SPGPU_BENCH_TRACE"):              # per-step times of this rank, for diagnosing rank skew
+            print(f"rank {rank} step ms: " + " ".join(f"{t:.4f}" for t in per_step), file=sys.stderr, flush=True)
+        return float(sum(per_step))
 
     # ---------------- optional multi-GPU self-check ------------------------------
     verified = None
