@@ -56,6 +56,13 @@ def row_blocks(nrows: int, world: int, align: int):
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
+def _check_block(lo: int, hi: int, halo: int, world: int):
+    """The exchange sends a rank's first / last `halo` OWNED entries to its neighbours: a block
+    must own at least that many rows (otherwise a halo would need entries of a rank two hops away)."""
+    if world > 1 and hi - lo < halo:
+        raise ValueError(f"row block [{lo}, {hi}) is smaller than the halo width {halo}: use fewer ranks or mode 'allgather'")
+
+
 @dataclass
 class LocalHell:
     """One rank's block in HELL layout with columns remapped into x_ext."""
@@ -436,6 +443,7 @@ class MgHellSpmv:
     def __init__(self, rank, world, nrows, halo, local_spmv, exchange: HaloExchange,
                  peer: PeerHalo | None = None, overlap=True, align=32, fused_spmv=None):
         self.rank, self.world, self.nrows, self.halo = rank, world, nrows, halo
+        _check_block(0, nrows, halo, world)
         self.local_spmv, self.ex, self.peer = local_spmv, exchange, peer
         # rows [0, head) and [tail, nrows) may touch a halo zone; both cuts sit on
         # hack boundaries so each piece is a valid HELL sub-matrix

@@ -42,6 +42,8 @@ def test_split_hell_remaps_into_x_ext():
         np.testing.assert_array_equal(got, want)
     with pytest.raises(ValueError):
         mg.split_hell(hell, 2, 0, 8)             # halo narrower than the stencil reach
+    with pytest.raises(ValueError):              # 32-row blocks cannot feed a 64-entry halo
+        mg.MgHellSpmv(3, 16, 32, 64, lambda *a: None, mg.HaloExchange(3, 16, 64, "gloo"))
 
 
 def test_split_hdia_shifts_offsets_into_x_ext():
