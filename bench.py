@@ -764,7 +764,9 @@ def main():
 
     # ---------------- the dominant kernel alone (roofline) ----------------------
     # per-launch duration of the full-block SpMV kernel on this rank's stream
-    ker_ms = []
+    # (all launches are queued before the one synchronise: a host-side delay between an event record and
+    # the launch behind it would otherwise be counted as kernel time)
+    ker_pairs = []
     for _ in range(min(K, 10)):
         if flush_l2:
             flush()
@@ -772,9 +774,9 @@ def main():
         a.record(stream)
         step()
         b.record(stream)
-        b.synchronize()
-        ker_ms.append(a.elapsed_time(b))
-    ker_ms = float(np.mean(ker_ms))
+        ker_pairs.append((a, b))
+    torch.cuda.synchronize()
+    ker_ms = float(np.mean([a.elapsed_time(b) for a, b in ker_pairs]))
     peak, peak_src = measured_peak()
     achieved = w["bytes"] / (ker_ms * 1e-3) / 1e9
     traffic = None
