@@ -222,6 +222,14 @@ void spgpuDhdiaspmvHalo(spgpuHandle_t handle, __device double* z, const __device
 	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
 	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq);
 
+/* HDIA twin of spgpuDhellspmvHaloDot (alpha = 1, beta = 0; dRes[0] = sum_i xExt[haloN+i]*z[i]).  With no
+ * neighbours (peer pointers NULL, haloN = 0, myFlags any 16-word device buffer) it is the single-GPU
+ * fused HDIA SpMV + dot. */
+void spgpuDhdiaspmvHaloDot(spgpuHandle_t handle, __device double* z, const __device double* dM,
+	const __device int* offsets, int hackSize, const __device int* hackOffsets, int rows, int cols,
+	__device double* xExt, int haloN, double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, __device double* dRes);
+
 /*
  * In-place sum all-reduce of ONE double over NVLink peer memory (latency-bound payload:
  * one round of remote 16-byte stores + local polling instead of an NCCL launch).

@@ -629,6 +629,32 @@ extern "C" void spgpuDhellspmvHaloDot(spgpuHandle_t handle, double* z, const dou
  * offsets address xExt = [halo | owned | halo] (mg.split_hdia: global offset + haloN, cols = the
  * length of xExt), with the same halo protocol inside the launch.
  */
+static void dhdia_spmv_halo_launch(spgpuHandle_t handle, double* z, const double* y, double alpha,
+	const double* dM, const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols,
+	double* xExt, double beta, int haloN, double* peerXLoUpperHalo, double* peerXHiLowerHalo,
+	unsigned* myFlags, unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, double* ctaPartials)
+{
+	const HdiaArgs<double> a = { z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta };
+	const HaloArgs hx = halo_args(handle, xExt, rows, haloN, peerXLoUpperHalo, peerXHiLowerHalo, myFlags,
+		peerFlagsLo, peerFlagsHi, seq);
+	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
+	cudaStream_t s = handle->currentStream;
+	const HdiaRowBody<9, 32> b32 = { a };
+	const HdiaRowBody<9, 0> b0 = { a };
+	if (ctaPartials) {
+		if (hackSize == 32)
+			spmv_halo_kernel<HdiaRowBody<9, 32>, 8, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		else
+			spmv_halo_kernel<HdiaRowBody<9, 0>, 8, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+	} else {
+		if (hackSize == 32)
+			spmv_halo_kernel<HdiaRowBody<9, 32>, 8, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		else
+			spmv_halo_kernel<HdiaRowBody<9, 0>, 8, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+	}
+	spgpu_count_launch(handle);
+}
+
 extern "C" void spgpuDhdiaspmvHalo(spgpuHandle_t handle, double* z, const double* y, double alpha,
 	const double* dM, const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols,
 	double* xExt, double beta, int haloN, double* peerXLoUpperHalo, double* peerXHiLowerHalo,
@@ -636,19 +662,28 @@ extern "C" void spgpuDhdiaspmvHalo(spgpuHandle_t handle, double* z, const double
 {
 	if (rows <= 0)
 		return;
-	const HdiaArgs<double> a = { z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta };
-	const HaloArgs hx = halo_args(handle, xExt, rows, haloN, peerXLoUpperHalo, peerXHiLowerHalo, myFlags,
-		peerFlagsLo, peerFlagsHi, seq);
-	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
-	cudaStream_t s = handle->currentStream;
-	if (hackSize == 32) {
-		const HdiaRowBody<9, 32> b = { a };
-		spmv_halo_kernel<HdiaRowBody<9, 32>, 8, false><<<grid, 128, 0, s>>>(b, hx, haloN, NULL);
-	} else {
-		const HdiaRowBody<9, 0> b = { a };
-		spmv_halo_kernel<HdiaRowBody<9, 0>, 8, false><<<grid, 128, 0, s>>>(b, hx, haloN, NULL);
+	dhdia_spmv_halo_launch(handle, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta, haloN,
+		peerXLoUpperHalo, peerXHiLowerHalo, myFlags, peerFlagsLo, peerFlagsHi, seq, NULL);
+}
+
+/* HDIA twin of spgpuDhellspmvHaloDot: z = A*xExt (+ halo exchange) and dRes[0] = sum_i xExt[haloN+i]*z[i].
+ * With no neighbours (both peer pointers NULL, haloN = 0) it is the single-GPU fused SpMV + dot. */
+extern "C" void spgpuDhdiaspmvHaloDot(spgpuHandle_t handle, double* z, const double* dM, const int* offsets,
+	int hackSize, const int* hackOffsets, int rows, int cols, double* xExt, int haloN,
+	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
+	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, double* dRes)
+{
+	if (rows <= 0) {
+		cudaMemsetAsync(dRes, 0, sizeof(double), handle->currentStream);
+		return;
 	}
-	spgpu_count_launch(handle);
+	const unsigned rowBlocks = spgpu_ceil_div(rows, 128);
+	double* partials = (double*)spgpuScratch(handle, (size_t)rowBlocks * sizeof(double));
+	if (!partials)
+		return;
+	dhdia_spmv_halo_launch(handle, z, NULL, 1.0, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, 0.0, haloN,
+		peerXLoUpperHalo, peerXHiLowerHalo, myFlags, peerFlagsLo, peerFlagsHi, seq, partials);
+	spgpuDsumDev(handle, (int)rowBlocks, partials, dRes);
 }
 
 /* ---- one-double sum all-reduce over NVLink peer memory ------------------------------- */

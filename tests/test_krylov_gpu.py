@@ -124,6 +124,50 @@ def test_cg_converges_like_the_cpu_recurrence(ours, gpu_handle, flavour):
     np.testing.assert_allclose(x_gpu, x, rtol=1e-9, atol=1e-12)
 
 
+def test_cg_on_hdia_with_the_fused_spmv_dot(ours, gpu_handle):
+    """the same device-scalar CG with the matrix in HDIA (27-point stencil, SPD): spgpuDhdiaspmvHaloDot with no
+    neighbours is the fused SpMV + p.Ap; residual history equals the CPU recurrence with the oracle"""
+    import torch
+    from spgpu_b200 import krylov
+    coo = G.stencil3d_27pt(12)
+    A = F.coo_to_hdia(coo, 32)
+    dv, doff, dho = (util.to_dev(t) for t in (A.values, A.offsets, A.hack_offsets))
+    n = coo.nrows
+    b = G.random_vector(n, np.float64, 9)
+    flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    seq = [0]
+
+    def apply_A_dot(z, x_ext, dres):
+        seq[0] += 1
+        ours.spgpuDhdiaspmvHaloDot(gpu_handle, z.data_ptr(), dv.data_ptr(), doff.data_ptr(), 32, dho.data_ptr(), n, n,
+                                   x_ext.data_ptr(), 0, 0, 0, flags.data_ptr(), 0, 0, seq[0], dres)
+
+    stream = torch.cuda.ExternalStream(ours.spgpuGetStream(gpu_handle))
+    with torch.cuda.stream(stream):
+        st = krylov.CgState(n, 0, "cuda")
+        cg = krylov.Cg(ours, gpu_handle, st, None, apply_A_dot)
+        rr0 = cg.start(util.to_dev(b))
+        hist = []
+        for _ in range(30):
+            cg.step_device()
+            hist.append(cg.residual_norm2())
+        torch.cuda.synchronize()
+        x_gpu = st.x.cpu().numpy()
+    x = np.zeros(n); r = b.copy(); p = b.copy(); rr = float(r @ r)
+    ref = []
+    for _ in range(30):
+        ap = util.oracle_spmv("hdia", A, p, None, 1.0, 0.0)
+        alpha = rr / float(p @ ap)
+        x += alpha * p; r -= alpha * ap
+        rr_new = float(r @ r)
+        p = r + (rr_new / rr) * p
+        rr = rr_new
+        ref.append(rr)
+    np.testing.assert_allclose(hist, ref, rtol=1e-8)
+    assert hist[-1] < 1e-6 * rr0
+    np.testing.assert_allclose(x_gpu, x, rtol=1e-9, atol=1e-12)
+
+
 def test_fused_cg_update(ours, gpu_handle):
     """x += a p ; r -= a Ap ; rr' = r.r in one pass, a = rr/pAp from device memory"""
     import torch
