@@ -148,7 +148,7 @@ def build_workload(name, rank, world, device, n_override=None, global_columns=Fa
             A = DB.hdia_row_block(A, lo, hi, halo)
         hd = int(A.offsets.numel())
         w.update(kind="hdia", sym="D", A=A, rows=A.nrows, nnz=A.nnz, halo=halo, x_len=A.ncols, sizeof=8,
-                 alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=total_rows,
+                 alpha=1.0, beta=0.0, flops_per_nnz=2, total_rows=total_rows, bandwidth=n * n + n + 1,
                  label=f"3-D 27-point stencil {n}^3, double HDIA hackSize 32 (BASELINE configs[1])")
         # cells_in_range*8 + 4*#hack-diagonals + 4*(hacks+1) + x (owned + the two halo windows) + z
         w["bytes"] = A.cells_in_range * 8 + 4 * hd + 4 * int(A.hack_offsets.numel()) + 8 * A.ncols + 8 * A.nrows
@@ -824,9 +824,10 @@ def main():
         hz = torch.empty(z.shape, dtype=z.dtype, pin_memory=True)
         Ke = max(2, min(K, 5))
         bw = w.get("bandwidth")
-        pipelined = world == 1 and w["kind"] == "hell" and bw is not None and rows >= (1 << 22)
+        pipelined = world == 1 and w["kind"] in ("hell", "hdia") and bw is not None and rows >= (1 << 20)
         if pipelined:
-            nchunk = 32
+            # at most 32 chunks, at least ~2 MB of x each (below that the per-chunk launches cost more than they hide)
+            nchunk = int(min(32, max(4, hx.numel() * hx.element_size() // (2 << 20))))
             unit = 32 * 1024                                   # chunk boundaries on hack boundaries
             csz = -(-rows // nchunk // unit) * unit
             assert csz >= bw
@@ -834,19 +835,32 @@ def main():
             s_in, s_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
             prev_done = torch.cuda.Event()
             prev_done.record(stream)
+            own_p, step_p = own, step
+            if w["kind"] == "hdia":
+                # HDIA addresses x relative to the row and the ABI has no row base: a sub-range call sees its rows
+                # as 0.., so diagonals reaching back before the chunk would fail the kernel's own range test.  The
+                # pipeline therefore runs on the row-block form of the SAME matrix (offsets + halo on
+                # x = [halo zeros | x | halo zeros], what mg.split_hdia produces for one rank): same cells, same
+                # order of operations, checked bit-equal to the one-shot product below.
+                from spgpu_b200 import device_build as DB
+                halo_p = -(-bw // 32) * 32
+                Ab = DB.hdia_row_block(w["A"], 0, rows, halo_p)
+                x_p = torch.zeros(rows + 2 * halo_p, dtype=own.dtype, device=device)
+                own_p = x_p[halo_p:halo_p + rows]
+                step_p = make_step(L, h, dict(w, A=Ab), x_p.data_ptr(), z.data_ptr(), y.data_ptr() if y is not None else 0)
 
             def e2e_step():
                 s_in.wait_event(prev_done)                     # x may be overwritten once the last SpMV is done
                 arrived = []
                 with torch.cuda.stream(s_in):
                     for (c0, c1) in bounds:
-                        own[c0:c1].copy_(hx[c0:c1], non_blocking=True)
+                        own_p[c0:c1].copy_(hx[c0:c1], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(s_in)
                         arrived.append(ev)
                 for c, (r0, r1) in enumerate(bounds):
                     stream.wait_event(arrived[min(c + 1, len(bounds) - 1)])   # needs x chunks c-1, c, c+1
-                    step(r0, r1)
+                    step_p(r0, r1)
                     done = torch.cuda.Event()
                     done.record(stream)
                     with torch.cuda.stream(s_out):
@@ -950,7 +964,7 @@ def main():
                "ms_per_step": ms_e2e, "steps": Ke,
                "transfers_only_ms": xfer_ms,     # the same H2D + D2H copies, concurrently, without the SpMV: the PCIe floor
                "what": ("x H2D from pinned memory, SpMV through the C ABI, z D2H to pinned memory, every step; matrix "
-                        "resident" + ("; the three stages pipelined over 32 row chunks on three streams "
+                        "resident" + ("; the three stages pipelined over row chunks on three streams "
                                       "(banded matrix; on a partition the boundary chunks go first and the halo "
                                       "planes are exchanged over NVLink as soon as they are on the device), result "
                                       "checked equal to the one-shot SpMV" if pipelined else ""))}
