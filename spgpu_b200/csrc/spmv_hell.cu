@@ -33,23 +33,12 @@ hell_spmv_kernel(const HellArgs<T> a)
 /*
  * Tail kernel of the split mode: persistent warps take (unit, chunk) items off the queue the
  * main kernel filled and walk slots [(c+1)T, (c+2)T) of the unit's 32 rows (row per lane,
- * coalesced), then add alpha * partial to z with an atomic (several chunks of one row finish
- * in any order; the main kernel has already stored beta*y + alpha*(first T slots)).
+ * coalesced), and leave one partial sum per lane in the item's slot of `partials`.  The fold
+ * kernel then adds a unit's partials to z IN CHUNK ORDER (the main kernel has already stored
+ * beta*y + alpha*(first T slots)), so the result does not depend on which warp took which
+ * item or when -- bit-reproducible from run to run, like every other kernel here (no
+ * floating-point atomics).
  */
-template <typename T> __device__ __forceinline__ void atomic_add_value(T* p, T v);
-template <> __device__ __forceinline__ void atomic_add_value<float>(float* p, float v) { atomicAdd(p, v); }
-template <> __device__ __forceinline__ void atomic_add_value<double>(double* p, double v) { atomicAdd(p, v); }
-template <> __device__ __forceinline__ void atomic_add_value<cuFloatComplex>(cuFloatComplex* p, cuFloatComplex v)
-{
-	atomicAdd(&p->x, v.x);
-	atomicAdd(&p->y, v.y);
-}
-template <> __device__ __forceinline__ void atomic_add_value<cuDoubleComplex>(cuDoubleComplex* p, cuDoubleComplex v)
-{
-	atomicAdd(&p->x, v.x);
-	atomicAdd(&p->y, v.y);
-}
-
 template <typename T, int UNROLL, int HACK>
 __global__ void __launch_bounds__(128, 8)
 hell_tail_kernel(const HellArgs<T> a)
@@ -104,9 +93,27 @@ hell_tail_kernel(const HellArgs<T> a)
 			for (int u = 0; u < UNROLL; ++u)
 				acc = Num<T>::fma(v[u], xv[u], acc);
 		}
-		if (live && kEnd > kBeg) {
+		a.partials[(size_t)idx * 32 + lane] = acc;               /* zero for lanes with nothing in this chunk */
+	}
+}
+
+/* one warp per unit that queued chunks: z[row] += alpha * (partials of its chunks, in chunk order) */
+template <typename T>
+__global__ void __launch_bounds__(128)
+hell_fold_kernel(const HellArgs<T> a)
+{
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned units = min(__ldg(a.workHeader + 2), (unsigned)a.workCap);
+	const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+	for (unsigned e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < units; e += warps) {
+		const uint4 u = a.foldList[e];
+		const unsigned i = (u.x << 5) + lane;
+		T sum = Num<T>::zero();
+		for (unsigned c = 0; c < u.z; ++c)
+			sum = Num<T>::add(sum, a.partials[(size_t)(u.y + c) * 32 + lane]);
+		if (i < (unsigned)a.rows && Num<T>::nonzero(sum)) {        /* rows without a deep part keep their bits */
 			const unsigned out = a.rIdx ? (unsigned)__ldg(a.rIdx + i) : i;
-			atomic_add_value<T>(a.z + out, Num<T>::mul(a.alpha, acc));
+			a.z[out] = Num<T>::fma(a.alpha, sum, a.z[out]);
 		}
 	}
 }
@@ -178,17 +185,22 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		0, NULL, NULL, 0 };
 	/* Split mode: on for length-sorted matrices (rIdx given: their long rows sit together in a
 	 * few hacks whose warps would be the critical path), or forced with hellSplit = 1; off with
-	 * hellSplit = -1.  Costs one 8-byte memset and one small extra launch per call. */
+	 * hellSplit = -1.  Costs one 16-byte memset and two small extra launches per call. */
 	const bool split = t->hellSplit > 0 || (t->hellSplit == 0 && rIdx != NULL);
 	if (split) {
 		const int cap = t->hellSplit > 1 ? t->hellSplit : (1 << 16);     /* hellSplit > 1: queue capacity (tests) */
-		unsigned* hdr = (unsigned*)spgpuScratch(handle, 16 + (size_t)cap * sizeof(uint2));
-		if (hdr) {
+		/* scratch: header | items | fold list | partials (32 lanes per item) */
+		const size_t itemsAt = 16, foldAt = itemsAt + (size_t)cap * sizeof(uint2);
+		const size_t partAt = foldAt + (size_t)cap * sizeof(uint4);
+		unsigned char* scratch = (unsigned char*)spgpuScratch(handle, partAt + (size_t)cap * 32 * sizeof(T));
+		if (scratch) {
 			args.splitT = longCut > 64 ? longCut : 64;
-			args.workHeader = hdr;
-			args.workItems = reinterpret_cast<uint2*>(hdr + 4);
+			args.workHeader = reinterpret_cast<unsigned*>(scratch);
+			args.workItems = reinterpret_cast<uint2*>(scratch + itemsAt);
+			args.foldList = reinterpret_cast<uint4*>(scratch + foldAt);
+			args.partials = reinterpret_cast<T*>(scratch + partAt);
 			args.workCap = cap;
-			cudaMemsetAsync(hdr, 0, 16, s);
+			cudaMemsetAsync(scratch, 0, 16, s);
 		}
 	}
 #define HELL_ARGS args
@@ -220,6 +232,8 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		if (hackSize == 32)      hell_tail_kernel<T, UNROLL, 32><<<tg, 128, 0, s>>>(args);
 		else if (hackSize == 64) hell_tail_kernel<T, UNROLL, 64><<<tg, 128, 0, s>>>(args);
 		else                     hell_tail_kernel<T, UNROLL, 0><<<tg, 128, 0, s>>>(args);
+		spgpu_count_launch(handle);
+		hell_fold_kernel<T><<<(unsigned)handle->multiProcessorCount, 128, 0, s>>>(args);
 		spgpu_count_launch(handle);
 	}
 }

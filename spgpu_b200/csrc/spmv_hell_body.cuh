@@ -29,9 +29,11 @@ struct HellArgs {
 	/* split mode (0 = off): rows are walked by their own warp only up to splitT slots; deeper
 	 * slots are cut into chunks of splitT and queued for hell_tail_kernel (spmv_hell.cu) */
 	int splitT;
-	unsigned* workHeader;        /* [0] items queued, [1] items taken */
+	unsigned* workHeader;        /* [0] items queued, [1] items taken, [2] units that queued */
 	uint2* workItems;            /* (32-row unit, chunk) */
 	int workCap;
+	uint4* foldList;             /* (32-row unit, first item, items, -) per unit that queued */
+	T* partials;                 /* one 32-lane partial sum per item */
 };
 
 #define SPGPU_WORK_INVALID 0xffffffffu
@@ -72,8 +74,11 @@ __device__ __forceinline__ void hell_warp_rows_value(const HellArgs<T>& a, unsig
 			for (unsigned c = lane; c < (unsigned)nchunks; c += 32)
 				if (base + c < (unsigned)a.workCap)
 					a.workItems[base + c] = fits ? make_uint2(warpRow >> 5, c) : make_uint2(SPGPU_WORK_INVALID, 0u);
-			if (fits)
+			if (fits) {
 				len = min(len, a.splitT);                            /* else: queue full, walk it all here */
+				if (lane == 0)                                       /* fits => at most workCap units get here */
+					a.foldList[atomicAdd(a.workHeader + 2, 1u)] = make_uint4(warpRow >> 5, base, (unsigned)nchunks, 0u);
+			}
 		}
 	}
 	const bool useBeta = Num<T>::nonzero(a.beta);

@@ -310,3 +310,28 @@ def test_hell_long_hack_split_mode(ours, gpu_handle, dtype, split):
         check(ours, gpu_handle, "hell", coo, B, x, y, alpha, 0.0, ridx=oell.ridx, avg=8)
     finally:
         ours.spgpuSetTuning(gpu_handle, b"hellSplit", 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex128])
+def test_split_mode_is_bit_reproducible(ours, gpu_handle, dtype):
+    """the long-hack split mode folds its partial sums in chunk order (no floating-point atomics): ten runs of the
+    same product give the same bits, whichever warp took which chunk"""
+    try:
+        assert ours.spgpuSetTuning(gpu_handle, b"hellSplit", 1) == 0
+        coo = G.powerlaw(20000, mean=10, maxlen=3000, spike_every=128, seed=8, dtype=np.float32)
+        coo = F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)
+        ell = F.coo_to_ell(coo)
+        oell = F.ell_to_oell(ell)
+        A = F.ell_to_hell(oell, 32)
+        x = G.random_vector(coo.ncols, dtype, 1, -1, 1)
+        y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
+        alpha, beta = scalars(dtype)
+        dA = util.upload(A)
+        first = util.dev_spmv(ours, gpu_handle, "hell", A, dA, x, y, alpha, beta, ridx=oell.ridx)
+        for _ in range(9):
+            again = util.dev_spmv(ours, gpu_handle, "hell", A, dA, x, y, alpha, beta, ridx=oell.ridx)
+            np.testing.assert_array_equal(first.view(np.uint8), again.view(np.uint8))
+        want = util.oracle_spmv("hell", A, x, y, alpha, beta, ridx=oell.ridx)
+        util.assert_rows_close(first, want, util.row_scale(coo, x, y, alpha, beta), util.sym_of(dtype), "split mode")
+    finally:
+        ours.spgpuSetTuning(gpu_handle, b"hellSplit", 0)
