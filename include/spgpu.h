@@ -323,6 +323,18 @@ void cooToHdia(void* hdiaValues, int* hdiaOffsets, const int* hackOffsets,
 	const int* cooRowIndices, const int* cooColsIndices, const void* cooValues,
 	int cooBaseIndex, spgpuType_t valuesType);
 
+/* hdia_conv.h:72 -- cooToHdia over blocks: every COO value is a block of blockSize elements. */
+void bcooToBhdia(void* hdiaValues, int* hdiaOffsets, const int* hackOffsets,
+	int hackSize, int rowsCount, int columnsCount, int nonZerosCount,
+	const int* cooRowIndices, const int* cooColsIndices, const void* cooValues,
+	int cooBaseIndex, spgpuType_t valuesType, int blockSize);
+
+/* coo_conv.h:20 -- number of non-zero blockRows x blockCols blocks of a 0-based COO matrix. */
+int computeBcooSize(int blockRows, int blockCols, const int* rows, const int* cols, int nonZeros);
+/* coo_conv.h:23 -- blocks in first-seen order, column-major inside a block, zero-filled. */
+void cooToBcoo(int* bRows, int* bCols, void* blockValues, int blockRows, int blockCols,
+	const int* rows, const int* cols, const void* values, int nonZeros, spgpuType_t valuesType);
+
 #ifdef __cplusplus
 }
 #endif

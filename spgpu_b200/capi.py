@@ -102,7 +102,7 @@ def abi_symbols():
     names += ["computeEllRowLenghts", "computeEllAllocPitch", "cooToEll", "ellToOell",
               "computeHellAllocSize", "ellToHell", "computeDiaDiagonalsCount", "coo2dia",
               "computeDiaAllocPitch", "getHdiaHacksCount", "computeHdiaHackOffsets",
-              "diaToHdia", "computeHdiaHackOffsetsFromCoo", "cooToHdia"]
+              "diaToHdia", "computeHdiaHackOffsetsFromCoo", "cooToHdia", "bcooToBhdia", "computeBcooSize", "cooToBcoo"]
     return names
 
 
@@ -213,6 +213,11 @@ class SpgpuLib:
             [ctypes.POINTER(c_int), P, c_int, c_int, c_int, c_int, P, P, c_int])
         f["cooToHdia"] = _sig(d, "cooToHdia", None,
             [P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_int])
+
+        f["bcooToBhdia"] = _sig(d, "bcooToBhdia", None,
+            [P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_int, c_int])
+        f["computeBcooSize"] = _sig(d, "computeBcooSize", c_int, [c_int, c_int, P, P, c_int])
+        f["cooToBcoo"] = _sig(d, "cooToBcoo", None, [P, P, P, c_int, c_int, P, P, P, c_int, c_int])
 
         # --- additive API (ours only)
         self.has_ext = False

@@ -171,18 +171,17 @@ void computeHdiaHackOffsetsFromCoo(int* allocationHeight, int* hackOffsets,
 	free_buckets(&b);
 }
 
-void cooToHdia(void* hdiaValues, int* hdiaOffsets, const int* hackOffsets,
-	int hackSize, int rowsCount, int columnsCount, int nonZerosCount,
-	const int* cooRowIndices, const int* cooColsIndices, const void* cooValues,
-	int cooBaseIndex, spgpuType_t valuesType)
+/* shared by cooToHdia and bcooToBhdia (reference hdia.cpp:230-325, cooToHdia_size): `bytes` is the
+ * size of one stored cell -- one element, or one block of elements */
+static void coo_to_hdia_cells(void* hdiaValues, int* hdiaOffsets, const int* hackOffsets,
+	int hackSize, int rowsCount, int nonZerosCount, const int* cooRowIndices,
+	const int* cooColsIndices, const void* cooValues, int cooBaseIndex, size_t bytes)
 {
-	const size_t bytes = spgpuSizeOf(valuesType);
 	const int hacks = getHdiaHacksCount(hackSize, rowsCount);
 	HackBuckets b;
 	int* keys;
 	int written = 0;   /* diagonals emitted so far (the reference advances its
 	                      offsets cursor by the count it finds, hdia.cpp:303) */
-	(void)columnsCount;
 
 	bucket_by_hack(&b, hacks, hackSize, nonZerosCount, cooRowIndices, cooBaseIndex);
 	keys = (int*)malloc((size_t)largest_bucket(&b, hacks) * sizeof(int));
@@ -208,4 +207,26 @@ void cooToHdia(void* hdiaValues, int* hdiaOffsets, const int* hackOffsets,
 	}
 	free(keys);
 	free_buckets(&b);
+}
+
+void cooToHdia(void* hdiaValues, int* hdiaOffsets, const int* hackOffsets,
+	int hackSize, int rowsCount, int columnsCount, int nonZerosCount,
+	const int* cooRowIndices, const int* cooColsIndices, const void* cooValues,
+	int cooBaseIndex, spgpuType_t valuesType)
+{
+	(void)columnsCount;
+	coo_to_hdia_cells(hdiaValues, hdiaOffsets, hackOffsets, hackSize, rowsCount, nonZerosCount,
+		cooRowIndices, cooColsIndices, cooValues, cooBaseIndex, spgpuSizeOf(valuesType));
+}
+
+/* reference hdia.cpp:351-373: cooToHdia over BLOCKS -- the COO entries are block coordinates
+ * (cooToBcoo's bRows / bCols) and every value is a block of blockSize elements. */
+void bcooToBhdia(void* hdiaValues, int* hdiaOffsets, const int* hackOffsets,
+	int hackSize, int rowsCount, int columnsCount, int nonZerosCount,
+	const int* cooRowIndices, const int* cooColsIndices, const void* cooValues,
+	int cooBaseIndex, spgpuType_t valuesType, int blockSize)
+{
+	(void)columnsCount;
+	coo_to_hdia_cells(hdiaValues, hdiaOffsets, hackOffsets, hackSize, rowsCount, nonZerosCount,
+		cooRowIndices, cooColsIndices, cooValues, cooBaseIndex, (size_t)blockSize * spgpuSizeOf(valuesType));
 }
