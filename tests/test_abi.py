@@ -38,6 +38,22 @@ def test_library_exports_the_matrixmarket_reader(ours):
     assert not [n for n in declared if not ours.has(n)]
 
 
+def test_every_c_symbol_of_the_reference_library_is_exported():
+    """link-level drop-in: whatever an application could have linked from the reference's libspgpu
+    (its own build, oracle/_ref/libspgpu_ref.so) resolves against ours; `merge` / `mergesort` are
+    ell.c's sort helpers leaking out of the reference (not declared in any header)"""
+    from tests import util
+    if not os.path.exists(util.REF_PATH):
+        pytest.skip("oracle/_ref/libspgpu_ref.so not built (needs /root/reference at build time)")
+
+    def exported(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+        return {ln.split()[2] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] == "T"}
+    theirs = {n for n in exported(util.REF_PATH) if not n.startswith("_")}
+    missing = theirs - exported(capi.LIB_PATH) - {"merge", "mergesort"}
+    assert len(theirs) > 150 and not missing, sorted(missing)
+
+
 def test_handle_struct_layout_is_the_reference_abi():
     """reference core.h:60-82: two pointers then nine ints, in this order"""
     S = capi.SpgpuHandleStruct
