@@ -51,7 +51,7 @@ def test_every_c_symbol_of_the_reference_library_is_exported():
         return {ln.split()[2] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] == "T"}
     theirs = {n for n in exported(util.REF_PATH) if not n.startswith("_")}
     missing = theirs - exported(capi.LIB_PATH) - {"merge", "mergesort"}
-    assert len(theirs) > 150 and not missing, sorted(missing)
+    assert len(theirs) > 100 and not missing, sorted(missing)
 
 
 def test_handle_struct_layout_is_the_reference_abi():
