@@ -57,9 +57,9 @@ spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
 	if (propErr == cudaSuccess) {
 		err = cudaMalloc(&h->dPartials, (size_t)SPGPU_RED_MAX_BLOCKS * SPGPU_RED_SLOT_BYTES);
 		if (err == cudaSuccess)
-			err = cudaMalloc((void**)&h->dTicket, 64);
+			err = cudaMalloc((void**)&h->dTicket, SPGPU_TICKET_WORDS * sizeof(unsigned));
 		if (err == cudaSuccess)
-			err = cudaMemset(h->dTicket, 0, 64);
+			err = cudaMemset(h->dTicket, 0, SPGPU_TICKET_WORDS * sizeof(unsigned));
 		if (err == cudaSuccess)
 			err = cudaHostAlloc(&h->hResult, 64, cudaHostAllocMapped);
 		if (err == cudaSuccess) {

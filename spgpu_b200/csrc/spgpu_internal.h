@@ -23,6 +23,12 @@ extern "C" {
 #define SPGPU_RED_MAX_BLOCKS 2048
 #define SPGPU_RED_SLOT_BYTES 16
 
+/* dTicket: a block of device counters, all zero between calls (every user resets what it used):
+ *   [0] reductions, [4] halo push, [8] halo exchange / fused push, [12..13] fused-halo done tickets,
+ *   [16..19] HELL split-mode header (items queued, items taken, units queued, tail warps done) */
+#define SPGPU_TICKET_WORDS 32
+#define SPGPU_TICKET_SPLIT 16
+
 /* Tunables that steer kernel selection; settable with spgpuSetTuning (ext). */
 typedef struct SpgpuTuning {
 	int hellVariant;     /* 0 auto, 1 direct loads predicated on rS, 2 direct loads with unpredicated slab reads, 3 bulk-async (TMA) pipeline */
@@ -40,7 +46,7 @@ typedef struct SpgpuHandlePriv {
 	SpgpuHandleStruct pub;         /* MUST stay first                            */
 	unsigned magic;
 	void* dPartials;               /* device: SPGPU_RED_MAX_BLOCKS slots          */
-	unsigned* dTicket;             /* device: last-block-done counter (kept 0)    */
+	unsigned* dTicket;             /* device: SPGPU_TICKET_WORDS counters (kept 0)  */
 	void* hResult;                 /* pinned, mapped host: final reduction value  */
 	void* dResult;                 /* device alias of hResult                     */
 	int l2Bytes;

@@ -33,11 +33,12 @@ hell_spmv_kernel(const HellArgs<T> a)
 /*
  * Tail kernel of the split mode: persistent warps take (unit, chunk) items off the queue the
  * main kernel filled and walk slots [(c+1)T, (c+2)T) of the unit's 32 rows (row per lane,
- * coalesced), and leave one partial sum per lane in the item's slot of `partials`.  The fold
- * kernel then adds a unit's partials to z IN CHUNK ORDER (the main kernel has already stored
- * beta*y + alpha*(first T slots)), so the result does not depend on which warp took which
- * item or when -- bit-reproducible from run to run, like every other kernel here (no
- * floating-point atomics).
+ * coalesced), and leave one partial sum per lane in the item's slot of `partials`.  The warp
+ * that finishes the LAST chunk of a unit (a counter in the unit's fold entry) adds the unit's
+ * partials to z IN CHUNK ORDER (the main kernel has already stored beta*y + alpha*(first T
+ * slots)), so the result does not depend on which warp took which item or when -- bit-
+ * reproducible from run to run, like every other kernel here (no floating-point atomics).
+ * The last warp to leave the kernel zeroes the header for the next call (no memset launch).
  */
 template <typename T, int UNROLL, int HACK>
 __global__ void __launch_bounds__(128, 8)
@@ -52,8 +53,8 @@ hell_tail_kernel(const HellArgs<T> a)
 			idx = atomicAdd(a.workHeader + 1, 1u);
 		idx = __shfl_sync(SPGPU_FULL_MASK, idx, 0);
 		if (idx >= queued)
-			return;
-		const uint2 item = a.workItems[idx];
+			break;
+		const uint4 item = a.workItems[idx];
 		if (item.x == SPGPU_WORK_INVALID)
 			continue;
 		const unsigned warpRow = item.x << 5;
@@ -94,27 +95,31 @@ hell_tail_kernel(const HellArgs<T> a)
 				acc = Num<T>::fma(v[u], xv[u], acc);
 		}
 		a.partials[(size_t)idx * 32 + lane] = acc;               /* zero for lanes with nothing in this chunk */
-	}
-}
-
-/* one warp per unit that queued chunks: z[row] += alpha * (partials of its chunks, in chunk order) */
-template <typename T>
-__global__ void __launch_bounds__(128)
-hell_fold_kernel(const HellArgs<T> a)
-{
-	const unsigned lane = threadIdx.x & 31;
-	const unsigned units = min(__ldg(a.workHeader + 2), (unsigned)a.workCap);
-	const unsigned warps = (gridDim.x * blockDim.x) >> 5;
-	for (unsigned e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < units; e += warps) {
-		const uint4 u = a.foldList[e];
-		const unsigned i = (u.x << 5) + lane;
-		T sum = Num<T>::zero();
-		for (unsigned c = 0; c < u.z; ++c)
-			sum = Num<T>::add(sum, a.partials[(size_t)(u.y + c) * 32 + lane]);
-		if (i < (unsigned)a.rows && Num<T>::nonzero(sum)) {        /* rows without a deep part keep their bits */
-			const unsigned out = a.rIdx ? (unsigned)__ldg(a.rIdx + i) : i;
-			a.z[out] = Num<T>::fma(a.alpha, sum, a.z[out]);
+		__threadfence();                                         /* partial visible before the counter moves */
+		unsigned finished = 0;
+		if (lane == 0)
+			finished = atomicAdd(&a.foldList[item.z].w, 1u);
+		finished = __shfl_sync(SPGPU_FULL_MASK, finished, 0);
+		const uint4 unit = a.foldList[item.z];                   /* x, y, z written by the main kernel */
+		if (finished + 1u == unit.z) {
+			/* this warp finished the unit's last chunk: fold in chunk order (loads bypass L1: the
+			 * other partials were written by other SMs, and the buffer is reused from call to call) */
+			__threadfence();
+			T sum = Num<T>::zero();
+			for (unsigned c = 0; c < unit.z; ++c)
+				sum = Num<T>::add(sum, __ldcg(a.partials + (size_t)(unit.y + c) * 32 + lane));
+			if (live && Num<T>::nonzero(sum)) {                  /* rows without a deep part keep their bits */
+				const unsigned out = a.rIdx ? (unsigned)__ldg(a.rIdx + i) : i;
+				a.z[out] = Num<T>::fma(a.alpha, sum, a.z[out]);
+			}
 		}
+	}
+	/* every warp of the grid ends here exactly once; the last one leaves the header zeroed */
+	if (lane == 0 && atomicAdd(a.workHeader + 3, 1u) == ((gridDim.x * blockDim.x) >> 5) - 1u) {
+		a.workHeader[0] = 0u;
+		a.workHeader[1] = 0u;
+		a.workHeader[2] = 0u;
+		a.workHeader[3] = 0u;
 	}
 }
 
@@ -185,22 +190,23 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		0, NULL, NULL, 0 };
 	/* Split mode: on for length-sorted matrices (rIdx given: their long rows sit together in a
 	 * few hacks whose warps would be the critical path), or forced with hellSplit = 1; off with
-	 * hellSplit = -1.  Costs one 16-byte memset and two small extra launches per call. */
+	 * hellSplit = -1.  Costs one small extra launch per call (no memset: the header resets itself). */
 	const bool split = t->hellSplit > 0 || (t->hellSplit == 0 && rIdx != NULL);
 	if (split) {
 		const int cap = t->hellSplit > 1 ? t->hellSplit : (1 << 16);     /* hellSplit > 1: queue capacity (tests) */
-		/* scratch: header | items | fold list | partials (32 lanes per item) */
-		const size_t itemsAt = 16, foldAt = itemsAt + (size_t)cap * sizeof(uint2);
+		/* scratch: items | fold list | partials (32 lanes per item); the 4-word header lives in the
+		 * handle's counter block (spgpu_internal.h; zero at creation and again after every call) */
+		const size_t foldAt = (size_t)cap * sizeof(uint4);
 		const size_t partAt = foldAt + (size_t)cap * sizeof(uint4);
 		unsigned char* scratch = (unsigned char*)spgpuScratch(handle, partAt + (size_t)cap * 32 * sizeof(T));
-		if (scratch) {
+		SpgpuHandlePriv* hp = spgpuPriv(handle);
+		if (scratch && hp->magic == SPGPU_PRIV_MAGIC) {
 			args.splitT = longCut > 64 ? longCut : 64;
-			args.workHeader = reinterpret_cast<unsigned*>(scratch);
-			args.workItems = reinterpret_cast<uint2*>(scratch + itemsAt);
+			args.workHeader = hp->dTicket + SPGPU_TICKET_SPLIT;
+			args.workItems = reinterpret_cast<uint4*>(scratch);
 			args.foldList = reinterpret_cast<uint4*>(scratch + foldAt);
 			args.partials = reinterpret_cast<T*>(scratch + partAt);
 			args.workCap = cap;
-			cudaMemsetAsync(scratch, 0, 16, s);
 		}
 	}
 #define HELL_ARGS args
@@ -232,8 +238,6 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		if (hackSize == 32)      hell_tail_kernel<T, UNROLL, 32><<<tg, 128, 0, s>>>(args);
 		else if (hackSize == 64) hell_tail_kernel<T, UNROLL, 64><<<tg, 128, 0, s>>>(args);
 		else                     hell_tail_kernel<T, UNROLL, 0><<<tg, 128, 0, s>>>(args);
-		spgpu_count_launch(handle);
-		hell_fold_kernel<T><<<(unsigned)handle->multiProcessorCount, 128, 0, s>>>(args);
 		spgpu_count_launch(handle);
 	}
 }

@@ -29,10 +29,11 @@ struct HellArgs {
 	/* split mode (0 = off): rows are walked by their own warp only up to splitT slots; deeper
 	 * slots are cut into chunks of splitT and queued for hell_tail_kernel (spmv_hell.cu) */
 	int splitT;
-	unsigned* workHeader;        /* [0] items queued, [1] items taken, [2] units that queued */
-	uint2* workItems;            /* (32-row unit, chunk) */
+	unsigned* workHeader;        /* [0] items queued, [1] items taken, [2] units that queued, [3] tail warps done;
+	                              * lives in the handle, zero between calls (the tail kernel's last warp resets it) */
+	uint4* workItems;            /* (32-row unit, chunk, its unit's fold entry, -) */
 	int workCap;
-	uint4* foldList;             /* (32-row unit, first item, items, -) per unit that queued */
+	uint4* foldList;             /* (32-row unit, first item, items, items finished) per unit that queued */
 	T* partials;                 /* one 32-lane partial sum per item */
 };
 
@@ -66,19 +67,21 @@ __device__ __forceinline__ void hell_warp_rows_value(const HellArgs<T>& a, unsig
 		const int longest = __reduce_max_sync(SPGPU_FULL_MASK, len);
 		if (longest > a.splitT) {
 			const int nchunks = (longest - 1) / a.splitT;            /* chunks c = 0.. cover [ (c+1)T, (c+2)T ) */
-			unsigned base = 0;
+			unsigned base = 0, entry = 0;
 			if (lane == 0)
 				base = atomicAdd(a.workHeader, (unsigned)nchunks);
 			base = __shfl_sync(SPGPU_FULL_MASK, base, 0);
 			const bool fits = base + (unsigned)nchunks <= (unsigned)a.workCap;
+			if (fits && lane == 0) {                                 /* fits => at most workCap units get here */
+				entry = atomicAdd(a.workHeader + 2, 1u);
+				a.foldList[entry] = make_uint4(warpRow >> 5, base, (unsigned)nchunks, 0u);
+			}
+			entry = __shfl_sync(SPGPU_FULL_MASK, entry, 0);
 			for (unsigned c = lane; c < (unsigned)nchunks; c += 32)
 				if (base + c < (unsigned)a.workCap)
-					a.workItems[base + c] = fits ? make_uint2(warpRow >> 5, c) : make_uint2(SPGPU_WORK_INVALID, 0u);
-			if (fits) {
+					a.workItems[base + c] = fits ? make_uint4(warpRow >> 5, c, entry, 0u) : make_uint4(SPGPU_WORK_INVALID, 0u, 0u, 0u);
+			if (fits)
 				len = min(len, a.splitT);                            /* else: queue full, walk it all here */
-				if (lane == 0)                                       /* fits => at most workCap units get here */
-					a.foldList[atomicAdd(a.workHeader + 2, 1u)] = make_uint4(warpRow >> 5, base, (unsigned)nchunks, 0u);
-			}
 		}
 	}
 	const bool useBeta = Num<T>::nonzero(a.beta);
