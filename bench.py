@@ -1033,6 +1033,67 @@ def main():
                                "frac_of_peak": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9 / (peak * world),
                                "kernels_per_iteration": (L.spgpuGetLaunchCount(h) - l0) / iters,
                                "residual_norm2_after": cg.residual_norm2() if flavour == "device" else st.rr_host}
+        # ---- the device-scalar iteration captured ONCE in a CUDA graph and replayed ---------------
+        # (at N > 1 the halo / all-reduce sequence numbers then have to live in device memory:
+        #  spgpuSetSeqCounters, include/spgpu_ext.h)
+        graph_ok = apply_A_dot is not None and (world == 1 or (peer is not None and args.halo == "fused" and peer_ar is not None))
+        if graph_ok:
+            try:
+                counters = torch.zeros(2, dtype=torch.int32, device=device)
+                apply_eager = apply_A_dot
+                if world > 1:
+                    assert L.spgpuSetSeqCounters(h, counters.data_ptr(), counters.data_ptr() + 4) == 0
+                    peer.to_device_seq(counters[0:1])
+                    peer_ar.to_device_seq(counters[1:2])
+
+                    def apply_A_dot_dev(_z, _x, dres):
+                        L.spgpuDhellspmvHaloDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
+                                                A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, A.base, halo,
+                                                plo, phi, myf, pflo, pfhi, 0, dres)
+                        L.spgpuHaloSeqAdvance(h)
+                    cg.apply_A_dot = apply_A_dot_dev
+                cg.start(bvec)
+                for _ in range(2):
+                    cg.step_device()
+                barrier()
+                g = torch.cuda.CUDAGraph()
+                cap = torch.cuda.Stream(device=device)
+                L.spgpuSetStream(h, cap.cuda_stream)
+                try:
+                    with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                        cg.step_device()
+                finally:
+                    L.spgpuSetStream(h, None)
+                torch.cuda.synchronize()
+                for _ in range(2):
+                    g.replay()
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                cur = torch.cuda.current_stream(device)
+                a.record(cur)
+                for _ in range(iters):
+                    g.replay()
+                b.record(cur)
+                barrier()
+                t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_it = float(t.item()) / iters
+                vec_bytes = krylov.CG_BYTES_PER_ROW_VECTOR_OPS["device"] * w["total_rows"]
+                cg_out["graph"] = {"ms_per_iteration": ms_it,
+                                   "algorithmic_gb_per_iteration": (bytes_total + vec_bytes) / 1e9,
+                                   "hbm_gbs": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9,
+                                   "frac_of_peak": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9 / (peak * world),
+                                   "residual_norm2_after": cg.residual_norm2(),
+                                   "what": "the device flavour captured once in a CUDA graph and replayed"}
+                del g
+                if world > 1:
+                    peer.from_device_seq(counters[0:1])
+                    peer_ar.from_device_seq(counters[1:2])
+                    L.spgpuSetSeqCounters(h, 0, 0)
+                cg.apply_A_dot = apply_eager
+            except Exception as exc:
+                print(f"CG graph flavour failed: {exc!r}", file=sys.stderr, flush=True)
         cg_out["allreduce"] = args.allreduce if world > 1 else "none"
         if peer_ar is not None:
             peer_ar.close()

@@ -240,6 +240,19 @@ void spgpuDhdiaspmvHaloDot(spgpuHandle_t handle, __device double* z, const __dev
 void spgpuAllreduceSumDev(spgpuHandle_t handle, __device double* dValue, int world, int myRank,
 	void* const* tables, unsigned seq);
 
+/*
+ * Sequence numbers in device memory, so that a partitioned iteration can be captured ONCE in a CUDA
+ * graph and replayed (a by-value seq would be frozen into the graph).  After spgpuSetSeqCounters the
+ * fused halo kernels (spgpu?{hell,hdia}spmvHalo[Dot]) and spgpuAllreduceSumDev, when called with
+ * seq == 0, take their sequence number from the counters: *dHaloSeq / *dAllreduceSeq hold the number of
+ * COMPLETED exchanges / all-reduces (start them at the host-side count, or 0).  The all-reduce kernel
+ * advances its counter itself; the halo counter is advanced by spgpuHaloSeqAdvance, a one-thread kernel
+ * the caller puts after each fused SpMV (the SpMV kernel's CTAs must all read the same value however
+ * late they are scheduled).  Returns 0, or -1 for a foreign handle.
+ */
+int spgpuSetSeqCounters(spgpuHandle_t handle, __device unsigned* dHaloSeq, __device unsigned* dAllreduceSeq);
+void spgpuHaloSeqAdvance(spgpuHandle_t handle);
+
 #ifdef __cplusplus
 }
 #endif

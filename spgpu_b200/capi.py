@@ -118,7 +118,7 @@ def ext_symbols():
               "spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
               "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag",
               "spgpuDhaloExchange", "spgpuHaloAck", "spgpuDhellspmvHalo",
-              "spgpuDhellspmvHaloDot", "spgpuDhdiaspmvHalo", "spgpuDhdiaspmvHaloDot", "spgpuAllreduceSumDev"]
+              "spgpuDhellspmvHaloDot", "spgpuDhdiaspmvHalo", "spgpuDhdiaspmvHaloDot", "spgpuAllreduceSumDev", "spgpuSetSeqCounters", "spgpuHaloSeqAdvance"]
     return names
 
 
@@ -267,6 +267,8 @@ class SpgpuLib:
                 [H, P, P, P, c_int, P, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, ctypes.c_uint, P], optional=True)
             f["spgpuAllreduceSumDev"] = _sig(d, "spgpuAllreduceSumDev", None,
                 [H, P, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.c_uint], optional=True)
+            f["spgpuSetSeqCounters"] = _sig(d, "spgpuSetSeqCounters", c_int, [H, P, P], optional=True)
+            f["spgpuHaloSeqAdvance"] = _sig(d, "spgpuHaloSeqAdvance", None, [H], optional=True)
             f["spgpuDhdiaspmvHaloDot"] = _sig(d, "spgpuDhdiaspmvHaloDot", None,
                 [H, P, P, P, c_int, P, c_int, c_int, P, c_int, P, P, P, P, P, ctypes.c_uint, P], optional=True)
             f["spgpuDhdiaspmvHalo"] = _sig(d, "spgpuDhdiaspmvHalo", None,

@@ -400,7 +400,8 @@ struct HaloArgs {
 	unsigned* peerReadyLo; unsigned* peerReadyHi;        /* remote: my halo for `seq` is in place         */
 	const unsigned* myReadyLo; const unsigned* myReadyHi;/* local : neighbour's halo for `seq` is in place */
 	unsigned* peerAckLo; unsigned* peerAckHi;            /* remote: I have consumed their halo for `seq`   */
-	unsigned seq;
+	unsigned seq;                            /* sequence number of this exchange, or ... */
+	const unsigned* seqPtr;                  /* ... (seq == 0) device counter of COMPLETED exchanges: this one is *seqPtr + 1 */
 	unsigned* pushTicket; unsigned* doneTicket;
 	int pushCtas;
 	int headBlocks, tailBlocks;              /* 128-row blocks that read the lower / upper halo zone */
@@ -460,14 +461,17 @@ template <typename Body, int MINB, bool DOT>
 __global__ void __launch_bounds__(128, MINB)
 spmv_halo_kernel(const Body body, const HaloArgs hx, int xOffset, double* __restrict__ ctaPartials)
 {
+	/* the counter is advanced by a later kernel in stream order (spgpuHaloSeqAdvance), never during this
+	 * one, so every CTA reads the same value whenever it is scheduled */
+	const unsigned seq = hx.seqPtr ? *reinterpret_cast<const volatile unsigned*>(hx.seqPtr) + 1u : hx.seq;
 	if (blockIdx.x < (unsigned)hx.pushCtas) {
 		const bool toHi = (blockIdx.x & 1) != 0;
 		double* dst = toHi ? hx.dstHi : hx.dstLo;
 		const double* src = toHi ? hx.srcHi : hx.srcLo;
 		const unsigned* ack = toHi ? hx.ackHi : hx.ackLo;
 		if (dst) {
-			if (threadIdx.x == 0 && ack && hx.seq > 1)
-				spin_until(ack, hx.seq - 1, hx.timeoutNs);
+			if (threadIdx.x == 0 && ack && seq > 1)
+				spin_until(ack, seq - 1, hx.timeoutNs);
 			__syncthreads();
 			const long long half = hx.pushCtas >> 1;
 			const long long tid = (long long)(blockIdx.x >> 1) * blockDim.x + threadIdx.x;
@@ -490,8 +494,8 @@ spmv_halo_kernel(const Body body, const HaloArgs hx, int xOffset, double* __rest
 			if (atomicAdd(hx.pushTicket, 1u) == (unsigned)hx.pushCtas - 1u) {
 				*hx.pushTicket = 0u;
 				__threadfence_system();
-				if (hx.peerReadyLo) st_release_sys(hx.peerReadyLo, hx.seq);
-				if (hx.peerReadyHi) st_release_sys(hx.peerReadyHi, hx.seq);
+				if (hx.peerReadyLo) st_release_sys(hx.peerReadyLo, seq);
+				if (hx.peerReadyHi) st_release_sys(hx.peerReadyHi, seq);
 			}
 		}
 	} else {
@@ -514,8 +518,8 @@ spmv_halo_kernel(const Body body, const HaloArgs hx, int xOffset, double* __rest
 			return;
 		}
 		if (threadIdx.x == 0) {
-			if (needLo && hx.myReadyLo) spin_until(hx.myReadyLo, hx.seq, hx.timeoutNs);
-			if (needHi && hx.myReadyHi) spin_until(hx.myReadyHi, hx.seq, hx.timeoutNs);
+			if (needLo && hx.myReadyLo) spin_until(hx.myReadyLo, seq, hx.timeoutNs);
+			if (needHi && hx.myReadyHi) spin_until(hx.myReadyHi, seq, hx.timeoutNs);
 		}
 		__syncthreads();
 		const double zval = body.run(rb * 128u + (threadIdx.x & ~31u));
@@ -529,12 +533,12 @@ spmv_halo_kernel(const Body body, const HaloArgs hx, int xOffset, double* __rest
 			if (needLo && atomicAdd(hx.doneTicket, 1u) == head - 1u) {
 				*hx.doneTicket = 0u;
 				__threadfence_system();
-				if (hx.peerAckLo) st_release_sys(hx.peerAckLo, hx.seq);
+				if (hx.peerAckLo) st_release_sys(hx.peerAckLo, seq);
 			}
 			if (needHi && atomicAdd(hx.doneTicket + 1, 1u) == tail - 1u) {
 				*(hx.doneTicket + 1) = 0u;
 				__threadfence_system();
-				if (hx.peerAckHi) st_release_sys(hx.peerAckHi, hx.seq);
+				if (hx.peerAckHi) st_release_sys(hx.peerAckHi, seq);
 			}
 		}
 	}
@@ -554,6 +558,7 @@ static HaloArgs halo_args(spgpuHandle_t handle, double* xExt, int rows, int halo
 	hx.myReadyLo = peerFlagsLo ? myFlags + 0 : NULL;  hx.myReadyHi = peerFlagsHi ? myFlags + 1 : NULL;
 	hx.peerAckLo = peerFlagsLo ? peerFlagsLo + 3 : NULL;  hx.peerAckHi = peerFlagsHi ? peerFlagsHi + 2 : NULL;
 	hx.seq = seq;
+	hx.seqPtr = (seq == 0u && h->magic == SPGPU_PRIV_MAGIC) ? h->dHaloSeq : NULL;
 	hx.pushTicket = h->dTicket + 8;
 	hx.doneTicket = h->dTicket + 12;
 	hx.pushCtas = 8;
@@ -701,8 +706,11 @@ struct alignas(16) ArSlot { double value; unsigned seq; unsigned pad; };
  * a fast rank can be at most one all-reduce ahead of the slowest.
  */
 __global__ void allreduce_sum_kernel(double* dValue, int world, int myRank, PeerTables tables,
-	unsigned seq, unsigned long long timeoutNs)
+	unsigned seqValue, unsigned* seqPtr, unsigned long long timeoutNs)
 {
+	/* seqPtr: device counter of completed all-reduces (this one is *seqPtr + 1, stored back at the end) */
+	const unsigned seq = seqPtr ? *reinterpret_cast<volatile unsigned*>(seqPtr) + 1u : seqValue;
+	__syncwarp();
 	const int r = threadIdx.x;
 	const unsigned parity = seq & 1u;
 	double v = 0.0;
@@ -719,8 +727,11 @@ __global__ void allreduce_sum_kernel(double* dValue, int world, int myRank, Peer
 	double total = 0.0;
 	for (int k = 0; k < world; ++k)
 		total += __shfl_sync(SPGPU_FULL_MASK, v, k);
-	if (r == 0)
+	if (r == 0) {
 		*dValue = total;
+		if (seqPtr)
+			*seqPtr = seq;
+	}
 }
 
 extern "C" void spgpuAllreduceSumDev(spgpuHandle_t handle, double* dValue, int world, int myRank,
@@ -731,7 +742,35 @@ extern "C" void spgpuAllreduceSumDev(spgpuHandle_t handle, double* dValue, int w
 	PeerTables pt;
 	for (int r = 0; r < SPGPU_MAX_RANKS; ++r)
 		pt.t[r] = r < world ? (unsigned char*)tables[r] : NULL;
-	allreduce_sum_kernel<<<1, 32, 0, handle->currentStream>>>(dValue, world, myRank, pt, seq, 2000000000ull);
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	unsigned* seqPtr = (seq == 0u && h->magic == SPGPU_PRIV_MAGIC) ? h->dArSeq : NULL;
+	allreduce_sum_kernel<<<1, 32, 0, handle->currentStream>>>(dValue, world, myRank, pt, seq, seqPtr, 2000000000ull);
+	spgpu_count_launch(handle);
+}
+
+/* ---- device-resident sequence numbers (CUDA-graph replay of a partitioned iteration) ---------------- */
+
+extern "C" int spgpuSetSeqCounters(spgpuHandle_t handle, unsigned* dHaloSeq, unsigned* dAllreduceSeq)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	if (!h || h->magic != SPGPU_PRIV_MAGIC)
+		return -1;
+	h->dHaloSeq = dHaloSeq;
+	h->dArSeq = dAllreduceSeq;
+	return 0;
+}
+
+__global__ void seq_advance_kernel(unsigned* counter)
+{
+	*counter += 1u;
+}
+
+extern "C" void spgpuHaloSeqAdvance(spgpuHandle_t handle)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	if (!h || h->magic != SPGPU_PRIV_MAGIC || !h->dHaloSeq)
+		return;
+	seq_advance_kernel<<<1, 1, 0, handle->currentStream>>>(h->dHaloSeq);
 	spgpu_count_launch(handle);
 }
 

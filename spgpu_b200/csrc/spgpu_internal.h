@@ -55,6 +55,8 @@ typedef struct SpgpuHandlePriv {
 	int debug;                     /* SPGPU_DEBUG set: check for CUDA errors after every launch */
 	void* dBig;                    /* device: grow-only scratch (per-CTA partials of fused kernels) */
 	size_t bigBytes;
+	unsigned* dHaloSeq;            /* device counters registered with spgpuSetSeqCounters (ext): completed halo */
+	unsigned* dArSeq;              /* exchanges / all-reduces; used by calls that pass seq == 0                 */
 	SpgpuTuning tune;
 } SpgpuHandlePriv;
 

@@ -353,6 +353,15 @@ class PeerHalo:
         self.seq += 1
         return self.seq
 
+    # -- sequence numbers in device memory (CUDA-graph replay, include/spgpu_ext.h) --------------
+    def to_device_seq(self, counter: torch.Tensor):
+        """hand the exchange count to a 1-element int32 device counter (the handle must have been given
+        it with spgpuSetSeqCounters): from now on the fused kernels are called with seq = 0"""
+        counter.fill_(self.seq)
+
+    def from_device_seq(self, counter: torch.Tensor):
+        self.seq = int(counter.item())
+
     def close(self):
         torch.cuda.synchronize()
         for px, pf, _ in self.peer.values():
@@ -395,8 +404,23 @@ class PeerAllreduce:
 
     def __call__(self, t: torch.Tensor):
         """in-place sum of a 1-element float64 device tensor across the ranks (stream-ordered)"""
+        if self.device_seq:
+            self.L.spgpuAllreduceSumDev(self.h, t.data_ptr(), self.world, self.rank, self.tables, 0)
+            return
         self.seq += 1
         self.L.spgpuAllreduceSumDev(self.h, t.data_ptr(), self.world, self.rank, self.tables, self.seq)
+
+    device_seq = False
+
+    def to_device_seq(self, counter: torch.Tensor):
+        """continue the sequence from a device counter (spgpuSetSeqCounters): calls pass seq = 0 and the
+        kernel advances the counter itself, so the call can be replayed from a CUDA graph"""
+        counter.fill_(self.seq)
+        self.device_seq = True
+
+    def from_device_seq(self, counter: torch.Tensor):
+        self.seq = int(counter.item())
+        self.device_seq = False
 
     def close(self):
         torch.cuda.synchronize()

@@ -196,3 +196,47 @@ def test_spmv_halo_dot(ours, gpu_handle):
     own = x_ext[plane:plane + loc.nrows]
     ref = float(np.dot(own, want))
     assert abs(float(dres.item()) - ref) <= 1e-12 * float(np.sum(np.abs(own) * np.abs(want)))
+
+
+def test_device_resident_sequence_numbers(ours, gpu_handle):
+    """seq == 0: the fused halo kernel and the all-reduce take their sequence number from device counters
+    (spgpuSetSeqCounters); spgpuHaloSeqAdvance / the all-reduce itself advance them -- what lets a partitioned
+    iteration be replayed from a CUDA graph.  Emulated neighbours as above."""
+    import struct
+    import torch
+    coo, loc, plane, x, x_ext, want = _middle_block()
+    dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
+    dx = util.to_dev(x_ext)
+    counters = torch.tensor([6, 10], dtype=torch.int32, device="cuda")       # 6 exchanges, 10 all-reduces done so far
+    assert ours.spgpuSetSeqCounters(gpu_handle, counters.data_ptr(), counters.data_ptr() + 4) == 0
+    try:
+        my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+        pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
+        ph = [torch.zeros(plane, dtype=torch.float64, device="cuda") for _ in range(2)]
+        for k in (7, 8):                                                     # two exchanges: 7 and 8
+            my_flags[0] = k; my_flags[1] = k; my_flags[2] = k - 1; my_flags[3] = k - 1
+            dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+            ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), 0, 1.0, dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
+                                    drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0.0, 0, plane, ph[0].data_ptr(),
+                                    ph[1].data_ptr(), my_flags.data_ptr(), pf[0].data_ptr(), pf[1].data_ptr(), 0)
+            ours.spgpuHaloSeqAdvance(gpu_handle)
+            torch.cuda.synchronize()
+            util.assert_rows_close(dz.cpu().numpy(), want, np.full(loc.nrows, 12.0), "D", "fused spmv+halo, device seq")
+            assert int(counters[0].item()) == k
+            assert pf[0].cpu().numpy()[1] == k and pf[0].cpu().numpy()[3] == k
+            assert pf[1].cpu().numpy()[0] == k and pf[1].cpu().numpy()[2] == k
+        # all-reduce number 11, world 2, this rank 0: the peer's slot is pre-filled
+        world, me, seq = 2, 0, 11
+        tabs = [torch.zeros(2 * world * 4, dtype=torch.int32, device="cuda") for _ in range(world)]
+        host = np.zeros(2 * world * 4, dtype=np.int32)
+        lo, hi = struct.unpack("<ii", struct.pack("<d", 2.5))
+        base = ((seq & 1) * world + 1) * 4
+        host[base:base + 4] = [lo, hi, seq, 0]
+        tabs[me].copy_(torch.from_numpy(host))
+        value = torch.tensor([4.0], dtype=torch.float64, device="cuda")
+        ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in tabs])
+        ours.spgpuAllreduceSumDev(gpu_handle, value.data_ptr(), world, me, ptrs, 0)
+        torch.cuda.synchronize()
+        assert float(value.item()) == 6.5 and int(counters[1].item()) == 11
+    finally:
+        ours.spgpuSetSeqCounters(gpu_handle, 0, 0)
