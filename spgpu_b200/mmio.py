@@ -107,12 +107,18 @@ def write_coo(path: str, coo: Coo, field="real", symmetry="general", comment="wr
     with open(path, "w") as f:
         f.write(f"%%MatrixMarket matrix coordinate {field} {symmetry}\n% {comment}\n")
         f.write(f"{coo.nrows} {coo.ncols} {rows.shape[0]}\n")
+        # %.17g round-trips every double (and every float) exactly
+        r1, c1 = rows.astype(np.int64) + 1, cols.astype(np.int64) + 1
         if field == "pattern":
-            for r, c in zip(rows, cols):
-                f.write(f"{r + 1} {c + 1}\n")
+            np.savetxt(f, np.column_stack((r1, c1)), fmt="%d %d")
         elif field == "integer":
-            for r, c, v in zip(rows, cols, vals):
-                f.write(f"{r + 1} {c + 1} {int(v)}\n")
+            np.savetxt(f, np.column_stack((r1, c1, np.asarray(vals).astype(np.int64))), fmt="%d %d %d")
         else:
-            for r, c, v in zip(rows, cols, vals):
-                f.write(f"{r + 1} {c + 1} {float(v)!r}\n")
+            v = np.asarray(vals, dtype=np.float64)
+            try:
+                import pandas as pd                    # an order of magnitude faster than savetxt on 10^6+ lines
+                pd.DataFrame({"r": r1, "c": c1, "v": v}).to_csv(f, sep=" ", header=False, index=False, float_format="%.17g")
+            except ImportError:
+                table = np.empty(rows.shape[0], dtype=[("r", np.int64), ("c", np.int64), ("v", np.float64)])
+                table["r"], table["c"], table["v"] = r1, c1, v
+                np.savetxt(f, table, fmt="%d %d %.17g")
