@@ -405,6 +405,7 @@ struct HaloArgs {
 	unsigned* pushTicket; unsigned* doneTicket;
 	int pushCtas;
 	int headBlocks, tailBlocks;              /* 128-row blocks that read the lower / upper halo zone */
+	int fillerBlocks;                        /* interior blocks scheduled behind the boundary blocks (about three waves) */
 	unsigned long long timeoutNs;
 };
 
@@ -412,9 +413,10 @@ struct HaloArgs {
  * grid = pushCtas + ceil(rows/128).  The first pushCtas CTAs move the two boundary planes
  * into the neighbours' halo zones over NVLink (after the neighbours acknowledged the
  * previous ones) and publish `seq`.  Every other CTA multiplies 128 rows; the CTAs are
- * numbered so that the interior row blocks come first and the blocks that read a halo zone
- * come LAST -- by the time the hardware schedules them the neighbours' planes have long
- * arrived, and if not they spin on the local ready flag.  The last CTA to finish tells the
+ * numbered so that most interior row blocks come first and the blocks that read a halo zone
+ * come late (followed only by a few waves of interior blocks) -- by the time the hardware
+ * schedules them the neighbours' planes have long arrived, and if not they spin on the local
+ * ready flag.  The last CTA to finish tells the
  * neighbours that their halo data has been consumed.  Transfer and multiply overlap inside
  * one launch; there is no separate pack / exchange / wait / ack kernel.
  */
@@ -504,10 +506,15 @@ spmv_halo_kernel(const Body body, const HaloArgs hx, int xOffset, double* __rest
 		const unsigned head = min((unsigned)hx.headBlocks, rowBlocks);
 		const unsigned tail = min((unsigned)hx.tailBlocks, rowBlocks - head);
 		const unsigned interior = rowBlocks - head - tail;
+		/* a few waves of interior blocks go BEHIND the boundary blocks: a boundary block ends with a barrier,
+		 * a fence and a ticket, and as the very last CTAs of the grid nothing would overlap that latency */
+		const unsigned filler = min(interior >> 2, (unsigned)hx.fillerBlocks);
+		const unsigned early = interior - filler;
 		unsigned rb;
-		if (b < interior) rb = head + b;                       /* interior first            */
-		else if (b < interior + head) rb = b - interior;       /* then the lower boundary   */
-		else rb = b;                                           /* then the upper boundary   */
+		if (b < early) rb = head + b;                                          /* most of the interior first   */
+		else if (b < early + head) rb = b - early;                             /* then the lower boundary      */
+		else if (b < early + head + tail) rb = rowBlocks - tail + (b - early - head);   /* the upper boundary */
+		else rb = head + early + (b - early - head - tail);                    /* the rest of the interior     */
 		const bool needLo = rb < head, needHi = rb >= rowBlocks - tail;
 		const unsigned myRow = rb * 128u + threadIdx.x;
 		if (!needLo && !needHi) {
@@ -564,6 +571,7 @@ static HaloArgs halo_args(spgpuHandle_t handle, double* xExt, int rows, int halo
 	hx.pushCtas = 8;
 	hx.headBlocks = peerFlagsLo ? (haloN + 127) / 128 : 0;
 	hx.tailBlocks = peerFlagsHi ? (haloN + 127) / 128 : 0;
+	hx.fillerBlocks = 3 * 10 * handle->multiProcessorCount;
 	hx.timeoutNs = 2000000000ull;
 	return hx;
 }
