@@ -83,6 +83,16 @@ class LocalHell:
         return self.nrows + 2 * self.halo
 
 
+def _live_slots(rs: np.ndarray, hack_offsets: np.ndarray, hs: int) -> np.ndarray:
+    """element positions of every stored entry of a HELL block: entry k of row r sits at
+    hackOffsets[r / hackSize] + k * hackSize + r % hackSize, for k < rS[r]"""
+    rs64 = rs.astype(np.int64)
+    rows = np.repeat(np.arange(rs.shape[0], dtype=np.int64), rs64)
+    first = np.cumsum(rs64) - rs64
+    k = np.arange(rows.shape[0], dtype=np.int64) - first[rows]
+    return np.asarray(hack_offsets, dtype=np.int64)[rows // hs] + k * hs + rows % hs
+
+
 def split_hell(hell, world: int, rank: int, halo: int) -> LocalHell:
     """Cut rank's block out of a global host-side formats.Hell and remap its
     column indices to x_ext positions.  Raises if a row references a column
@@ -98,21 +108,12 @@ def split_hell(hell, world: int, rank: int, halo: int) -> LocalHell:
     rs = np.array(hell.rs[lo:hi], copy=True)
     local_hoff = (hoff[h0:h1] - e0).astype(np.int32)
     # remap only the slots that exist (padding is undefined and stays so)
-    nnz = 0
-    for h in range(h1 - h0):
-        rows = rs[h * hs:(h + 1) * hs]
-        if rows.size == 0:
-            continue
-        at = int(local_hoff[h])
-        for k in range(int(rows.max())):
-            live = np.nonzero(rows > k)[0]
-            sl = at + k * hs + live
-            g = indices[sl] - hell.base
-            if ((g < lo - halo) | (g >= hi + halo)).any():
-                raise ValueError("column outside the halo window; use mode='allgather'")
-            indices[sl] = g - (lo - halo) + hell.base
-            nnz += live.size
-    return LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, halo, hell.base, nnz)
+    sl = _live_slots(rs, local_hoff, hs)
+    g = indices[sl].astype(np.int64) - hell.base
+    if ((g < lo - halo) | (g >= hi + halo)).any():
+        raise ValueError("column outside the halo window; use mode='allgather'")
+    indices[sl] = (g - (lo - halo) + hell.base).astype(np.int32)
+    return LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, halo, hell.base, int(sl.size))
 
 
 def split_hell_allgather(hell, world: int, rank: int) -> LocalHell:
@@ -134,20 +135,11 @@ def split_hell_allgather(hell, world: int, rank: int) -> LocalHell:
     local_hoff = (hoff[h0:h1] - e0).astype(np.int32)
     starts = np.array([b[0] for b in blocks], dtype=np.int64)
     widest = max(b[1] - b[0] for b in blocks)
-    nnz = 0
-    for h in range(h1 - h0):
-        rows = rs[h * hs:(h + 1) * hs]
-        if rows.size == 0:
-            continue
-        at = int(local_hoff[h])
-        for k in range(int(rows.max())):
-            live = np.nonzero(rows > k)[0]
-            sl = at + k * hs + live
-            g = indices[sl].astype(np.int64) - hell.base
-            owner = np.searchsorted(starts, g, side="right") - 1
-            indices[sl] = (owner * widest + (g - starts[owner]) + hell.base).astype(np.int32)
-            nnz += live.size
-    out = LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, 0, hell.base, nnz)
+    sl = _live_slots(rs, local_hoff, hs)
+    g = indices[sl].astype(np.int64) - hell.base
+    owner = np.searchsorted(starts, g, side="right") - 1
+    indices[sl] = (owner * widest + (g - starts[owner]) + hell.base).astype(np.int32)
+    out = LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, 0, hell.base, int(sl.size))
     out.widest = widest
     return out
 
