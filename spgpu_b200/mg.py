@@ -466,8 +466,11 @@ class MgHellSpmv:
         self.head = min(nrows, -(-halo // align) * align)
         self.tail = max(self.head, ((nrows - halo) // align) * align)
         self.overlap = overlap and world > 1 and halo > 0 and self.tail > self.head
-        # fused_spmv(seq): the SpMV kernel that carries its own halo exchange (spgpuDhellspmvHalo)
-        self.fused_spmv = fused_spmv
+        # fused_spmv(seq): the SpMV kernel that carries its own halo exchange (spgpuDhellspmvHalo).  Its row
+        # blocks wait for ONE halo zone each (the first ceil(halo/128) blocks for the lower, the last for the
+        # upper); a block shorter than two halo widths has rows that read both, so it takes the separate
+        # exchange (which completes before any row is multiplied) instead.
+        self.fused_spmv = fused_spmv if nrows >= 2 * halo else None
 
     def apply(self, z, x_ext):
         w, n = self.halo, self.nrows
