@@ -191,9 +191,13 @@ void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi
  * rank: [0] ready-from-below, [1] ready-from-above, [2] ack-from-below,
  * [3] ack-from-above.  seq = 1, 2, 3, ... (same on every rank) numbers the exchanges.
  * The first CTAs push the two boundary planes over NVLink (after the neighbour
- * acknowledged the previous ones) and publish seq; interior row blocks are scheduled
- * first, the row blocks that read a halo zone last (they wait on the local ready
- * flag); the last CTA acknowledges the neighbours' halos.
+ * acknowledged the previous ones) and publish seq; most interior row blocks are scheduled
+ * first, then the row blocks that read a halo zone (they wait on the local ready flag),
+ * then a few waves of interior blocks; the last boundary CTA of each side acknowledges
+ * that neighbour's halo.  A row block waits for ONE zone (the first ceil(haloN/128)
+ * blocks for the lower, the last for the upper), so with neighbours on both sides the
+ * block must own at least 2*haloN rows; shorter blocks use spgpuDhaloExchange + the plain
+ * SpMV (spgpu_b200/mg.py does this by itself).
  */
 void spgpuDhellspmvHalo(spgpuHandle_t handle, __device double* z, const __device double* y,
 	double alpha, const __device double* cM, const __device int* rP, int hackSize,
