@@ -341,9 +341,23 @@ def make_step(L, h, w, x_ext_ptr, z_ptr, y_ptr):
 # CPU arm (OpenMP port of the same loop) -- oracle/liboracle.so
 # --------------------------------------------------------------------------- #
 
-def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
-    """Times the OpenMP host SpMV (oracle port) over the SAME format on a bounded
-    sample of the workload, all host threads.  Returns the cpu_baseline object."""
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_baseline(workload_name, budget_s=20.0, repeats=5, warmup=1, size=None):
+    """Times the OpenMP host SpMV (oracle port) over the SAME format, all host threads: `warmup`
+    untimed calls, then up to `repeats` timed calls (stops early once budget_s is spent).  cfg5 is
+    multiplied at FULL size when the host has the memory for it (14 GB of arrays), else on a
+    128-plane slab of the same grid; the `sample` string says which.  Returns (cpu_baseline
+    object, times) with times = the wall time of every timed call."""
     import torch
     from tests import util
     from spgpu_b200 import device_build as DB
@@ -360,16 +374,24 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
     cores = O.dll.oracle_num_threads()
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     if workload_name == "cfg5":
-        n, nz = 512, 128         # 128 planes of 512x512: 33.5 M rows, 234 M nnz (1/4 of the workload)
+        n = size or 512
+        full = host_mem_available_gb() > 3.5 * (n ** 3) * 7 * 12 / 1e9     # arrays + the pageable staging of the copy
+        nz = n if full else max(1, n // 4)
         A = DB.hell_laplace3d_7pt(n, 0, nz, local_columns=False, device=dev, nz=nz)
-        sample = f"{nz} z-planes of the same 512x512-plane 7-point Laplacian ({A.nrows} rows, {A.nnz} nnz), HELL double"
+        sample = (f"the FULL workload ({A.nrows} rows, {A.nnz} nnz), HELL double" if full else
+                  f"{nz} z-planes of the same {n}x{n}-plane 7-point Laplacian ({A.nrows} rows, {A.nnz} nnz; "
+                  f"host memory too small for the full matrix), HELL double")
         vals, idx, ho, rs = (t.cpu().numpy() for t in (A.values, A.indices, A.hack_offsets, A.rs))
-        x = np.random.default_rng(12345).random(A.ncols)
-        z = np.zeros(A.nrows)
+        nrows, ncols, nnz = A.nrows, A.ncols, A.nnz
+        del A
+        if dev == "cuda":
+            torch.cuda.empty_cache()
+        x = np.random.default_rng(12345).random(ncols)
+        z = np.zeros(nrows)
         T = util.TYPES["D"]
         call = lambda: O.Dhellspmv(util.ptr(z), None, T.scalar(1.0), util.ptr(vals), util.ptr(idx), 32,
-                                   util.ptr(ho), util.ptr(rs), None, 7, A.nrows, util.ptr(x), T.scalar(0.0), 0)
-        flops = 2 * A.nnz
+                                   util.ptr(ho), util.ptr(rs), None, 7, nrows, util.ptr(x), T.scalar(0.0), 0)
+        flops = 2 * nnz
     elif workload_name == "cfg2":
         A = DB.hdia_stencil27(128, device=dev)
         sample = f"the full 128^3 27-point HDIA matrix ({A.nrows} rows, {A.nnz} nnz)"
@@ -432,18 +454,21 @@ def cpu_baseline(workload_name, budget_s=20.0, repeats=5):
         flops = fl * A.nnz
     else:
         return None
-    call()                       # warm-up (page faults, thread pool)
-    best, spent = float("inf"), 0.0
-    for _ in range(repeats):
+    for _ in range(max(1, warmup)):          # untimed (page faults, thread pool)
+        call()
+    times, spent = [], 0.0
+    for _ in range(max(1, repeats)):
         t0 = time.perf_counter()
         call()
         dt = time.perf_counter() - t0
-        best = min(best, dt)
+        times.append(dt)
         spent += dt
         if spent > budget_s:
             break
-    return {"value": flops / best / 1e9, "unit": "GFLOP/s", "cores": int(cores), "kind": "port",
-            "sample": sample + f"; OpenMP schedule(static) over rows, best of {repeats}"}, best
+    mean = float(np.mean(times))
+    return {"value": flops / mean / 1e9, "unit": "GFLOP/s", "cores": int(cores), "kind": "port",
+            "best_value": flops / min(times) / 1e9,
+            "sample": sample + f"; OpenMP schedule(static) over rows, {max(1, warmup)} warm-up + mean of {len(times)} timed calls"}, times
 
 
 def cpu_baseline_mtx(w, budget_s=20.0, repeats=5):
@@ -488,6 +513,96 @@ def cpu_baseline_mtx(w, budget_s=20.0, repeats=5):
                       f"best of {repeats}"}
 
 
+def reference_kernels_leg(w, x_ptr, y, z_ours, step_ours, stream, device, dev_index, flush, reps, ours_ms):
+    """Times the reference library's own kernel for this workload's entry point on the SAME device buffers:
+    one CUDA-event pair per call on the reference handle's stream (its default, blocking stream), cold L2 where
+    our own timing flushes it.  The texture bind the reference issues per call is, under oracle/texshim.h, an
+    8-byte pointer upload; SPGPU_REF_ASYNC_BIND=1 makes it asynchronous so the pair brackets the kernel and not
+    a host synchronisation.  Also checks the reference's result against ours on these buffers."""
+    import torch
+    os.environ["SPGPU_REF_ASYNC_BIND"] = "1"          # read by the shim at its first bind
+    from tests import util
+    R = util.ref_lib()
+    if R is None:
+        return {"unavailable": "oracle/_ref/libspgpu_ref.so not built (needs /root/reference at build time)"}
+    rh = ctypes.c_void_p()
+    assert R.spgpuCreate(ctypes.byref(rh), dev_index) == 0
+    rstream = torch.cuda.ExternalStream(R.spgpuGetStream(rh), device=device)
+    z_ref = torch.full_like(z_ours, float("nan"))
+    step_ref = make_step(R, rh, w, x_ptr, z_ref.data_ptr(), y.data_ptr() if y is not None else 0)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        step_ref()
+    torch.cuda.synchronize()
+    pairs = []
+    for _ in range(reps):
+        if flush is not None:
+            flush()
+            rstream.wait_stream(stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(rstream)
+        step_ref()
+        b.record(rstream)
+        pairs.append((a, b))
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in pairs]))
+    step_ours()
+    torch.cuda.synchronize()
+    zr, zo = torch.view_as_real(z_ref) if z_ref.is_complex() else z_ref, torch.view_as_real(z_ours) if z_ours.is_complex() else z_ours
+    diff = float((zr - zo).abs().max().item())
+    scale = float(zo.abs().max().item())
+    R.spgpuDestroy(rh)
+    s, kind = w["sym"], w["kind"]
+    return {"entry": f"spgpu{s}{kind}spmv", "library": "oracle/_ref/libspgpu_ref.so (the reference's unmodified kernels, nvcc sm_100a, "
+            "texture fetches mapped to plain loads by oracle/texshim.h)",
+            "kernel_ms": ms, "gflops": w["flops_per_nnz"] * w["nnz"] / (ms * 1e-3) / 1e9,
+            "hbm_gbs": w["bytes"] / (ms * 1e-3) / 1e9, "ours_kernel_ms": ours_ms, "speedup_ours_vs_reference_kernels": ms / ours_ms,
+            "launches_timed": reps, "l2": "cold (flushed before every call)" if flush is not None else "inputs larger than L2",
+            "max_abs_diff_vs_ours": diff, "max_abs_ours": scale,
+            "what": "one CUDA-event pair per call on the reference handle's stream, same device buffers as our kernel"}
+
+
+def workload_label(name, size=None):
+    """The `config.workload` string of a synthetic workload (the same in both arms)."""
+    n = size
+    return {
+        "cfg5": f"3-D 7-point Laplacian {n or 512}^3, double HELL hackSize 32 (BASELINE configs[4])",
+        "cfg2": f"3-D 27-point stencil {n or 128}^3, double HDIA hackSize 32 (BASELINE configs[1])",
+        "cfg2dia": f"3-D 27-point stencil {n or 128}^3, double DIA (27 diagonals; BASELINE configs[1] stored as plain DIA)",
+        "cfg1": f"2-D 5-point Laplacian {n or 1000}x{n or 1000}, double ELL with rS (BASELINE configs[0])",
+        "cfg3": f"power-law rows {n or (1 << 22)} avg 16 max 4096, float HELL hackSize 32 (BASELINE configs[2])",
+        "cfg3o": f"power-law rows {n or (1 << 22)} avg 16 max 4096, float OHELL (rows sorted by length + rIdx) hackSize 32",
+        "cfg4": f"banded complex-double {n or 2_000_000} rows ~40 nnz/row, HELL hackSize 32 (BASELINE configs[3])",
+    }[name]
+
+
+def workload_config(name, size, world, halo, overlap, rows=None, nnz=None, flush_l2=None, alpha=None, beta=None):
+    """The `config` object of the JSON line.  Both arms print the same one (the reference arm fills in the
+    analytic row / nnz counts of the workloads it knows)."""
+    if rows is None and name == "cfg5":
+        n = size or 512
+        rows, nnz = n ** 3, 7 * n ** 3 - 6 * n * n
+    if rows is None and name in ("cfg2", "cfg2dia"):
+        n = size or 128
+        rows, nnz = n ** 3, (3 * n - 2) ** 3
+    if rows is None and name == "cfg1":
+        n = size or 1000
+        rows, nnz = n * n, 5 * n * n - 4 * n
+    if rows is None and name in ("cfg3", "cfg3o", "cfg4"):
+        rows = size or ((1 << 22) if name != "cfg4" else 2_000_000)      # nnz is only known once generated
+    if flush_l2 is None:
+        flush_l2 = name in ("cfg1", "cfg2", "cfg2dia", "cfg3", "cfg3o")
+    if alpha is None:
+        alpha, beta = ((0.7 - 0.3j), (-0.5 + 0.25j)) if name == "cfg4" else (1.0, 0.0)
+    cfg = {"workload": workload_label(name, size), "rows": rows, "nnz": nnz,
+           "parallelism": f"row-sharded z-slabs x{world}, halo={halo if world > 1 else 'none'}"
+                          f"{', interior/boundary overlap' if overlap and world > 1 else ''}",
+           "l2": "L2 evicted between timed steps by reading a 512 MB scratch (clean lines), outside the event pairs" if flush_l2
+                 else "inputs larger than L2 (>= 8x 126 MB per GPU), no flush",
+           "alpha": str(alpha), "beta": str(beta)}
+    return cfg
+
+
 # --------------------------------------------------------------------------- #
 # main
 # --------------------------------------------------------------------------- #
@@ -512,34 +627,47 @@ def main():
                          "default: one fused exchange kernel, then one SpMV launch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cg", action="store_true", help="also time CG iterations (SpMV + 2 dots + 3 axpby), cfg5 only")
+    ap.add_argument("--cg", dest="cg", action="store_true", default=None,
+                    help="also time CG iterations (SpMV + 2 dots + 3 axpby); default: on for cfg5 (BASELINE configs[4] reads 'plus CG step')")
+    ap.add_argument("--no-cg", dest="cg", action="store_false")
+    ap.add_argument("--no-ref-kernels", action="store_true",
+                    help="skip the reference_kernels leg (the reference's own kernels, oracle/_ref, on the same buffers; N=1, cfg5/cfg2)")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
                     help="CG scalars across GPUs: peer = one-double all-reduce over NVLink peer memory; nccl")
-    ap.add_argument("--verify", action="store_true",
-                    help="cfg5, N>1: check the partitioned result bit-for-bit against the same rows multiplied with global columns")
+    ap.add_argument("--verify", dest="verify", action="store_true", default=None,
+                    help="N>1: check the partitioned result bit-for-bit against the same rows multiplied with global columns "
+                         "(outside the timed region; default: on)")
+    ap.add_argument("--no-verify", dest="verify", action="store_false")
     ap.add_argument("--tune", default="", help="key=value,... passed to spgpuSetTuning")
     ap.add_argument("--sweep", default="", help="'k=v,k=v;k=v;...': kernel-only timing per tuning set (stderr)")
     args = ap.parse_args()
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
+    if args.cg is None:
+        args.cg = args.workload == "cfg5" and not args.matrix
+    if args.verify is None:
+        args.verify = True
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     # ---------------- reference arm: host OpenMP on rank 0 only -----------------
+    # W untimed + exactly K timed multiplications of the workload on the host cores; the line carries
+    # the same `config` as our arm's (workload_config) and says in cpu_baseline.sample what was multiplied.
     if args.impl == "reference":
         if rank != 0:
             return 0
-        arm = args.workload if args.workload in ("cfg1", "cfg2", "cfg2dia", "cfg3", "cfg3o", "cfg4", "cfg5") else "cfg5"
-        res = cpu_baseline(arm)
-        cb, best = res
-        # K timed steps of the bounded sample, W warm-ups (already warm after cpu_baseline)
+        arm = args.workload
+        cb, times = cpu_baseline(arm, budget_s=120.0, repeats=K, warmup=W, size=args.size)
+        mean = float(np.mean(times))
         out = {"impl": "reference", "metric": "spmv_gflops", "value": cb["value"], "unit": "GFLOP/s",
-               "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": best * 1e3,
+               "n_gpus": args.gpus, "steps": len(times), "warmup": W, "ms_per_step": mean * 1e3,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": {"cfg3": "f32", "cfg3o": "f32", "cfg4": "c128"}.get(arm, "f64"),
-               "data": "synthetic", "config": {"workload": arm, "arm": "host OpenMP SpMV over the same format"},
+               "data": "synthetic", "config": workload_config(arm, args.size, args.gpus, args.halo, args.overlap),
+               "arm": "host OpenMP SpMV (oracle port of the reference's kernel loop) over the same format on rank 0's host "
+                      "cores; the reference ships no CPU SpMV of its own",
                "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
@@ -574,8 +702,11 @@ def main():
         k, v = kv.split("=")
         assert L.spgpuSetTuning(h, k.encode(), int(v)) == 0, f"unknown tuning key {k}"
 
-    # everything (torch ops, NCCL, our kernels) is ordered on ONE stream: the handle's
-    stream = torch.cuda.ExternalStream(L.spgpuGetStream(h), device=device)
+    # everything (torch ops, NCCL, our kernels) is ordered on ONE stream.  It is a stream torch owns, handed
+    # to the handle with spgpuSetStream (reference core.c:62-72): torch's allocators remember the stream a
+    # block was used on, so the stream has to outlive the handle for the interpreter to exit normally.
+    stream = torch.cuda.Stream(device=device)
+    L.spgpuSetStream(h, stream.cuda_stream)
     torch.cuda.set_stream(stream)
 
     if args.matrix:
@@ -805,6 +936,19 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": w.get("kernel", f"{w['kind']}_spmv_kernel<{w['sym']}>"),
                 "kernel_ms": ker_ms, "algorithmic_bytes_per_launch": w["bytes"]}
+
+    # ---------------- the REFERENCE'S OWN kernels on the same buffers (N=1) ------
+    # SURVEY 8(d) "reference on B200" column: oracle/_ref/libspgpu_ref.so = the reference's unmodified sources
+    # compiled for sm_100a (test infrastructure; here only as a timed-beside baseline, outside the timed region,
+    # protocol of reference hellPerf.cpp:236-252 with CUDA events instead of a wall clock).
+    ref_kernels = None
+    if world == 1 and rank == 0 and not args.no_ref_kernels and not args.matrix and w["kind"] in ("hell", "hdia", "ell", "dia"):
+        try:
+            ref_kernels = reference_kernels_leg(w, x_ptr, y, z, step, stream, device, local_rank, flush if flush_l2 else None,
+                                                min(K, 10), ker_ms)
+        except Exception as exc:
+            print(f"reference_kernels leg failed: {exc!r}", file=sys.stderr, flush=True)
+            ref_kernels = {"unavailable": repr(exc)}
 
     # ---------------- optional tuning sweep (kernel only, stderr) ---------------
     for setting in filter(None, args.sweep.split(";")):
@@ -1080,7 +1224,7 @@ def main():
                     with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
                         cg.step_device()
                 finally:
-                    L.spgpuSetStream(h, None)
+                    L.spgpuSetStream(h, stream.cuda_stream)
                 torch.cuda.synchronize()
                 for _ in range(2):
                     g.replay()
@@ -1123,7 +1267,7 @@ def main():
             if args.matrix:
                 cb = cpu_baseline_mtx(w)
             else:
-                res = cpu_baseline(args.workload)
+                res = cpu_baseline(args.workload, size=args.size)
                 cb = res[0] if res else None
         except Exception as exc:          # a missing checker must not void the GPU measurement
             print(f"cpu_baseline leg failed: {exc!r}", file=sys.stderr, flush=True)
@@ -1134,16 +1278,15 @@ def main():
     if peer is not None:
         peer.close()
     if rank == 0:
+        cfg = workload_config(args.workload, args.size, world, args.halo, args.overlap, rows=w["total_rows"], nnz=int(nnz_total),
+                              flush_l2=flush_l2, alpha=w["alpha"], beta=w["beta"]) if not args.matrix else \
+            {"workload": w["label"], "rows": w["total_rows"], "nnz": int(nnz_total), "parallelism": "one GPU",
+             "l2": "flushed" if flush_l2 else "inputs larger than L2", "alpha": str(w["alpha"]), "beta": str(w["beta"])}
         out = {
             "metric": "spmv_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"S": "f32", "D": "f64", "C": "c64", "Z": "c128"}[w["sym"]], "data": "synthetic",
-            "config": {"workload": w["label"], "rows": w["total_rows"], "nnz": int(nnz_total),
-                       "parallelism": f"row-sharded z-slabs x{world}, halo={args.halo if world > 1 else 'none'}"
-                                      f"{', interior/boundary overlap' if args.overlap and world > 1 else ''}",
-                       "l2": "L2 evicted between timed steps by reading a 512 MB scratch (clean lines), outside the event pairs" if flush_l2
-                             else "inputs larger than L2 (>= 8x 126 MB per GPU), no flush",
-                       "alpha": str(w["alpha"]), "beta": str(w["beta"])},
+            "config": cfg,
             "hbm_gbs": bytes_total / (ms_step * 1e-3) / 1e9,
             "hbm_frac_of_peak": bytes_total / (ms_step * 1e-3) / 1e9 / (peak * world),
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
@@ -1153,8 +1296,12 @@ def main():
             out["verified_vs_global_columns"] = verified
         if cg_out is not None:
             out["cg"] = cg_out
+        if ref_kernels is not None:
+            out["reference_kernels"] = ref_kernels
         os.write(json_fd, (json.dumps(out) + "\n").encode())
-    # hand the stream back before the handle (and its stream) go away
+    # Teardown in dependency order, then a NORMAL return: the driver's exit hooks (which record the shared
+    # objects this process loaded) must run.  The stream is torch's (see above), so nothing torch still holds
+    # refers to a stream the handle owned.
     torch.cuda.synchronize()
     torch.cuda.set_stream(torch.cuda.default_stream(device))
     del step, op, z, y, x_ext, w, scratch
@@ -1162,11 +1309,12 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    L.spgpuSetStream(h, None)
     L.spgpuDestroy(h)
-    # pinned buffers and cached blocks that were used on the handle's (now destroyed) stream
-    # would make torch's allocators record events on it at interpreter exit: leave directly
     sys.stderr.flush()
-    os._exit(0)
+    os.dup2(json_fd, 1)                  # give stdout back (exit hooks may print)
+    os.close(json_fd)
+    return 0
 
 
 if __name__ == "__main__":
