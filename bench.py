@@ -742,24 +742,27 @@ def main():
     peer = None
     ex = mg.HaloExchange(rank, world, halo, "nccl")
     if world > 1 and args.halo in ("push", "fused"):
-        peer = mg.PeerHalo(L, h, rank, world, x_ptr, ext_len, halo)
+        peer = mg.PeerHalo(L, h, rank, world, x_ptr, ext_len, halo, itemsize=w["sizeof"])
 
     def make_fused(z_ptr_):
-        if peer is None or args.halo != "fused" or w["kind"] not in ("hell", "hdia") or w["sym"] != "D":
+        if peer is None or args.halo != "fused" or w["kind"] not in ("hell", "hdia"):
             return None
-        A = w["A"]
-        plo, phi, myf, pflo, pfhi = peer.fused_pointers()
+        A, s = w["A"], w["sym"]
+        t = capi.TYPES[s]
+        one, zero = t.scalar(1.0), t.scalar(0.0)
+        links = peer.links_ref()
         if w["kind"] == "hdia":
+            fn = getattr(L, f"spgpu{s}hdiaspmvHalo")
+
             def fused_hdia(seq):
-                L.spgpuDhdiaspmvHalo(h, z_ptr_, 0, 1.0, A.values.data_ptr(), A.offsets.data_ptr(), A.hack_size,
-                                     A.hack_offsets.data_ptr(), rows, A.ncols, x_ptr, 0.0, halo,
-                                     plo, phi, myf, pflo, pfhi, seq)
+                fn(h, z_ptr_, 0, one, A.values.data_ptr(), A.offsets.data_ptr(), A.hack_size,
+                   A.hack_offsets.data_ptr(), rows, A.ncols, x_ptr, zero, halo, links, seq)
             return fused_hdia
+        fn = getattr(L, f"spgpu{s}hellspmvHalo")
 
         def fused(seq):
-            L.spgpuDhellspmvHalo(h, z_ptr_, 0, 1.0, A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
-                                 A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, 0.0, A.base,
-                                 halo, plo, phi, myf, pflo, pfhi, seq)
+            fn(h, z_ptr_, 0, one, A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
+               A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, zero, A.base, halo, links, seq)
         return fused
 
     op = mg.MgHellSpmv(rank, world, rows, halo, lambda _z, _x, r0, r1: step(r0, r1), ex, peer,
@@ -867,6 +870,9 @@ def main():
     w.pop("full", None)
 
     # ---------------- device-resident timing ------------------------------------
+    halo_trace = bool(os.environ.get("SPGPU_BENCH_TRACE")) and peer is not None and args.halo == "fused"
+    if halo_trace:
+        L.spgpuSetTuning(h, b"haloTrace", 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                 # nvidia-smi needs ~0.1 s to start printing: begin before the warm-up
@@ -895,6 +901,19 @@ def main():
     barrier()
     ms_total = elapsed(e0, e1, pairs)
     launches = L.spgpuGetLaunchCount(h) - launches0
+    if halo_trace:
+        # per-exchange trace of the fused kernel for the K timed steps (include/spgpu_ext.h: spgpuHaloTraceRead)
+        buf = (ctypes.c_ulonglong * (8 * K))()
+        if L.spgpuHaloTraceRead(h, buf, peer.fseq - K + 1, K) == 0:
+            tr = np.frombuffer(buf, dtype=np.uint64).reshape(K, 8).astype(np.int64)
+            t0 = tr[0, 0]
+            for k in range(K):
+                r_ = tr[k]
+                print(f"rank {rank} seq {peer.fseq - K + 1 + k}: start {(r_[0] - t0) / 1e3:9.1f} us  push {(r_[1] - r_[0]) / 1e3:6.1f} us  "
+                      f"boundary first..last {(r_[6] - r_[0]) / 1e3:7.1f}..{(r_[7] - r_[0]) / 1e3:7.1f} us  "
+                      f"waited lo {r_[2] / 1e3:7.1f} us in {r_[4]} blocks, hi {r_[3] / 1e3:7.1f} us in {r_[5]} blocks",
+                      file=sys.stderr, flush=True)
+        L.spgpuSetTuning(h, b"haloTrace", 0)
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
@@ -1146,16 +1165,16 @@ def main():
             op_cg.apply(st.ap, x_ext)
 
         if world == 1:
-            def apply_A_dot(_z, _x, dres):
+            def apply_A_dot(_z, _x, dres, _ar):
                 L.spgpuDhellspmvDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
                                     A.hack_offsets.data_ptr(), A.rs.data_ptr(), rows, x_ptr, A.base, 0, dres)
         elif peer is not None and args.halo == "fused":
-            plo, phi, myf, pflo, pfhi = peer.fused_pointers()
+            links = peer.links_ref()
 
-            def apply_A_dot(_z, _x, dres):      # halo exchange + SpMV + this rank's p.Ap in one kernel (+ fold)
+            def apply_A_dot(_z, _x, dres, ar):  # halo exchange + SpMV + this rank's p.Ap in one kernel (+ fold + all-reduce)
                 L.spgpuDhellspmvHaloDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
                                         A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, A.base, halo,
-                                        plo, phi, myf, pflo, pfhi, peer.next_seq(), dres)
+                                        links, peer.next_seq(), dres, ar)
         else:
             apply_A_dot = None
 
@@ -1165,7 +1184,9 @@ def main():
             allred = peer_ar
         else:
             allred = (lambda t: dist.all_reduce(t)) if world > 1 else None
-        cg = krylov.Cg(L, h, st, apply_A, apply_A_dot, allred)
+        # the scalars of the device flavour are all-reduced by the last CTA of the kernel that produces them
+        # (no separate launch) when the peer all-reduce is in use
+        cg = krylov.Cg(L, h, st, apply_A, apply_A_dot, allred, ar_fused=peer_ar if apply_A_dot is not None else None)
         bvec = torch.rand(rows, generator=gen, device=device, dtype=torch.float64)
         iters = 10
         cg_out = {"iterations": iters}
@@ -1207,10 +1228,10 @@ def main():
                     peer.to_device_seq(counters[0:1])
                     peer_ar.to_device_seq(counters[1:2])
 
-                    def apply_A_dot_dev(_z, _x, dres):
+                    def apply_A_dot_dev(_z, _x, dres, ar):
                         L.spgpuDhellspmvHaloDot(h, st.ap.data_ptr(), A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
                                                 A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, A.base, halo,
-                                                plo, phi, myf, pflo, pfhi, 0, dres)
+                                                links, 0, dres, ar)
                         L.spgpuHaloSeqAdvance(h)
                     cg.apply_A_dot = apply_A_dot_dev
                 cg.start(bvec)
@@ -1277,6 +1298,7 @@ def main():
         rendezvous.close()
     if peer is not None:
         peer.close()
+    dev_status = L.spgpuGetDeviceStatus(h, 0)
     if rank == 0:
         cfg = workload_config(args.workload, args.size, world, args.halo, args.overlap, rows=w["total_rows"], nnz=int(nnz_total),
                               flush_l2=flush_l2, alpha=w["alpha"], beta=w["beta"]) if not args.matrix else \
@@ -1292,6 +1314,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        out["device_status"] = dev_status          # 0, or SPGPU_DEVSTATUS_TIMEOUT if a wait for a peer GPU gave up
         if verified is not None:
             out["verified_vs_global_columns"] = verified
         if cg_out is not None:

@@ -55,7 +55,7 @@ def main():
         "spgpuDasum (blocking)": (lambda: L.spgpuDasum(h, n, X), 8 * n),
         "spgpuDdotDev (device result)": (lambda: L.spgpuDdotDev(h, n, X, Y, dres.data_ptr()), 16 * n),
         "spgpuDcgUpdateDev": (lambda: L.spgpuDcgUpdateDev(h, Z, Y, X, w.data_ptr(), n, dres.data_ptr() + 8, dres.data_ptr() + 16,
-                                                          dres.data_ptr()), 48 * n),
+                                                          dres.data_ptr(), None), 48 * n),
         "spgpuDgath (n/16 random indices)": (lambda: L.spgpuDgath(h, xv.data_ptr(), m, idx.data_ptr(), 0, X), 20 * m),
         "spgpuDscat (n/16 random indices, beta=2)": (lambda: L.spgpuDscat(h, Z, m, xv.data_ptr(), idx.data_ptr(), 0,
                                                                            T.scalar(2.0)), 28 * m),

@@ -30,12 +30,32 @@ unsigned long long spgpuGetLaunchCount(spgpuHandle_t handle);
 
 /*
  * Kernel-selection knobs (per handle).  Keys: hellVariant, hellBlock,
- * hellLongFactor, hellSplit, hdiaVariant, hdiaBlock, redBlocksPerSm,
- * vecBlocksPerSm (meanings: csrc/spgpu_internal.h).  Returns 0, or -1 for an
- * unknown key.
+ * hellLongFactor, hellSplit, hdiaVariant, hdiaBlock, ellRows, ellShortMinB,
+ * redBlocksPerSm, vecBlocksPerSm, spinTimeoutMs, haloTrace, l2Fetch (meanings:
+ * csrc/spgpu_internal.h).  Returns 0, or -1 for an unknown key.
  */
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value);
 int spgpuGetTuning(spgpuHandle_t handle, const char* key);
+
+/*
+ * Sticky device-side status of the handle.  The kernels that wait for a peer GPU (halo flags,
+ * all-reduce slots, spgpuWaitFlag) never hang: a wait longer than the spinTimeoutMs tuning key
+ * (default 20000 ms, 0 = for ever) gives up, stores SPGPU_DEVSTATUS_TIMEOUT in a word of mapped
+ * pinned memory and finishes with the data it has; later waits of the handle then return at once.
+ * Returns the current status (clearing it when `clear` is non-zero), or -1 for a foreign handle.
+ * A non-zero status means results since the last clear must be discarded.
+ */
+#define SPGPU_DEVSTATUS_OK       0
+#define SPGPU_DEVSTATUS_TIMEOUT  1
+int spgpuGetDeviceStatus(spgpuHandle_t handle, int clear);
+
+/*
+ * Sizes the handle's grow-only device scratch (per-row-block partials of the fused SpMV + dot
+ * kernels: 16 bytes per 128 rows; the split-mode queue of sorted HELL matrices; multi-vector
+ * reduction results).  Growing synchronises the stream and allocates, which a CUDA-graph capture
+ * does not allow -- reserve before capturing (or run the same call once eagerly).  0, or -1.
+ */
+int spgpuReserveScratch(spgpuHandle_t handle, size_t bytes);
 
 /* ---- non-blocking reductions: result left in DEVICE memory ---------------- */
 
@@ -50,8 +70,33 @@ int spgpuGetTuning(spgpuHandle_t handle, const char* key);
 		const __device T* x, __device R* dRes);
 SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_DOT_DEV)
 
-/* dRes[0] = sum x_i, left in device memory (deterministic; folds per-CTA partials). */
-void spgpuDsumDev(spgpuHandle_t handle, int n, const __device double* x, __device double* dRes);
+/* dRes[0] = sum x_i, left in device memory (deterministic: per-CTA partials folded in index order). */
+#define SPGPU_DECL_SUM_DEV(S, T, R)                                          \
+	void spgpu##S##sumDev(spgpuHandle_t handle, int n, const __device T* x, __device T* dRes);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_SUM_DEV)
+
+/*
+ * One-value sum all-reduce across the ranks of a partition over NVLink peer memory (latency-bound
+ * payload: one round of remote 32-byte stores + local polling instead of an NCCL launch).
+ * tables[r] = pointer (a PEER pointer for r != myRank) to rank r's zero-initialised table of
+ * 2 * world slots of SPGPU_AR_SLOT_BYTES bytes; world <= 16; seq = 1, 2, 3, ... identical on every
+ * rank (0: taken from the device counter registered with spgpuSetSeqCounters).  All ranks obtain the
+ * same bits (values are added in rank order, in double).  The entry points below that take a
+ * `const spgpuPeerAllreduce* ar` run this exchange in the LAST CTA of the kernel that produces the
+ * scalar -- no separate launch in the dependent chain of an iteration; ar == NULL (or world <= 1)
+ * leaves the local value.
+ */
+#define SPGPU_AR_SLOT_BYTES 32
+typedef struct spgpuPeerAllreduce {
+	int world;
+	int myRank;
+	void* const* tables;
+	unsigned seq;
+} spgpuPeerAllreduce;
+#define SPGPU_DECL_ALLREDUCE(S, T, R)                                        \
+	void spgpu##S##allreduceSumDev(spgpuHandle_t handle, __device T* dValue, \
+		const spgpuPeerAllreduce* ar);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_ALLREDUCE)
 
 /*
  * z = (*dBetaNum / *dBetaDen) * betaSign * y + (*dAlphaNum / *dAlphaDen) *
@@ -59,33 +104,39 @@ void spgpuDsumDev(spgpuHandle_t handle, int n, const __device double* x, __devic
  * (pass NULL for a numerator/denominator pair to mean 1).  This is the shape of
  * every CG update: x += (rr/pAp) p ; r -= (rr/pAp) Ap ; p = r + (rr'/rr) p.
  */
-void spgpuDaxpbyDev(spgpuHandle_t handle, __device double* z, int n,
-	const __device double* dBetaNum, const __device double* dBetaDen,
-	double betaSign, const __device double* y,
-	const __device double* dAlphaNum, const __device double* dAlphaDen,
-	double alphaSign, const __device double* x);
+#define SPGPU_DECL_AXPBY_DEV(S, T, R)                                        \
+	void spgpu##S##axpbyDev(spgpuHandle_t handle, __device T* z, int n,      \
+		const __device T* dBetaNum, const __device T* dBetaDen,              \
+		double betaSign, const __device T* y,                                \
+		const __device T* dAlphaNum, const __device T* dAlphaDen,            \
+		double alphaSign, const __device T* x);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_AXPBY_DEV)
 
 /* ---- fused Krylov kernels --------------------- */
 
 /*
- * HELL SpMV z = A*x fused with dRes[0] = sum_i x[xOffset+i]*z[i] (the p.Ap of CG)
- * in the SpMV epilogue.  xOffset = position of row 0's own entry inside x
- * (0 on one GPU, the lower halo width on a partition).  Two launches: the SpMV leaves one
- * partial per CTA in handle-owned scratch, spgpuDsumDev folds them (deterministic).
+ * HELL SpMV z = A*x fused with dRes[0] = sum_i x[xOffset+i]*z[i] (the p.Ap of CG; unconjugated
+ * for C/Z like spgpu?dot) in the SpMV epilogue.  xOffset = position of row 0's own entry inside x
+ * (0 on one GPU).  Two launches: the SpMV leaves one partial per 128-row block in handle-owned
+ * scratch, a small kernel folds them (deterministic).
  */
-void spgpuDhellspmvDot(spgpuHandle_t handle, __device double* z,
-	const __device double* cM, const __device int* rP, int hackSize,
-	const __device int* hackOffsets, const __device int* rS, int rows,
-	const __device double* x, int baseIndex, int xOffset,
-	__device double* dRes);
+#define SPGPU_DECL_HELLSPMV_DOT(S, T, R)                                     \
+	void spgpu##S##hellspmvDot(spgpuHandle_t handle, __device T* z,          \
+		const __device T* cM, const __device int* rP, int hackSize,          \
+		const __device int* hackOffsets, const __device int* rS, int rows,   \
+		const __device T* x, int baseIndex, int xOffset, __device T* dRes);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_HELLSPMV_DOT)
 
 /*
- * Fused CG update: x += a*p ; r -= a*Ap ; dRrNew[0] = r.r, with a = *dRr / *dPAp read
- * from device memory.  One pass over four vectors instead of three kernels.
+ * Fused CG update: x += a*p ; r -= a*Ap ; dRrNew[0] = r.r (all-reduced when ar is given), with
+ * a = *dRr / *dPAp read from device memory.  One pass over four vectors instead of three kernels.
  */
-void spgpuDcgUpdateDev(spgpuHandle_t handle, __device double* x, __device double* r,
-	const __device double* p, const __device double* ap, int n,
-	const __device double* dRr, const __device double* dPAp, __device double* dRrNew);
+#define SPGPU_DECL_CGUPDATE_DEV(S, T, R)                                     \
+	void spgpu##S##cgUpdateDev(spgpuHandle_t handle, __device T* x, __device T* r, \
+		const __device T* p, const __device T* ap, int n,                    \
+		const __device T* dRr, const __device T* dPAp, __device T* dRrNew,   \
+		const spgpuPeerAllreduce* ar);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_CGUPDATE_DEV)
 
 /* ---- device-side format construction -------------------- */
 
@@ -155,26 +206,44 @@ int spgpuDeviceAlloc(void** devPtr, size_t bytes);
 int spgpuDeviceFree(void* devPtr);
 
 /*
- * Halo push over NVLink: copy n elements src[0..n) of this GPU into a PEER
- * pointer (obtained through spgpuIpcOpenHandle) with 128-bit stores, then
- * release-store `flagValue` to the peer's flag word so the consumer can wait on
- * it (spgpuWaitFlag).  One kernel, on the handle's stream.
+ * Flag block of a rank: SPGPU_HALO_FLAG_WORDS zero-initialised unsigned words in device memory that the
+ * neighbours can write (peer pointer / CUDA IPC).
+ *   separate-kernel protocol (spgpuHaloExchange / spgpuHaloAck / spgpuHaloPush / spgpuWaitFlag):
+ *     [0] ready-from-below  [1] ready-from-above  [2] ack-from-below  [3] ack-from-above
+ *   fused protocol (spgpu?{hell,hdia}spmvHalo[Dot]):
+ *     [4] ready-from-below  [5] ready-from-above
+ * The two protocols number their exchanges independently; both write the halo zones inside xExt, so
+ * the neighbouring ranks must be synchronised (any barrier) when a caller switches between them.
  */
+#define SPGPU_HALO_FLAG_WORDS 16
+
+/*
+ * Halo push over NVLink: copy `bytes` bytes of this GPU into a PEER pointer (CUDA IPC or peer
+ * access) with 128-bit stores, then release-store `flagValue` to the peer's flag word so the
+ * consumer can wait on it (spgpuWaitFlag).  One kernel, on the handle's stream.  peerDst == NULL
+ * with bytes == 0 only sets the flag.  spgpuDhaloPush: the same for n doubles.
+ */
+void spgpuHaloPush(spgpuHandle_t handle, void* peerDst, const void* src, size_t bytes,
+	unsigned* peerFlag, unsigned flagValue);
 void spgpuDhaloPush(spgpuHandle_t handle, double* peerDst, const double* src,
 	int n, unsigned* peerFlag, unsigned flagValue);
-/* Stream-ordered wait until *flag >= value (bounded spin, gives up after 2 s). */
+/* Stream-ordered wait until *flag >= value (bounded spin, see spgpuGetDeviceStatus). */
 void spgpuWaitFlag(spgpuHandle_t handle, const unsigned* flag, unsigned value);
 
 /*
- * Fused halo exchange of a 1-D chain of ranks, ONE kernel per SpMV: waits until
+ * Halo exchange of a 1-D chain of ranks as ONE kernel in front of the SpMV: waits until
  * the neighbours have acknowledged the previous halo (ackLo/ackHi, local flags,
- * value seq-1), pushes srcLo[0..n) into the lower neighbour's upper halo zone and
- * srcHi[0..n) into the upper neighbour's lower halo zone (peer pointers), release-
+ * value seq-1), pushes srcLo[0..bytes) into the lower neighbour's upper halo zone and
+ * srcHi[0..bytes) into the upper neighbour's lower halo zone (peer pointers), release-
  * stores seq into the neighbours' ready flags and returns when this rank's own
  * ready flags (myReadyLo/myReadyHi) have reached seq.  NULL pointers = no
  * neighbour on that side.  spgpuHaloAck (after the SpMV has consumed the halos)
- * stores seq into the neighbours' ack flags.
+ * stores seq into the neighbours' ack flags.  spgpuDhaloExchange: the same for n doubles.
  */
+void spgpuHaloExchange(spgpuHandle_t handle, void* peerDstLo, const void* srcLo,
+	void* peerDstHi, const void* srcHi, size_t bytes, const unsigned* ackLo,
+	const unsigned* ackHi, unsigned* peerReadyLo, unsigned* peerReadyHi,
+	const unsigned* myReadyLo, const unsigned* myReadyHi, unsigned seq);
 void spgpuDhaloExchange(spgpuHandle_t handle, double* peerDstLo, const double* srcLo,
 	double* peerDstHi, const double* srcHi, int n, const unsigned* ackLo,
 	const unsigned* ackHi, unsigned* peerReadyLo, unsigned* peerReadyHi,
@@ -182,80 +251,86 @@ void spgpuDhaloExchange(spgpuHandle_t handle, double* peerDstLo, const double* s
 void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq);
 
 /*
- * HELL SpMV of one row block FUSED with its halo exchange -- one kernel per
- * partitioned SpMV, transfer and multiply overlapped inside the launch.
- * xExt = [lower halo (haloN) | owned (rows) | upper halo (haloN)], columns of the
- * block index into it.  peerXLoUpperHalo / peerXHiLowerHalo are PEER pointers to the
- * neighbours' halo zones this rank fills (NULL = no neighbour on that side).
- * myFlags / peerFlagsLo / peerFlagsHi point at 4+ zero-initialised unsigned words per
- * rank: [0] ready-from-below, [1] ready-from-above, [2] ack-from-below,
- * [3] ack-from-above.  seq = 1, 2, 3, ... (same on every rank) numbers the exchanges.
- * The first CTAs push the two boundary planes over NVLink (after the neighbour
- * acknowledged the previous ones) and publish seq; most interior row blocks are scheduled
- * first, then the row blocks that read a halo zone (they wait on the local ready flag),
- * then a few waves of interior blocks; the last boundary CTA of each side acknowledges
- * that neighbour's halo.  A row block waits for ONE zone (the first ceil(haloN/128)
- * blocks for the lower, the last for the upper), so with neighbours on both sides the
- * block must own at least 2*haloN rows; shorter blocks use spgpuDhaloExchange + the plain
- * SpMV (spgpu_b200/mg.py does this by itself).
+ * Where the fused SpMV + halo kernels of a rank find its neighbours.  xExt = [lower zone (haloN) |
+ * owned (rows) | upper zone (haloN)].  Exchanges are double-buffered: exchange seq uses zone pair
+ * (seq & 1) -- the EVEN pair is the two zones inside xExt, the ODD pair a second set of zones
+ * outside it (haloN elements each, anywhere in the rank's device memory).  Index [0] = even,
+ * [1] = odd.  NULL peer flags = no neighbour on that side.
  */
-void spgpuDhellspmvHalo(spgpuHandle_t handle, __device double* z, const __device double* y,
-	double alpha, const __device double* cM, const __device int* rP, int hackSize,
-	const __device int* hackOffsets, const __device int* rS, int avgNnzPerRow, int rows,
-	__device double* xExt, double beta, int baseIndex, int haloN,
-	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
-	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq);
-
-/* The same kernel with this rank's share of p.Ap = sum_i xExt[haloN+i]*z[i] left in dRes
- * (alpha = 1, beta = 0); partials per row block in handle scratch, folded by spgpuDsumDev. */
-void spgpuDhellspmvHaloDot(spgpuHandle_t handle, __device double* z, const __device double* cM,
-	const __device int* rP, int hackSize, const __device int* hackOffsets, const __device int* rS,
-	int avgNnzPerRow, int rows, __device double* xExt, int baseIndex, int haloN,
-	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
-	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, __device double* dRes);
+typedef struct spgpuHaloLinks {
+	void* peerLoUpperZone[2];   /* PEER pointers: the LOWER neighbour's upper zones (this rank's first haloN owned entries go there) */
+	void* peerHiLowerZone[2];   /* PEER pointers: the UPPER neighbour's lower zones (this rank's last haloN owned entries go there)  */
+	void* myLoZoneOdd;          /* this rank's own odd lower / upper zones (the even ones are inside xExt) */
+	void* myHiZoneOdd;
+	unsigned* myFlags;          /* this rank's flag block */
+	unsigned* peerFlagsLo;      /* PEER pointers to the neighbours' flag blocks */
+	unsigned* peerFlagsHi;
+} spgpuHaloLinks;
 
 /*
- * HDIA twin of spgpuDhellspmvHalo (same halo protocol, same flag words): the row block is in
- * HDIA layout with its diagonal offsets addressing xExt = [halo | owned | halo], i.e. global
- * offset + haloN, and cols = rows + 2*haloN (what mg.split_hdia / device_build.hdia_row_block
- * produce).  Arguments up to beta as spgpuDhdiaspmv (reference hdia.h:38-142).
+ * HELL / HDIA SpMV of one row block FUSED with its halo exchange -- one kernel per partitioned SpMV,
+ * transfer and multiply overlapped inside the launch, for all four value types.  Arguments up to
+ * baseIndex as spgpu?hellspmv (reference hell.h:45-169) without rIdx, columns indexing xExt; the HDIA
+ * form takes the row block with its diagonal offsets addressing xExt, i.e. global offset + haloN,
+ * and cols = rows + 2*haloN (mg.split_hdia / device_build.hdia_row_block / spgpuMg*Create).
+ * seq = 1, 2, 3, ... (the same on every rank) numbers the exchanges; 0 = taken from the device counter
+ * registered with spgpuSetSeqCounters.
+ *
+ * The first CTAs push this rank's two boundary runs into the neighbours' zones of pair (seq & 1) over
+ * NVLink and publish seq; most interior row blocks are scheduled first, then the row blocks that read
+ * a zone (they wait on the local ready word and read the zones with coherent loads), then a few waves
+ * of interior blocks.  There are no acknowledgements: with two zone pairs a rank that starts exchange
+ * seq + 2 has seen its neighbour's ready(seq + 1), which the neighbour publishes only after its kernel
+ * seq has finished reading.  Requirements: every row references only columns within haloN of its own
+ * position (rows [0, haloN) may read the lower zone, rows [rows - haloN, rows) the upper one -- the
+ * host layers check this when they split a matrix); a rank with a neighbour owns at least haloN rows;
+ * consecutive fused calls of a rank are ordered on one stream.
+ *
+ * ...HaloDot: alpha = 1, beta = 0, plus dRes[0] = sum_i xExt[haloN+i]*z[i] (this rank's share of p.Ap,
+ * summed over all ranks when `ar` is given): per-row-block partials in handle scratch + one fold kernel
+ * whose last CTA runs the all-reduce.  links == NULL: the single-GPU fused SpMV + dot.
  */
-void spgpuDhdiaspmvHalo(spgpuHandle_t handle, __device double* z, const __device double* y, double alpha,
-	const __device double* dM, const __device int* offsets, int hackSize, const __device int* hackOffsets,
-	int rows, int cols, __device double* xExt, double beta, int haloN,
-	double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
-	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq);
-
-/* HDIA twin of spgpuDhellspmvHaloDot (alpha = 1, beta = 0; dRes[0] = sum_i xExt[haloN+i]*z[i]).  With no
- * neighbours (peer pointers NULL, haloN = 0, myFlags any 16-word device buffer) it is the single-GPU
- * fused HDIA SpMV + dot. */
-void spgpuDhdiaspmvHaloDot(spgpuHandle_t handle, __device double* z, const __device double* dM,
-	const __device int* offsets, int hackSize, const __device int* hackOffsets, int rows, int cols,
-	__device double* xExt, int haloN, double* peerXLoUpperHalo, double* peerXHiLowerHalo, unsigned* myFlags,
-	unsigned* peerFlagsLo, unsigned* peerFlagsHi, unsigned seq, __device double* dRes);
-
-/*
- * In-place sum all-reduce of ONE double over NVLink peer memory (latency-bound payload:
- * one round of remote 16-byte stores + local polling instead of an NCCL launch).
- * tables[r] = pointer (peer pointer for r != myRank) to rank r's zero-initialised table of
- * 2 * world 16-byte slots; world <= 16; seq = 1, 2, 3, ... identical on every rank.  All
- * ranks obtain the same bits (values are added in rank order).
- */
-void spgpuAllreduceSumDev(spgpuHandle_t handle, __device double* dValue, int world, int myRank,
-	void* const* tables, unsigned seq);
+#define SPGPU_DECL_SPMV_HALO(S, T, R)                                                                  \
+	void spgpu##S##hellspmvHalo(spgpuHandle_t handle, __device T* z, const __device T* y, T alpha,     \
+		const __device T* cM, const __device int* rP, int hackSize, const __device int* hackOffsets,   \
+		const __device int* rS, int avgNnzPerRow, int rows, __device T* xExt, T beta, int baseIndex,   \
+		int haloN, const spgpuHaloLinks* links, unsigned seq);                                         \
+	void spgpu##S##hellspmvHaloDot(spgpuHandle_t handle, __device T* z, const __device T* cM,          \
+		const __device int* rP, int hackSize, const __device int* hackOffsets, const __device int* rS, \
+		int avgNnzPerRow, int rows, __device T* xExt, int baseIndex, int haloN,                        \
+		const spgpuHaloLinks* links, unsigned seq, __device T* dRes, const spgpuPeerAllreduce* ar);    \
+	void spgpu##S##hdiaspmvHalo(spgpuHandle_t handle, __device T* z, const __device T* y, T alpha,     \
+		const __device T* dM, const __device int* offsets, int hackSize,                               \
+		const __device int* hackOffsets, int rows, int cols, __device T* xExt, T beta, int haloN,      \
+		const spgpuHaloLinks* links, unsigned seq);                                                    \
+	void spgpu##S##hdiaspmvHaloDot(spgpuHandle_t handle, __device T* z, const __device T* dM,          \
+		const __device int* offsets, int hackSize, const __device int* hackOffsets, int rows,          \
+		int cols, __device T* xExt, int haloN, const spgpuHaloLinks* links, unsigned seq,              \
+		__device T* dRes, const spgpuPeerAllreduce* ar);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_SPMV_HALO)
 
 /*
  * Sequence numbers in device memory, so that a partitioned iteration can be captured ONCE in a CUDA
  * graph and replayed (a by-value seq would be frozen into the graph).  After spgpuSetSeqCounters the
- * fused halo kernels (spgpu?{hell,hdia}spmvHalo[Dot]) and spgpuAllreduceSumDev, when called with
- * seq == 0, take their sequence number from the counters: *dHaloSeq / *dAllreduceSeq hold the number of
- * COMPLETED exchanges / all-reduces (start them at the host-side count, or 0).  The all-reduce kernel
- * advances its counter itself; the halo counter is advanced by spgpuHaloSeqAdvance, a one-thread kernel
- * the caller puts after each fused SpMV (the SpMV kernel's CTAs must all read the same value however
- * late they are scheduled).  Returns 0, or -1 for a foreign handle.
+ * fused halo kernels and the all-reduces, when called with seq == 0, take their sequence number from
+ * the counters: *dHaloSeq / *dAllreduceSeq hold the number of COMPLETED exchanges / all-reduces (start
+ * them at the host-side count, or 0).  An all-reduce advances its counter itself; the halo counter is
+ * advanced by spgpuHaloSeqAdvance, a one-thread kernel the caller puts after each fused SpMV (the SpMV
+ * kernel's CTAs must all read the same value however late they are scheduled).  Returns 0, or -1 for a
+ * foreign handle.
  */
 int spgpuSetSeqCounters(spgpuHandle_t handle, __device unsigned* dHaloSeq, __device unsigned* dAllreduceSeq);
 void spgpuHaloSeqAdvance(spgpuHandle_t handle);
+
+/*
+ * Per-exchange trace of the fused kernels (tuning key haloTrace = 1): 8 words for each of `count`
+ * exchanges starting at sequence number firstSeq (a ring of 1024): [0] first push CTA started,
+ * [1] ready flags published (device nanoseconds, %globaltimer), [2] / [3] nanoseconds the row blocks
+ * spent waiting for the lower / upper ready word (summed over blocks, waits > 2 us only), [4] / [5]
+ * how many blocks waited, [6] first boundary block started, [7] last boundary block finished.
+ * Synchronises the stream.  0, or -1.
+ */
+int spgpuHaloTraceRead(spgpuHandle_t handle, unsigned long long* hostOut, int firstSeq, int count);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,24 @@ class SpgpuHandleStruct(ctypes.Structure):
     ]
 
 
+class HaloLinks(ctypes.Structure):
+    """spgpuHaloLinks (include/spgpu_ext.h): where a rank's fused SpMV + halo kernels find the neighbours."""
+    _fields_ = [
+        ("peerLoUpperZone", c_void_p * 2), ("peerHiLowerZone", c_void_p * 2),
+        ("myLoZoneOdd", c_void_p), ("myHiZoneOdd", c_void_p),
+        ("myFlags", c_void_p), ("peerFlagsLo", c_void_p), ("peerFlagsHi", c_void_p),
+    ]
+
+
+class PeerAllreduceArgs(ctypes.Structure):
+    """spgpuPeerAllreduce (include/spgpu_ext.h)."""
+    _fields_ = [("world", c_int), ("myRank", c_int), ("tables", ctypes.POINTER(c_void_p)), ("seq", ctypes.c_uint)]
+
+
+AR_SLOT_BYTES = 32
+HALO_FLAG_WORDS = 16
+
+
 class TypeInfo:
     def __init__(self, sym, ctype, rtype, np_dtype, code, is_complex):
         self.sym, self.ctype, self.rtype = sym, ctype, rtype
@@ -108,17 +126,19 @@ def abi_symbols():
 
 def ext_symbols():
     """Every symbol include/spgpu_ext.h declares (additive API)."""
-    names = ["spgpuB200Version", "spgpuGetLaunchCount", "spgpuSetTuning", "spgpuGetTuning"]
+    names = ["spgpuB200Version", "spgpuGetLaunchCount", "spgpuSetTuning", "spgpuGetTuning",
+             "spgpuGetDeviceStatus", "spgpuReserveScratch"]
     for s in FLOAT_SYMS:
-        names += [f"spgpu{s}dotDev", f"spgpu{s}nrm2sqDev"]
+        names += [f"spgpu{s}dotDev", f"spgpu{s}nrm2sqDev", f"spgpu{s}sumDev", f"spgpu{s}allreduceSumDev",
+                  f"spgpu{s}axpbyDev", f"spgpu{s}hellspmvDot", f"spgpu{s}cgUpdateDev",
+                  f"spgpu{s}hellspmvHalo", f"spgpu{s}hellspmvHaloDot", f"spgpu{s}hdiaspmvHalo", f"spgpu{s}hdiaspmvHaloDot"]
     names += ["spgpuCsrToHellLayoutDevice"] + [f"spgpu{s}csrToHellDevice" for s in FLOAT_SYMS]
     names += ["spgpuCsrToOhellLayoutDevice"] + [f"spgpu{s}csrToOhellDevice" for s in FLOAT_SYMS]
     names += ["spgpuHdiaHackOffsetsFromCooDevice"] + [f"spgpu{s}cooToHdiaDevice" for s in FLOAT_SYMS]
-    names += ["spgpuDaxpbyDev", "spgpuDhellspmvDot", "spgpuDcgUpdateDev", "spgpuDsumDev",
-              "spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
-              "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuDhaloPush", "spgpuWaitFlag",
-              "spgpuDhaloExchange", "spgpuHaloAck", "spgpuDhellspmvHalo",
-              "spgpuDhellspmvHaloDot", "spgpuDhdiaspmvHalo", "spgpuDhdiaspmvHaloDot", "spgpuAllreduceSumDev", "spgpuSetSeqCounters", "spgpuHaloSeqAdvance"]
+    names += ["spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
+              "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuHaloPush", "spgpuDhaloPush", "spgpuWaitFlag",
+              "spgpuHaloExchange", "spgpuDhaloExchange", "spgpuHaloAck", "spgpuSetSeqCounters", "spgpuHaloSeqAdvance",
+              "spgpuHaloTraceRead"]
     return names
 
 
@@ -230,10 +250,26 @@ class SpgpuLib:
             for s in FLOAT_SYMS:
                 f[f"spgpu{s}dotDev"] = _sig(d, f"spgpu{s}dotDev", None, [H, c_int, P, P, P], optional=True)
                 f[f"spgpu{s}nrm2sqDev"] = _sig(d, f"spgpu{s}nrm2sqDev", None, [H, c_int, P, P], optional=True)
-            f["spgpuDaxpbyDev"] = _sig(d, "spgpuDaxpbyDev", None,
-                [H, P, c_int, P, P, c_double, P, P, P, c_double, P], optional=True)
-            f["spgpuDhellspmvDot"] = _sig(d, "spgpuDhellspmvDot", None,
-                [H, P, P, P, c_int, P, P, c_int, P, c_int, c_int, P], optional=True)
+            f["spgpuGetDeviceStatus"] = _sig(d, "spgpuGetDeviceStatus", c_int, [H, c_int], optional=True)
+            f["spgpuReserveScratch"] = _sig(d, "spgpuReserveScratch", c_int, [H, c_size_t], optional=True)
+            LK, AR, U = ctypes.POINTER(HaloLinks), ctypes.POINTER(PeerAllreduceArgs), ctypes.c_uint
+            for s in FLOAT_SYMS:
+                T = TYPES[s].ctype
+                f[f"spgpu{s}sumDev"] = _sig(d, f"spgpu{s}sumDev", None, [H, c_int, P, P], optional=True)
+                f[f"spgpu{s}allreduceSumDev"] = _sig(d, f"spgpu{s}allreduceSumDev", None, [H, P, AR], optional=True)
+                f[f"spgpu{s}axpbyDev"] = _sig(d, f"spgpu{s}axpbyDev", None,
+                    [H, P, c_int, P, P, c_double, P, P, P, c_double, P], optional=True)
+                f[f"spgpu{s}hellspmvDot"] = _sig(d, f"spgpu{s}hellspmvDot", None,
+                    [H, P, P, P, c_int, P, P, c_int, P, c_int, c_int, P], optional=True)
+                f[f"spgpu{s}cgUpdateDev"] = _sig(d, f"spgpu{s}cgUpdateDev", None, [H, P, P, P, P, c_int, P, P, P, AR], optional=True)
+                f[f"spgpu{s}hellspmvHalo"] = _sig(d, f"spgpu{s}hellspmvHalo", None,
+                    [H, P, P, T, P, P, c_int, P, P, c_int, c_int, P, T, c_int, c_int, LK, U], optional=True)
+                f[f"spgpu{s}hellspmvHaloDot"] = _sig(d, f"spgpu{s}hellspmvHaloDot", None,
+                    [H, P, P, P, c_int, P, P, c_int, c_int, P, c_int, c_int, LK, U, P, AR], optional=True)
+                f[f"spgpu{s}hdiaspmvHalo"] = _sig(d, f"spgpu{s}hdiaspmvHalo", None,
+                    [H, P, P, T, P, P, c_int, P, c_int, c_int, P, T, c_int, LK, U], optional=True)
+                f[f"spgpu{s}hdiaspmvHaloDot"] = _sig(d, f"spgpu{s}hdiaspmvHaloDot", None,
+                    [H, P, P, P, c_int, P, c_int, c_int, P, c_int, LK, U, P, AR], optional=True)
             f["spgpuCsrToHellLayoutDevice"] = _sig(d, "spgpuCsrToHellLayoutDevice", c_int,
                 [H, c_int, P, c_int, P, P, ctypes.POINTER(ctypes.c_longlong)], optional=True)
             for s in FLOAT_SYMS:
@@ -248,8 +284,6 @@ class SpgpuLib:
                     [H, c_int, P, P, P, c_int, c_int, P, P, c_int, P, P], optional=True)
                 f[f"spgpu{s}cooToHdiaDevice"] = _sig(d, f"spgpu{s}cooToHdiaDevice", c_int,
                     [H, P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int], optional=True)
-            f["spgpuDsumDev"] = _sig(d, "spgpuDsumDev", None, [H, c_int, P, P], optional=True)
-            f["spgpuDcgUpdateDev"] = _sig(d, "spgpuDcgUpdateDev", None, [H, P, P, P, P, c_int, P, P, P], optional=True)
             f["spgpuIpcGetHandle"] = _sig(d, "spgpuIpcGetHandle", c_int, [P, P], optional=True)
             f["spgpuIpcOpenHandle"] = _sig(d, "spgpuIpcOpenHandle", c_int,
                 [P, ctypes.POINTER(c_void_p)], optional=True)
@@ -257,26 +291,17 @@ class SpgpuLib:
             f["spgpuDeviceAlloc"] = _sig(d, "spgpuDeviceAlloc", c_int,
                 [ctypes.POINTER(c_void_p), c_size_t], optional=True)
             f["spgpuDeviceFree"] = _sig(d, "spgpuDeviceFree", c_int, [P], optional=True)
-            f["spgpuDhaloPush"] = _sig(d, "spgpuDhaloPush", None,
-                [H, P, P, c_int, P, ctypes.c_uint], optional=True)
-            f["spgpuWaitFlag"] = _sig(d, "spgpuWaitFlag", None, [H, P, ctypes.c_uint], optional=True)
+            f["spgpuHaloPush"] = _sig(d, "spgpuHaloPush", None, [H, P, P, c_size_t, P, U], optional=True)
+            f["spgpuDhaloPush"] = _sig(d, "spgpuDhaloPush", None, [H, P, P, c_int, P, U], optional=True)
+            f["spgpuWaitFlag"] = _sig(d, "spgpuWaitFlag", None, [H, P, U], optional=True)
+            f["spgpuHaloExchange"] = _sig(d, "spgpuHaloExchange", None,
+                [H, P, P, P, P, c_size_t, P, P, P, P, P, P, U], optional=True)
             f["spgpuDhaloExchange"] = _sig(d, "spgpuDhaloExchange", None,
-                [H, P, P, P, P, c_int, P, P, P, P, P, P, ctypes.c_uint], optional=True)
-            f["spgpuHaloAck"] = _sig(d, "spgpuHaloAck", None, [H, P, P, ctypes.c_uint], optional=True)
-            f["spgpuDhellspmvHaloDot"] = _sig(d, "spgpuDhellspmvHaloDot", None,
-                [H, P, P, P, c_int, P, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, ctypes.c_uint, P], optional=True)
-            f["spgpuAllreduceSumDev"] = _sig(d, "spgpuAllreduceSumDev", None,
-                [H, P, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.c_uint], optional=True)
+                [H, P, P, P, P, c_int, P, P, P, P, P, P, U], optional=True)
+            f["spgpuHaloAck"] = _sig(d, "spgpuHaloAck", None, [H, P, P, U], optional=True)
             f["spgpuSetSeqCounters"] = _sig(d, "spgpuSetSeqCounters", c_int, [H, P, P], optional=True)
             f["spgpuHaloSeqAdvance"] = _sig(d, "spgpuHaloSeqAdvance", None, [H], optional=True)
-            f["spgpuDhdiaspmvHaloDot"] = _sig(d, "spgpuDhdiaspmvHaloDot", None,
-                [H, P, P, P, c_int, P, c_int, c_int, P, c_int, P, P, P, P, P, ctypes.c_uint, P], optional=True)
-            f["spgpuDhdiaspmvHalo"] = _sig(d, "spgpuDhdiaspmvHalo", None,
-                [H, P, P, c_double, P, P, c_int, P, c_int, c_int, P, c_double, c_int,
-                 P, P, P, P, P, ctypes.c_uint], optional=True)
-            f["spgpuDhellspmvHalo"] = _sig(d, "spgpuDhellspmvHalo", None,
-                [H, P, P, c_double, P, P, c_int, P, P, c_int, c_int, P, c_double, c_int, c_int,
-                 P, P, P, P, P, ctypes.c_uint], optional=True)
+            f["spgpuHaloTraceRead"] = _sig(d, "spgpuHaloTraceRead", c_int, [H, P, c_int, c_int], optional=True)
 
     def __getattr__(self, name):
         try:

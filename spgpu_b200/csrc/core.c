@@ -26,6 +26,10 @@ static void default_tuning(SpgpuTuning* t)
 	t->ellRows = 0;
 	t->redBlocksPerSm = 4;
 	t->vecBlocksPerSm = 8;
+	t->spinTimeoutMs = 20000;
+	t->haloTrace = 0;
+	t->l2Fetch = 0;
+	t->ellShortMinB = 0;
 }
 
 spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
@@ -108,6 +112,9 @@ void spgpuDestroy(spgpuHandle_t pHandle)
 		if (h->dTicket) cudaFree(h->dTicket);
 		if (h->hResult) cudaFreeHost(h->hResult);
 		if (h->dBig) cudaFree(h->dBig);
+		if (h->dTrace) cudaFree(h->dTrace);
+		if (h->dTicketsMany) cudaFree(h->dTicketsMany);
+		if (h->switchEvent) cudaEventDestroy(h->switchEvent);
 		h->magic = 0;
 	}
 	free(h);
@@ -127,10 +134,34 @@ void spgpuStreamDestroy(cudaStream_t stream)
 	cudaStreamDestroy(stream);
 }
 
+/*
+ * Reference core.c:62-72 only swaps the pointer.  Here the handle owns scratch that its kernels
+ * reuse in stream order (reduction partials, tickets, the split-mode queue), so work queued on the
+ * new stream must not overtake what is still in flight on the old one: an event recorded on the
+ * old stream is waited for by the new one (a device-side dependency, no host synchronisation).
+ * Skipped while either stream is being captured into a CUDA graph (the caller orders those).
+ */
 void spgpuSetStream(spgpuHandle_t pHandle, cudaStream_t stream)
 {
-	SpgpuHandleStruct* h = (SpgpuHandleStruct*)pHandle;
-	h->currentStream = stream ? stream : h->defaultStream;
+	SpgpuHandlePriv* h = spgpuPriv(pHandle);
+	cudaStream_t next = stream ? stream : h->pub.defaultStream;
+	cudaStream_t prev = h->pub.currentStream;
+	if (next != prev && h->magic == SPGPU_PRIV_MAGIC && h->switchEvent) {
+		enum cudaStreamCaptureStatus a = cudaStreamCaptureStatusNone, b = cudaStreamCaptureStatusNone;
+		int previous = 0;
+		cudaGetDevice(&previous);
+		if (previous != h->pub.device)
+			cudaSetDevice(h->pub.device);
+		if (cudaStreamIsCapturing(prev, &a) == cudaSuccess && cudaStreamIsCapturing(next, &b) == cudaSuccess &&
+				a == cudaStreamCaptureStatusNone && b == cudaStreamCaptureStatusNone) {
+			if (cudaEventRecord(h->switchEvent, prev) == cudaSuccess)
+				cudaStreamWaitEvent(next, h->switchEvent, 0);
+		}
+		(void)cudaGetLastError();        /* a stream the caller has already destroyed is not this call's error */
+		if (previous != h->pub.device)
+			cudaSetDevice(previous);
+	}
+	h->pub.currentStream = next;
 }
 
 cudaStream_t spgpuGetStream(spgpuHandle_t pHandle)
@@ -156,16 +187,75 @@ void* spgpuScratch(spgpuHandle_t handle, size_t bytes)
 		return NULL;
 	if (h->bigBytes >= bytes)
 		return h->dBig;
-	/* grow: earlier work on the stream may still use the old block */
-	cudaStreamSynchronize(h->pub.currentStream);
-	if (h->dBig)
-		cudaFree(h->dBig);
-	h->dBig = NULL;
-	h->bigBytes = 0;
-	if (cudaMalloc(&h->dBig, bytes) != cudaSuccess)
-		return NULL;
-	h->bigBytes = bytes;
+	/* grow: earlier work on the stream may still use the old block.  This synchronises and allocates, which a
+	 * CUDA-graph capture does not allow: callers that capture size the scratch first (spgpuReserveScratch, or one
+	 * eager call of the same shape).  The block lives on the HANDLE's device whatever device is current. */
+	{
+		int previous = 0;
+		void* fresh = NULL;
+		cudaGetDevice(&previous);
+		if (previous != h->pub.device)
+			cudaSetDevice(h->pub.device);
+		cudaStreamSynchronize(h->pub.currentStream);
+		if (h->dBig)
+			cudaFree(h->dBig);
+		h->dBig = NULL;
+		h->bigBytes = 0;
+		if (cudaMalloc(&fresh, bytes) == cudaSuccess) {
+			h->dBig = fresh;
+			h->bigBytes = bytes;
+		}
+		if (previous != h->pub.device)
+			cudaSetDevice(previous);
+	}
 	return h->dBig;
+}
+
+unsigned* spgpuTickets(spgpuHandle_t handle, size_t count)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	if (!h || h->magic != SPGPU_PRIV_MAGIC)
+		return NULL;
+	if (h->ticketsMany < count) {
+		int previous = 0;
+		void* fresh = NULL;
+		size_t want = count < 1024 ? 1024 : count;
+		cudaGetDevice(&previous);
+		if (previous != h->pub.device)
+			cudaSetDevice(h->pub.device);
+		cudaStreamSynchronize(h->pub.currentStream);
+		if (h->dTicketsMany)
+			cudaFree(h->dTicketsMany);
+		h->dTicketsMany = NULL;
+		h->ticketsMany = 0;
+		if (cudaMalloc(&fresh, want * sizeof(unsigned)) == cudaSuccess &&
+				cudaMemset(fresh, 0, want * sizeof(unsigned)) == cudaSuccess) {
+			h->dTicketsMany = (unsigned*)fresh;
+			h->ticketsMany = want;
+		} else if (fresh) {
+			cudaFree(fresh);
+		}
+		if (previous != h->pub.device)
+			cudaSetDevice(previous);
+	}
+	return h->dTicketsMany;
+}
+
+int spgpuReserveScratch(spgpuHandle_t handle, size_t bytes)
+{
+	return spgpuScratch(handle, bytes) ? 0 : -1;
+}
+
+int spgpuGetDeviceStatus(spgpuHandle_t handle, int clear)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	unsigned v;
+	if (!h || h->magic != SPGPU_PRIV_MAGIC || !h->hStatus)
+		return -1;
+	v = *(volatile unsigned*)h->hStatus;
+	if (clear)
+		*(volatile unsigned*)h->hStatus = 0u;
+	return (int)v;
 }
 
 /* ---- additive API (include/spgpu_ext.h) ---------------------------------- */
@@ -179,13 +269,50 @@ void* spgpuScratch(spgpuHandle_t handle, size_t bytes)
 	X(hdiaBlock)              \
 	X(ellRows)                \
 	X(redBlocksPerSm)         \
-	X(vecBlocksPerSm)
+	X(vecBlocksPerSm)         \
+	X(spinTimeoutMs)          \
+	X(haloTrace)              \
+	X(l2Fetch)                \
+	X(ellShortMinB)
 
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value)
 {
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	if (!h || h->magic != SPGPU_PRIV_MAGIC || !key)
 		return -1;
+	/* keys with a side effect on the device */
+	if (strcmp(key, "haloTrace") == 0 || strcmp(key, "l2Fetch") == 0) {
+		int previous = 0, rc = 0;
+		cudaGetDevice(&previous);
+		if (previous != h->pub.device)
+			cudaSetDevice(h->pub.device);
+		if (key[0] == 'h') {
+			if (value && !h->dTrace) {
+				void* p = NULL;
+				const size_t bytes = (size_t)1024 * 8 * sizeof(unsigned long long);
+				if (cudaMalloc(&p, bytes) == cudaSuccess && cudaMemset(p, 0, bytes) == cudaSuccess)
+					h->dTrace = (unsigned long long*)p;
+				else
+					rc = -1;
+			} else if (!value && h->dTrace) {
+				cudaStreamSynchronize(h->pub.currentStream);
+				cudaFree(h->dTrace);
+				h->dTrace = NULL;
+			}
+			if (rc == 0)
+				h->tune.haloTrace = value;
+		} else {
+			if (value > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value) != cudaSuccess) {
+				(void)cudaGetLastError();
+				rc = -1;
+			} else {
+				h->tune.l2Fetch = value;
+			}
+		}
+		if (previous != h->pub.device)
+			cudaSetDevice(previous);
+		return rc;
+	}
 #define SET_KEY(name) if (strcmp(key, #name) == 0) { h->tune.name = value; return 0; }
 	TUNE_KEYS(SET_KEY)
 #undef SET_KEY
@@ -211,5 +338,5 @@ unsigned long long spgpuGetLaunchCount(spgpuHandle_t handle)
 
 const char* spgpuB200Version(void)
 {
-	return "spgpu-b200 0.1 (sm_100a)";
+	return "spgpu-b200 0.2 (sm_100a)";
 }

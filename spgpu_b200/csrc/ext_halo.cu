@@ -1,0 +1,614 @@
+/*
+ * Row-partitioned multi-GPU SpMV, device side (include/spgpu_ext.h).  No reference counterpart:
+ * the reference is one handle per device with no communication (reference core.h:88-93).
+ *
+ *   - spgpuHaloPush / spgpuWaitFlag / spgpuHaloExchange / spgpuHaloAck: the halo exchange of a
+ *     1-D chain of ranks as separate kernels (NVLink peer stores + flag words);
+ *   - spgpu?{hell,hdia}spmvHalo[Dot]: ONE kernel per partitioned SpMV -- the exchange travels
+ *     inside the SpMV launch, for all four value types;
+ *   - spgpu?allreduceSumDev: one-value sum all-reduce over NVLink peer memory.
+ */
+#include <cstring>
+#include "launch.cuh"
+#include "peer_sync.cuh"
+#include "spmv_hell_body.cuh"
+#include "spmv_hdia_body.cuh"
+
+/* byte copy into (peer) memory by the CTAs [cta, ctas) of a group: 128-bit stores when both sides allow */
+__device__ __forceinline__ void copy_bytes(void* dst, const void* src, size_t bytes, unsigned cta, unsigned ctas)
+{
+	const size_t tid = (size_t)cta * blockDim.x + threadIdx.x;
+	const size_t nthreads = (size_t)ctas * blockDim.x;
+	if ((((size_t)dst | (size_t)src) & 15) == 0) {
+		const size_t nv = bytes >> 4;
+		uint4* d4 = reinterpret_cast<uint4*>(dst);
+		const uint4* s4 = reinterpret_cast<const uint4*>(src);
+		size_t p = tid;
+		for (; p + nthreads < nv; p += 2 * nthreads) {          /* two loads in flight per thread */
+			const uint4 a = s4[p], b = s4[p + nthreads];
+			d4[p] = a;
+			d4[p + nthreads] = b;
+		}
+		if (p < nv)
+			d4[p] = s4[p];
+		for (size_t e = (nv << 4) + tid; e < bytes; e += nthreads)
+			reinterpret_cast<unsigned char*>(dst)[e] = reinterpret_cast<const unsigned char*>(src)[e];
+	} else if ((((size_t)dst | (size_t)src | bytes) & 3) == 0) {
+		unsigned* d = reinterpret_cast<unsigned*>(dst);
+		const unsigned* s = reinterpret_cast<const unsigned*>(src);
+		for (size_t e = tid; e < (bytes >> 2); e += nthreads)
+			d[e] = s[e];
+	} else {
+		for (size_t e = tid; e < bytes; e += nthreads)
+			reinterpret_cast<unsigned char*>(dst)[e] = reinterpret_cast<const unsigned char*>(src)[e];
+	}
+}
+
+static SpinCtl spin_ctl(spgpuHandle_t handle)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	SpinCtl c;
+	const int ms = h->magic == SPGPU_PRIV_MAGIC ? h->tune.spinTimeoutMs : 20000;
+	c.timeoutNs = ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
+	c.status = h->magic == SPGPU_PRIV_MAGIC ? h->dStatus : NULL;
+	return c;
+}
+
+/* ---- halo exchange as separate kernels ------------------------------------------------- */
+
+/*
+ * Copies `bytes` bytes of this GPU into a peer GPU's memory; the last CTA to finish (ticket in
+ * local memory) makes the data visible system-wide and release-stores flagValue into the peer's
+ * flag word.
+ */
+__global__ void __launch_bounds__(256)
+halo_push_kernel(void* peerDst, const void* src, size_t bytes, unsigned* peerFlag, unsigned flagValue, unsigned* ticket)
+{
+	__shared__ bool amLast;
+	if (peerDst)
+		copy_bytes(peerDst, src, bytes, blockIdx.x, gridDim.x);
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0)
+		amLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (amLast && threadIdx.x == 0) {
+		*ticket = 0u;
+		if (peerFlag) {
+			__threadfence_system();
+			st_release_sys(peerFlag, flagValue);
+		}
+	}
+}
+
+static unsigned push_grid(spgpuHandle_t handle, size_t bytes)
+{
+	long long want = (long long)((bytes / 16 + 255) / 256);
+	if (want > 2 * handle->multiProcessorCount) want = 2 * handle->multiProcessorCount;
+	if (want < 1) want = 1;
+	return (unsigned)want;
+}
+
+extern "C" void spgpuHaloPush(spgpuHandle_t handle, void* peerDst, const void* src, size_t bytes,
+	unsigned* peerFlag, unsigned flagValue)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	/* the ticket word next to the reductions' one (offset 16 bytes) */
+	halo_push_kernel<<<push_grid(handle, bytes), 256, 0, handle->currentStream>>>(peerDst, src, bytes,
+		peerFlag, flagValue, h->dTicket + 4);
+	spgpu_count_launch(handle);
+}
+
+extern "C" void spgpuDhaloPush(spgpuHandle_t handle, double* peerDst, const double* src,
+	int n, unsigned* peerFlag, unsigned flagValue)
+{
+	spgpuHaloPush(handle, peerDst, src, n > 0 ? (size_t)n * sizeof(double) : 0, peerFlag, flagValue);
+}
+
+/*
+ * One kernel: even CTAs copy srcLo into the LOWER neighbour's upper halo zone, odd CTAs srcHi into
+ * the UPPER neighbour's lower halo zone.  Before copying, a CTA waits until that neighbour has
+ * acknowledged the previous halo (so it is not overwritten while still being read).  The last CTA
+ * to finish release-stores the sequence number into both neighbours' "ready" flags and then waits
+ * for this rank's own two "ready" flags, so the kernel completes exactly when this rank's halos
+ * have arrived.
+ */
+__global__ void __launch_bounds__(256)
+halo_exchange_kernel(void* dstLo, const void* srcLo, void* dstHi, const void* srcHi,
+	size_t bytes, const unsigned* ackLo, const unsigned* ackHi, unsigned* peerReadyLo,
+	unsigned* peerReadyHi, const unsigned* myReadyLo, const unsigned* myReadyHi,
+	unsigned seq, unsigned* ticket, SpinCtl spin)
+{
+	__shared__ bool amLast;
+	const bool toHi = (blockIdx.x & 1) != 0;
+	void* dst = toHi ? dstHi : dstLo;
+	const void* src = toHi ? srcHi : srcLo;
+	const unsigned* ack = toHi ? ackHi : ackLo;
+	if (dst) {
+		if (threadIdx.x == 0 && ack && seq > 1)
+			spin_until(ack, seq - 1, spin);
+		__syncthreads();
+		copy_bytes(dst, src, bytes, blockIdx.x >> 1, gridDim.x >> 1);
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0)
+		amLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (amLast && threadIdx.x == 0) {
+		*ticket = 0u;
+		__threadfence_system();
+		if (peerReadyLo) st_release_sys(peerReadyLo, seq);
+		if (peerReadyHi) st_release_sys(peerReadyHi, seq);
+		if (myReadyLo) spin_until(myReadyLo, seq, spin);
+		if (myReadyHi) spin_until(myReadyHi, seq, spin);
+	}
+}
+
+extern "C" void spgpuHaloExchange(spgpuHandle_t handle, void* peerDstLo, const void* srcLo,
+	void* peerDstHi, const void* srcHi, size_t bytes, const unsigned* ackLo, const unsigned* ackHi,
+	unsigned* peerReadyLo, unsigned* peerReadyHi, const unsigned* myReadyLo,
+	const unsigned* myReadyHi, unsigned seq)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	long long want = 2 * (long long)((bytes / 32 + 255) / 256);
+	const long long cap = 2LL * (handle->multiProcessorCount / 2 > 0 ? handle->multiProcessorCount / 2 : 1);
+	if (want > cap) want = cap;
+	if (want < 2) want = 2;
+	halo_exchange_kernel<<<(unsigned)want, 256, 0, handle->currentStream>>>(peerDstLo, srcLo, peerDstHi, srcHi,
+		bytes, ackLo, ackHi, peerReadyLo, peerReadyHi, myReadyLo, myReadyHi, seq, h->dTicket + 8, spin_ctl(handle));
+	spgpu_count_launch(handle);
+}
+
+extern "C" void spgpuDhaloExchange(spgpuHandle_t handle, double* peerDstLo, const double* srcLo,
+	double* peerDstHi, const double* srcHi, int n, const unsigned* ackLo, const unsigned* ackHi,
+	unsigned* peerReadyLo, unsigned* peerReadyHi, const unsigned* myReadyLo,
+	const unsigned* myReadyHi, unsigned seq)
+{
+	spgpuHaloExchange(handle, peerDstLo, srcLo, peerDstHi, srcHi, n > 0 ? (size_t)n * sizeof(double) : 0,
+		ackLo, ackHi, peerReadyLo, peerReadyHi, myReadyLo, myReadyHi, seq);
+}
+
+__global__ void halo_ack_kernel(unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq)
+{
+	__threadfence_system();
+	if (peerAckLo) st_release_sys(peerAckLo, seq);
+	if (peerAckHi) st_release_sys(peerAckHi, seq);
+}
+
+extern "C" void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi, unsigned seq)
+{
+	halo_ack_kernel<<<1, 1, 0, handle->currentStream>>>(peerAckLo, peerAckHi, seq);
+	spgpu_count_launch(handle);
+}
+
+/* Bounded spin on a flag in LOCAL device memory written by a peer GPU. */
+__global__ void wait_flag_kernel(const unsigned* flag, unsigned value, SpinCtl spin)
+{
+	spin_until(flag, value, spin);
+}
+
+extern "C" void spgpuWaitFlag(spgpuHandle_t handle, const unsigned* flag, unsigned value)
+{
+	wait_flag_kernel<<<1, 1, 0, handle->currentStream>>>(flag, value, spin_ctl(handle));
+	spgpu_count_launch(handle);
+}
+
+/* ---- HELL / HDIA SpMV fused with the halo exchange: ONE kernel per partitioned SpMV ---- */
+
+/*
+ * Protocol (per side; words of the per-rank flag block, spgpu_ext.h): exchange number seq = 1, 2, ...
+ * uses zone pair (seq & 1): the even pair is the two halo zones inside x_ext, the odd pair a second
+ * set of zones outside it (spgpuHaloLinks.my*ZoneOdd).  The push CTAs copy this rank's boundary
+ * entries into the neighbours' zones of that pair and release-store seq into the neighbours' ready
+ * words; the row blocks that read a zone acquire-spin on the local ready word.  There is NO
+ * acknowledgement: a rank can only start exchange seq + 2 (which overwrites pair seq & 1) after its
+ * own kernel seq + 1 has finished, that kernel's boundary rows have waited for the neighbour's
+ * ready(seq + 1), and the neighbour publishes that from its kernel seq + 1, which starts -- same
+ * stream -- after its kernel seq has read the pair for the last time.  So neighbours may drift a
+ * whole kernel apart without waiting for each other, and a boundary row block costs one flag load
+ * more than an interior one (no fence, no ticket).  Consecutive fused calls of a rank must be
+ * ordered on ONE stream.
+ */
+template <typename T>
+struct HaloArgs {
+	T* dstLo[2]; const T* srcLo;            /* my first n owned entries -> lower neighbour's upper zone (even, odd) */
+	T* dstHi[2]; const T* srcHi;            /* my last n owned entries  -> upper neighbour's lower zone            */
+	int n;
+	long long dLoOdd, dHiOdd;               /* element distance from my zones inside x_ext to my odd zones          */
+	unsigned* peerReadyLo; unsigned* peerReadyHi;        /* remote: my entries for `seq` are in place          */
+	const unsigned* myReadyLo; const unsigned* myReadyHi;/* local : the neighbour's entries for `seq` are in place */
+	unsigned seq;                           /* sequence number of this exchange, or ... */
+	const unsigned* seqPtr;                 /* ... (seq == 0) device counter of COMPLETED exchanges: this one is *seqPtr + 1 */
+	unsigned* pushTicket;
+	int pushCtas;
+	unsigned headBlocks;                    /* 128-row blocks [0, headBlocks) hold a row that reads the lower zone */
+	unsigned firstHiBlock;                  /* 128-row blocks [firstHiBlock, ..) hold a row that reads the upper zone */
+	unsigned fillerBlocks;                  /* interior blocks scheduled behind the boundary blocks */
+	SpinCtl spin;
+	unsigned long long* trace;              /* NULL, or 8 words per exchange (haloTrace tuning key) */
+};
+
+#define SPGPU_TRACE_SLOTS 1024
+
+/* z_i * x[xOffset+i] summed over the CTA, one partial per ROW BLOCK (fixed order) */
+__device__ __forceinline__ void cta_dot_partial(Acc2 contrib, Acc2* ctaPartials, unsigned slot)
+{
+	__shared__ Acc2 ws[4];
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1) {
+		contrib.a += __shfl_xor_sync(SPGPU_FULL_MASK, contrib.a, m);
+		contrib.b += __shfl_xor_sync(SPGPU_FULL_MASK, contrib.b, m);
+	}
+	if ((threadIdx.x & 31) == 0)
+		ws[threadIdx.x >> 5] = contrib;
+	__syncthreads();
+	if (threadIdx.x == 0)
+		ctaPartials[slot] = Acc2{ (ws[0].a + ws[1].a) + (ws[2].a + ws[3].a), (ws[0].b + ws[1].b) + (ws[2].b + ws[3].b) };
+}
+
+/* what a row block of the fused kernel multiplies: the HELL or the HDIA warp body */
+template <typename T, int UNROLL, int HACK>
+struct HellRowBody {
+	HellArgs<T> a;
+	__device__ __forceinline__ int rows() const { return a.rows; }
+	__device__ __forceinline__ const T* x() const { return a.x; }
+	template <class XG>
+	__device__ __forceinline__ T run(unsigned warpRow, const XG xg) const
+	{
+		T zval;
+		hell_warp_rows_value_x<T, UNROLL, HACK, XG>(a, warpRow, zval, xg);
+		return zval;
+	}
+};
+
+template <typename T, int UNROLL, int HACK>
+struct HdiaRowBody {
+	HdiaArgs<T> a;
+	__device__ __forceinline__ int rows() const { return a.rows; }
+	__device__ __forceinline__ const T* x() const { return a.x; }
+	template <class XG>
+	__device__ __forceinline__ T run(unsigned warpRow, const XG xg) const
+	{
+		T zval;
+		hdia_warp_rows_value_x<T, UNROLL, HACK, false, XG>(a, warpRow, zval, xg);
+		return zval;
+	}
+};
+
+/*
+ * grid = pushCtas + ceil(rows/128).  The first pushCtas CTAs move the two boundary runs into the
+ * neighbours' zones over NVLink and publish `seq`.  Every other CTA multiplies 128 rows; the CTAs
+ * are numbered so that most interior row blocks come first and the blocks that read a zone come
+ * late (followed only by a few waves of interior blocks, so that a late neighbour delays nothing
+ * but the blocks that need it) -- by the time the hardware schedules them the neighbours' entries
+ * have normally long arrived.  A block may read both zones (a rank with fewer rows than two halo
+ * widths): it then waits for both words.
+ */
+template <typename T, class Body, int MINB, bool DOT>
+__global__ void __launch_bounds__(128, MINB)
+spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, Acc2* __restrict__ ctaPartials)
+{
+	/* the counter is advanced by a later kernel in stream order (spgpuHaloSeqAdvance), never during this
+	 * one, so every CTA reads the same value whenever it is scheduled */
+	const unsigned seq = hx.seqPtr ? *reinterpret_cast<const volatile unsigned*>(hx.seqPtr) + 1u : hx.seq;
+	const unsigned par = seq & 1u;
+	unsigned long long* tr = hx.trace ? hx.trace + (size_t)(seq & (SPGPU_TRACE_SLOTS - 1)) * 8 : NULL;
+	if (blockIdx.x < (unsigned)hx.pushCtas) {
+		const bool toHi = (blockIdx.x & 1) != 0;
+		T* dst = toHi ? hx.dstHi[par] : hx.dstLo[par];
+		const T* src = toHi ? hx.srcHi : hx.srcLo;
+		if (tr && threadIdx.x == 0 && blockIdx.x == 0) {
+			for (int k = 2; k < 8; ++k)
+				tr[k] = 0ull;
+			tr[0] = global_timer_ns();
+		}
+		if (dst)
+			copy_bytes(dst, src, (size_t)hx.n * sizeof(T), blockIdx.x >> 1, (unsigned)hx.pushCtas >> 1);
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			if (atomicAdd(hx.pushTicket, 1u) == (unsigned)hx.pushCtas - 1u) {
+				*hx.pushTicket = 0u;
+				__threadfence_system();
+				if (hx.peerReadyLo) st_release_sys(hx.peerReadyLo, seq);
+				if (hx.peerReadyHi) st_release_sys(hx.peerReadyHi, seq);
+				if (tr)
+					tr[1] = global_timer_ns();
+			}
+		}
+		return;
+	}
+	const unsigned b = blockIdx.x - hx.pushCtas;
+	const unsigned rows = (unsigned)body.rows();
+	const unsigned rowBlocks = (rows + 127u) >> 7;
+	const unsigned nLo = min(hx.headBlocks, rowBlocks);
+	const unsigned hiStart = max(min(hx.firstHiBlock, rowBlocks), nLo);
+	const unsigned nHi = rowBlocks - hiStart;
+	const unsigned interior = hiStart - nLo;
+	const unsigned filler = min(interior >> 2, hx.fillerBlocks);
+	const unsigned early = interior - filler;
+	unsigned rb;
+	if (b < early) rb = nLo + b;                                          /* most of the interior first   */
+	else if (b < early + nLo) rb = b - early;                             /* then the lower boundary      */
+	else if (b < early + nLo + nHi) rb = hiStart + (b - early - nLo);     /* the upper boundary           */
+	else rb = nLo + early + (b - early - nLo - nHi);                      /* the rest of the interior     */
+	const bool needLo = rb < hx.headBlocks && hx.myReadyLo != NULL;
+	const bool needHi = rb >= hx.firstHiBlock && hx.myReadyHi != NULL;
+	const unsigned myRow = rb * 128u + threadIdx.x;
+	T zval;
+	if (!needLo && !needHi) {
+		/* interior: no flags -- exactly the plain kernel */
+		const XPlain<T> xg = { body.x() };
+		zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
+	} else {
+		if (threadIdx.x == 0) {
+			unsigned long long t0 = 0;
+			if (tr) {
+				t0 = global_timer_ns();
+				atomicCAS(tr + 6, 0ull, t0);
+			}
+			if (needLo) spin_until(hx.myReadyLo, seq, hx.spin);
+			if (tr) {
+				const unsigned long long t1 = global_timer_ns();
+				if (needLo && t1 - t0 > 2000ull) { atomicAdd(tr + 2, t1 - t0); atomicAdd(tr + 4, 1ull); }
+				t0 = t1;
+			}
+			if (needHi) spin_until(hx.myReadyHi, seq, hx.spin);
+			if (tr) {
+				const unsigned long long t1 = global_timer_ns();
+				if (needHi && t1 - t0 > 2000ull) { atomicAdd(tr + 3, t1 - t0); atomicAdd(tr + 5, 1ull); }
+			}
+		}
+		__syncthreads();
+		const XZones<T> xg = { body.x(), par ? hx.dLoOdd : 0ll, par ? hx.dHiOdd : 0ll, hx.n, hx.n + (int)rows };
+		zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
+		if (tr && threadIdx.x == 0)
+			atomicMax(tr + 7, global_timer_ns());
+	}
+	if (DOT) {
+		Acc2 c = { 0.0, 0.0 };
+		if (myRow < rows)
+			c = to_acc2<T>(Num<T>::mul(zval, __ldg(body.x() + xOffset + myRow)));
+		cta_dot_partial(c, ctaPartials, rb);
+	}
+}
+
+/* flag words (spgpu_ext.h): [4] fused-ready-from-below [5] fused-ready-from-above */
+template <typename T>
+static HaloArgs<T> halo_args(spgpuHandle_t handle, T* xExt, int rows, int haloN, const spgpuHaloLinks* L, unsigned seq)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	HaloArgs<T> hx;
+	memset(&hx, 0, sizeof(hx));
+	const bool lo = L && L->peerFlagsLo && haloN > 0, hi = L && L->peerFlagsHi && haloN > 0;
+	/* a rank with a neighbour sends its first / last haloN OWNED entries: it must own at least that many
+	 * (the host layers check this: mg.py _check_block, spgpuMg*Create) */
+	const int n = haloN < rows ? haloN : rows;
+	hx.n = haloN;
+	if (lo) {
+		hx.dstLo[0] = (T*)L->peerLoUpperZone[0]; hx.dstLo[1] = (T*)L->peerLoUpperZone[1];
+		hx.peerReadyLo = L->peerFlagsLo + 5;
+		hx.myReadyLo = L->myFlags + 4;
+		hx.dLoOdd = (const T*)L->myLoZoneOdd - xExt;
+	}
+	if (hi) {
+		hx.dstHi[0] = (T*)L->peerHiLowerZone[0]; hx.dstHi[1] = (T*)L->peerHiLowerZone[1];
+		hx.peerReadyHi = L->peerFlagsHi + 4;
+		hx.myReadyHi = L->myFlags + 5;
+		hx.dHiOdd = (const T*)L->myHiZoneOdd - (xExt + haloN + rows);
+	}
+	hx.srcLo = xExt + haloN;
+	hx.srcHi = xExt + rows;                                 /* last haloN owned entries */
+	hx.seq = seq;
+	hx.seqPtr = (seq == 0u && h->magic == SPGPU_PRIV_MAGIC) ? h->dHaloSeq : NULL;
+	hx.pushTicket = h->dTicket + 8;
+	hx.pushCtas = (lo || hi) ? 8 : 0;
+	/* rows [0, haloN) may read the lower zone, rows [rows - haloN, rows) the upper one (band |col - row| <= haloN) */
+	hx.headBlocks = lo ? (unsigned)((n + 127) / 128) : 0u;
+	hx.firstHiBlock = hi ? (unsigned)((rows - n) / 128) : 0xffffffffu;
+	hx.fillerBlocks = 3u * 10u * (unsigned)handle->multiProcessorCount;
+	hx.spin = spin_ctl(handle);
+	hx.trace = h->magic == SPGPU_PRIV_MAGIC ? h->dTrace : NULL;
+	return hx;
+}
+
+/* resident CTAs per SM the register allocator must leave room for (spmv_hell.cu: float 48 warps, double 40, complex 32) */
+template <typename T> struct HaloMinB { static constexpr int hell = Num<T>::is_complex ? 8 : (sizeof(T) == 4 ? 12 : 10); };
+
+template <typename T, int UNROLL>
+static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
+	const T* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
+	int avgNnzPerRow, int rows, T* xExt, T beta, int baseIndex, int haloN,
+	const spgpuHaloLinks* links, unsigned seq, Acc2* ctaPartials)
+{
+	const SpgpuTuning* t = spgpu_tuning(handle);
+	const HellArgs<T> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
+		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1, 0, NULL, NULL, 0, NULL, NULL };
+	const HaloArgs<T> hx = halo_args<T>(handle, xExt, rows, haloN, links, seq);
+	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
+	cudaStream_t s = handle->currentStream;
+	constexpr int MB = HaloMinB<T>::hell;
+	const HellRowBody<T, UNROLL, 32> b32 = { a };
+	const HellRowBody<T, UNROLL, 0> b0 = { a };
+	if (ctaPartials) {
+		if (hackSize == 32)
+			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		else
+			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+	} else {
+		if (hackSize == 32)
+			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		else
+			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+	}
+	spgpu_count_launch(handle);
+}
+
+template <typename T, int UNROLL>
+static void hdia_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
+	const T* dM, const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols,
+	T* xExt, T beta, int haloN, const spgpuHaloLinks* links, unsigned seq, Acc2* ctaPartials)
+{
+	const HdiaArgs<T> a = { z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta };
+	const HaloArgs<T> hx = halo_args<T>(handle, xExt, rows, haloN, links, seq);
+	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
+	cudaStream_t s = handle->currentStream;
+	const HdiaRowBody<T, UNROLL, 32> b32 = { a };
+	const HdiaRowBody<T, UNROLL, 0> b0 = { a };
+	if (ctaPartials) {
+		if (hackSize == 32)
+			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		else
+			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+	} else {
+		if (hackSize == 32)
+			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		else
+			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+	}
+	spgpu_count_launch(handle);
+}
+
+/* folds per-row-block partials (ext_krylov.cu), optionally all-reducing the total across the ranks in its last CTA */
+template <typename T>
+void spgpu_fold_partials(spgpuHandle_t handle, const Acc2* partials, long long n, T* dRes, const spgpuPeerAllreduce* ar);
+
+ArArgs spgpu_ar_args(spgpuHandle_t handle, const spgpuPeerAllreduce* ar)
+{
+	ArArgs a;
+	memset(&a, 0, sizeof(a));
+	if (!ar || ar->world <= 1)
+		return a;
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	a.world = ar->world < SPGPU_MAX_RANKS ? ar->world : SPGPU_MAX_RANKS;
+	a.myRank = ar->myRank;
+	for (int r = 0; r < a.world; ++r)
+		a.tables.t[r] = (unsigned char*)ar->tables[r];
+	a.seq = ar->seq;
+	a.seqPtr = (ar->seq == 0u && h->magic == SPGPU_PRIV_MAGIC) ? h->dArSeq : NULL;
+	a.spin = spin_ctl(handle);
+	return a;
+}
+
+#define SPGPU_DEFINE_HALO(S, T, UH, UD)                                                              \
+	extern "C" void spgpu##S##hellspmvHalo(spgpuHandle_t handle, T* z, const T* y, T alpha,             \
+		const T* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,                \
+		int avgNnzPerRow, int rows, T* xExt, T beta, int baseIndex, int haloN,                          \
+		const spgpuHaloLinks* links, unsigned seq)                                                      \
+	{                                                                                                   \
+		if (rows <= 0) return;                                                                          \
+		hell_spmv_halo_launch<T, UH>(handle, z, y, alpha, cM, rP, hackSize, hackOffsets, rS,            \
+			avgNnzPerRow, rows, xExt, beta, baseIndex, haloN, links, seq, NULL);                        \
+	}                                                                                                   \
+	/* z = A*xExt with the halo exchange inside, plus dRes[0] = sum_i xExt[haloN+i]*z[i] (this rank's   \
+	 * share of p.Ap, all-reduced when ar is given): per-row-block partials in handle scratch */       \
+	extern "C" void spgpu##S##hellspmvHaloDot(spgpuHandle_t handle, T* z, const T* cM, const int* rP,   \
+		int hackSize, const int* hackOffsets, const int* rS, int avgNnzPerRow, int rows, T* xExt,       \
+		int baseIndex, int haloN, const spgpuHaloLinks* links, unsigned seq, T* dRes,                   \
+		const spgpuPeerAllreduce* ar)                                                                   \
+	{                                                                                                   \
+		const unsigned rowBlocks = spgpu_ceil_div(rows > 0 ? rows : 0, 128);                            \
+		Acc2* partials = rowBlocks ? (Acc2*)spgpuScratch(handle, (size_t)rowBlocks * sizeof(Acc2)) : NULL; \
+		if (rowBlocks && !partials) return;                                                             \
+		if (rowBlocks)                                                                                  \
+			hell_spmv_halo_launch<T, UH>(handle, z, NULL, Num<T>::from_real(1), cM, rP, hackSize,       \
+				hackOffsets, rS, avgNnzPerRow, rows, xExt, Num<T>::zero(), baseIndex, haloN, links,     \
+				seq, partials);                                                                         \
+		spgpu_fold_partials<T>(handle, partials, rowBlocks, dRes, ar);                                  \
+	}                                                                                                   \
+	extern "C" void spgpu##S##hellspmvDot(spgpuHandle_t handle, T* z, const T* cM, const int* rP,       \
+		int hackSize, const int* hackOffsets, const int* rS, int rows, const T* x, int baseIndex,       \
+		int xOffset, T* dRes)                                                                           \
+	{                                                                                                   \
+		spgpu##S##hellspmvHaloDot(handle, z, cM, rP, hackSize, hackOffsets, rS, 8, rows,                \
+			const_cast<T*>(x), baseIndex, xOffset, NULL, 1u, dRes, NULL);                               \
+	}                                                                                                   \
+	extern "C" void spgpu##S##hdiaspmvHalo(spgpuHandle_t handle, T* z, const T* y, T alpha,             \
+		const T* dM, const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols,      \
+		T* xExt, T beta, int haloN, const spgpuHaloLinks* links, unsigned seq)                          \
+	{                                                                                                   \
+		if (rows <= 0) return;                                                                          \
+		hdia_spmv_halo_launch<T, UD>(handle, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows,     \
+			cols, xExt, beta, haloN, links, seq, NULL);                                                 \
+	}                                                                                                   \
+	extern "C" void spgpu##S##hdiaspmvHaloDot(spgpuHandle_t handle, T* z, const T* dM,                  \
+		const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols, T* xExt,          \
+		int haloN, const spgpuHaloLinks* links, unsigned seq, T* dRes, const spgpuPeerAllreduce* ar)    \
+	{                                                                                                   \
+		const unsigned rowBlocks = spgpu_ceil_div(rows > 0 ? rows : 0, 128);                            \
+		Acc2* partials = rowBlocks ? (Acc2*)spgpuScratch(handle, (size_t)rowBlocks * sizeof(Acc2)) : NULL; \
+		if (rowBlocks && !partials) return;                                                             \
+		if (rowBlocks)                                                                                  \
+			hdia_spmv_halo_launch<T, UD>(handle, z, NULL, Num<T>::from_real(1), dM, offsets, hackSize,  \
+				hackOffsets, rows, cols, xExt, Num<T>::zero(), haloN, links, seq, partials);            \
+		spgpu_fold_partials<T>(handle, partials, rowBlocks, dRes, ar);                                  \
+	}
+
+SPGPU_DEFINE_HALO(S, float, 8, 9)
+SPGPU_DEFINE_HALO(D, double, 8, 9)
+SPGPU_DEFINE_HALO(C, cuFloatComplex, 8, 9)
+SPGPU_DEFINE_HALO(Z, cuDoubleComplex, 4, 4)
+
+/* ---- one-value sum all-reduce over NVLink peer memory as a kernel of its own --------- */
+
+template <typename T>
+__global__ void allreduce_sum_kernel(T* dValue, ArArgs ar)
+{
+	const Acc2 total = peer_allreduce_sum_warp(to_acc2<T>(*dValue), ar);
+	if (threadIdx.x == 0)
+		*dValue = from_acc2<T>(total);
+}
+
+#define SPGPU_DEFINE_ALLREDUCE(S, T, R)                                                          \
+	extern "C" void spgpu##S##allreduceSumDev(spgpuHandle_t handle, T* dValue,                      \
+		const spgpuPeerAllreduce* ar)                                                               \
+	{                                                                                               \
+		if (!ar || ar->world <= 1) return;                                                          \
+		allreduce_sum_kernel<T><<<1, 32, 0, handle->currentStream>>>(dValue, spgpu_ar_args(handle, ar)); \
+		spgpu_count_launch(handle);                                                                 \
+	}
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DEFINE_ALLREDUCE)
+
+/* ---- device-resident sequence numbers (CUDA-graph replay of a partitioned iteration) ---------------- */
+
+extern "C" int spgpuSetSeqCounters(spgpuHandle_t handle, unsigned* dHaloSeq, unsigned* dAllreduceSeq)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	if (!h || h->magic != SPGPU_PRIV_MAGIC)
+		return -1;
+	h->dHaloSeq = dHaloSeq;
+	h->dArSeq = dAllreduceSeq;
+	return 0;
+}
+
+__global__ void seq_advance_kernel(unsigned* counter)
+{
+	*counter += 1u;
+}
+
+extern "C" void spgpuHaloSeqAdvance(spgpuHandle_t handle)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	if (!h || h->magic != SPGPU_PRIV_MAGIC || !h->dHaloSeq)
+		return;
+	seq_advance_kernel<<<1, 1, 0, handle->currentStream>>>(h->dHaloSeq);
+	spgpu_count_launch(handle);
+}
+
+/* ---- per-exchange trace of the fused kernel (haloTrace tuning key) ---------------------------------- */
+
+extern "C" int spgpuHaloTraceRead(spgpuHandle_t handle, unsigned long long* hostOut, int firstSeq, int count)
+{
+	SpgpuHandlePriv* h = spgpuPriv(handle);
+	if (!h || h->magic != SPGPU_PRIV_MAGIC || !h->dTrace || count < 0 || count > SPGPU_TRACE_SLOTS)
+		return -1;
+	cudaStreamSynchronize(handle->currentStream);
+	for (int k = 0; k < count; ++k) {
+		const size_t slot = (size_t)((unsigned)(firstSeq + k) & (SPGPU_TRACE_SLOTS - 1));
+		if (cudaMemcpy(hostOut + (size_t)k * 8, h->dTrace + slot * 8, 8 * sizeof(unsigned long long),
+				cudaMemcpyDeviceToHost) != cudaSuccess)
+			return -1;
+	}
+	return 0;
+}

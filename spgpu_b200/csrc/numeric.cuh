@@ -27,11 +27,12 @@ template <> struct Num<float> {
 	static __host__ __device__ __forceinline__ float zero() { return 0.0f; }
 	static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
 	static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+	static __device__ __forceinline__ float div(float a, float b) { return a / b; }
 	static __device__ __forceinline__ float add(float a, float b) { return a + b; }
 	static __host__ __device__ __forceinline__ bool nonzero(float a) { return a != 0.0f; }
 	static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
 	static __device__ __forceinline__ float sqabs(float a) { return a * a; }
-	static __device__ __forceinline__ float from_real(float r) { return r; }
+	static __host__ __device__ __forceinline__ float from_real(float r) { return r; }
 };
 
 template <> struct Num<double> {
@@ -40,11 +41,12 @@ template <> struct Num<double> {
 	static __host__ __device__ __forceinline__ double zero() { return 0.0; }
 	static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
 	static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+	static __device__ __forceinline__ double div(double a, double b) { return a / b; }
 	static __device__ __forceinline__ double add(double a, double b) { return a + b; }
 	static __host__ __device__ __forceinline__ bool nonzero(double a) { return a != 0.0; }
 	static __device__ __forceinline__ double abs(double a) { return fabs(a); }
 	static __device__ __forceinline__ double sqabs(double a) { return a * a; }
-	static __device__ __forceinline__ double from_real(double r) { return r; }
+	static __host__ __device__ __forceinline__ double from_real(double r) { return r; }
 };
 
 template <> struct Num<cuFloatComplex> {
@@ -53,11 +55,12 @@ template <> struct Num<cuFloatComplex> {
 	static __host__ __device__ __forceinline__ cuFloatComplex zero() { return make_cuFloatComplex(0.0f, 0.0f); }
 	static __device__ __forceinline__ cuFloatComplex fma(cuFloatComplex a, cuFloatComplex b, cuFloatComplex c) { return cuCfmaf(a, b, c); }
 	static __device__ __forceinline__ cuFloatComplex mul(cuFloatComplex a, cuFloatComplex b) { return cuCmulf(a, b); }
+	static __device__ __forceinline__ cuFloatComplex div(cuFloatComplex a, cuFloatComplex b) { return cuCdivf(a, b); }
 	static __device__ __forceinline__ cuFloatComplex add(cuFloatComplex a, cuFloatComplex b) { return cuCaddf(a, b); }
 	static __host__ __device__ __forceinline__ bool nonzero(cuFloatComplex a) { return a.x != 0.0f || a.y != 0.0f; }
 	static __device__ __forceinline__ float abs(cuFloatComplex a) { return cuCabsf(a); }
 	static __device__ __forceinline__ float sqabs(cuFloatComplex a) { return fmaf(a.x, a.x, a.y * a.y); }
-	static __device__ __forceinline__ cuFloatComplex from_real(float r) { return make_cuFloatComplex(r, 0.0f); }
+	static __host__ __device__ __forceinline__ cuFloatComplex from_real(float r) { return make_cuFloatComplex(r, 0.0f); }
 };
 
 template <> struct Num<cuDoubleComplex> {
@@ -66,11 +69,12 @@ template <> struct Num<cuDoubleComplex> {
 	static __host__ __device__ __forceinline__ cuDoubleComplex zero() { return make_cuDoubleComplex(0.0, 0.0); }
 	static __device__ __forceinline__ cuDoubleComplex fma(cuDoubleComplex a, cuDoubleComplex b, cuDoubleComplex c) { return cuCfma(a, b, c); }
 	static __device__ __forceinline__ cuDoubleComplex mul(cuDoubleComplex a, cuDoubleComplex b) { return cuCmul(a, b); }
+	static __device__ __forceinline__ cuDoubleComplex div(cuDoubleComplex a, cuDoubleComplex b) { return cuCdiv(a, b); }
 	static __device__ __forceinline__ cuDoubleComplex add(cuDoubleComplex a, cuDoubleComplex b) { return cuCadd(a, b); }
 	static __host__ __device__ __forceinline__ bool nonzero(cuDoubleComplex a) { return a.x != 0.0 || a.y != 0.0; }
 	static __device__ __forceinline__ double abs(cuDoubleComplex a) { return cuCabs(a); }
 	static __device__ __forceinline__ double sqabs(cuDoubleComplex a) { return ::fma(a.x, a.x, a.y * a.y); }
-	static __device__ __forceinline__ cuDoubleComplex from_real(double r) { return make_cuDoubleComplex(r, 0.0); }
+	static __host__ __device__ __forceinline__ cuDoubleComplex from_real(double r) { return make_cuDoubleComplex(r, 0.0); }
 };
 
 /* int "arithmetic" for the I gather/scatter (reference mathbase.cuh int_fma) */
@@ -90,6 +94,35 @@ template <> struct Num<int> {
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 /* read-only, cache normally (x gathers) */
 template <typename T> __device__ __forceinline__ T ld_keep(const T* p) { return __ldg(p); }
+
+/* ---- how a row walk fetches x[c] ------------------------------------------- */
+
+/* the single-GPU kernels: x is read-only for the whole launch -> read-only path (ld.global.nc) */
+template <typename T> struct XPlain {
+	const T* x;
+	__device__ __forceinline__ T ld(int c) const { return __ldg(x + c); }
+};
+
+/*
+ * Boundary rows of the kernel fused with the halo exchange (ext_halo.cu): the two halo zones of
+ * x_ext = [lower zone | owned | upper zone] are written by PEER GPUs during the launch, so they are
+ * read with coherent loads (ld.global.ca after the CTA's acquire on the ready flag; .nc loads are
+ * outside the memory model), and odd-numbered exchanges use a second pair of zones outside x_ext
+ * (double buffering: dLo / dHi = element distance from a zone inside x_ext to its twin, 0 for even
+ * exchanges).  c < loEnd addresses the lower zone, c >= hiBegin the upper one.
+ */
+template <typename T> struct XZones {
+	const T* x;
+	long long dLo, dHi;
+	int loEnd, hiBegin;
+	__device__ __forceinline__ T ld(int c) const
+	{
+		const T* p = x + c;
+		if (c < loEnd) p += dLo;
+		else if (c >= hiBegin) p += dHi;
+		return __ldca(p);
+	}
+};
 
 /* ---- warp helpers --------------------------------------------------------- */
 

@@ -40,6 +40,12 @@ typedef struct SpgpuTuning {
 	int ellRows;         /* ELL, short regular rows: 0/1 = exact-slot-count kernel (default), 2 = the same with 2 rows per lane, -1 = general kernel */
 	int redBlocksPerSm;  /* CTAs per SM for the reductions                      */
 	int vecBlocksPerSm;  /* CTAs per SM for grid-stride vector kernels          */
+	int spinTimeoutMs;   /* how long a device-side wait on a peer's flag may last before it gives up and sets the
+	                      * handle's sticky device status (default 20000; 0 = wait for ever) */
+	int haloTrace;       /* 1: the fused SpMV + halo kernels record per-exchange timestamps (spgpuHaloTraceRead) */
+	int l2Fetch;         /* > 0: cudaLimitMaxL2FetchGranularity of the handle's device is set to this many bytes
+	                      * (32 / 64 / 128) when the key is set -- a DEVICE-wide limit, an experiment knob */
+	int ellShortMinB;    /* ELL exact-slot-count kernel: resident CTAs per SM asked of the register allocator (0 = default) */
 } SpgpuTuning;
 
 typedef struct SpgpuHandlePriv {
@@ -57,11 +63,19 @@ typedef struct SpgpuHandlePriv {
 	size_t bigBytes;
 	unsigned* dHaloSeq;            /* device counters registered with spgpuSetSeqCounters (ext): completed halo */
 	unsigned* dArSeq;              /* exchanges / all-reduces; used by calls that pass seq == 0                 */
+	unsigned* hStatus;             /* sticky device status word (SPGPU_DEVSTATUS_*), mapped pinned: byte 32 of hResult */
+	unsigned* dStatus;             /* its device alias                                                            */
+	cudaEvent_t switchEvent;       /* orders work across a spgpuSetStream (the handle's scratch is reused in stream order) */
+	unsigned long long* dTrace;    /* device: SPGPU_TRACE_SLOTS x 8 words, allocated when haloTrace is set        */
+	unsigned* dTicketsMany;        /* device: one ticket word per vector of a multi-vector reduction (kept 0)     */
+	size_t ticketsMany;
 	SpgpuTuning tune;
 } SpgpuHandlePriv;
 
 /* grow-only device scratch owned by the handle; NULL on failure (core.c) */
 void* spgpuScratch(spgpuHandle_t handle, size_t bytes);
+/* `count` zero-initialised ticket words (their users leave them zero); NULL on failure (core.c) */
+unsigned* spgpuTickets(spgpuHandle_t handle, size_t count);
 
 static inline SpgpuHandlePriv* spgpuPriv(spgpuHandle_t h)
 {

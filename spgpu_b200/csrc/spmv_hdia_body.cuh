@@ -33,9 +33,9 @@ struct HdiaArgs {
 
 /* one round of the direct kernel: UNROLL diagonals starting at diagonal u0 of the 32 whose offsets
  * the warp holds in mineOff; GUARD = the round may run past the hack's last diagonal (n) */
-template <typename T, int UNROLL, bool GUARD, bool PREDICATED>
+template <typename T, int UNROLL, bool GUARD, bool PREDICATED, class XG>
 __device__ __forceinline__ T hdia_round(T acc, const T* __restrict__ cp, long long hackSize, int mineOff,
-	int u0, int n, unsigned i, unsigned colsEff, const T* __restrict__ x)
+	int u0, int n, unsigned i, unsigned colsEff, const XG xg)
 {
 	T a[UNROLL];
 	T xv[UNROLL];
@@ -57,7 +57,7 @@ __device__ __forceinline__ T hdia_round(T acc, const T* __restrict__ cp, long lo
 		if (PREDICATED)
 			a[u] = Num<T>::zero();
 		if (on[u]) {
-			xv[u] = ld_keep(x + c);
+			xv[u] = xg.ld(c);
 			if (PREDICATED)                           /* cells outside the matrix are not read */
 				a[u] = ld_stream(cp + u * hackSize);
 		}
@@ -70,8 +70,8 @@ __device__ __forceinline__ T hdia_round(T acc, const T* __restrict__ cp, long lo
 }
 
 /* returns the value stored for this lane's row in `zval` (zero for lanes without a row) */
-template <typename T, int UNROLL, int HACK, bool PREDICATED>
-__device__ __forceinline__ void hdia_warp_rows_value(const HdiaArgs<T>& a, unsigned warpRow, T& zval)
+template <typename T, int UNROLL, int HACK, bool PREDICATED, class XG>
+__device__ __forceinline__ void hdia_warp_rows_value_x(const HdiaArgs<T>& a, unsigned warpRow, T& zval, const XG xg)
 {
 	zval = Num<T>::zero();
 	const int hackSize = HACK > 0 ? HACK : a.hackSize;
@@ -99,15 +99,22 @@ __device__ __forceinline__ void hdia_warp_rows_value(const HdiaArgs<T>& a, unsig
 		int u0 = 0;
 		/* full rounds need no per-diagonal guard; the last, partial round does */
 		for (; u0 + UNROLL <= n; u0 += UNROLL)
-			acc = hdia_round<T, UNROLL, false, PREDICATED>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, a.x);
+			acc = hdia_round<T, UNROLL, false, PREDICATED, XG>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, xg);
 		if (u0 < n)
-			acc = hdia_round<T, UNROLL, true, PREDICATED>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, a.x);
+			acc = hdia_round<T, UNROLL, true, PREDICATED, XG>(acc, cell + (long long)(j0 + u0) * hackSize, hackSize, mineOff, u0, n, i, colsEff, xg);
 	}
 
 	if (live) {
 		zval = spmv_epilogue<T>(acc, a.alpha, a.beta, useBeta, yv);
 		a.z[i] = zval;
 	}
+}
+
+template <typename T, int UNROLL, int HACK, bool PREDICATED>
+__device__ __forceinline__ void hdia_warp_rows_value(const HdiaArgs<T>& a, unsigned warpRow, T& zval)
+{
+	const XPlain<T> xg = { a.x };
+	hdia_warp_rows_value_x<T, UNROLL, HACK, PREDICATED, XPlain<T> >(a, warpRow, zval, xg);
 }
 
 #endif

@@ -40,8 +40,8 @@ struct HellArgs {
 #define SPGPU_WORK_INVALID 0xffffffffu
 
 /* returns the value stored for this lane's row in `zval` (zero for lanes without a row) */
-template <typename T, int UNROLL, int HACK>
-__device__ __forceinline__ void hell_warp_rows_value(const HellArgs<T>& a, unsigned warpRow, T& zval)
+template <typename T, int UNROLL, int HACK, class XG>
+__device__ __forceinline__ void hell_warp_rows_value_x(const HellArgs<T>& a, unsigned warpRow, T& zval, const XG xg)
 {
 	zval = Num<T>::zero();
 	const int hackSize = HACK > 0 ? HACK : a.hackSize;
@@ -91,13 +91,20 @@ __device__ __forceinline__ void hell_warp_rows_value(const HellArgs<T>& a, unsig
 		yv = a.y[out];
 
 	const long long at = (long long)slab + (warpRow % (unsigned)hackSize) + lane;
-	T acc = warp_rows_dot<T, UNROLL, HACK>(a.cM + at, a.rP + at, hackSize, hackSize, len, a.longCut,
-		allocated, a.x, a.baseIndex);
+	T acc = warp_rows_dot_x<T, UNROLL, HACK, XG>(a.cM + at, a.rP + at, hackSize, hackSize, len, a.longCut,
+		allocated, xg, a.baseIndex);
 
 	if (live) {
 		zval = spmv_epilogue<T>(acc, a.alpha, a.beta, useBeta, yv);
 		a.z[out] = zval;
 	}
+}
+
+template <typename T, int UNROLL, int HACK>
+__device__ __forceinline__ void hell_warp_rows_value(const HellArgs<T>& a, unsigned warpRow, T& zval)
+{
+	const XPlain<T> xg = { a.x };
+	hell_warp_rows_value_x<T, UNROLL, HACK, XPlain<T> >(a, warpRow, zval, xg);
 }
 
 template <typename T, int UNROLL, int HACK>

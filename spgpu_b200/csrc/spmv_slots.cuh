@@ -38,14 +38,15 @@
 
 #include "numeric.cuh"
 
-template <typename T, int UNROLL, int STRIDE>
-__device__ __forceinline__ T warp_rows_dot(
+template <typename T, int UNROLL, int STRIDE, class XG>
+__device__ __forceinline__ T warp_rows_dot_x(
 	const T* __restrict__ vals, const int* __restrict__ idxs,   /* already at this lane's slot 0 */
 	int valStrideRt, int idxStrideRt,
 	int rowLen,              /* slots of this lane's row (0 for lanes past the end) */
 	int longCut,             /* depth beyond which a row counts as a spike (host: 4 x avgNnzPerRow, >= 32) */
 	int allocated,           /* slots guaranteed to exist for the whole warp, 0 = unknown */
-	const T* __restrict__ x, int baseIndex)
+	const XG xg,             /* how x[c] is fetched (numeric.cuh: XPlain, XZones) */
+	int baseIndex)
 {
 	const int lane = threadIdx.x & 31;
 	const long long valStride = STRIDE > 0 ? STRIDE : valStrideRt;
@@ -70,7 +71,7 @@ __device__ __forceinline__ T warp_rows_dot(
 				const bool on = u < rowLen;
 				T xv = Num<T>::zero();
 				if (on)
-					xv = ld_keep(x + (col[u] - baseIndex));
+					xv = xg.ld(col[u] - baseIndex);
 				acc = on ? Num<T>::fma(a[u], xv, acc) : acc;
 			}
 		}
@@ -121,7 +122,7 @@ __device__ __forceinline__ T warp_rows_dot(
 				const bool on = (k0 + u) < mine;
 				xv[u] = Num<T>::zero();
 				if (on)
-					xv[u] = ld_keep(x + (col[u] - baseIndex));
+					xv[u] = xg.ld(col[u] - baseIndex);
 			}
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u)
@@ -160,7 +161,7 @@ __device__ __forceinline__ T warp_rows_dot(
 				const bool on = (k0 + 32 * u) < len;
 				T xv = Num<T>::zero();
 				if (on)
-					xv = ld_keep(x + (col[u] - baseIndex));
+					xv = xg.ld(col[u] - baseIndex);
 				part = Num<T>::fma(a[u], xv, part);
 			}
 		}
@@ -169,6 +170,16 @@ __device__ __forceinline__ T warp_rows_dot(
 			acc = Num<T>::add(acc, part);
 	}
 	return acc;
+}
+
+template <typename T, int UNROLL, int STRIDE>
+__device__ __forceinline__ T warp_rows_dot(
+	const T* __restrict__ vals, const int* __restrict__ idxs, int valStrideRt, int idxStrideRt,
+	int rowLen, int longCut, int allocated, const T* __restrict__ x, int baseIndex)
+{
+	const XPlain<T> xg = { x };
+	return warp_rows_dot_x<T, UNROLL, STRIDE, XPlain<T> >(vals, idxs, valStrideRt, idxStrideRt, rowLen, longCut,
+		allocated, xg, baseIndex);
 }
 
 #endif

@@ -10,10 +10,12 @@ Two flavours of the same recurrence:
 * `step_device`    the additive entry points of include/spgpu_ext.h: the SpMV is
   fused with p.Ap (spgpuDhellspmvDot); the x and r updates and r.r are one pass
   over the four vectors (spgpuDcgUpdateDev); the p update reads beta = rr'/rr
-  from device memory (spgpuDaxpbyDev) -- 3 kernels, no host synchronisation,
-  CUDA-graph capturable.  With several GPUs the two scalars are all-reduced in
-  place (NCCL) and the halo of the new p travels inside the SpMV kernel
-  (spgpuDhellspmvHalo, spgpu_b200/mg.py).
+  from device memory (spgpuDaxpbyDev) -- 4 launches, no host synchronisation,
+  CUDA-graph capturable.  With several GPUs the halo of the new p travels inside
+  the SpMV kernel (spgpuDhellspmvHaloDot, spgpu_b200/mg.py) and the two scalars are
+  all-reduced over NVLink peer memory by the LAST CTA of the kernel that produces
+  them (`ar_fused`, a mg.PeerAllreduce) -- still 4 launches; with `allreduce`
+  only (e.g. NCCL) each scalar costs a separate collective.
 
 Vectors of a partition: p lives inside p_ext = [halo | owned | halo]; x, r, Ap
 are owned-length.
@@ -41,11 +43,14 @@ class CgState:
 
 class Cg:
     """apply_A(z_tensor, x_ext_tensor) must compute z = A * x_ext (incl. halo exchange);
-    apply_A_dot(z, x_ext, d_out_ptr) optionally the fused SpMV + p.Ap (single GPU)."""
+    apply_A_dot(z, x_ext, d_out_ptr, ar_ref) optionally the fused SpMV + p.Ap, where ar_ref is None or the
+    spgpuPeerAllreduce* to hand to spgpu?h{ell,dia}spmvHaloDot.  allreduce(t): in-place sum of a 1-element
+    tensor over the ranks (a collective of its own); ar_fused: a mg.PeerAllreduce whose exchange the
+    producing kernels run themselves."""
 
-    def __init__(self, L, handle, state: CgState, apply_A, apply_A_dot=None, allreduce=None):
+    def __init__(self, L, handle, state: CgState, apply_A, apply_A_dot=None, allreduce=None, ar_fused=None):
         self.L, self.h, self.st = L, handle, state
-        self.apply_A, self.apply_A_dot, self.allreduce = apply_A, apply_A_dot, allreduce
+        self.apply_A, self.apply_A_dot, self.allreduce, self.ar_fused = apply_A, apply_A_dot, allreduce, ar_fused
         self.T = TYPES["D"]
 
     def start(self, b: torch.Tensor):
@@ -87,9 +92,11 @@ class Cg:
         st, L, h, n = self.st, self.L, self.h, self.st.n
         s = st.s.data_ptr()
         rr, pap, rrn = s, s + 8, s + 16
+        fused = self.ar_fused
         if self.apply_A_dot is not None:
-            self.apply_A_dot(st.ap, st.p_ext, pap)          # SpMV (+ halo exchange) fused with p.Ap
-            if self.allreduce:
+            # SpMV (+ halo exchange) fused with p.Ap (+ its all-reduce in the fold kernel's last CTA)
+            self.apply_A_dot(st.ap, st.p_ext, pap, fused.next_ref() if fused else None)
+            if self.allreduce and not fused:
                 self.allreduce(st.s[1:2])
         else:
             self.apply_A(st.ap, st.p_ext)
@@ -97,12 +104,14 @@ class Cg:
             if self.allreduce:
                 self.allreduce(st.s[1:2])
         # x += (rr/pAp) p ;  r -= (rr/pAp) Ap ;  rr' = r.r   -- one pass (spgpuDcgUpdateDev)
-        L.spgpuDcgUpdateDev(h, st.x.data_ptr(), st.r.data_ptr(), st.p.data_ptr(), st.ap.data_ptr(), n, rr, pap, rrn)
-        if self.allreduce:
+        L.spgpuDcgUpdateDev(h, st.x.data_ptr(), st.r.data_ptr(), st.p.data_ptr(), st.ap.data_ptr(), n, rr, pap, rrn,
+                            fused.next_ref() if fused else None)
+        if self.allreduce and not fused:
             self.allreduce(st.s[2:3])
         # p = r + (rr'/rr) p ; then rr <- rr'
         L.spgpuDaxpbyDev(h, st.p.data_ptr(), n, rrn, rr, 1.0, st.p.data_ptr(), 0, 0, 1.0, st.r.data_ptr())
-        st.s[0:1].copy_(st.s[2:3])
+        # through the library so that it is ordered on the HANDLE's stream whatever torch's current stream is
+        L.spgpuDscal(h, rr, 1, self.T.scalar(1.0), rrn)
 
     def residual_norm2(self):
         return float(self.st.s[0].item())

@@ -13,12 +13,14 @@ single-GPU kernel (spgpu?hellspmv through the C ABI) runs on it.  Before a SpMV
 the two halo zones are filled from the neighbours' boundary entries:
 
   * mode "nccl":  grouped ncclSend/ncclRecv (torch.distributed P2P ops);
-  * mode "fused" (default on GPUs): ONE kernel per SpMV, spgpuDhellspmvHalo: its
+  * mode "fused" (default on GPUs): ONE kernel per SpMV, spgpu?hellspmvHalo: its
     first CTAs store this rank's boundary entries straight into the neighbours' halo
     zones through CUDA-IPC peer pointers over NVLink and publish a sequence number;
     the interior row blocks are scheduled first and the row blocks that read a halo
-    zone last (they wait on the local ready flag); the last CTA acknowledges the
-    neighbours' halos.  Transfer and multiply overlap inside one launch.
+    zone late (they wait on the local ready flag).  The zones are double-buffered by
+    the parity of the sequence number, so there are no acknowledgements and
+    neighbours may drift a whole kernel apart.  Transfer and multiply overlap inside
+    one launch.
   * mode "push":  each rank's spgpuDhaloPush kernel stores its boundary entries
     straight into the neighbour's halo zone through a CUDA-IPC peer pointer over
     NVLink and release-stores a sequence number into the neighbour's flag word;
@@ -112,6 +114,14 @@ def split_hell(hell, world: int, rank: int, halo: int) -> LocalHell:
     g = indices[sl].astype(np.int64) - hell.base
     if ((g < lo - halo) | (g >= hi + halo)).any():
         raise ValueError("column outside the halo window; use mode='allgather'")
+    # The overlapped and the fused exchange multiply rows [halo, nrows - halo) BEFORE the halos have arrived
+    # (they are "interior"): only the first `halo` rows may read the lower zone and only the last `halo` rows
+    # the upper one.  A banded matrix (|col - row| <= halo) always satisfies this; anything else is refused.
+    rs64 = rs.astype(np.int64)
+    row_of = np.repeat(np.arange(hi - lo, dtype=np.int64), rs64)
+    if world > 1 and (((g < lo) & (row_of >= halo)) | ((g >= hi) & (row_of < (hi - lo) - halo))).any():
+        raise ValueError("a row outside the first / last `halo` rows of the block references a halo column "
+                         "(the pattern is not banded within the halo width); use mode='allgather'")
     indices[sl] = (g - (lo - halo) + hell.base).astype(np.int32)
     return LocalHell(values, indices, local_hoff, rs, hs, hi - lo, lo, hi, halo, hell.base, int(sl.size))
 
@@ -190,6 +200,11 @@ def split_hdia(hdia, world: int, rank: int, halo: int) -> LocalHdia:
     if (values[outside_window] != 0).any():
         raise ValueError("diagonal reaches outside the halo window")
     values[outside_window] = 0
+    # same band requirement as split_hell: interior rows are multiplied before the halos arrive
+    early = ~outside_matrix & (((cols < lo) & (rows >= halo)) | ((cols >= hi) & (rows < (hi - lo) - halo)))
+    if world > 1 and (values[early] != 0).any():
+        raise ValueError("a row outside the first / last `halo` rows of the block reads a halo column "
+                         "(the pattern is not banded within the halo width)")
     return LocalHdia(values.reshape(-1), (offs + halo).astype(np.int32), local_hoff, hs, hi - lo, lo, hi, halo)
 
 
@@ -241,45 +256,60 @@ class HaloExchange:
 
 
 class PeerHalo:
-    """mode 'push': NVLink peer stores + flags (CUDA IPC between the rank processes)."""
+    """NVLink peer stores + flags between the rank processes (CUDA IPC): the separate-kernel exchange
+    (exchange / wait / ack, exchange_fused / ack_fused) and the links of the kernels that carry the
+    exchange inside the SpMV (spgpu?{hell,hdia}spmvHalo[Dot], double-buffered zones, no acks)."""
 
-    FLAG_WORDS = 16     # [0] ready-from-below  [1] ready-from-above  [2] ack-from-below  [3] ack-from-above
-
-    def __init__(self, L, handle, rank, world, x_ext_ptr, ext_len, halo, group=None):
+    def __init__(self, L, handle, rank, world, x_ext_ptr, ext_len, halo, group=None, itemsize=8):
+        from .capi import HALO_FLAG_WORDS, HaloLinks
         self.L, self.h, self.rank, self.world, self.halo = L, handle, rank, world, halo
-        self.x_ptr, self.ext_len = x_ext_ptr, ext_len
-        self.seq = 0
+        self.x_ptr, self.ext_len, self.isz = x_ext_ptr, ext_len, itemsize
+        self.seq = 0            # exchanges of the separate-kernel protocol
+        self.fseq = 0           # exchanges of the fused protocol
         flags = ctypes.c_void_p()
-        assert L.spgpuDeviceAlloc(ctypes.byref(flags), 4 * self.FLAG_WORDS) == 0
+        assert L.spgpuDeviceAlloc(ctypes.byref(flags), 4 * HALO_FLAG_WORDS) == 0
         self.flags = flags.value
-        # zero the flags through a torch view of the raw allocation
-        self._flag_view = _as_tensor(self.flags, self.FLAG_WORDS, torch.int32)
+        self._flag_view = _as_tensor(self.flags, HALO_FLAG_WORDS, torch.int32)
         self._flag_view.zero_()
+        # the ODD zone pair of the fused protocol: [lower | upper], `halo` elements each
+        alt = ctypes.c_void_p()
+        assert L.spgpuDeviceAlloc(ctypes.byref(alt), max(2 * halo * itemsize, 16)) == 0
+        self.alt = alt.value
         torch.cuda.synchronize()
-        hx = (ctypes.c_char * 64)()
-        hf = (ctypes.c_char * 64)()
+        hx, hf, ha = ((ctypes.c_char * 64)() for _ in range(3))
         assert L.spgpuIpcGetHandle(x_ext_ptr, hx) == 0
         assert L.spgpuIpcGetHandle(self.flags, hf) == 0
-        mine = (bytes(hx), bytes(hf), ext_len)
+        assert L.spgpuIpcGetHandle(self.alt, ha) == 0
+        mine = (bytes(hx), bytes(hf), ext_len, bytes(ha))
         everyone = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
         self.peer = {}
         for nb in (rank - 1, rank + 1):
             if 0 <= nb < world:
-                px, pf = ctypes.c_void_p(), ctypes.c_void_p()
-                bx = (ctypes.c_char * 64).from_buffer_copy(everyone[nb][0])
-                bf = (ctypes.c_char * 64).from_buffer_copy(everyone[nb][1])
-                rc = L.spgpuIpcOpenHandle(bx, ctypes.byref(px))
-                assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
-                rc = L.spgpuIpcOpenHandle(bf, ctypes.byref(pf))
-                assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
-                self.peer[nb] = (px.value, pf.value, everyone[nb][2])
+                opened = []
+                for blob in (everyone[nb][0], everyone[nb][1], everyone[nb][3]):
+                    q = ctypes.c_void_p()
+                    rc = L.spgpuIpcOpenHandle((ctypes.c_char * 64).from_buffer_copy(blob), ctypes.byref(q))
+                    assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
+                    opened.append(q.value)
+                self.peer[nb] = (opened[0], opened[1], everyone[nb][2], opened[2])
+        lo, hi = self.peer.get(rank - 1), self.peer.get(rank + 1)
+        w, b = halo, itemsize
+        lk = HaloLinks()
+        if lo:      # the lower neighbour's UPPER zones: inside its x_ext (even), second half of its alt block (odd)
+            lk.peerLoUpperZone[0], lk.peerLoUpperZone[1] = lo[0] + b * (lo[2] - w), lo[3] + b * w
+            lk.peerFlagsLo = lo[1]
+        if hi:      # the upper neighbour's LOWER zones: start of its x_ext (even), first half of its alt block (odd)
+            lk.peerHiLowerZone[0], lk.peerHiLowerZone[1] = hi[0], hi[3]
+            lk.peerFlagsHi = hi[1]
+        lk.myLoZoneOdd, lk.myHiZoneOdd, lk.myFlags = self.alt, self.alt + b * w, self.flags
+        self.links = lk
         dist.barrier(group=group)
 
     def exchange(self):
         """push my boundary entries to both neighbours, then make my stream wait
         until both of mine have arrived (all stream-ordered, no host sync)."""
-        L, h, w = self.L, self.h, self.halo
+        L, h, w, b = self.L, self.h, self.halo, self.isz
         n = self.ext_len - 2 * w
         self.seq += 1
         seq = self.seq
@@ -291,11 +321,11 @@ class PeerHalo:
             if hi_nb in self.peer:
                 L.spgpuWaitFlag(h, self.flags + 4 * 3, seq - 1)
         if lo_nb in self.peer:       # my first w owned entries -> their upper halo, their flag[1]
-            px, pf, plen = self.peer[lo_nb]
-            L.spgpuDhaloPush(h, px + 8 * (plen - w), self.x_ptr + 8 * w, w, pf + 4 * 1, seq)
+            px, pf, plen, _ = self.peer[lo_nb]
+            L.spgpuHaloPush(h, px + b * (plen - w), self.x_ptr + b * w, w * b, pf + 4 * 1, seq)
         if hi_nb in self.peer:       # my last w owned entries -> their lower halo, their flag[0]
-            px, pf, plen = self.peer[hi_nb]
-            L.spgpuDhaloPush(h, px, self.x_ptr + 8 * n, w, pf + 4 * 0, seq)
+            px, pf, plen, _ = self.peer[hi_nb]
+            L.spgpuHaloPush(h, px, self.x_ptr + b * n, w * b, pf + 4 * 0, seq)
 
     def wait(self):
         L, h, seq = self.L, self.h, self.seq
@@ -309,21 +339,21 @@ class PeerHalo:
         L, h, seq = self.L, self.h, self.seq
         for nb, word in ((self.rank - 1, 3), (self.rank + 1, 2)):
             if nb in self.peer:
-                _px, pf, _plen = self.peer[nb]
-                L.spgpuDhaloPush(h, 0, 0, 0, pf + 4 * word, seq)
+                pf = self.peer[nb][1]
+                L.spgpuHaloPush(h, 0, 0, 0, pf + 4 * word, seq)
 
     def exchange_fused(self):
-        """ONE kernel: wait acks, push both planes, signal, wait for my own halos."""
-        L, h, w = self.L, self.h, self.halo
+        """ONE kernel: wait acks, push both boundary runs, signal, wait for my own halos."""
+        L, h, w, b = self.L, self.h, self.halo, self.isz
         n = self.ext_len - 2 * w
         self.seq += 1
         lo, hi = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
         f = self.flags
-        L.spgpuDhaloExchange(
+        L.spgpuHaloExchange(
             h,
-            (lo[0] + 8 * (lo[2] - w)) if lo else 0, self.x_ptr + 8 * w,      # -> lower neighbour's upper halo
-            hi[0] if hi else 0, self.x_ptr + 8 * n,                           # -> upper neighbour's lower halo
-            w,
+            (lo[0] + b * (lo[2] - w)) if lo else 0, self.x_ptr + b * w,      # -> lower neighbour's upper halo
+            hi[0] if hi else 0, self.x_ptr + b * n,                           # -> upper neighbour's lower halo
+            w * b,
             (f + 4 * 2) if lo else 0, (f + 4 * 3) if hi else 0,               # acks I wait for
             (lo[1] + 4 * 1) if lo else 0, (hi[1] + 4 * 0) if hi else 0,       # their ready flags
             (f + 4 * 0) if lo else 0, (f + 4 * 1) if hi else 0,               # my ready flags
@@ -333,44 +363,44 @@ class PeerHalo:
         lo, hi = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
         self.L.spgpuHaloAck(self.h, (lo[1] + 4 * 3) if lo else 0, (hi[1] + 4 * 2) if hi else 0, self.seq)
 
-    def fused_pointers(self):
-        """(peerXLoUpperHalo, peerXHiLowerHalo, myFlags, peerFlagsLo, peerFlagsHi) for
-        spgpuDhellspmvHalo; 0 where there is no neighbour."""
-        w = self.halo
-        lo, hi = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
-        return ((lo[0] + 8 * (lo[2] - w)) if lo else 0, hi[0] if hi else 0, self.flags,
-                lo[1] if lo else 0, hi[1] if hi else 0)
+    def links_ref(self):
+        """the spgpuHaloLinks* argument of spgpu?{hell,hdia}spmvHalo[Dot]"""
+        return ctypes.byref(self.links)
 
     def next_seq(self):
-        self.seq += 1
-        return self.seq
+        """sequence number of the next exchange of the FUSED protocol"""
+        self.fseq += 1
+        return self.fseq
 
     # -- sequence numbers in device memory (CUDA-graph replay, include/spgpu_ext.h) --------------
     def to_device_seq(self, counter: torch.Tensor):
-        """hand the exchange count to a 1-element int32 device counter (the handle must have been given
+        """hand the fused-exchange count to a 1-element int32 device counter (the handle must have been given
         it with spgpuSetSeqCounters): from now on the fused kernels are called with seq = 0"""
-        counter.fill_(self.seq)
+        counter.fill_(self.fseq)
 
     def from_device_seq(self, counter: torch.Tensor):
-        self.seq = int(counter.item())
+        self.fseq = int(counter.item())
 
     def close(self):
         torch.cuda.synchronize()
-        for px, pf, _ in self.peer.values():
+        for px, pf, _, pa in self.peer.values():
             self.L.spgpuIpcCloseHandle(px)
             self.L.spgpuIpcCloseHandle(pf)
+            self.L.spgpuIpcCloseHandle(pa)
         self.peer = {}
 
 
 class PeerAllreduce:
-    """Sum all-reduce of one double over NVLink peer memory (spgpuAllreduceSumDev): every
-    rank's 2*world-slot table is CUDA-IPC mapped into every other rank."""
+    """Sum all-reduce of one value over NVLink peer memory (spgpu?allreduceSumDev, or inside the last CTA of
+    the kernel that produces the value -- `next_ref()` is the spgpuPeerAllreduce* argument of those entry
+    points): every rank's 2*world-slot table is CUDA-IPC mapped into every other rank."""
 
     def __init__(self, L, handle, rank, world, group=None):
+        from .capi import AR_SLOT_BYTES, PeerAllreduceArgs
         assert world <= 16
         self.L, self.h, self.rank, self.world = L, handle, rank, world
         self.seq = 0
-        nbytes = 2 * world * 16
+        nbytes = 2 * world * AR_SLOT_BYTES
         p = ctypes.c_void_p()
         assert L.spgpuDeviceAlloc(ctypes.byref(p), nbytes) == 0
         self.table = p.value
@@ -392,15 +422,22 @@ class PeerAllreduce:
                 assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
                 self.tables[r] = q.value
                 self.opened.append(q.value)
+        self.args = PeerAllreduceArgs(world, rank, ctypes.cast(self.tables, ctypes.POINTER(ctypes.c_void_p)), 0)
         dist.barrier(group=group)
 
-    def __call__(self, t: torch.Tensor):
-        """in-place sum of a 1-element float64 device tensor across the ranks (stream-ordered)"""
+    def next_ref(self):
+        """spgpuPeerAllreduce* for the NEXT all-reduce (the struct is read during the call that takes it)"""
         if self.device_seq:
-            self.L.spgpuAllreduceSumDev(self.h, t.data_ptr(), self.world, self.rank, self.tables, 0)
-            return
-        self.seq += 1
-        self.L.spgpuAllreduceSumDev(self.h, t.data_ptr(), self.world, self.rank, self.tables, self.seq)
+            self.args.seq = 0
+        else:
+            self.seq += 1
+            self.args.seq = self.seq
+        return ctypes.byref(self.args)
+
+    def __call__(self, t: torch.Tensor):
+        """in-place sum of a 1-element device tensor across the ranks (stream-ordered, its own kernel)"""
+        sym = {torch.float32: "S", torch.float64: "D", torch.complex64: "C", torch.complex128: "Z"}[t.dtype]
+        getattr(self.L, f"spgpu{sym}allreduceSumDev")(self.h, t.data_ptr(), self.next_ref())
 
     device_seq = False
 
@@ -430,7 +467,8 @@ class _RawCuda:
 
 
 def _as_tensor(ptr: int, n: int, dtype: torch.dtype) -> torch.Tensor:
-    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4", torch.complex64: "<c8",
+               torch.complex128: "<c16"}[dtype]
     return torch.as_tensor(_RawCuda(ptr, n, typestr), device="cuda")
 
 
@@ -466,11 +504,9 @@ class MgHellSpmv:
         self.head = min(nrows, -(-halo // align) * align)
         self.tail = max(self.head, ((nrows - halo) // align) * align)
         self.overlap = overlap and world > 1 and halo > 0 and self.tail > self.head
-        # fused_spmv(seq): the SpMV kernel that carries its own halo exchange (spgpuDhellspmvHalo).  Its row
-        # blocks wait for ONE halo zone each (the first ceil(halo/128) blocks for the lower, the last for the
-        # upper); a block shorter than two halo widths has rows that read both, so it takes the separate
-        # exchange (which completes before any row is multiplied) instead.
-        self.fused_spmv = fused_spmv if nrows >= 2 * halo else None
+        # fused_spmv(seq): the SpMV kernel that carries its own halo exchange (spgpu?hellspmvHalo); a row block
+        # of it that reads both zones (fewer rows than two halo widths) simply waits for both neighbours
+        self.fused_spmv = fused_spmv
 
     def apply(self, z, x_ext):
         w, n = self.halo, self.nrows

@@ -6,6 +6,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import bench  # noqa: E402
 
 
 def run(env_extra):
@@ -25,7 +28,10 @@ def test_reference_arm_prints_one_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"] == "cfg1" and d["dtype"] == "f64"
+    # the reference arm prints the SAME config object our arm prints for this workload, and says what it timed
+    assert d["config"] == bench.workload_config("cfg1", None, 1, "fused", False) and d["dtype"] == "f64"
+    assert d["config"]["rows"] == 1_000_000 and d["config"]["nnz"] == 4_996_000
+    assert d["steps"] == 2 and d["warmup"] == 3 and "2 timed calls" in cb["sample"]
 
 
 def test_reference_arm_is_silent_on_other_ranks():

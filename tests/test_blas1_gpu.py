@@ -187,3 +187,38 @@ def test_multivector_and_elementwise_helpers(ours, gpu_handle, dtype):
     torch.cuda.synchronize()
     w = dw.cpu().numpy()
     assert (w[10:20] == np.asarray(alpha, dtype=dtype)).all() and w[9] != np.asarray(alpha, dtype=dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex64])
+def test_multivector_reductions_are_one_launch(ours, gpu_handle, dtype):
+    """spgpu?m{dot,nrm2,amax,asum}: the reference loops the blocking scalar routine `count` times (count launches +
+    count host synchronisations, reference ddot.cu:152-160); here a batch is ONE launch (grid.y = vector) whatever
+    `count` is -- also for odd pitches (unaligned vectors), and in slices of 65535 for huge batches -- and every
+    vector's result equals the scalar routine's bit for bit."""
+    s = util.sym_of(dtype)
+    for n, count, pitch in ((4097, 12, 4099), (5, 70001, 7), (1 << 16, 37, 1 << 16)):
+        x = G.random_vector(count * pitch, dtype, 3, -1, 1)
+        y = G.random_vector(count * pitch, dtype, 4, -1, 1)
+        dx, dy = util.to_dev(x), util.to_dev(y)
+        expect_launches = -(-count // 65535)
+        out = np.zeros(count, dtype=dtype)
+        before = ours.spgpuGetLaunchCount(gpu_handle)
+        getattr(ours, f"spgpu{s}mdot")(gpu_handle, util.ptr(out), n, dx.data_ptr(), dy.data_ptr(), count, pitch)
+        assert ours.spgpuGetLaunchCount(gpu_handle) - before == expect_launches
+        X, Y = (a.reshape(count, pitch)[:, :n] for a in (x, y))
+        np.testing.assert_allclose(out, (X.astype(np.complex128) * Y).sum(1), rtol=0,
+                                   atol=(1e-4 if s in "SC" else 1e-12) * np.abs(X.astype(np.complex128) * Y).sum(1).max())
+        outr = np.zeros(count, dtype=util.real_of(dtype))
+        for op, ref in (("nrm2", np.linalg.norm(X.astype(np.complex128), axis=1)), ("amax", np.abs(X).max(1)),
+                        ("asum", np.abs(X.astype(np.complex128)).sum(1))):
+            before = ours.spgpuGetLaunchCount(gpu_handle)
+            getattr(ours, f"spgpu{s}m{op}")(gpu_handle, util.ptr(outr), n, dx.data_ptr(), count, pitch)
+            assert ours.spgpuGetLaunchCount(gpu_handle) - before == expect_launches
+            np.testing.assert_allclose(outr, ref, rtol=1e-5 if s in "SC" else 1e-13)
+        # a few vectors against the scalar entry points
+        isz = np.dtype(dtype).itemsize
+        for v in (0, count // 2, count - 1):
+            one = getattr(ours, f"spgpu{s}nrm2")(gpu_handle, n, dx.data_ptr() + v * pitch * isz)
+            getattr(ours, f"spgpu{s}mnrm2")(gpu_handle, util.ptr(outr), n, dx.data_ptr(), count, pitch)
+            if count <= 148 * 4:       # same grid shape per vector only when the batch does not shrink the per-vector grid
+                assert abs(outr[v] - one) <= 1e-6 * abs(one)

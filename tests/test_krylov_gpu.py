@@ -89,7 +89,7 @@ def test_cg_converges_like_the_cpu_recurrence(ours, gpu_handle, flavour):
         ours.spgpuDhellspmv(gpu_handle, z.data_ptr(), 0, T.scalar(1.0), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
                             dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), 0, 7, n, x_ext.data_ptr(), T.scalar(0.0), 0)
 
-    def apply_A_dot(z, x_ext, dres):
+    def apply_A_dot(z, x_ext, dres, ar=None):
         ours.spgpuDhellspmvDot(gpu_handle, z.data_ptr(), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
                                dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), n, x_ext.data_ptr(), 0, 0, dres)
 
@@ -134,13 +134,12 @@ def test_cg_on_hdia_with_the_fused_spmv_dot(ours, gpu_handle):
     dv, doff, dho = (util.to_dev(t) for t in (A.values, A.offsets, A.hack_offsets))
     n = coo.nrows
     b = G.random_vector(n, np.float64, 9)
-    flags = torch.zeros(16, dtype=torch.int32, device="cuda")
     seq = [0]
 
-    def apply_A_dot(z, x_ext, dres):
+    def apply_A_dot(z, x_ext, dres, ar=None):
         seq[0] += 1
         ours.spgpuDhdiaspmvHaloDot(gpu_handle, z.data_ptr(), dv.data_ptr(), doff.data_ptr(), 32, dho.data_ptr(), n, n,
-                                   x_ext.data_ptr(), 0, 0, 0, flags.data_ptr(), 0, 0, seq[0], dres)
+                                   x_ext.data_ptr(), 0, None, seq[0], dres, None)
 
     stream = torch.cuda.ExternalStream(ours.spgpuGetStream(gpu_handle))
     with torch.cuda.stream(stream):
@@ -177,7 +176,7 @@ def test_fused_cg_update(ours, gpu_handle):
         sc = np.array([3.5, 1.25, 0.0])
         dx, dr, dp, dap, ds = (util.to_dev(a) for a in (x, r, p, ap, sc))
         s = ds.data_ptr()
-        ours.spgpuDcgUpdateDev(gpu_handle, dx.data_ptr(), dr.data_ptr(), dp.data_ptr(), dap.data_ptr(), n, s, s + 8, s + 16)
+        ours.spgpuDcgUpdateDev(gpu_handle, dx.data_ptr(), dr.data_ptr(), dp.data_ptr(), dap.data_ptr(), n, s, s + 8, s + 16, None)
         torch.cuda.synchronize()
         a = 3.5 / 1.25
         np.testing.assert_allclose(dx.cpu().numpy(), x + a * p, rtol=1e-14, atol=1e-14)
@@ -203,7 +202,7 @@ def test_cuda_graph_capture_of_a_device_cg_iteration(ours, gpu_handle):
         ours.spgpuDhellspmv(gpu_handle, z.data_ptr(), 0, T.scalar(1.0), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
                             dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), 0, 7, n, x_ext.data_ptr(), T.scalar(0.0), 0)
 
-    def apply_A_dot(z, x_ext, dres):
+    def apply_A_dot(z, x_ext, dres, ar=None):
         ours.spgpuDhellspmvDot(gpu_handle, z.data_ptr(), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
                                dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), n, x_ext.data_ptr(), 0, 0, dres)
 
@@ -237,3 +236,73 @@ def test_cuda_graph_capture_of_a_device_cg_iteration(ours, gpu_handle):
     x_graph, rr_graph = run(6, graph=True)
     np.testing.assert_array_equal(x_graph, x_eager)
     assert rr_graph == rr_eager
+
+
+@pytest.mark.parametrize("sym", ["S", "C", "Z"])
+def test_device_scalar_twins_for_the_other_value_types(ours, gpu_handle, sym):
+    """spgpu{S,C,Z}axpbyDev / cgUpdateDev / hellspmvDot / sumDev: the same kernels for float and the complex types
+    (complex products are the library's unconjugated ones, reference zdot.cu:54)"""
+    import torch
+    t = util.TYPES[sym]
+    dt = t.np_dtype
+    tol = 1e-5 if sym in "SC" else 1e-12
+    rng = np.random.default_rng(17)
+
+    def rnd(n):
+        v = rng.standard_normal(n)
+        if t.is_complex:
+            v = v + 1j * rng.standard_normal(n)
+        return v.astype(dt)
+
+    for n in (1, 1001, (1 << 18) + 3):
+        x, y, r, p, ap = (rnd(n) for _ in range(5))
+        sc = rnd(4)
+        dx, dy, ds = util.to_dev(x), util.to_dev(y), util.to_dev(sc)
+        dz = torch.zeros_like(dx)
+        sp, isz = ds.data_ptr(), dt.itemsize
+        getattr(ours, f"spgpu{sym}axpbyDev")(gpu_handle, dz.data_ptr(), n, sp, sp + isz, 1.0, dy.data_ptr(), sp + 2 * isz,
+                                             sp + 3 * isz, -1.0, dx.data_ptr())
+        torch.cuda.synchronize()
+        want = (sc[0] / sc[1]) * y - (sc[2] / sc[3]) * x
+        np.testing.assert_allclose(dz.cpu().numpy(), want, rtol=50 * tol, atol=50 * tol)
+        # fused CG update
+        sc3 = np.array([sc[0], sc[1], 0], dtype=dt)
+        dxx, dr, dp, dap, ds3 = (util.to_dev(a) for a in (x, r, p, ap, sc3))
+        s3 = ds3.data_ptr()
+        getattr(ours, f"spgpu{sym}cgUpdateDev")(gpu_handle, dxx.data_ptr(), dr.data_ptr(), dp.data_ptr(), dap.data_ptr(), n,
+                                                s3, s3 + isz, s3 + 2 * isz, None)
+        torch.cuda.synchronize()
+        a = sc[0] / sc[1]
+        rn = r - a * ap
+        np.testing.assert_allclose(dxx.cpu().numpy(), x + a * p, rtol=50 * tol, atol=50 * tol)
+        np.testing.assert_allclose(dr.cpu().numpy(), rn, rtol=50 * tol, atol=50 * tol)
+        rr = np.sum(rn.astype(np.complex128) * rn.astype(np.complex128))
+        got = complex(ds3.cpu().numpy()[2])
+        assert abs(got - rr) <= 20 * tol * float(np.sum(np.abs(rn) ** 2)), (got, rr)
+        # sum
+        dres = torch.zeros(1, dtype=dx.dtype, device="cuda")
+        getattr(ours, f"spgpu{sym}sumDev")(gpu_handle, n, dx.data_ptr(), dres.data_ptr())
+        torch.cuda.synchronize()
+        assert abs(complex(dres.cpu().numpy()[0]) - np.sum(x.astype(np.complex128))) <= 20 * tol * float(np.sum(np.abs(x)))
+
+    # fused SpMV + dot
+    coo = G.laplace3d_7pt(16)
+    vals = coo.vals.astype(dt)
+    if t.is_complex:
+        vals = (vals + 0.5j * rng.standard_normal(vals.shape[0])).astype(dt)
+    coo = F.Coo(coo.rows, coo.cols, vals, coo.nrows, coo.ncols, coo.base)
+    A = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    dA = util.upload(A)
+    n = coo.nrows
+    x = rnd(n)
+    dx = util.to_dev(x)
+    dz = torch.zeros(n, dtype=dx.dtype, device="cuda")
+    dres = torch.zeros(1, dtype=dx.dtype, device="cuda")
+    getattr(ours, f"spgpu{sym}hellspmvDot")(gpu_handle, dz.data_ptr(), dA["values"].data_ptr(), dA["indices"].data_ptr(), 32,
+                                            dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), n, dx.data_ptr(), 0, 0,
+                                            dres.data_ptr())
+    torch.cuda.synchronize()
+    want = util.oracle_spmv("hell", A, x, None, 1.0, 0.0)
+    util.assert_rows_close(dz.cpu().numpy(), want, util.row_scale(coo, x, None, 1.0, 0.0), sym, f"fused spmv+dot {sym}")
+    ref = np.sum(x.astype(np.complex128) * want.astype(np.complex128))
+    assert abs(complex(dres.cpu().numpy()[0]) - ref) <= 20 * tol * float(np.sum(np.abs(x) * np.abs(want)))

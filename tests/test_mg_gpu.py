@@ -1,57 +1,163 @@
 """Single-GPU checks of the multi-GPU device code (include/spgpu_ext.h).  Kernels of
 different ranks must never wait on each other on ONE GPU, so the neighbours are emulated:
-their "pushes" are pre-filled halo zones + pre-set ready flags, and this rank's pushes land
-in scratch buffers standing in for the neighbours' memory.  The real multi-rank runs are
-bench.py --verify under torchrun (bit-exact against global columns) and the gloo tests."""
+their "pushes" are pre-filled halo zones + pre-set ready flags (or set LATE from a second
+stream), and this rank's pushes land in scratch buffers standing in for the neighbours'
+memory.  The real multi-rank runs are tests/test_mg_multi_gpu.py (needs >= 2 GPUs), bench.py
+under torchrun (bit-exact against global columns, on by default) and the gloo tests."""
 import ctypes
+import struct
 
 import numpy as np
 import pytest
 
-from spgpu_b200 import formats as F, generators as G, mg
+from spgpu_b200 import capi, formats as F, generators as G, mg
 from tests import util
 
 pytestmark = pytest.mark.gpu
 
+TORCH_OF = {"S": "float32", "D": "float64", "C": "complex64", "Z": "complex128"}
 
-def _middle_block(n=24, world=3, rank=1):
+
+def _middle_block(n=24, world=3, rank=1, sym="D"):
     coo = G.laplace3d_7pt(n)
+    dt = util.TYPES[sym].np_dtype
+    if sym != "D":
+        rng = np.random.default_rng(5)
+        vals = coo.vals.astype(dt)
+        if util.TYPES[sym].is_complex:
+            vals = vals + 1j * rng.uniform(-1, 1, vals.shape[0]).astype(util.real_of(dt))
+        coo = F.Coo(coo.rows, coo.cols, vals.astype(dt), coo.nrows, coo.ncols, coo.base)
     plane = n * n
     hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
     loc = mg.split_hell(hell, world, rank, plane)
-    x = G.random_vector(coo.nrows, np.float64, 12345)
+    x = G.random_vector(coo.nrows, dt, 12345, -1, 1)
     x_ext = x[loc.lo - plane: loc.hi + plane].copy()
     want = util.oracle_spmv("hell", hell, x, None, 1.0, 0.0)[loc.lo:loc.hi]
-    return coo, loc, plane, x, x_ext, want
+    scale = util.row_scale(coo, x, None, 1.0, 0.0)[loc.lo:loc.hi]
+    return coo, loc, plane, x, x_ext, want, scale
 
 
-@pytest.mark.parametrize("seq", [1, 5])
-def test_spmv_fused_with_halo_exchange(ours, gpu_handle, seq):
+class Emulated:
+    """One rank's view with emulated neighbours: flag blocks, the neighbours' zones (as plain local buffers),
+    this rank's odd zones, and the spgpuHaloLinks struct pointing at them."""
+
+    def __init__(self, halo, tdtype, has_lo=True, has_hi=True):
+        import torch
+        nan = float("nan")
+        self.my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+        self.pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
+        # [side][parity]: where my pushes land
+        self.pz = [[torch.full((max(halo, 1),), nan, dtype=tdtype, device="cuda") for _ in range(2)] for _ in range(2)]
+        self.alt = torch.full((2 * max(halo, 1),), nan, dtype=tdtype, device="cuda")
+        lk = capi.HaloLinks()
+        if has_lo:
+            lk.peerLoUpperZone[0], lk.peerLoUpperZone[1] = self.pz[0][0].data_ptr(), self.pz[0][1].data_ptr()
+            lk.peerFlagsLo = self.pf[0].data_ptr()
+        if has_hi:
+            lk.peerHiLowerZone[0], lk.peerHiLowerZone[1] = self.pz[1][0].data_ptr(), self.pz[1][1].data_ptr()
+            lk.peerFlagsHi = self.pf[1].data_ptr()
+        lk.myLoZoneOdd = self.alt.data_ptr()
+        lk.myHiZoneOdd = self.alt.data_ptr() + halo * self.alt.element_size()
+        lk.myFlags = self.my_flags.data_ptr()
+        self.links, self.halo = lk, halo
+
+    def ref(self):
+        return ctypes.byref(self.links)
+
+    def place_halos(self, dx, x_ext, nrows, seq, tdtype):
+        """what the neighbours' pushes of exchange `seq` leave behind: even -> zones inside x_ext, odd -> the odd
+        zones; the OTHER pair is poisoned so that a read from the wrong pair shows"""
+        import torch
+        w = self.halo
+        lo = torch.from_numpy(x_ext[:w].copy()).cuda()
+        hi = torch.from_numpy(x_ext[w + nrows:].copy()).cuda()
+        nan = float("nan")
+        if seq & 1:
+            self.alt[:w] = lo
+            self.alt[w:2 * w] = hi
+            dx[:w] = nan
+            dx[w + nrows:] = nan
+        else:
+            dx[:w] = lo
+            dx[w + nrows:] = hi
+            self.alt[:] = nan
+
+
+@pytest.mark.parametrize("seq", [1, 4])
+@pytest.mark.parametrize("sym", ["S", "D", "C", "Z"])
+def test_spmv_fused_with_halo_exchange(ours, gpu_handle, seq, sym):
     import torch
-    coo, loc, plane, x, x_ext, want = _middle_block()
+    coo, loc, plane, x, x_ext, want, scale = _middle_block(sym=sym)
+    tdt = getattr(torch, TORCH_OF[sym])
+    t = util.TYPES[sym]
     dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
     dx = util.to_dev(x_ext)
-    dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
-    my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    my_flags[0] = seq; my_flags[1] = seq          # both neighbours' halos "have arrived"
-    my_flags[2] = seq - 1; my_flags[3] = seq - 1  # and they acknowledged my previous pushes
-    peer_lo_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    peer_hi_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    peer_lo_halo = torch.full((plane,), float("nan"), dtype=torch.float64, device="cuda")
-    peer_hi_halo = torch.full((plane,), float("nan"), dtype=torch.float64, device="cuda")
-    ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), 0, 1.0, dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
-                            drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0.0, 0, plane,
-                            peer_lo_halo.data_ptr(), peer_hi_halo.data_ptr(), my_flags.data_ptr(),
-                            peer_lo_flags.data_ptr(), peer_hi_flags.data_ptr(), seq)
+    em = Emulated(plane, tdt)
+    em.place_halos(dx, x_ext, loc.nrows, seq, tdt)
+    em.my_flags[4] = seq; em.my_flags[5] = seq          # both neighbours' entries "have arrived"
+    dz = torch.full((loc.nrows,), float("nan"), dtype=tdt, device="cuda")
+    getattr(ours, f"spgpu{sym}hellspmvHalo")(gpu_handle, dz.data_ptr(), 0, t.scalar(1.0), dv.data_ptr(), di.data_ptr(), 32,
+                                             dho.data_ptr(), drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), t.scalar(0.0), 0,
+                                             plane, em.ref(), seq)
     torch.cuda.synchronize()
-    util.assert_rows_close(dz.cpu().numpy(), want, np.full(loc.nrows, 12.0), "D", "fused spmv+halo")
-    # my first / last owned plane landed in the neighbours' halo zones
-    np.testing.assert_array_equal(peer_lo_halo.cpu().numpy(), x_ext[plane:2 * plane])
-    np.testing.assert_array_equal(peer_hi_halo.cpu().numpy(), x_ext[loc.nrows:loc.nrows + plane])
-    lo_f, hi_f = peer_lo_flags.cpu().numpy(), peer_hi_flags.cpu().numpy()
-    assert lo_f[1] == seq and lo_f[3] == seq       # lower neighbour: ready-from-above, ack-from-above
-    assert hi_f[0] == seq and hi_f[2] == seq       # upper neighbour: ready-from-below, ack-from-below
-    assert lo_f[0] == 0 and hi_f[1] == 0
+    util.assert_rows_close(dz.cpu().numpy(), want, scale, sym, f"fused spmv+halo {sym}")
+    # my first / last owned plane landed in the neighbours' zones of this parity, and only there
+    par = seq & 1
+    np.testing.assert_array_equal(em.pz[0][par].cpu().numpy(), x_ext[plane:2 * plane])
+    np.testing.assert_array_equal(em.pz[1][par].cpu().numpy(), x_ext[loc.nrows:loc.nrows + plane])
+    assert torch.isnan(torch.view_as_real(em.pz[0][1 - par]) if tdt.is_complex else em.pz[0][1 - par]).all()
+    lo_f, hi_f = em.pf[0].cpu().numpy(), em.pf[1].cpu().numpy()
+    assert lo_f[5] == seq and hi_f[4] == seq            # lower neighbour: ready-from-above; upper: ready-from-below
+    assert lo_f[4] == 0 and hi_f[5] == 0 and not lo_f[:4].any() and not hi_f[:4].any()
+    assert ours.spgpuGetDeviceStatus(gpu_handle, 0) == 0
+
+
+def _banded_block(nrows_total=3000, world=3, rank=1, halo=128, seed=3):
+    rng = np.random.default_rng(seed)
+    rows = np.repeat(np.arange(nrows_total), 9)
+    cols = rows + rng.integers(-halo, halo + 1, rows.shape[0])
+    keep = (cols >= 0) & (cols < nrows_total)
+    rows, cols = rows[keep], cols[keep]
+    key = np.unique(rows.astype(np.int64) * nrows_total + cols)
+    rows, cols = (key // nrows_total).astype(np.int32), (key % nrows_total).astype(np.int32)
+    vals = rng.uniform(-1, 1, rows.shape[0])
+    coo = F.Coo(rows, cols, vals, nrows_total, nrows_total, 0)
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    loc = mg.split_hell(hell, world, rank, halo)
+    x = G.random_vector(nrows_total, np.float64, 99, -1, 1)
+    want = util.oracle_spmv("hell", hell, x, None, 1.0, 0.0)[loc.lo:loc.hi]
+    scale = util.row_scale(coo, x, None, 1.0, 0.0)[loc.lo:loc.hi]
+    return loc, x[loc.lo - halo: loc.hi + halo].copy(), want, scale
+
+
+@pytest.mark.parametrize("seq", [2, 3])
+def test_fused_rows_not_a_multiple_of_128_and_late_flags(ours, gpu_handle, seq):
+    """992 rows, halo 128: rows 864..991 read the upper zone, i.e. row blocks 6 AND 7 (block 6 holds rows
+    768..895).  The neighbours' entries and ready flags arrive LATE, from a second stream: every row that reads a
+    zone must have waited (a block that did not would multiply the NaN the zones hold before)."""
+    import torch
+    halo = 128
+    loc, x_ext, want, scale = _banded_block(halo=halo)
+    assert loc.nrows % 128 != 0 and (loc.nrows - halo) % 128 != 0
+    dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
+    dx = util.to_dev(x_ext)
+    em = Emulated(halo, torch.float64)
+    # both pairs poisoned for now
+    dx[:halo] = float("nan"); dx[halo + loc.nrows:] = float("nan")
+    dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+    late = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    ours.spgpuSetTuning(gpu_handle, b"spinTimeoutMs", 5000)
+    ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), 0, 1.0, dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
+                            drs.data_ptr(), 9, loc.nrows, dx.data_ptr(), 0.0, 0, halo, em.ref(), seq)
+    with torch.cuda.stream(late):
+        torch.cuda._sleep(200_000_000)                    # ~0.1 s: the boundary blocks are spinning by now
+        em.place_halos(dx, x_ext, loc.nrows, seq, torch.float64)
+        em.my_flags[4:6] = seq
+    torch.cuda.synchronize()
+    ours.spgpuSetTuning(gpu_handle, b"spinTimeoutMs", 20000)
+    assert ours.spgpuGetDeviceStatus(gpu_handle, 1) == 0
+    util.assert_rows_close(dz.cpu().numpy(), want, scale, "D", "fused spmv+halo, late flags")
 
 
 @pytest.mark.parametrize("seq", [1, 4])
@@ -59,7 +165,8 @@ def test_spmv_fused_with_halo_exchange(ours, gpu_handle, seq):
 def test_hdia_spmv_fused_with_halo_exchange(ours, gpu_handle, seq, rank):
     """spgpuDhdiaspmvHalo on the first / a middle / the last block of a 27-point stencil split in three
     (emulated neighbours): rows equal the global product, boundary entries land in the neighbours'
-    halo zones, flags carry seq; also equal to the plain spgpuDhdiaspmv on the same block bit for bit"""
+    zones of the exchange's parity, flags carry seq; also equal to the plain spgpuDhdiaspmv on the same
+    block bit for bit"""
     import torch
     n, world = 16, 3
     coo = G.stencil3d_27pt(n)
@@ -76,30 +183,33 @@ def test_hdia_spmv_fused_with_halo_exchange(ours, gpu_handle, seq, rank):
     dx, dy = util.to_dev(x_ext), util.to_dev(y[loc.lo:loc.hi])
     dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
     has_lo, has_hi = rank > 0, rank < world - 1
-    my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    my_flags[0] = seq; my_flags[1] = seq
-    my_flags[2] = seq - 1; my_flags[3] = seq - 1
-    pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
-    ph = [torch.full((halo,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(2)]
+    em = Emulated(halo, torch.float64, has_lo, has_hi)
+    if has_lo and has_hi:
+        em.place_halos(dx, x_ext, loc.nrows, seq, torch.float64)
+    elif seq & 1:                                         # only the zone that has a neighbour moves to the odd pair
+        if has_lo:
+            em.alt[:halo] = dx[:halo]; dx[:halo] = float("nan")
+        if has_hi:
+            em.alt[halo:] = dx[halo + loc.nrows:]; dx[halo + loc.nrows:] = float("nan")
+    em.my_flags[4] = seq; em.my_flags[5] = seq
     ours.spgpuDhdiaspmvHalo(gpu_handle, dz.data_ptr(), dy.data_ptr(), 1.5, dv.data_ptr(), doff.data_ptr(), 32, dho.data_ptr(),
-                            loc.nrows, loc.ext_len, dx.data_ptr(), -0.5, halo,
-                            ph[0].data_ptr() if has_lo else 0, ph[1].data_ptr() if has_hi else 0, my_flags.data_ptr(),
-                            pf[0].data_ptr() if has_lo else 0, pf[1].data_ptr() if has_hi else 0, seq)
+                            loc.nrows, loc.ext_len, dx.data_ptr(), -0.5, halo, em.ref(), seq)
     torch.cuda.synchronize()
     scale = util.row_scale(coo, x, y, 1.5, -0.5)[loc.lo:loc.hi]
     util.assert_rows_close(dz.cpu().numpy(), want, scale, "D", "fused hdia spmv+halo")
+    par = seq & 1
     if has_lo:
-        np.testing.assert_array_equal(ph[0].cpu().numpy(), x_ext[halo:2 * halo])
-        f = pf[0].cpu().numpy()
-        assert f[1] == seq and f[3] == seq and f[0] == 0
+        np.testing.assert_array_equal(em.pz[0][par].cpu().numpy(), x_ext[halo:2 * halo])
+        assert em.pf[0].cpu().numpy()[5] == seq
     if has_hi:
-        np.testing.assert_array_equal(ph[1].cpu().numpy(), x_ext[loc.nrows:loc.nrows + halo])
-        f = pf[1].cpu().numpy()
-        assert f[0] == seq and f[2] == seq and f[1] == 0
+        np.testing.assert_array_equal(em.pz[1][par].cpu().numpy(), x_ext[loc.nrows:loc.nrows + halo])
+        assert em.pf[1].cpu().numpy()[4] == seq
+    # the plain kernel on the same block with every zone inside x_ext
+    dx2 = util.to_dev(x_ext)
     dz2 = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
     T = util.TYPES["D"]
     ours.spgpuDhdiaspmv(gpu_handle, dz2.data_ptr(), dy.data_ptr(), T.scalar(1.5), dv.data_ptr(), doff.data_ptr(), 32,
-                        dho.data_ptr(), loc.nrows, loc.ext_len, dx.data_ptr(), T.scalar(-0.5))
+                        dho.data_ptr(), loc.nrows, loc.ext_len, dx2.data_ptr(), T.scalar(-0.5))
     torch.cuda.synchronize()
     assert torch.equal(dz, dz2)
 
@@ -113,17 +223,17 @@ def test_spmv_fused_without_neighbours_is_the_plain_kernel(ours, gpu_handle):
     y = G.random_vector(coo.nrows, np.float64, 4)
     plain = util.dev_spmv(ours, gpu_handle, "hell", A, dA, x, y, 1.5, -0.5)
     dx, dy = util.to_dev(x), util.to_dev(y)
-    dz = torch.full((coo.nrows,), float("nan"), dtype=torch.float64, device="cuda")
-    flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), dy.data_ptr(), 1.5, dA["values"].data_ptr(), dA["indices"].data_ptr(),
-                            32, dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), 7, coo.nrows, dx.data_ptr(), -0.5, 0, 0,
-                            0, 0, flags.data_ptr(), 0, 0, 1)
-    torch.cuda.synchronize()
-    np.testing.assert_array_equal(dz.cpu().numpy(), plain)
+    for links in (None, Emulated(0, torch.float64, False, False).ref()):
+        dz = torch.full((coo.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+        ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), dy.data_ptr(), 1.5, dA["values"].data_ptr(), dA["indices"].data_ptr(),
+                                32, dA["hack_offsets"].data_ptr(), dA["rs"].data_ptr(), 7, coo.nrows, dx.data_ptr(), -0.5, 0, 0,
+                                links, 1)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(dz.cpu().numpy(), plain)
 
 
 def test_halo_exchange_kernel_and_ack(ours, gpu_handle):
-    """spgpuDhaloExchange / spgpuHaloAck / spgpuDhaloPush / spgpuWaitFlag with emulated neighbours"""
+    """spgpuDhaloExchange / spgpuHaloAck / spgpuDhaloPush / spgpuHaloPush / spgpuWaitFlag with emulated neighbours"""
     import torch
     n = 5000
     src = torch.arange(3 * n, dtype=torch.float64, device="cuda")
@@ -142,101 +252,172 @@ def test_halo_exchange_kernel_and_ack(ours, gpu_handle):
     # the two-kernel form
     dst = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
     flag = torch.zeros(4, dtype=torch.int32, device="cuda")
-    ours.spgpuDhaloPush(gpu_handle, dst.data_ptr() + 8, src.data_ptr() + 8, n, flag.data_ptr(), 7)   # unaligned -> scalar path
+    ours.spgpuDhaloPush(gpu_handle, dst.data_ptr() + 8, src.data_ptr() + 8, n, flag.data_ptr(), 7)   # 8-byte aligned only
     ours.spgpuWaitFlag(gpu_handle, flag.data_ptr(), 7)
     torch.cuda.synchronize()
     assert torch.equal(dst[1:], src[1:n + 1]) and int(flag[0].item()) == 7
+    # byte form: odd length, odd alignment
+    bsrc = torch.arange(1003, dtype=torch.uint8, device="cuda")
+    bdst = torch.zeros(1003, dtype=torch.uint8, device="cuda")
+    ours.spgpuHaloPush(gpu_handle, bdst.data_ptr() + 1, bsrc.data_ptr() + 1, 1001, flag.data_ptr() + 4, 9)
+    torch.cuda.synchronize()
+    assert torch.equal(bdst[1:1002], bsrc[1:1002]) and int(bdst[0].item()) == 0 and int(bdst[1002].item()) == 0
+    assert int(flag[1].item()) == 9
 
 
-def test_peer_allreduce_kernel_with_emulated_peer(ours, gpu_handle):
-    """spgpuAllreduceSumDev, world = 3, this rank = 1: the two peers' contributions are pre-filled in
+def test_wait_timeout_sets_the_sticky_status(ours, gpu_handle):
+    """a wait for a peer that never comes gives up after spinTimeoutMs, records SPGPU_DEVSTATUS_TIMEOUT in the
+    handle (host-readable), and later waits of the handle return at once until the status is cleared"""
+    import time
+    import torch
+    flag = torch.zeros(4, dtype=torch.int32, device="cuda")
+    assert ours.spgpuGetDeviceStatus(gpu_handle, 1) >= 0
+    ours.spgpuSetTuning(gpu_handle, b"spinTimeoutMs", 30)
+    try:
+        ours.spgpuWaitFlag(gpu_handle, flag.data_ptr(), 1)
+        torch.cuda.synchronize()
+        assert ours.spgpuGetDeviceStatus(gpu_handle, 0) == 1
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ours.spgpuWaitFlag(gpu_handle, flag.data_ptr(), 1)
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 0.3              # 20 full timeouts would be >= 0.6 s
+        assert ours.spgpuGetDeviceStatus(gpu_handle, 1) == 1
+        assert ours.spgpuGetDeviceStatus(gpu_handle, 0) == 0
+    finally:
+        ours.spgpuSetTuning(gpu_handle, b"spinTimeoutMs", 20000)
+
+
+def _slot_words(a, b, seq):
+    alo, ahi = struct.unpack("<ii", struct.pack("<d", a))
+    blo, bhi = struct.unpack("<ii", struct.pack("<d", b))
+    return [alo, ahi, blo, bhi, seq, 0, 0, 0]
+
+
+def _tables(world, me, seq, contributions):
+    """device tables of all ranks; this rank's own holds the peers' contributions for `seq`"""
+    import torch
+    W = capi.AR_SLOT_BYTES // 4
+    tabs = [torch.zeros(2 * world * W, dtype=torch.int32, device="cuda") for _ in range(world)]
+    host = np.zeros(2 * world * W, dtype=np.int32)
+    for r, (a, b) in contributions.items():
+        base = ((seq & 1) * world + r) * W
+        host[base:base + W] = _slot_words(a, b, seq)
+    tabs[me].copy_(torch.from_numpy(host))
+    ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in tabs])
+    args = capi.PeerAllreduceArgs(world, me, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), seq)
+    return tabs, ptrs, args
+
+
+@pytest.mark.parametrize("sym", ["S", "D", "C", "Z"])
+def test_peer_allreduce_kernel_with_emulated_peer(ours, gpu_handle, sym):
+    """spgpu?allreduceSumDev, world = 3, this rank = 1: the two peers' contributions are pre-filled in
     this rank's table; this rank's (value, seq) must land in slot 1 of every table and the sum must
-    be taken in rank order"""
-    import ctypes
-    import struct
+    be taken in rank order, in double"""
     import torch
     world, me = 3, 1
+    tdt = getattr(torch, TORCH_OF[sym])
+    W = capi.AR_SLOT_BYTES // 4
+    cplx = util.TYPES[sym].is_complex
     for seq in (1, 2, 7):
-        tabs = [torch.zeros(2 * world * 4, dtype=torch.int32, device="cuda") for _ in range(world)]
-        parity = seq & 1
-        vals = {0: 0.125, 2: -3.5}
-        host = np.zeros(2 * world * 4, dtype=np.int32)
-        for r, v in vals.items():
-            lo, hi = struct.unpack("<ii", struct.pack("<d", v))
-            base = (parity * world + r) * 4
-            host[base:base + 4] = [lo, hi, seq, 0]
-        tabs[me].copy_(torch.from_numpy(host))
-        value = torch.tensor([10.0], dtype=torch.float64, device="cuda")
-        ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in tabs])
-        ours.spgpuAllreduceSumDev(gpu_handle, value.data_ptr(), world, me, ptrs, seq)
+        tabs, ptrs, args = _tables(world, me, seq, {0: (0.125, 1.0), 2: (-3.5, 0.25)})
+        mine = (10.0 - 2.0j) if cplx else 10.0
+        value = torch.tensor([mine], dtype=tdt, device="cuda")
+        getattr(ours, f"spgpu{sym}allreduceSumDev")(gpu_handle, value.data_ptr(), ctypes.byref(args))
         torch.cuda.synchronize()
-        assert float(value.item()) == (0.125 + 10.0) + -3.5
+        got = value.cpu().numpy()[0]
+        assert got.real == (0.125 + 10.0) + -3.5
+        if cplx:
+            assert got.imag == (1.0 + -2.0) + 0.25
         for t in tabs:
-            got = t.cpu().numpy()[(parity * world + me) * 4:(parity * world + me) * 4 + 3]
-            assert struct.unpack("<d", struct.pack("<ii", int(got[0]), int(got[1])))[0] == 10.0 and got[2] == seq
+            w = t.cpu().numpy()[((seq & 1) * world + me) * W:((seq & 1) * world + me + 1) * W]
+            assert w.tolist()[:5] == _slot_words(10.0, -2.0 if cplx else 0.0, seq)[:5]
 
 
-def test_spmv_halo_dot(ours, gpu_handle):
-    """spgpuDhellspmvHaloDot: fused exchange + SpMV + this rank's share of p.Ap"""
+@pytest.mark.parametrize("sym", ["D", "Z", "S"])
+def test_spmv_halo_dot_with_fused_allreduce(ours, gpu_handle, sym):
+    """spgpu?hellspmvHaloDot: fused exchange + SpMV + this rank's share of p.Ap, all-reduced by the fold kernel's
+    last CTA (emulated peers, world 3)"""
     import torch
-    coo, loc, plane, x, x_ext, want = _middle_block()
+    coo, loc, plane, x, x_ext, want, scale = _middle_block(sym=sym)
+    tdt = getattr(torch, TORCH_OF[sym])
+    cplx = util.TYPES[sym].is_complex
     dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
     dx = util.to_dev(x_ext)
-    dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
-    my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    my_flags[0] = 1; my_flags[1] = 1
-    pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
-    ph = [torch.zeros(plane, dtype=torch.float64, device="cuda") for _ in range(2)]
-    dres = torch.full((1,), float("nan"), dtype=torch.float64, device="cuda")
-    ours.spgpuDhellspmvHaloDot(gpu_handle, dz.data_ptr(), dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(), drs.data_ptr(),
-                               7, loc.nrows, dx.data_ptr(), 0, plane, ph[0].data_ptr(), ph[1].data_ptr(),
-                               my_flags.data_ptr(), pf[0].data_ptr(), pf[1].data_ptr(), 1, dres.data_ptr())
-    torch.cuda.synchronize()
-    util.assert_rows_close(dz.cpu().numpy(), want, np.full(loc.nrows, 12.0), "D", "fused spmv+halo+dot")
     own = x_ext[plane:plane + loc.nrows]
-    ref = float(np.dot(own, want))
-    assert abs(float(dres.item()) - ref) <= 1e-12 * float(np.sum(np.abs(own) * np.abs(want)))
+    local = np.sum(own.astype(np.complex128) * want.astype(np.complex128))          # unconjugated, like spgpu?dot
+    mag = float(np.sum(np.abs(own) * np.abs(want)))
+    tol = 1e-12 if sym in "DZ" else 2e-6
+    for seq, ar_on in ((1, False), (2, True)):
+        em = Emulated(plane, tdt)
+        em.place_halos(dx, x_ext, loc.nrows, seq, tdt)
+        em.my_flags[4] = seq; em.my_flags[5] = seq
+        dz = torch.full((loc.nrows,), float("nan"), dtype=tdt, device="cuda")
+        dres = torch.full((1,), float("nan"), dtype=tdt, device="cuda")
+        tabs, ptrs, args = _tables(3, 1, 5, {0: (100.0, 7.0), 2: (-50.0, 1.0)})
+        getattr(ours, f"spgpu{sym}hellspmvHaloDot")(gpu_handle, dz.data_ptr(), dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
+                                                    drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0, plane, em.ref(), seq,
+                                                    dres.data_ptr(), ctypes.byref(args) if ar_on else None)
+        torch.cuda.synchronize()
+        util.assert_rows_close(dz.cpu().numpy(), want, scale, sym, "fused spmv+halo+dot")
+        got = complex(dres.cpu().numpy()[0])
+        ref = local + ((50.0 + (8.0j if cplx else 0.0)) if ar_on else 0.0)
+        if not cplx:
+            ref = ref.real
+        assert abs(got - ref) <= tol * (mag + 160.0), (got, ref)
+    assert ours.spgpuGetDeviceStatus(gpu_handle, 0) == 0
 
 
 def test_device_resident_sequence_numbers(ours, gpu_handle):
     """seq == 0: the fused halo kernel and the all-reduce take their sequence number from device counters
     (spgpuSetSeqCounters); spgpuHaloSeqAdvance / the all-reduce itself advance them -- what lets a partitioned
     iteration be replayed from a CUDA graph.  Emulated neighbours as above."""
-    import struct
     import torch
-    coo, loc, plane, x, x_ext, want = _middle_block()
+    coo, loc, plane, x, x_ext, want, scale = _middle_block()
     dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
     dx = util.to_dev(x_ext)
     counters = torch.tensor([6, 10], dtype=torch.int32, device="cuda")       # 6 exchanges, 10 all-reduces done so far
     assert ours.spgpuSetSeqCounters(gpu_handle, counters.data_ptr(), counters.data_ptr() + 4) == 0
     try:
-        my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
-        pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
-        ph = [torch.zeros(plane, dtype=torch.float64, device="cuda") for _ in range(2)]
-        for k in (7, 8):                                                     # two exchanges: 7 and 8
-            my_flags[0] = k; my_flags[1] = k; my_flags[2] = k - 1; my_flags[3] = k - 1
+        em = Emulated(plane, torch.float64)
+        for k in (7, 8):                                                     # two exchanges: 7 (odd pair) and 8 (even)
+            em.place_halos(dx, x_ext, loc.nrows, k, torch.float64)
+            em.my_flags[4] = k; em.my_flags[5] = k
             dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
             ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), 0, 1.0, dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
-                                    drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0.0, 0, plane, ph[0].data_ptr(),
-                                    ph[1].data_ptr(), my_flags.data_ptr(), pf[0].data_ptr(), pf[1].data_ptr(), 0)
+                                    drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0.0, 0, plane, em.ref(), 0)
             ours.spgpuHaloSeqAdvance(gpu_handle)
             torch.cuda.synchronize()
-            util.assert_rows_close(dz.cpu().numpy(), want, np.full(loc.nrows, 12.0), "D", "fused spmv+halo, device seq")
+            util.assert_rows_close(dz.cpu().numpy(), want, scale, "D", "fused spmv+halo, device seq")
             assert int(counters[0].item()) == k
-            assert pf[0].cpu().numpy()[1] == k and pf[0].cpu().numpy()[3] == k
-            assert pf[1].cpu().numpy()[0] == k and pf[1].cpu().numpy()[2] == k
+            assert em.pf[0].cpu().numpy()[5] == k and em.pf[1].cpu().numpy()[4] == k
         # all-reduce number 11, world 2, this rank 0: the peer's slot is pre-filled
-        world, me, seq = 2, 0, 11
-        tabs = [torch.zeros(2 * world * 4, dtype=torch.int32, device="cuda") for _ in range(world)]
-        host = np.zeros(2 * world * 4, dtype=np.int32)
-        lo, hi = struct.unpack("<ii", struct.pack("<d", 2.5))
-        base = ((seq & 1) * world + 1) * 4
-        host[base:base + 4] = [lo, hi, seq, 0]
-        tabs[me].copy_(torch.from_numpy(host))
+        tabs, ptrs, args = _tables(2, 0, 11, {1: (2.5, 0.0)})
+        args.seq = 0
         value = torch.tensor([4.0], dtype=torch.float64, device="cuda")
-        ptrs = (ctypes.c_void_p * world)(*[t.data_ptr() for t in tabs])
-        ours.spgpuAllreduceSumDev(gpu_handle, value.data_ptr(), world, me, ptrs, 0)
+        ours.spgpuDallreduceSumDev(gpu_handle, value.data_ptr(), ctypes.byref(args))
         torch.cuda.synchronize()
         assert float(value.item()) == 6.5 and int(counters[1].item()) == 11
     finally:
         ours.spgpuSetSeqCounters(gpu_handle, 0, 0)
+
+
+def test_halo_trace(ours, gpu_handle):
+    """haloTrace tuning key + spgpuHaloTraceRead: timestamps of one fused exchange are recorded and ordered"""
+    import torch
+    coo, loc, plane, x, x_ext, want, scale = _middle_block()
+    dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
+    dx = util.to_dev(x_ext)
+    em = Emulated(plane, torch.float64)
+    em.my_flags[4] = 2; em.my_flags[5] = 2
+    dz = torch.zeros(loc.nrows, dtype=torch.float64, device="cuda")
+    assert ours.spgpuSetTuning(gpu_handle, b"haloTrace", 1) == 0
+    try:
+        ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), 0, 1.0, dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
+                                drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0.0, 0, plane, em.ref(), 2)
+        buf = (ctypes.c_ulonglong * 8)()
+        assert ours.spgpuHaloTraceRead(gpu_handle, buf, 2, 1) == 0
+        t = list(buf)
+        assert t[0] > 0 and t[1] >= t[0] and t[6] > 0 and t[7] >= t[6]
+    finally:
+        assert ours.spgpuSetTuning(gpu_handle, b"haloTrace", 0) == 0

@@ -122,3 +122,49 @@ def test_reference_amax_defect_is_documented(ours, ref, gpu_handle, ref_handle):
     dx = util.to_dev(x)
     assert ours.spgpuDamax(gpu_handle, n, dx.data_ptr()) == 9.0
     assert ref.spgpuDamax(ref_handle, n, dx.data_ptr()) != 9.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("base", [0, 1])
+def test_ellcsput_against_the_reference_kernel(ours, ref, gpu_handle, ref_handle, dtype, base):
+    """spgpu?ellcsput (reference ell.h:194-302, kernels/ell_csput_base.cuh:33-75): per (aI, aJ, aVal) triple the slot of
+    row aI - baseIndex whose stored column equals aJ is overwritten.  The reference's quirks are the contract and are
+    pinned here against its own kernel: `alpha` is ignored (ell_csput_base.cuh:42-44 never reads it), aJ is compared
+    with the STORED index as is (no base adjustment, :66), triples whose row is negative are skipped (:46-47), and a
+    column that is absent from the row changes nothing.  Result must be bit-identical."""
+    import torch
+    s = util.sym_of(dtype)
+    t = util.TYPES[s]
+    nrows = 3000
+    coo = G.random_coo(nrows, nrows, (0, 20), 77, dtype, 0)             # columns ascending inside a row
+    ell = F.coo_to_ell(coo)                                             # stored indices are 0-based
+    rng = np.random.default_rng(base + 10)
+    # half of the triples hit existing entries, a quarter name absent columns, the rest sit in row -1
+    k = rng.choice(coo.nnz, size=coo.nnz // 2, replace=False)
+    ai = np.concatenate([coo.rows[k] + base, rng.integers(0, nrows, 400) + base, np.full(50, base - 1)]).astype(np.int32)
+    aj = np.concatenate([coo.cols[k], rng.integers(0, nrows, 400), rng.integers(0, nrows, 50)]).astype(np.int32)
+    av = G.random_vector(ai.shape[0], dtype, 5, -1, 1)
+    # duplicates of one (row, column) would race (last writer wins in either library): keep the first
+    _, first = np.unique(ai.astype(np.int64) * nrows + aj, return_index=True)
+    ai, aj, av = ai[first], aj[first], av[first]
+    results = []
+    for L, h in ((ours, gpu_handle), (ref, ref_handle)):
+        d_vals, d_idx, d_rs = util.to_dev(ell.values), util.to_dev(ell.indices), util.to_dev(ell.rs)
+        d_i, d_j, d_v = util.to_dev(ai), util.to_dev(aj), util.to_dev(av)
+        getattr(L, f"spgpu{s}ellcsput")(h, t.scalar(123.0), d_vals.data_ptr(), d_idx.data_ptr(), ell.pitch, ell.pitch,
+                                        d_rs.data_ptr(), ai.shape[0], d_i.data_ptr(), d_j.data_ptr(), d_v.data_ptr(), base)
+        torch.cuda.synchronize()
+        results.append(d_vals.cpu().numpy())
+    assert np.array_equal(results[0].view(np.uint8), results[1].view(np.uint8))
+    # and the host statement of the same rule
+    want = ell.values.copy()
+    changed = 0
+    for r, c, v in zip(ai - base, aj, av):
+        if r < 0:
+            continue
+        cols = ell.indices[r + np.arange(ell.rs[r]) * ell.pitch]
+        hit = np.nonzero(cols == c)[0]
+        if hit.size:
+            want[r + hit[0] * ell.pitch] = v
+            changed += 1
+    assert changed >= coo.nnz // 2 and np.array_equal(results[0].view(np.uint8), want.view(np.uint8))
