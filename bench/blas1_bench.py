@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1 << 27)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--sweep", action="store_true", help="also sweep the reductions' redInflight x redBlocksPerSm knobs")
     args = ap.parse_args()
     import torch
     from spgpu_b200 import capi
@@ -75,6 +76,29 @@ def main():
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / args.reps
         out[name] = {"ms": ms, "algorithmic_gb": nbytes / 1e9, "gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+    if args.sweep:
+        sweep = {}
+        red = {k: v for k, v in ops.items() if any(t in k for t in ("DdotDev", "Dnrm2", "Damax", "Ddot (blocking)"))}
+        for infl in (2, 4, 8):
+            for bps in (2, 4, 6, 8):
+                L.spgpuSetTuning(h, b"redInflight", infl)
+                L.spgpuSetTuning(h, b"redBlocksPerSm", bps)
+                row = {}
+                for name, (fn, nbytes) in red.items():
+                    for _ in range(2):
+                        fn()
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    for _ in range(args.reps):
+                        fn()
+                    b.record(stream)
+                    torch.cuda.synchronize()
+                    row[name] = round(nbytes / (a.elapsed_time(b) / args.reps) / 1e6 / peak, 4)
+                sweep[f"inflight={infl},blocksPerSm={bps}"] = row
+        L.spgpuSetTuning(h, b"redInflight", 0)
+        L.spgpuSetTuning(h, b"redBlocksPerSm", 8)
+        out["reduction_sweep_frac_of_peak"] = sweep
     print(json.dumps(out, indent=1))
     torch.cuda.synchronize()
     torch.cuda.set_stream(torch.cuda.default_stream())

@@ -142,6 +142,21 @@ def ext_symbols():
     return names
 
 
+def mg_symbols():
+    """Every symbol include/spgpu_mg.h declares (the C-level multi-GPU API)."""
+    names = ["spgpuMgCreate", "spgpuMgDestroy", "spgpuMgWorld", "spgpuMgRankHandle", "spgpuMgSetExchange", "spgpuMgExchange",
+             "spgpuMgSynchronize", "spgpuMgHellCreateFromBlocks", "spgpuMgMatrixDestroy", "spgpuMgMatrixHalo",
+             "spgpuMgMatrixRows", "spgpuMgMatrixRowBlock", "spgpuMgVectorCreate", "spgpuMgVectorDestroy", "spgpuMgVectorSet",
+             "spgpuMgVectorGet", "spgpuMgVectorLocal", "spgpuMgDcgCreate", "spgpuMgDcgStart", "spgpuMgDcgStep",
+             "spgpuMgDcgSolution", "spgpuMgDcgDestroy"]
+    for s in FLOAT_SYMS:
+        names += [f"spgpuMg{s}hellCreate", f"spgpuMg{s}hellspmv", f"spgpuMg{s}dot", f"spgpuMg{s}nrm2", f"spgpuMg{s}axpby"]
+    return names
+
+
+MG_AUTO, MG_FUSED, MG_EVENTS = 0, 1, 2
+
+
 class SpgpuLib:
     """One loaded spGPU-ABI shared library with typed entry points."""
 
@@ -302,6 +317,43 @@ class SpgpuLib:
             f["spgpuSetSeqCounters"] = _sig(d, "spgpuSetSeqCounters", c_int, [H, P, P], optional=True)
             f["spgpuHaloSeqAdvance"] = _sig(d, "spgpuHaloSeqAdvance", None, [H], optional=True)
             f["spgpuHaloTraceRead"] = _sig(d, "spgpuHaloTraceRead", c_int, [H, P, c_int, c_int], optional=True)
+
+            # --- C-level multi-GPU API (include/spgpu_mg.h)
+            PP = ctypes.POINTER(c_void_p)
+            f["spgpuMgCreate"] = _sig(d, "spgpuMgCreate", c_int, [PP, ctypes.POINTER(c_int), c_int], optional=True)
+            f["spgpuMgDestroy"] = _sig(d, "spgpuMgDestroy", None, [P], optional=True)
+            f["spgpuMgWorld"] = _sig(d, "spgpuMgWorld", c_int, [P], optional=True)
+            f["spgpuMgRankHandle"] = _sig(d, "spgpuMgRankHandle", c_void_p, [P, c_int], optional=True)
+            f["spgpuMgSetExchange"] = _sig(d, "spgpuMgSetExchange", c_int, [P, c_int], optional=True)
+            f["spgpuMgExchange"] = _sig(d, "spgpuMgExchange", c_int, [P], optional=True)
+            f["spgpuMgSynchronize"] = _sig(d, "spgpuMgSynchronize", c_int, [P], optional=True)
+            f["spgpuMgHellCreateFromBlocks"] = _sig(d, "spgpuMgHellCreateFromBlocks", c_int,
+                [P, PP, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), PP, PP, PP, PP,
+                 ctypes.POINTER(ctypes.c_longlong), c_int], optional=True)
+            f["spgpuMgMatrixDestroy"] = _sig(d, "spgpuMgMatrixDestroy", None, [P], optional=True)
+            f["spgpuMgMatrixHalo"] = _sig(d, "spgpuMgMatrixHalo", c_int, [P], optional=True)
+            f["spgpuMgMatrixRows"] = _sig(d, "spgpuMgMatrixRows", c_int, [P], optional=True)
+            f["spgpuMgMatrixRowBlock"] = _sig(d, "spgpuMgMatrixRowBlock", None,
+                [P, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)], optional=True)
+            f["spgpuMgVectorCreate"] = _sig(d, "spgpuMgVectorCreate", c_int, [P, PP], optional=True)
+            f["spgpuMgVectorDestroy"] = _sig(d, "spgpuMgVectorDestroy", None, [P], optional=True)
+            f["spgpuMgVectorSet"] = _sig(d, "spgpuMgVectorSet", c_int, [P, P], optional=True)
+            f["spgpuMgVectorGet"] = _sig(d, "spgpuMgVectorGet", c_int, [P, P], optional=True)
+            f["spgpuMgVectorLocal"] = _sig(d, "spgpuMgVectorLocal", c_void_p, [P, c_int], optional=True)
+            f["spgpuMgDcgCreate"] = _sig(d, "spgpuMgDcgCreate", c_int, [P, PP], optional=True)
+            f["spgpuMgDcgStart"] = _sig(d, "spgpuMgDcgStart", c_int, [P, P, ctypes.POINTER(c_double)], optional=True)
+            f["spgpuMgDcgStep"] = _sig(d, "spgpuMgDcgStep", c_int, [P, c_int, ctypes.POINTER(c_double)], optional=True)
+            f["spgpuMgDcgSolution"] = _sig(d, "spgpuMgDcgSolution", c_void_p, [P], optional=True)
+            f["spgpuMgDcgDestroy"] = _sig(d, "spgpuMgDcgDestroy", None, [P], optional=True)
+            for s in FLOAT_SYMS:
+                t = TYPES[s]
+                T, R = t.ctype, t.rtype
+                f[f"spgpuMg{s}hellCreate"] = _sig(d, f"spgpuMg{s}hellCreate", c_int,
+                    [P, PP, P, P, c_int, P, P, c_int, c_int, c_int, c_int], optional=True)
+                f[f"spgpuMg{s}hellspmv"] = _sig(d, f"spgpuMg{s}hellspmv", c_int, [P, P, P, T, P, P, T], optional=True)
+                f[f"spgpuMg{s}dot"] = _sig(d, f"spgpuMg{s}dot", c_int, [P, ctypes.POINTER(T), P, P], optional=True)
+                f[f"spgpuMg{s}nrm2"] = _sig(d, f"spgpuMg{s}nrm2", c_int, [P, ctypes.POINTER(R), P], optional=True)
+                f[f"spgpuMg{s}axpby"] = _sig(d, f"spgpuMg{s}axpby", c_int, [P, P, T, P, T, P], optional=True)
 
     def __getattr__(self, name):
         try:

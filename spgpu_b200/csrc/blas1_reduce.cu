@@ -94,11 +94,9 @@ template <typename T> struct OpAbsMax {
  * elements after vector v-1, has its own run of gridDim.x partial slots, its own ticket word and
  * its own result slot (outBytes apart) -- `count` reductions in ONE launch.
  *
- * Loads in flight per thread: 2 packs per input for the two-input dot, 4 for the one-input ops
- * (they move half the bytes per element, and 4 CTAs x 256 threads x 32 B per SM is under what the
- * HBM latency-bandwidth product asks for: measured 0.92 of the copy peak vs 1.03 for the dot).
+ * INFL = 16-byte packs a thread keeps in flight per input (reduce_inflight below).
  */
-template <typename T, typename Op>
+template <typename T, typename Op, int INFL>
 __global__ void __launch_bounds__(RED_BLOCK)
 reduce_kernel(const T* x, const T* y, long long n, long long pitch, Acc2* partials,
 	unsigned* tickets, void* out, int outBytes, int finish, int outKind)
@@ -108,7 +106,6 @@ reduce_kernel(const T* x, const T* y, long long n, long long pitch, Acc2* partia
 	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long nthreads = (long long)gridDim.x * blockDim.x;
 	constexpr int N = RPack<T>::N;
-	constexpr int INFL = Op::NIN > 1 ? 2 : 4;
 
 	x += (long long)blockIdx.y * pitch;
 	if (Op::NIN > 1)
@@ -176,11 +173,22 @@ reduce_kernel(const T* x, const T* y, long long n, long long pitch, Acc2* partia
 	}
 }
 
+/* 16-byte packs a thread keeps in flight per input: redInflight tuning key, default 4.  Measured on 1 GiB double
+ * vectors (profiles/r2_blas1.json, fraction of the copy peak; 2 / 4 / 8 packs at 8 CTAs per SM): dot 0.98 / 1.09 / 1.08,
+ * nrm2 0.84 / 0.99 / 0.80, amax 0.91 / 0.97 / 0.68 -- 4 is the one depth that serves both shapes. */
+template <typename Op>
+static int reduce_inflight(const SpgpuTuning* t)
+{
+	const int v = t->redInflight;
+	if (v == 2 || v == 4 || v == 8)
+		return v;
+	return 4;
+}
+
 /* CTAs of one reduction over n elements when `cap` CTAs may run */
 template <typename T, typename Op>
-static unsigned reduce_grid(long long n, long long cap)
+static unsigned reduce_grid(long long n, long long cap, int INFL)
 {
-	constexpr int INFL = Op::NIN > 1 ? 2 : 4;
 	const long long items = (n / RPack<T>::N + INFL - 1) / INFL + 1;
 	long long want = (items + RED_BLOCK - 1) / RED_BLOCK;
 	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
@@ -191,13 +199,25 @@ static unsigned reduce_grid(long long n, long long cap)
 }
 
 template <typename T, typename Op>
+static void reduce_dispatch(int infl, dim3 grid, cudaStream_t s, const T* x, const T* y, long long n, long long pitch,
+	Acc2* partials, unsigned* tickets, void* out, int outBytes, int finish, int outKind)
+{
+	if (infl == 8)
+		reduce_kernel<T, Op, 8><<<grid, RED_BLOCK, 0, s>>>(x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
+	else if (infl == 4)
+		reduce_kernel<T, Op, 4><<<grid, RED_BLOCK, 0, s>>>(x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
+	else
+		reduce_kernel<T, Op, 2><<<grid, RED_BLOCK, 0, s>>>(x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
+}
+
+template <typename T, typename Op>
 static void reduce_launch(spgpuHandle_t handle, const T* x, const T* y, long long n,
 	void* out, int finish, int outKind)
 {
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	const SpgpuTuning* t = spgpu_tuning(handle);
-	const long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 4);
-	reduce_kernel<T, Op><<<reduce_grid<T, Op>(n, cap), RED_BLOCK, 0, handle->currentStream>>>(
+	const long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 8);
+	reduce_dispatch<T, Op>(reduce_inflight<Op>(t), dim3(reduce_grid<T, Op>(n, cap, reduce_inflight<Op>(t))), handle->currentStream,
 		x, y, n, 0, reinterpret_cast<Acc2*>(h->dPartials), h->dTicket, out, 0, finish, outKind);
 	spgpu_count_launch(handle);
 }
@@ -239,8 +259,9 @@ static void reduce_many(spgpuHandle_t handle, Ret* hostOut, const T* x, const T*
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const int slice = count < 65535 ? count : 65535;
 	/* the CTAs the device holds, shared out among the vectors of a slice (at least one each) */
-	const long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 4);
-	const unsigned gx = reduce_grid<T, Op>(n, cap / slice > 0 ? cap / slice : 1);
+	const long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 8);
+	const int infl = reduce_inflight<Op>(t);
+	const unsigned gx = reduce_grid<T, Op>(n, cap / slice > 0 ? cap / slice : 1, infl);
 	/* scratch: [results | partials]; tickets in their own zero-kept block */
 	const size_t resBytes = ((sizeof(Ret) * (size_t)count + 255) / 256) * 256;
 	char* base = (char*)spgpuScratch(handle, resBytes + (size_t)slice * gx * sizeof(Acc2));
@@ -251,7 +272,7 @@ static void reduce_many(spgpuHandle_t handle, Ret* hostOut, const T* x, const T*
 	for (int v0 = 0; v0 < count; v0 += slice) {
 		const int nv = count - v0 < slice ? count - v0 : slice;
 		const long long o = (long long)v0 * pitch;
-		reduce_kernel<T, Op><<<dim3(gx, (unsigned)nv), RED_BLOCK, 0, handle->currentStream>>>(
+		reduce_dispatch<T, Op>(infl, dim3(gx, (unsigned)nv), handle->currentStream,
 			x + o, y ? y + o : (const T*)0, n, pitch, reinterpret_cast<Acc2*>(base + resBytes), tickets,
 			dOut + v0, (int)sizeof(Ret), finish, outKind);
 		spgpu_count_launch(handle);

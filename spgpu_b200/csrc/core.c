@@ -24,11 +24,12 @@ static void default_tuning(SpgpuTuning* t)
 	t->hdiaVariant = 0;
 	t->hdiaBlock = 0;
 	t->ellRows = 0;
-	t->redBlocksPerSm = 4;
+	t->redBlocksPerSm = 8;
 	t->vecBlocksPerSm = 8;
 	t->spinTimeoutMs = 20000;
 	t->haloTrace = 0;
 	t->l2Fetch = 0;
+	t->redInflight = 0;
 	t->ellShortMinB = 0;
 }
 
@@ -69,6 +70,12 @@ spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
 		if (err == cudaSuccess) {
 			memset(h->hResult, 0, 64);
 			err = cudaHostGetDevicePointer(&h->dResult, h->hResult, 0);
+		}
+		if (err == cudaSuccess) {
+			/* sticky device status word: byte 32 of the same mapped pinned block */
+			h->hStatus = (unsigned*)((char*)h->hResult + 32);
+			h->dStatus = (unsigned*)((char*)h->dResult + 32);
+			err = cudaEventCreateWithFlags(&h->switchEvent, cudaEventDisableTiming);
 		}
 	}
 	cudaSetDevice(previous);
@@ -273,6 +280,7 @@ int spgpuGetDeviceStatus(spgpuHandle_t handle, int clear)
 	X(spinTimeoutMs)          \
 	X(haloTrace)              \
 	X(l2Fetch)                \
+	X(redInflight)            \
 	X(ellShortMinB)
 
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value)

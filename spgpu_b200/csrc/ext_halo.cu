@@ -285,88 +285,105 @@ struct HdiaRowBody {
  * have normally long arrived.  A block may read both zones (a rank with fewer rows than two halo
  * widths): it then waits for both words.
  */
-template <typename T, class Body, int MINB, bool DOT>
+/* The rows that read a halo zone, out of line: the interior path then keeps the register allocation of the plain
+ * kernel (inlined next to it, the second copy of the row walk cost 32 bytes of spills in EVERY block; the call
+ * costs a few dozen cycles in the ~3 % of blocks that take it). */
+template <typename T, class Body>
+__device__ __noinline__ T halo_boundary_rows(const Body body, unsigned warpRow, const XZones<T> xg)
+{
+	return body.run(warpRow, xg);
+}
+
+/*
+ * HALO = false: no neighbours at all (single-GPU fused SpMV + dot) -- the exchange code is compiled out.
+ */
+template <typename T, class Body, int MINB, bool DOT, bool HALO>
 __global__ void __launch_bounds__(128, MINB)
 spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, Acc2* __restrict__ ctaPartials)
 {
-	/* the counter is advanced by a later kernel in stream order (spgpuHaloSeqAdvance), never during this
-	 * one, so every CTA reads the same value whenever it is scheduled */
-	const unsigned seq = hx.seqPtr ? *reinterpret_cast<const volatile unsigned*>(hx.seqPtr) + 1u : hx.seq;
-	const unsigned par = seq & 1u;
-	unsigned long long* tr = hx.trace ? hx.trace + (size_t)(seq & (SPGPU_TRACE_SLOTS - 1)) * 8 : NULL;
-	if (blockIdx.x < (unsigned)hx.pushCtas) {
-		const bool toHi = (blockIdx.x & 1) != 0;
-		T* dst = toHi ? hx.dstHi[par] : hx.dstLo[par];
-		const T* src = toHi ? hx.srcHi : hx.srcLo;
-		if (tr && threadIdx.x == 0 && blockIdx.x == 0) {
-			for (int k = 2; k < 8; ++k)
-				tr[k] = 0ull;
-			tr[0] = global_timer_ns();
-		}
-		if (dst)
-			copy_bytes(dst, src, (size_t)hx.n * sizeof(T), blockIdx.x >> 1, (unsigned)hx.pushCtas >> 1);
-		__threadfence_system();
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			if (atomicAdd(hx.pushTicket, 1u) == (unsigned)hx.pushCtas - 1u) {
-				*hx.pushTicket = 0u;
-				__threadfence_system();
-				if (hx.peerReadyLo) st_release_sys(hx.peerReadyLo, seq);
-				if (hx.peerReadyHi) st_release_sys(hx.peerReadyHi, seq);
-				if (tr)
-					tr[1] = global_timer_ns();
-			}
-		}
-		return;
-	}
-	const unsigned b = blockIdx.x - hx.pushCtas;
 	const unsigned rows = (unsigned)body.rows();
-	const unsigned rowBlocks = (rows + 127u) >> 7;
-	const unsigned nLo = min(hx.headBlocks, rowBlocks);
-	const unsigned hiStart = max(min(hx.firstHiBlock, rowBlocks), nLo);
-	const unsigned nHi = rowBlocks - hiStart;
-	const unsigned interior = hiStart - nLo;
-	const unsigned filler = min(interior >> 2, hx.fillerBlocks);
-	const unsigned early = interior - filler;
-	unsigned rb;
-	if (b < early) rb = nLo + b;                                          /* most of the interior first   */
-	else if (b < early + nLo) rb = b - early;                             /* then the lower boundary      */
-	else if (b < early + nLo + nHi) rb = hiStart + (b - early - nLo);     /* the upper boundary           */
-	else rb = nLo + early + (b - early - nLo - nHi);                      /* the rest of the interior     */
-	const bool needLo = rb < hx.headBlocks && hx.myReadyLo != NULL;
-	const bool needHi = rb >= hx.firstHiBlock && hx.myReadyHi != NULL;
-	const unsigned myRow = rb * 128u + threadIdx.x;
+	unsigned rb = blockIdx.x;
 	T zval;
-	if (!needLo && !needHi) {
-		/* interior: no flags -- exactly the plain kernel */
+	if (HALO) {
+		/* the counter is advanced by a later kernel in stream order (spgpuHaloSeqAdvance), never during this
+		 * one, so every CTA reads the same value whenever it is scheduled */
+		const unsigned seq = hx.seqPtr ? *reinterpret_cast<const volatile unsigned*>(hx.seqPtr) + 1u : hx.seq;
+		const unsigned par = seq & 1u;
+		unsigned long long* tr = hx.trace ? hx.trace + (size_t)(seq & (SPGPU_TRACE_SLOTS - 1)) * 8 : NULL;
+		if (blockIdx.x < (unsigned)hx.pushCtas) {
+			const bool toHi = (blockIdx.x & 1) != 0;
+			T* dst = toHi ? hx.dstHi[par] : hx.dstLo[par];
+			const T* src = toHi ? hx.srcHi : hx.srcLo;
+			if (tr && threadIdx.x == 0 && blockIdx.x == 0) {
+				for (int k = 2; k < 8; ++k)
+					tr[k] = 0ull;
+				tr[0] = global_timer_ns();
+			}
+			if (dst)
+				copy_bytes(dst, src, (size_t)hx.n * sizeof(T), blockIdx.x >> 1, (unsigned)hx.pushCtas >> 1);
+			__threadfence_system();
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				if (atomicAdd(hx.pushTicket, 1u) == (unsigned)hx.pushCtas - 1u) {
+					*hx.pushTicket = 0u;
+					__threadfence_system();
+					if (hx.peerReadyLo) st_release_sys(hx.peerReadyLo, seq);
+					if (hx.peerReadyHi) st_release_sys(hx.peerReadyHi, seq);
+					if (tr)
+						tr[1] = global_timer_ns();
+				}
+			}
+			return;
+		}
+		const unsigned b = blockIdx.x - hx.pushCtas;
+		const unsigned rowBlocks = (rows + 127u) >> 7;
+		const unsigned nLo = min(hx.headBlocks, rowBlocks);
+		const unsigned hiStart = max(min(hx.firstHiBlock, rowBlocks), nLo);
+		const unsigned nHi = rowBlocks - hiStart;
+		const unsigned interior = hiStart - nLo;
+		const unsigned filler = min(interior >> 2, hx.fillerBlocks);
+		const unsigned early = interior - filler;
+		if (b < early) rb = nLo + b;                                          /* most of the interior first   */
+		else if (b < early + nLo) rb = b - early;                             /* then the lower boundary      */
+		else if (b < early + nLo + nHi) rb = hiStart + (b - early - nLo);     /* the upper boundary           */
+		else rb = nLo + early + (b - early - nLo - nHi);                      /* the rest of the interior     */
+		const bool needLo = rb < hx.headBlocks && hx.myReadyLo != NULL;
+		const bool needHi = rb >= hx.firstHiBlock && hx.myReadyHi != NULL;
+		if (needLo || needHi) {
+			if (threadIdx.x == 0) {
+				unsigned long long t0 = 0;
+				if (tr) {
+					t0 = global_timer_ns();
+					atomicCAS(tr + 6, 0ull, t0);
+				}
+				if (needLo) spin_until(hx.myReadyLo, seq, hx.spin);
+				if (tr) {
+					const unsigned long long t1 = global_timer_ns();
+					if (needLo && t1 - t0 > 2000ull) { atomicAdd(tr + 2, t1 - t0); atomicAdd(tr + 4, 1ull); }
+					t0 = t1;
+				}
+				if (needHi) spin_until(hx.myReadyHi, seq, hx.spin);
+				if (tr) {
+					const unsigned long long t1 = global_timer_ns();
+					if (needHi && t1 - t0 > 2000ull) { atomicAdd(tr + 3, t1 - t0); atomicAdd(tr + 5, 1ull); }
+				}
+			}
+			__syncthreads();
+			const XZones<T> xz = { body.x(), par ? hx.dLoOdd : 0ll, par ? hx.dHiOdd : 0ll, hx.n, hx.n + (int)rows };
+			zval = halo_boundary_rows<T, Body>(body, rb * 128u + (threadIdx.x & ~31u), xz);
+			if (tr && threadIdx.x == 0)
+				atomicMax(tr + 7, global_timer_ns());
+		} else {
+			/* interior: no flags -- exactly the plain kernel */
+			const XPlain<T> xg = { body.x() };
+			zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
+		}
+	} else {
 		const XPlain<T> xg = { body.x() };
 		zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
-	} else {
-		if (threadIdx.x == 0) {
-			unsigned long long t0 = 0;
-			if (tr) {
-				t0 = global_timer_ns();
-				atomicCAS(tr + 6, 0ull, t0);
-			}
-			if (needLo) spin_until(hx.myReadyLo, seq, hx.spin);
-			if (tr) {
-				const unsigned long long t1 = global_timer_ns();
-				if (needLo && t1 - t0 > 2000ull) { atomicAdd(tr + 2, t1 - t0); atomicAdd(tr + 4, 1ull); }
-				t0 = t1;
-			}
-			if (needHi) spin_until(hx.myReadyHi, seq, hx.spin);
-			if (tr) {
-				const unsigned long long t1 = global_timer_ns();
-				if (needHi && t1 - t0 > 2000ull) { atomicAdd(tr + 3, t1 - t0); atomicAdd(tr + 5, 1ull); }
-			}
-		}
-		__syncthreads();
-		const XZones<T> xg = { body.x(), par ? hx.dLoOdd : 0ll, par ? hx.dHiOdd : 0ll, hx.n, hx.n + (int)rows };
-		zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
-		if (tr && threadIdx.x == 0)
-			atomicMax(tr + 7, global_timer_ns());
 	}
 	if (DOT) {
+		const unsigned myRow = rb * 128u + threadIdx.x;
 		Acc2 c = { 0.0, 0.0 };
 		if (myRow < rows)
 			c = to_acc2<T>(Num<T>::mul(zval, __ldg(body.x() + xOffset + myRow)));
@@ -416,6 +433,21 @@ static HaloArgs<T> halo_args(spgpuHandle_t handle, T* xExt, int rows, int haloN,
 /* resident CTAs per SM the register allocator must leave room for (spmv_hell.cu: float 48 warps, double 40, complex 32) */
 template <typename T> struct HaloMinB { static constexpr int hell = Num<T>::is_complex ? 8 : (sizeof(T) == 4 ? 12 : 10); };
 
+#define SPGPU_DECL_PLAIN_SPMV(S, T, R)                                                                \
+	extern "C" void spgpu##S##hellspmv(spgpuHandle_t, T*, const T*, T, const T*, const int*, int, const int*, \
+		const int*, const int*, int, int, const T*, T, int);                                               \
+	extern "C" void spgpu##S##hdiaspmv(spgpuHandle_t, T*, const T*, T, const T*, const int*, int, const int*, \
+		int, int, const T*, T);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_PLAIN_SPMV)
+static inline void plain_hellspmv(spgpuHandle_t h, float* z, const float* y, float a, const float* cM, const int* rP, int hs, const int* ho, const int* rS, int avg, int rows, const float* x, float b, int base) { spgpuShellspmv(h, z, y, a, cM, rP, hs, ho, rS, NULL, avg, rows, x, b, base); }
+static inline void plain_hellspmv(spgpuHandle_t h, double* z, const double* y, double a, const double* cM, const int* rP, int hs, const int* ho, const int* rS, int avg, int rows, const double* x, double b, int base) { spgpuDhellspmv(h, z, y, a, cM, rP, hs, ho, rS, NULL, avg, rows, x, b, base); }
+static inline void plain_hellspmv(spgpuHandle_t h, cuFloatComplex* z, const cuFloatComplex* y, cuFloatComplex a, const cuFloatComplex* cM, const int* rP, int hs, const int* ho, const int* rS, int avg, int rows, const cuFloatComplex* x, cuFloatComplex b, int base) { spgpuChellspmv(h, z, y, a, cM, rP, hs, ho, rS, NULL, avg, rows, x, b, base); }
+static inline void plain_hellspmv(spgpuHandle_t h, cuDoubleComplex* z, const cuDoubleComplex* y, cuDoubleComplex a, const cuDoubleComplex* cM, const int* rP, int hs, const int* ho, const int* rS, int avg, int rows, const cuDoubleComplex* x, cuDoubleComplex b, int base) { spgpuZhellspmv(h, z, y, a, cM, rP, hs, ho, rS, NULL, avg, rows, x, b, base); }
+static inline void plain_hdiaspmv(spgpuHandle_t h, float* z, const float* y, float a, const float* dM, const int* off, int hs, const int* ho, int rows, int cols, const float* x, float b) { spgpuShdiaspmv(h, z, y, a, dM, off, hs, ho, rows, cols, x, b); }
+static inline void plain_hdiaspmv(spgpuHandle_t h, double* z, const double* y, double a, const double* dM, const int* off, int hs, const int* ho, int rows, int cols, const double* x, double b) { spgpuDhdiaspmv(h, z, y, a, dM, off, hs, ho, rows, cols, x, b); }
+static inline void plain_hdiaspmv(spgpuHandle_t h, cuFloatComplex* z, const cuFloatComplex* y, cuFloatComplex a, const cuFloatComplex* dM, const int* off, int hs, const int* ho, int rows, int cols, const cuFloatComplex* x, cuFloatComplex b) { spgpuChdiaspmv(h, z, y, a, dM, off, hs, ho, rows, cols, x, b); }
+static inline void plain_hdiaspmv(spgpuHandle_t h, cuDoubleComplex* z, const cuDoubleComplex* y, cuDoubleComplex a, const cuDoubleComplex* dM, const int* off, int hs, const int* ho, int rows, int cols, const cuDoubleComplex* x, cuDoubleComplex b) { spgpuZhdiaspmv(h, z, y, a, dM, off, hs, ho, rows, cols, x, b); }
+
 template <typename T, int UNROLL>
 static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const T* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
@@ -426,21 +458,29 @@ static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 	const HellArgs<T> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
 		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1, 0, NULL, NULL, 0, NULL, NULL };
 	const HaloArgs<T> hx = halo_args<T>(handle, xExt, rows, haloN, links, seq);
+	const bool halo = hx.pushCtas > 0;
+	if (!halo && !ctaPartials) {                 /* no neighbours, no dot: the plain entry point */
+		plain_hellspmv(handle, z, y, alpha, cM, rP, hackSize, hackOffsets, rS, avgNnzPerRow, rows, xExt, beta, baseIndex);
+		return;
+	}
 	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
 	constexpr int MB = HaloMinB<T>::hell;
 	const HellRowBody<T, UNROLL, 32> b32 = { a };
 	const HellRowBody<T, UNROLL, 0> b0 = { a };
 	if (ctaPartials) {
-		if (hackSize == 32)
-			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-		else
-			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+		if (hackSize == 32) {
+			if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		} else {
+			if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+		}
 	} else {
 		if (hackSize == 32)
-			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, false, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
 		else
-			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, false, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
 	}
 	spgpu_count_launch(handle);
 }
@@ -452,20 +492,28 @@ static void hdia_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 {
 	const HdiaArgs<T> a = { z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta };
 	const HaloArgs<T> hx = halo_args<T>(handle, xExt, rows, haloN, links, seq);
+	const bool halo = hx.pushCtas > 0;
+	if (!halo && !ctaPartials) {
+		plain_hdiaspmv(handle, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta);
+		return;
+	}
 	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
 	cudaStream_t s = handle->currentStream;
 	const HdiaRowBody<T, UNROLL, 32> b32 = { a };
 	const HdiaRowBody<T, UNROLL, 0> b0 = { a };
 	if (ctaPartials) {
-		if (hackSize == 32)
-			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-		else
-			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+		if (hackSize == 32) {
+			if (halo) spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			else      spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+		} else {
+			if (halo) spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			else      spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+		}
 	} else {
 		if (hackSize == 32)
-			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, false, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
 		else
-			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, false, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
 	}
 	spgpu_count_launch(handle);
 }

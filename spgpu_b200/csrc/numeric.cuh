@@ -92,6 +92,45 @@ template <> struct Num<int> {
 
 /* read-once stream: evict-first */
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+/*
+ * Read-once stream whose 128-byte lines may be only PARTLY used (rows of unequal length: lanes past their row's
+ * end are switched off): evict-first AND an L2 fetch granularity of 64 bytes (SASS LDG.E.EF.LTC64B).  Measured on
+ * B200 (bench/probes/sector_probe.cu, profiles/r2_sector_probe.md): whatever the load flavour, an L2 miss on one
+ * 32-byte sector fetches the WHOLE 128-byte line from DRAM -- cudaLimitMaxL2FetchGranularity is ignored -- except
+ * with the .L2::64B qualifier, which halves it; there is no 32-byte option.  Full lines cost the same either way.
+ */
+template <typename T> __device__ __forceinline__ T ld_stream64(const T* p);
+template <> __device__ __forceinline__ int ld_stream64<int>(const int* p)
+{
+	int v;
+	asm("ld.global.cs.L2::64B.s32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+template <> __device__ __forceinline__ float ld_stream64<float>(const float* p)
+{
+	float v;
+	asm("ld.global.cs.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+	return v;
+}
+template <> __device__ __forceinline__ double ld_stream64<double>(const double* p)
+{
+	double v;
+	asm("ld.global.cs.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+	return v;
+}
+template <> __device__ __forceinline__ cuFloatComplex ld_stream64<cuFloatComplex>(const cuFloatComplex* p)
+{
+	cuFloatComplex v;
+	asm("ld.global.cs.L2::64B.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+	return v;
+}
+template <> __device__ __forceinline__ cuDoubleComplex ld_stream64<cuDoubleComplex>(const cuDoubleComplex* p)
+{
+	cuDoubleComplex v;
+	asm("ld.global.cs.L2::64B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+	return v;
+}
+
 /* read-only, cache normally (x gathers) */
 template <typename T> __device__ __forceinline__ T ld_keep(const T* p) { return __ldg(p); }
 

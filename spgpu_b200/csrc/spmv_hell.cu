@@ -79,8 +79,8 @@ hell_tail_kernel(const HellArgs<T> a)
 				col[u] = a.baseIndex;
 				v[u] = Num<T>::zero();
 				if (on) {
-					col[u] = ld_stream(ip + (long long)(k0 + u) * hackSize);
-					v[u] = ld_stream(vp + (long long)(k0 + u) * hackSize);
+					col[u] = ld_stream64(ip + (long long)(k0 + u) * hackSize);
+					v[u] = ld_stream64(vp + (long long)(k0 + u) * hackSize);
 				}
 			}
 #pragma unroll

@@ -112,9 +112,9 @@ __device__ __forceinline__ T warp_rows_dot_x(
 				const bool on = (k0 + u) < mine;
 				col[u] = baseIndex;
 				a[u] = Num<T>::zero();
-				if (on) {
-					col[u] = ld_stream(ip + u * idxStride);
-					a[u] = ld_stream(vp + u * valStride);
+				if (on) {                              /* partly used lines: 64-byte L2 fetch granularity */
+					col[u] = ld_stream64(ip + u * idxStride);
+					a[u] = ld_stream64(vp + u * valStride);
 				}
 			}
 #pragma unroll
@@ -151,9 +151,9 @@ __device__ __forceinline__ T warp_rows_dot_x(
 				const bool on = k < len;
 				col[u] = baseIndex;
 				a[u] = Num<T>::zero();
-				if (on) {
-					col[u] = ld_stream(ri + k * idxStride);
-					a[u] = ld_stream(rv + k * valStride);
+				if (on) {                              /* one row's slots are a whole stride apart: one element per line */
+					col[u] = ld_stream64(ri + k * idxStride);
+					a[u] = ld_stream64(rv + k * valStride);
 				}
 			}
 #pragma unroll

@@ -23,7 +23,8 @@ def declared_symbols(header):
 
 
 def test_library_exports_every_declared_symbol(ours):
-    for header, listed in (("spgpu.h", capi.abi_symbols()), ("spgpu_ext.h", capi.abi_symbols() + capi.ext_symbols())):
+    for header, listed in (("spgpu.h", capi.abi_symbols()), ("spgpu_ext.h", capi.abi_symbols() + capi.ext_symbols()),
+                           ("spgpu_mg.h", capi.abi_symbols() + capi.ext_symbols() + capi.mg_symbols())):
         declared = declared_symbols(header)
         assert len(declared) > 100
         missing = sorted(n for n in declared if not ours.has(n))

@@ -1,0 +1,287 @@
+"""The C-level multi-GPU API (include/spgpu_mg.h, csrc/mg.c): ONE process drives N ranks.
+
+On a one-GPU box the ranks are the SAME device listed several times: the partition, the column remap, the
+vectors with their halo zones and the EVENTS exchange (push kernels + CUDA events between the ranks' streams)
+all run for real, only the transport is local.  With two or more GPUs the same tests also run with distinct
+devices, i.e. the FUSED exchange (NVLink peer stores inside the SpMV kernel) -- tests/test_mg_multi_gpu.py.
+Reference: the single-GPU product of the same library (spgpu?hellspmv on the whole matrix) and the CPU oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from spgpu_b200 import capi, formats as F, generators as G
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DTYPES = [np.float32, np.float64, np.complex64, np.complex128]
+
+
+def scalars(dtype):
+    if np.dtype(dtype).kind == "c":
+        return (0.7 - 0.3j), (-0.5 + 0.25j)
+    return 2.0, -3.0
+
+
+class Mg:
+    """thin ctypes convenience over the C API"""
+
+    def __init__(self, L, devices, exchange=capi.MG_AUTO):
+        self.L = L
+        self.h = ctypes.c_void_p()
+        devs = (ctypes.c_int * len(devices))(*devices)
+        st = L.spgpuMgCreate(ctypes.byref(self.h), devs, len(devices))
+        assert st == 0, f"spgpuMgCreate -> {st}"
+        assert L.spgpuMgSetExchange(self.h, exchange) == 0
+        self.world = L.spgpuMgWorld(self.h)
+
+    def matrix(self, hell):
+        s = util.sym_of(hell.values.dtype)
+        A = ctypes.c_void_p()
+        avg = max(1, int(round(hell.rs.mean()))) if hell.nrows else 1
+        st = getattr(self.L, f"spgpuMg{s}hellCreate")(self.h, ctypes.byref(A), util.ptr(hell.values), util.ptr(hell.indices),
+                                                      hell.hack_size, util.ptr(hell.hack_offsets), util.ptr(hell.rs), avg,
+                                                      hell.nrows, hell.ncols, hell.base)
+        assert st == 0, f"spgpuMg{s}hellCreate -> {st}"
+        return A
+
+    def vector(self, A, values=None):
+        v = ctypes.c_void_p()
+        assert self.L.spgpuMgVectorCreate(A, ctypes.byref(v)) == 0
+        if values is not None:
+            assert self.L.spgpuMgVectorSet(v, util.ptr(np.ascontiguousarray(values))) == 0
+        return v
+
+    def get(self, v, n, dtype):
+        out = np.zeros(n, dtype=dtype)
+        assert self.L.spgpuMgVectorGet(v, util.ptr(out)) == 0
+        return out
+
+    def close(self):
+        self.L.spgpuMgDestroy(self.h)
+
+
+def _device_lists():
+    import torch
+    lists = [([0], "1 rank"), ([0, 0], "2 ranks on one device (events)"), ([0, 0, 0], "3 ranks on one device (events)")]
+    if torch.cuda.device_count() >= 2:
+        lists.append(([0, 1], "2 devices (fused)"))
+    return lists
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_partitioned_spmv_equals_the_single_gpu_product(ours, gpu_handle, dtype):
+    """z = alpha A x + beta y through spgpuMg?hellspmv on 1 / 2 / 3 ranks == spgpu?hellspmv on the whole matrix
+    (bit for bit: the same kernels multiply the same rows in the same order) == the CPU oracle within tolerance"""
+    s = util.sym_of(dtype)
+    t = util.TYPES[s]
+    n = 20
+    coo = G.laplace3d_7pt(n)
+    vals = coo.vals.astype(dtype)
+    if t.is_complex:
+        vals = (vals + 0.25j * np.random.default_rng(1).standard_normal(vals.shape[0])).astype(dtype)
+    coo = F.Coo(coo.rows, coo.cols, vals, coo.nrows, coo.ncols, coo.base)
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    x = G.random_vector(coo.nrows, dtype, 1, -1, 1)
+    y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
+    alpha, beta = scalars(dtype)
+    single = util.dev_spmv(ours, gpu_handle, "hell", hell, util.upload(hell), x, y, alpha, beta, avg=7)
+    want = util.oracle_spmv("hell", hell, x, y, alpha, beta)
+    util.assert_rows_close(single, want, util.row_scale(coo, x, y, alpha, beta), s, "single-GPU product")
+    for devices, what in _device_lists():
+        mg = Mg(ours, devices)
+        try:
+            A = mg.matrix(hell)
+            halo = ours.spgpuMgMatrixHalo(A)
+            assert halo == (0 if len(devices) == 1 else -(-(n * n) // 32) * 32), (what, halo)
+            vx, vy, vz = mg.vector(A, x), mg.vector(A, y), mg.vector(A)
+            for _ in range(3):                               # three exchanges: both zone pairs of the fused protocol
+                st = getattr(ours, f"spgpuMg{s}hellspmv")(mg.h, vz, vy, t.scalar(alpha), A, vx, t.scalar(beta))
+                assert st == 0
+            assert ours.spgpuMgSynchronize(mg.h) == 0
+            got = mg.get(vz, coo.nrows, dtype)
+            assert np.array_equal(got.view(np.uint8), single.view(np.uint8)), what
+            # in place on y, beta != 0
+            st = getattr(ours, f"spgpuMg{s}hellspmv")(mg.h, vy, vy, t.scalar(alpha), A, vx, t.scalar(beta))
+            assert st == 0 and ours.spgpuMgSynchronize(mg.h) == 0
+            assert np.array_equal(mg.get(vy, coo.nrows, dtype).view(np.uint8), single.view(np.uint8)), what
+            for v in (vx, vy, vz):
+                ours.spgpuMgVectorDestroy(v)
+            ours.spgpuMgMatrixDestroy(A)
+        finally:
+            mg.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex64])
+def test_unstructured_matrix_goes_through_the_all_gather_mode(ours, gpu_handle, dtype):
+    """random columns reach anywhere: the matrix is kept with global columns and every rank gathers the whole x"""
+    s = util.sym_of(dtype)
+    t = util.TYPES[s]
+    nrows = 1000
+    coo = G.random_coo(nrows, nrows, (0, 12), 3, dtype, 1)             # base 1, some empty rows
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    x = G.random_vector(nrows, dtype, 1, -1, 1)
+    single = util.dev_spmv(ours, gpu_handle, "hell", hell, util.upload(hell), x, None, 1.0, 0.0)
+    for devices, what in _device_lists()[1:]:
+        mg = Mg(ours, devices)
+        try:
+            A = mg.matrix(hell)
+            assert ours.spgpuMgMatrixHalo(A) == -1
+            vx, vz = mg.vector(A, x), mg.vector(A)
+            for _ in range(2):
+                assert getattr(ours, f"spgpuMg{s}hellspmv")(mg.h, vz, None, t.scalar(1.0), A, vx, t.scalar(0.0)) == 0
+            assert ours.spgpuMgSynchronize(mg.h) == 0
+            assert np.array_equal(mg.get(vz, nrows, dtype).view(np.uint8), single.view(np.uint8)), what
+            ours.spgpuMgVectorDestroy(vx); ours.spgpuMgVectorDestroy(vz)
+            ours.spgpuMgMatrixDestroy(A)
+        finally:
+            mg.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_partitioned_blas1(ours, dtype):
+    """spgpuMg?dot (unconjugated, like spgpu?dot), nrm2, axpby over a 3-rank partition"""
+    s = util.sym_of(dtype)
+    t = util.TYPES[s]
+    coo = G.laplace3d_7pt(12)
+    hell = F.ell_to_hell(F.coo_to_ell(F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base)), 32)
+    n = coo.nrows
+    a = G.random_vector(n, dtype, 5, -1, 1)
+    b = G.random_vector(n, dtype, 6, -1, 1)
+    alpha, beta = scalars(dtype)
+    tol = util.TOL[s] * 8
+    mg = Mg(ours, [0, 0, 0])
+    try:
+        A = mg.matrix(hell)
+        va, vb, vz = mg.vector(A, a), mg.vector(A, b), mg.vector(A)
+        res = t.ctype()
+        assert getattr(ours, f"spgpuMg{s}dot")(mg.h, ctypes.byref(res), va, vb) == 0
+        ref = np.sum(a.astype(np.complex128) * b.astype(np.complex128))
+        got = complex(res.x, res.y) if t.is_complex else complex(res.value)
+        assert abs(got - ref) <= tol * float(np.sum(np.abs(a) * np.abs(b)))
+        nr = t.rtype()
+        assert getattr(ours, f"spgpuMg{s}nrm2")(mg.h, ctypes.byref(nr), va) == 0
+        assert abs(nr.value - np.linalg.norm(a.astype(np.complex128))) <= tol * np.linalg.norm(a.astype(np.complex128))
+        assert getattr(ours, f"spgpuMg{s}axpby")(mg.h, vz, t.scalar(beta), vb, t.scalar(alpha), va) == 0
+        assert ours.spgpuMgSynchronize(mg.h) == 0
+        np.testing.assert_allclose(mg.get(vz, n, dtype), beta * b + alpha * a, atol=tol * 4, rtol=0)
+        for v in (va, vb, vz):
+            ours.spgpuMgVectorDestroy(v)
+        ours.spgpuMgMatrixDestroy(A)
+    finally:
+        mg.close()
+
+
+def test_partitioned_cg(ours, oracle):
+    """spgpuMgDcgStart / spgpuMgDcgStep on 1 rank (device flavour: fused SpMV + dot, device scalars) and on 3 ranks
+    of one device (the blocking recurrence of the EVENTS mode): same residual history as the CPU recurrence"""
+    coo = G.laplace3d_7pt(14)
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    n = coo.nrows
+    b = G.random_vector(n, np.float64, 9)
+    x = np.zeros(n); r = b.copy(); p = b.copy(); rr = float(r @ r)
+    ref = []
+    for _ in range(30):
+        ap = util.oracle_spmv("hell", hell, p, None, 1.0, 0.0)
+        a = rr / float(p @ ap)
+        x += a * p; r -= a * ap
+        rrn = float(r @ r)
+        p = r + (rrn / rr) * p
+        rr = rrn
+        ref.append(rr)
+    for devices, what in _device_lists():
+        mg = Mg(ours, devices)
+        try:
+            A = mg.matrix(hell)
+            vb = mg.vector(A, b)
+            cg = ctypes.c_void_p()
+            assert ours.spgpuMgDcgCreate(A, ctypes.byref(cg)) == 0
+            rr0 = ctypes.c_double()
+            assert ours.spgpuMgDcgStart(cg, vb, ctypes.byref(rr0)) == 0
+            assert abs(rr0.value - float(b @ b)) <= 1e-12 * float(b @ b)
+            hist = []
+            for _ in range(15):                                # one iteration per call, residual read back
+                out = ctypes.c_double()
+                assert ours.spgpuMgDcgStep(cg, 1, ctypes.byref(out)) == 0
+                hist.append(out.value)
+            assert ours.spgpuMgDcgStep(cg, 14, None) == 0      # 14 iterations without touching the host
+            out = ctypes.c_double()
+            assert ours.spgpuMgDcgStep(cg, 1, ctypes.byref(out)) == 0
+            np.testing.assert_allclose(hist, ref[:15], rtol=1e-8, err_msg=what)
+            assert abs(out.value - ref[29]) <= 1e-7 * ref[29], what
+            sol = mg.get(ours.spgpuMgDcgSolution(cg), n, np.float64)
+            np.testing.assert_allclose(sol, x, rtol=1e-8, atol=1e-11, err_msg=what)
+            ours.spgpuMgDcgDestroy(cg)
+            ours.spgpuMgVectorDestroy(vb)
+            ours.spgpuMgMatrixDestroy(A)
+        finally:
+            mg.close()
+
+
+def test_blocks_handed_over_pre_partitioned(ours, gpu_handle):
+    """spgpuMgHellCreateFromBlocks: per-rank blocks with LOCAL columns (what a caller that assembles its own slab
+    hands over; BASELINE configs[4] is built this way), host arrays and device arrays"""
+    import torch
+    from spgpu_b200 import mg as pymg
+    n, world = 16, 2
+    coo = G.laplace3d_7pt(n)
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    halo = n * n
+    x = G.random_vector(coo.nrows, np.float64, 4, -1, 1)
+    single = util.dev_spmv(ours, gpu_handle, "hell", hell, util.upload(hell), x, None, 1.0, 0.0, avg=7)
+    blocks = [pymg.split_hell(hell, world, r, halo) for r in range(world)]
+    T = util.TYPES["D"]
+    for on_device in (0, 1):
+        mg = Mg(ours, [0] * world)
+        try:
+            keep = []
+            def arr(a):
+                if not on_device:
+                    return util.ptr(a)
+                t = util.to_dev(a); keep.append(t)
+                return t.data_ptr()
+            PP = ctypes.c_void_p * world
+            rows = (ctypes.c_int * world)(*[b.nrows for b in blocks])
+            elements = (ctypes.c_longlong * world)(*[b.values.shape[0] for b in blocks])
+            A = ctypes.c_void_p()
+            st = ours.spgpuMgHellCreateFromBlocks(mg.h, ctypes.byref(A), capi.SPGPU_TYPE_DOUBLE, 32, halo, 0, 7, rows,
+                                                  PP(*[arr(b.values) for b in blocks]), PP(*[arr(b.indices) for b in blocks]),
+                                                  PP(*[arr(b.hack_offsets) for b in blocks]), PP(*[arr(b.rs) for b in blocks]),
+                                                  elements, on_device)
+            assert st == 0
+            lo, hi = ctypes.c_int(), ctypes.c_int()
+            ours.spgpuMgMatrixRowBlock(A, 1, ctypes.byref(lo), ctypes.byref(hi))
+            assert (lo.value, hi.value) == (blocks[1].lo, blocks[1].hi) and ours.spgpuMgMatrixRows(A) == coo.nrows
+            vx, vz = mg.vector(A, x), mg.vector(A)
+            assert ours.spgpuMgDhellspmv(mg.h, vz, None, T.scalar(1.0), A, vx, T.scalar(0.0)) == 0
+            assert ours.spgpuMgSynchronize(mg.h) == 0
+            assert np.array_equal(mg.get(vz, coo.nrows, np.float64), single)
+            ours.spgpuMgVectorDestroy(vx); ours.spgpuMgVectorDestroy(vz)
+            ours.spgpuMgMatrixDestroy(A)
+            torch.cuda.synchronize()
+        finally:
+            mg.close()
+
+
+def test_argument_checks(ours):
+    mg = Mg(ours, [0, 0])
+    try:
+        coo = G.laplace3d_7pt(8)
+        hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+        A = mg.matrix(hell)
+        vx = mg.vector(A)
+        T = util.TYPES["D"]
+        assert ours.spgpuMgDhellspmv(mg.h, vx, None, T.scalar(1.0), A, vx, T.scalar(0.0)) == capi.SPGPU_UNSUPPORTED   # z == x
+        assert ours.spgpuMgShellspmv(mg.h, vx, None, 1.0, A, vx, 0.0) == capi.SPGPU_UNSUPPORTED                       # wrong type
+        assert ours.spgpuMgSetExchange(mg.h, capi.MG_FUSED) == capi.SPGPU_UNSUPPORTED      # the same device twice cannot spin on itself
+        assert ours.spgpuMgExchange(mg.h) == capi.MG_EVENTS
+        bad = ctypes.c_void_p()
+        assert ours.spgpuMgDhellCreate(mg.h, ctypes.byref(bad), util.ptr(hell.values), util.ptr(hell.indices), 32,
+                                       util.ptr(hell.hack_offsets), util.ptr(hell.rs), 7, hell.nrows, hell.nrows + 1, 0) \\
+            == capi.SPGPU_UNSUPPORTED                                                      # not square
+        ours.spgpuMgVectorDestroy(vx)
+        ours.spgpuMgMatrixDestroy(A)
+    finally:
+        mg.close()
+    h = ctypes.c_void_p()
+    assert ours.spgpuMgCreate(ctypes.byref(h), (ctypes.c_int * 1)(0), 0) == capi.SPGPU_UNSUPPORTED
