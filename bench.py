@@ -1215,6 +1215,39 @@ def main():
                                "frac_of_peak": (bytes_total + vec_bytes) / (ms_it * 1e-3) / 1e9 / (peak * world),
                                "kernels_per_iteration": (L.spgpuGetLaunchCount(h) - l0) / iters,
                                "residual_norm2_after": cg.residual_norm2() if flavour == "device" else st.rr_host}
+        if os.environ.get("SPGPU_BENCH_TRACE"):
+            # per-phase device time of the device flavour on this rank (events between the phases; a phase that
+            # waits for a peer -- halo, all-reduce -- shows the wait)
+            phases = {}
+            for _ in range(6):
+                evs = [("start", torch.cuda.Event(enable_timing=True))]
+                evs[0][1].record(stream)
+
+                def mark(label):
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(stream)
+                    evs.append((label, e))
+                cg.step_device(mark)
+                torch.cuda.synchronize()
+                for (_, a_), (lab, b_) in zip(evs[:-1], evs[1:]):
+                    phases.setdefault(lab, []).append(a_.elapsed_time(b_))
+            print(f"rank {rank} CG phases (ms, median of 6): " +
+                  "; ".join(f"{k}: {float(np.median(v)):.4f}" for k, v in phases.items()), file=sys.stderr, flush=True)
+            if peer is not None and args.halo == "fused":
+                # the fused kernel's own record of its last 4 exchanges inside the iteration
+                L.spgpuSetTuning(h, b"haloTrace", 1)
+                for _ in range(4):
+                    cg.step_device()
+                buf = (ctypes.c_ulonglong * (8 * 4))()
+                if L.spgpuHaloTraceRead(h, buf, peer.fseq - 3, 4) == 0:
+                    tr = np.frombuffer(buf, dtype=np.uint64).reshape(4, 8).astype(np.int64)
+                    for k in range(4):
+                        r_ = tr[k]
+                        print(f"rank {rank} CG exchange {peer.fseq - 3 + k}: start {(r_[0] - tr[0, 0]) / 1e3:9.1f} us  push {(r_[1] - r_[0]) / 1e3:6.1f} us  "
+                              f"boundary first..last {(r_[6] - r_[0]) / 1e3:7.1f}..{(r_[7] - r_[0]) / 1e3:7.1f} us  "
+                              f"waited lo {r_[2] / 1e3:7.1f} us in {r_[4]} blocks, hi {r_[3] / 1e3:7.1f} us in {r_[5]} blocks",
+                              file=sys.stderr, flush=True)
+                L.spgpuSetTuning(h, b"haloTrace", 0)
         # ---- the device-scalar iteration captured ONCE in a CUDA graph and replayed ---------------
         # (at N > 1 the halo / all-reduce sequence numbers then have to live in device memory:
         #  spgpuSetSeqCounters, include/spgpu_ext.h)

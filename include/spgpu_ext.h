@@ -50,8 +50,8 @@ int spgpuGetTuning(spgpuHandle_t handle, const char* key);
 int spgpuGetDeviceStatus(spgpuHandle_t handle, int clear);
 
 /*
- * Sizes the handle's grow-only device scratch (per-row-block partials of the fused SpMV + dot
- * kernels: 16 bytes per 128 rows; the split-mode queue of sorted HELL matrices; multi-vector
+ * Sizes the handle's grow-only device scratch (per-warp partials of the fused SpMV + dot
+ * kernels: 8 or 16 bytes per 32 rows; the split-mode queue of sorted HELL matrices; multi-vector
  * reduction results).  Growing synchronises the stream and allocates, which a CUDA-graph capture
  * does not allow -- reserve before capturing (or run the same call once eagerly).  0, or -1.
  */
@@ -287,7 +287,7 @@ typedef struct spgpuHaloLinks {
  * consecutive fused calls of a rank are ordered on one stream.
  *
  * ...HaloDot: alpha = 1, beta = 0, plus dRes[0] = sum_i xExt[haloN+i]*z[i] (this rank's share of p.Ap,
- * summed over all ranks when `ar` is given): per-row-block partials in handle scratch + one fold kernel
+ * summed over all ranks when `ar` is given): per-warp partials in handle scratch + one fold kernel
  * whose last CTA runs the all-reduce.  links == NULL: the single-GPU fused SpMV + dot.
  */
 #define SPGPU_DECL_SPMV_HALO(S, T, R)                                                                  \
@@ -321,6 +321,16 @@ SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_SPMV_HALO)
  */
 int spgpuSetSeqCounters(spgpuHandle_t handle, __device unsigned* dHaloSeq, __device unsigned* dAllreduceSeq);
 void spgpuHaloSeqAdvance(spgpuHandle_t handle);
+
+/*
+ * Loads every kernel that can wait for a peer GPU (the fused SpMV + halo kernels, the exchange kernels, the Krylov
+ * kernels whose last CTA all-reduces) into the CURRENT device now.  CUDA otherwise loads a kernel at its first launch,
+ * and that load waits for the kernels already running on the device -- a process that drives several ranks from one
+ * thread would deadlock if the first launch of one rank's kernel met another rank's kernel spinning on it.
+ * spgpuMgCreate does this for its devices; one-process-per-GPU callers do not need it.  0, or -1.
+ */
+int spgpuPreloadHaloKernels(void);
+int spgpuPreloadKrylovKernels(void);
 
 /*
  * Per-exchange trace of the fused kernels (tuning key haloTrace = 1): 8 words for each of `count`

@@ -138,7 +138,7 @@ def ext_symbols():
     names += ["spgpuIpcGetHandle", "spgpuIpcOpenHandle", "spgpuIpcCloseHandle",
               "spgpuDeviceAlloc", "spgpuDeviceFree", "spgpuHaloPush", "spgpuDhaloPush", "spgpuWaitFlag",
               "spgpuHaloExchange", "spgpuDhaloExchange", "spgpuHaloAck", "spgpuSetSeqCounters", "spgpuHaloSeqAdvance",
-              "spgpuHaloTraceRead"]
+              "spgpuHaloTraceRead", "spgpuPreloadHaloKernels", "spgpuPreloadKrylovKernels"]
     return names
 
 

@@ -31,6 +31,7 @@ static void default_tuning(SpgpuTuning* t)
 	t->l2Fetch = 0;
 	t->redInflight = 0;
 	t->ellShortMinB = 0;
+	t->hellPrefetch = 0;
 }
 
 spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
@@ -281,7 +282,8 @@ int spgpuGetDeviceStatus(spgpuHandle_t handle, int clear)
 	X(haloTrace)              \
 	X(l2Fetch)                \
 	X(redInflight)            \
-	X(ellShortMinB)
+	X(ellShortMinB)           \
+	X(hellPrefetch)
 
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value)
 {

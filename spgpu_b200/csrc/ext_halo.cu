@@ -224,27 +224,35 @@ struct HaloArgs {
 	int pushCtas;
 	unsigned headBlocks;                    /* 128-row blocks [0, headBlocks) hold a row that reads the lower zone */
 	unsigned firstHiBlock;                  /* 128-row blocks [firstHiBlock, ..) hold a row that reads the upper zone */
-	unsigned fillerBlocks;                  /* interior blocks scheduled behind the boundary blocks */
+	/* the block order, worked out on the host (every instruction in front of a warp's first load adds to its
+	 * lifetime, and this kernel lives on the edge of being latency-bound): CTAs [0, early) multiply interior
+	 * blocks nLo.., then come the nLo lower-boundary blocks, the nHi upper-boundary blocks (from hiStart), and a
+	 * few waves of interior blocks behind them */
+	unsigned early, nLo, nHi, hiStart;
 	SpinCtl spin;
 	unsigned long long* trace;              /* NULL, or 8 words per exchange (haloTrace tuning key) */
 };
 
 #define SPGPU_TRACE_SLOTS 1024
 
-/* z_i * x[xOffset+i] summed over the CTA, one partial per ROW BLOCK (fixed order) */
-__device__ __forceinline__ void cta_dot_partial(Acc2 contrib, Acc2* ctaPartials, unsigned slot)
+/*
+ * z_i * x[xOffset+i] summed over the WARP, one partial per 32 rows (fixed order).  Per warp, not per CTA: this
+ * kernel sits on the edge of being latency-bound (40 resident warps just cover the HBM latency), so whatever a warp
+ * does besides its loads shows up in the run time.  Measured on the 512^3 slab of one of two ranks (plain kernel
+ * 1.094 ms, fused halo 1.083 ms): CTA-wide sum behind a barrier 1.276 ms; the block's last warp to arrive adds the
+ * products the others left in shared memory (needs an opening barrier) 1.276 ms; a butterfly in every warp 1.233 ms.
+ */
+template <typename T>
+__device__ __forceinline__ void warp_dot_partial(Acc2 contrib, typename DotPartial<T>::type* partials, unsigned slot)
 {
-	__shared__ Acc2 ws[4];
 #pragma unroll
 	for (int m = 16; m > 0; m >>= 1) {
 		contrib.a += __shfl_xor_sync(SPGPU_FULL_MASK, contrib.a, m);
-		contrib.b += __shfl_xor_sync(SPGPU_FULL_MASK, contrib.b, m);
+		if (Num<T>::is_complex)
+			contrib.b += __shfl_xor_sync(SPGPU_FULL_MASK, contrib.b, m);
 	}
 	if ((threadIdx.x & 31) == 0)
-		ws[threadIdx.x >> 5] = contrib;
-	__syncthreads();
-	if (threadIdx.x == 0)
-		ctaPartials[slot] = Acc2{ (ws[0].a + ws[1].a) + (ws[2].a + ws[3].a), (ws[0].b + ws[1].b) + (ws[2].b + ws[3].b) };
+		acc2_to_partial(contrib, partials[slot]);
 }
 
 /* what a row block of the fused kernel multiplies: the HELL or the HDIA warp body */
@@ -299,7 +307,7 @@ __device__ __noinline__ T halo_boundary_rows(const Body body, unsigned warpRow, 
  */
 template <typename T, class Body, int MINB, bool DOT, bool HALO>
 __global__ void __launch_bounds__(128, MINB)
-spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, Acc2* __restrict__ ctaPartials)
+spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, typename DotPartial<T>::type* __restrict__ warpPartials /* one per 32 rows */)
 {
 	const unsigned rows = (unsigned)body.rows();
 	unsigned rb = blockIdx.x;
@@ -336,17 +344,10 @@ spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, Acc2* __res
 			return;
 		}
 		const unsigned b = blockIdx.x - hx.pushCtas;
-		const unsigned rowBlocks = (rows + 127u) >> 7;
-		const unsigned nLo = min(hx.headBlocks, rowBlocks);
-		const unsigned hiStart = max(min(hx.firstHiBlock, rowBlocks), nLo);
-		const unsigned nHi = rowBlocks - hiStart;
-		const unsigned interior = hiStart - nLo;
-		const unsigned filler = min(interior >> 2, hx.fillerBlocks);
-		const unsigned early = interior - filler;
-		if (b < early) rb = nLo + b;                                          /* most of the interior first   */
-		else if (b < early + nLo) rb = b - early;                             /* then the lower boundary      */
-		else if (b < early + nLo + nHi) rb = hiStart + (b - early - nLo);     /* the upper boundary           */
-		else rb = nLo + early + (b - early - nLo - nHi);                      /* the rest of the interior     */
+		if (b < hx.early) rb = hx.nLo + b;                                            /* most of the interior first */
+		else if (b < hx.early + hx.nLo) rb = b - hx.early;                            /* then the lower boundary    */
+		else if (b < hx.early + hx.nLo + hx.nHi) rb = hx.hiStart + (b - hx.early - hx.nLo);   /* the upper boundary */
+		else rb = b - hx.nHi;                                                         /* the rest of the interior   */
 		const bool needLo = rb < hx.headBlocks && hx.myReadyLo != NULL;
 		const bool needHi = rb >= hx.firstHiBlock && hx.myReadyHi != NULL;
 		if (needLo || needHi) {
@@ -387,7 +388,7 @@ spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, Acc2* __res
 		Acc2 c = { 0.0, 0.0 };
 		if (myRow < rows)
 			c = to_acc2<T>(Num<T>::mul(zval, __ldg(body.x() + xOffset + myRow)));
-		cta_dot_partial(c, ctaPartials, rb);
+		warp_dot_partial<T>(c, warpPartials, rb * 4u + (threadIdx.x >> 5));
 	}
 }
 
@@ -424,7 +425,19 @@ static HaloArgs<T> halo_args(spgpuHandle_t handle, T* xExt, int rows, int haloN,
 	/* rows [0, haloN) may read the lower zone, rows [rows - haloN, rows) the upper one (band |col - row| <= haloN) */
 	hx.headBlocks = lo ? (unsigned)((n + 127) / 128) : 0u;
 	hx.firstHiBlock = hi ? (unsigned)((rows - n) / 128) : 0xffffffffu;
-	hx.fillerBlocks = 3u * 10u * (unsigned)handle->multiProcessorCount;
+	{
+		const unsigned rowBlocks = (unsigned)((rows + 127) / 128);
+		const unsigned fillerCap = 3u * 10u * (unsigned)handle->multiProcessorCount;    /* about three waves */
+		hx.nLo = hx.headBlocks < rowBlocks ? hx.headBlocks : rowBlocks;
+		hx.hiStart = hx.firstHiBlock < rowBlocks ? hx.firstHiBlock : rowBlocks;
+		if (hx.hiStart < hx.nLo) hx.hiStart = hx.nLo;
+		hx.nHi = rowBlocks - hx.hiStart;
+		{
+			const unsigned interior = hx.hiStart - hx.nLo;
+			const unsigned filler = (interior >> 2) < fillerCap ? (interior >> 2) : fillerCap;
+			hx.early = interior - filler;
+		}
+	}
 	hx.spin = spin_ctl(handle);
 	hx.trace = h->magic == SPGPU_PRIV_MAGIC ? h->dTrace : NULL;
 	return hx;
@@ -452,11 +465,12 @@ template <typename T, int UNROLL>
 static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const T* cM, const int* rP, int hackSize, const int* hackOffsets, const int* rS,
 	int avgNnzPerRow, int rows, T* xExt, T beta, int baseIndex, int haloN,
-	const spgpuHaloLinks* links, unsigned seq, Acc2* ctaPartials)
+	const spgpuHaloLinks* links, unsigned seq, typename DotPartial<T>::type* ctaPartials)
 {
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const HellArgs<T> a = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, NULL, rows, xExt, beta,
-		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1, 0, NULL, NULL, 0, NULL, NULL };
+		baseIndex, spgpu_long_cut(t, avgNnzPerRow), t->hellVariant != 1, 0, NULL, NULL, 0, NULL, NULL,
+		spgpu_hell_prefetch(handle, t) };
 	const HaloArgs<T> hx = halo_args<T>(handle, xExt, rows, haloN, links, seq);
 	const bool halo = hx.pushCtas > 0;
 	if (!halo && !ctaPartials) {                 /* no neighbours, no dot: the plain entry point */
@@ -470,8 +484,17 @@ static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 	const HellRowBody<T, UNROLL, 0> b0 = { a };
 	if (ctaPartials) {
 		if (hackSize == 32) {
-			if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			/* The dot variants run at 48 resident warps per SM for the real types (40 registers) where the plain kernel
+			 * runs double at 40 warps: the extra code in front of and behind the row walk lengthens a warp's life, and the
+			 * kernel lives on the edge of being latency-bound.  Measured on the 512^3 slab of one of two ranks (plain
+			 * 1.080 ms): dot + halo 1.197 ms at 40 warps, 1.127 ms at 48; dot alone 1.125 -> 1.094 ms.  hellBlock = 192
+			 * selects the type's plain-kernel occupancy for an A/B. */
+			constexpr int MD = Num<T>::is_complex ? 8 : 12;
+			if (t->hellBlock == 192) {
+				if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+				else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			} else if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
 		} else {
 			if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
 			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
@@ -488,7 +511,7 @@ static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 template <typename T, int UNROLL>
 static void hdia_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const T* dM, const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols,
-	T* xExt, T beta, int haloN, const spgpuHaloLinks* links, unsigned seq, Acc2* ctaPartials)
+	T* xExt, T beta, int haloN, const spgpuHaloLinks* links, unsigned seq, typename DotPartial<T>::type* ctaPartials)
 {
 	const HdiaArgs<T> a = { z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, xExt, beta };
 	const HaloArgs<T> hx = halo_args<T>(handle, xExt, rows, haloN, links, seq);
@@ -520,7 +543,8 @@ static void hdia_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 
 /* folds per-row-block partials (ext_krylov.cu), optionally all-reducing the total across the ranks in its last CTA */
 template <typename T>
-void spgpu_fold_partials(spgpuHandle_t handle, const Acc2* partials, long long n, T* dRes, const spgpuPeerAllreduce* ar);
+void spgpu_fold_partials(spgpuHandle_t handle, const typename DotPartial<T>::type* partials, long long n, T* dRes,
+	const spgpuPeerAllreduce* ar);
 
 ArArgs spgpu_ar_args(spgpuHandle_t handle, const spgpuPeerAllreduce* ar)
 {
@@ -550,20 +574,21 @@ ArArgs spgpu_ar_args(spgpuHandle_t handle, const spgpuPeerAllreduce* ar)
 			avgNnzPerRow, rows, xExt, beta, baseIndex, haloN, links, seq, NULL);                        \
 	}                                                                                                   \
 	/* z = A*xExt with the halo exchange inside, plus dRes[0] = sum_i xExt[haloN+i]*z[i] (this rank's   \
-	 * share of p.Ap, all-reduced when ar is given): per-row-block partials in handle scratch */       \
+	 * share of p.Ap, all-reduced when ar is given): one partial per 32 rows in handle scratch */       \
 	extern "C" void spgpu##S##hellspmvHaloDot(spgpuHandle_t handle, T* z, const T* cM, const int* rP,   \
 		int hackSize, const int* hackOffsets, const int* rS, int avgNnzPerRow, int rows, T* xExt,       \
 		int baseIndex, int haloN, const spgpuHaloLinks* links, unsigned seq, T* dRes,                   \
 		const spgpuPeerAllreduce* ar)                                                                   \
 	{                                                                                                   \
+		typedef DotPartial<T>::type P;                                                                  \
 		const unsigned rowBlocks = spgpu_ceil_div(rows > 0 ? rows : 0, 128);                            \
-		Acc2* partials = rowBlocks ? (Acc2*)spgpuScratch(handle, (size_t)rowBlocks * sizeof(Acc2)) : NULL; \
+		P* partials = rowBlocks ? (P*)spgpuScratch(handle, (size_t)rowBlocks * 4 * sizeof(P)) : NULL;   \
 		if (rowBlocks && !partials) return;                                                             \
 		if (rowBlocks)                                                                                  \
 			hell_spmv_halo_launch<T, UH>(handle, z, NULL, Num<T>::from_real(1), cM, rP, hackSize,       \
 				hackOffsets, rS, avgNnzPerRow, rows, xExt, Num<T>::zero(), baseIndex, haloN, links,     \
 				seq, partials);                                                                         \
-		spgpu_fold_partials<T>(handle, partials, rowBlocks, dRes, ar);                                  \
+		spgpu_fold_partials<T>(handle, partials, (long long)rowBlocks * 4, dRes, ar);                   \
 	}                                                                                                   \
 	extern "C" void spgpu##S##hellspmvDot(spgpuHandle_t handle, T* z, const T* cM, const int* rP,       \
 		int hackSize, const int* hackOffsets, const int* rS, int rows, const T* x, int baseIndex,       \
@@ -584,13 +609,14 @@ ArArgs spgpu_ar_args(spgpuHandle_t handle, const spgpuPeerAllreduce* ar)
 		const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols, T* xExt,          \
 		int haloN, const spgpuHaloLinks* links, unsigned seq, T* dRes, const spgpuPeerAllreduce* ar)    \
 	{                                                                                                   \
+		typedef DotPartial<T>::type P;                                                                  \
 		const unsigned rowBlocks = spgpu_ceil_div(rows > 0 ? rows : 0, 128);                            \
-		Acc2* partials = rowBlocks ? (Acc2*)spgpuScratch(handle, (size_t)rowBlocks * sizeof(Acc2)) : NULL; \
+		P* partials = rowBlocks ? (P*)spgpuScratch(handle, (size_t)rowBlocks * 4 * sizeof(P)) : NULL;   \
 		if (rowBlocks && !partials) return;                                                             \
 		if (rowBlocks)                                                                                  \
 			hdia_spmv_halo_launch<T, UD>(handle, z, NULL, Num<T>::from_real(1), dM, offsets, hackSize,  \
 				hackOffsets, rows, cols, xExt, Num<T>::zero(), haloN, links, seq, partials);            \
-		spgpu_fold_partials<T>(handle, partials, rowBlocks, dRes, ar);                                  \
+		spgpu_fold_partials<T>(handle, partials, (long long)rowBlocks * 4, dRes, ar);                   \
 	}
 
 SPGPU_DEFINE_HALO(S, float, 8, 9)
@@ -659,4 +685,45 @@ extern "C" int spgpuHaloTraceRead(spgpuHandle_t handle, unsigned long long* host
 			return -1;
 	}
 	return 0;
+}
+
+/* ---- forcing the kernels of this file into the device ahead of time ------------------------------------ */
+
+/*
+ * CUDA loads a kernel when it is first launched (lazy loading), and that load waits for the kernels already
+ * running on the device.  A process that drives SEVERAL ranks must therefore never meet a first launch while
+ * one of its own kernels is spinning on a peer: the load would wait for the spinning kernel, which waits for
+ * a kernel the same host thread has not launched yet.  spgpuMgCreate calls this once per device.
+ */
+template <typename K>
+static int preload_one(K kernel)
+{
+	cudaFuncAttributes a;
+	return cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(kernel)) == cudaSuccess ? 0 : 1;
+}
+
+template <typename T, class Body, int MINB>
+static int preload_body()
+{
+	/* also the 48-warp variants the hellBlock knob selects */
+	return preload_one(spmv_halo_kernel<T, Body, MINB, false, true>) + preload_one(spmv_halo_kernel<T, Body, MINB, true, true>)
+		+ preload_one(spmv_halo_kernel<T, Body, MINB, true, false>);
+}
+
+template <typename T, int UH, int UD>
+static int preload_type()
+{
+	return preload_body<T, HellRowBody<T, UH, 32>, HaloMinB<T>::hell>() + preload_body<T, HellRowBody<T, UH, 32>, 12>()
+		+ preload_body<T, HellRowBody<T, UH, 0>, 8>()
+		+ preload_body<T, HdiaRowBody<T, UD, 32>, 8>() + preload_body<T, HdiaRowBody<T, UD, 0>, 8>()
+		+ preload_one(allreduce_sum_kernel<T>);
+}
+
+extern "C" int spgpuPreloadHaloKernels(void)
+{
+	int bad = preload_type<float, 8, 9>() + preload_type<double, 8, 9>() + preload_type<cuFloatComplex, 8, 9>()
+		+ preload_type<cuDoubleComplex, 4, 4>();
+	bad += preload_one(halo_push_kernel) + preload_one(halo_exchange_kernel) + preload_one(halo_ack_kernel)
+		+ preload_one(wait_flag_kernel) + preload_one(seq_advance_kernel);
+	return bad ? -1 : 0;
 }

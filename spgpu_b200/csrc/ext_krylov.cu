@@ -179,21 +179,27 @@ static void cg_update_launch(spgpuHandle_t handle, T* x, T* r, const T* p, const
 	spgpu_count_launch(handle);
 }
 
-/* ---- fold of Acc2 partials (one per row block of a fused SpMV + dot) -------------------- */
+/* ---- fold of the per-warp partials a fused SpMV + dot leaves behind -------------------------- */
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-fold_partials_kernel(const Acc2* __restrict__ in, long long n, Acc2* partials, unsigned* ticket, T* dRes, const ArArgs ar)
+fold_partials_kernel(const typename DotPartial<T>::type* __restrict__ in, long long n, Acc2* partials, unsigned* ticket,
+	T* dRes, const ArArgs ar)
 {
 	__shared__ Acc2 smem[32];
 	__shared__ bool amLast;
 	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long nthreads = (long long)gridDim.x * blockDim.x;
 	Acc2 s = { 0.0, 0.0 };
-	for (long long e = tid; e < n; e += nthreads) {
-		const double2 v = __ldcs(reinterpret_cast<const double2*>(in) + e);
-		s.a += v.x;
-		s.b += v.y;
+	for (long long e = tid; e < n; e += 4 * nthreads) {
+		Acc2 v[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const long long q = e + u * nthreads;
+			v[u] = q < n ? ld_partial(in + q) : Acc2{ 0.0, 0.0 };
+		}
+		s.a += (v[0].a + v[1].a) + (v[2].a + v[3].a);
+		s.b += (v[0].b + v[1].b) + (v[2].b + v[3].b);
 	}
 	Acc2 v = block_reduce<false>(s, smem);
 	Acc2 total = { 0.0, 0.0 };
@@ -204,11 +210,12 @@ fold_partials_kernel(const Acc2* __restrict__ in, long long n, Acc2* partials, u
 }
 
 template <typename T>
-void spgpu_fold_partials(spgpuHandle_t handle, const Acc2* partials, long long n, T* dRes, const spgpuPeerAllreduce* ar)
+void spgpu_fold_partials(spgpuHandle_t handle, const typename DotPartial<T>::type* partials, long long n, T* dRes,
+	const spgpuPeerAllreduce* ar)
 {
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	long long want = (n + 4 * 256 - 1) / (4 * 256);
-	long long cap = (long long)handle->multiProcessorCount * 4;
+	long long cap = (long long)handle->multiProcessorCount * 8;
 	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
 	if (want > cap) want = cap;
 	if (want < 1) want = 1;
@@ -217,8 +224,8 @@ void spgpu_fold_partials(spgpuHandle_t handle, const Acc2* partials, long long n
 	spgpu_count_launch(handle);
 }
 
-template void spgpu_fold_partials<float>(spgpuHandle_t, const Acc2*, long long, float*, const spgpuPeerAllreduce*);
-template void spgpu_fold_partials<double>(spgpuHandle_t, const Acc2*, long long, double*, const spgpuPeerAllreduce*);
+template void spgpu_fold_partials<float>(spgpuHandle_t, const double*, long long, float*, const spgpuPeerAllreduce*);
+template void spgpu_fold_partials<double>(spgpuHandle_t, const double*, long long, double*, const spgpuPeerAllreduce*);
 template void spgpu_fold_partials<cuFloatComplex>(spgpuHandle_t, const Acc2*, long long, cuFloatComplex*, const spgpuPeerAllreduce*);
 template void spgpu_fold_partials<cuDoubleComplex>(spgpuHandle_t, const Acc2*, long long, cuDoubleComplex*, const spgpuPeerAllreduce*);
 
@@ -238,3 +245,21 @@ template void spgpu_fold_partials<cuDoubleComplex>(spgpuHandle_t, const Acc2*, l
 		cg_update_launch<T>(handle, x, r, p, ap, n, dRr, dPAp, dRrNew, ar);                        \
 	}
 SPGPU_FOR_FLOAT_TYPES(SPGPU_DEFINE_KRYLOV)
+
+/* see spgpuPreloadHaloKernels (ext_halo.cu): the kernels of this file whose last CTA may wait for a peer */
+template <typename T>
+static int preload_krylov_type()
+{
+	cudaFuncAttributes a;
+	int bad = 0;
+	bad += cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(axpby_dev_kernel<T>)) != cudaSuccess;
+	bad += cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(cg_update_kernel<T>)) != cudaSuccess;
+	bad += cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(fold_partials_kernel<T>)) != cudaSuccess;
+	return bad;
+}
+
+extern "C" int spgpuPreloadKrylovKernels(void)
+{
+	return (preload_krylov_type<float>() + preload_krylov_type<double>() + preload_krylov_type<cuFloatComplex>()
+		+ preload_krylov_type<cuDoubleComplex>()) ? -1 : 0;
+}

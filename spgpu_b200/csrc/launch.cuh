@@ -27,7 +27,7 @@ static inline void spgpu_count_launch(spgpuHandle_t handle)
 
 static inline const SpgpuTuning* spgpu_tuning(spgpuHandle_t handle)
 {
-	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 0, 0, 8, 8, 20000, 0, 0, 0, 0 };
+	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 0, 0, 8, 8, 20000, 0, 0, 0, 0, 0 };
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	return h->magic == SPGPU_PRIV_MAGIC ? &h->tune : &fallback;
 }
@@ -35,6 +35,16 @@ static inline const SpgpuTuning* spgpu_tuning(spgpuHandle_t handle)
 static inline unsigned spgpu_ceil_div(long long a, long long b)
 {
 	return (unsigned)((a + b - 1) / b);
+}
+
+/* how many hacks ahead a HELL warp prefetches its hackOffsets entry (spmv_hell_body.cuh): hellPrefetch tuning key,
+ * in waves of resident CTAs; 0 = default (2 waves), < 0 = off */
+static inline int spgpu_hell_prefetch(spgpuHandle_t handle, const SpgpuTuning* t)
+{
+	const int waves = t->hellPrefetch == 0 ? 2 : t->hellPrefetch;
+	if (waves < 0)
+		return 0;
+	return waves * 10 * 4 * (handle->multiProcessorCount > 0 ? handle->multiProcessorCount : 148);
 }
 
 /* rows deeper than this many slots count as spikes (spmv_slots.cuh decides per warp what to do with them) */

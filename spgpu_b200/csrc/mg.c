@@ -26,6 +26,7 @@ struct spgpuMgContext {
 	int dev[MG_MAX_RANKS];
 	spgpuHandle_t h[MG_MAX_RANKS];
 	int fusedCapable;                 /* distinct devices, peer access between every pair */
+	int direct[MG_MAX_RANKS][MG_MAX_RANKS];   /* rank r's kernels can store into rank q's memory (same device or peer access) */
 	int exchange;                     /* SPGPU_MG_FUSED or SPGPU_MG_EVENTS */
 	unsigned* flags[MG_MAX_RANKS];    /* device: SPGPU_HALO_FLAG_WORDS words per rank */
 	void* arTable[MG_MAX_RANKS];      /* device: 2 * world slots of SPGPU_AR_SLOT_BYTES */
@@ -104,20 +105,24 @@ spgpuStatus_t spgpuMgCreate(spgpuMgHandle_t* pMg, const int* devices, int n)
 			return st;
 		}
 	}
-	for (r = 0; r < n && distinct; ++r) {
+	for (r = 0; r < n; ++r) {
 		use_rank(mg, r);
 		for (q = 0; q < n; ++q) {
 			int can = 0;
 			cudaError_t e;
-			if (q == r)
+			mg->direct[r][q] = 1;
+			if (mg->dev[q] == mg->dev[r])
 				continue;
 			if (cudaDeviceCanAccessPeer(&can, mg->dev[r], mg->dev[q]) != cudaSuccess || !can) {
+				mg->direct[r][q] = 0;
 				peers = 0;
 				continue;
 			}
 			e = cudaDeviceEnablePeerAccess(mg->dev[q], 0);
-			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+				mg->direct[r][q] = 0;
 				peers = 0;
+			}
 			(void)cudaGetLastError();
 		}
 	}
@@ -139,6 +144,18 @@ spgpuStatus_t spgpuMgCreate(spgpuMgHandle_t* pMg, const int* devices, int n)
 		if (e == cudaSuccess) e = cudaMalloc(&mg->dScalar[r], 64);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&mg->evPush[r], cudaEventDisableTiming);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&mg->evDone[r], cudaEventDisableTiming);
+		/* every kernel that may wait for a peer is loaded NOW: a first launch (lazy loading) waits for the kernels
+		 * running on the device, and one host thread launches all the ranks (spgpu_ext.h: spgpuPreloadHaloKernels) */
+		if (e == cudaSuccess && (spgpuPreloadHaloKernels() != 0 || spgpuPreloadKrylovKernels() != 0))
+			e = cudaErrorUnknown;
+		if (e == cudaSuccess) {
+			/* ... and the kernels that run between them in an iteration, by running them once */
+			double* d = (double*)mg->dScalar[r];
+			e = cudaMemset(d, 0, 64);
+			spgpuDscal(mg->h[r], d, 1, 1.0, d + 1);
+			spgpuDdotDev(mg->h[r], 1, d, d + 1, d + 2);
+			spgpuDaxpby(mg->h[r], d, 1, 1.0, d + 1, 1.0, d + 2);
+		}
 		if (e == cudaSuccess) e = cudaDeviceSynchronize();
 		if (e != cudaSuccess) {
 			cudaSetDevice(previous);
@@ -297,7 +314,7 @@ spgpuStatus_t spgpuMgHellCreateFromBlocks(spgpuMgHandle_t mg, spgpuMgMatrix_t* p
 		}
 		/* per-row-block partials of the fused SpMV + dot: size the handle's scratch now, not inside an iteration */
 		use_rank(mg, r);
-		spgpuReserveScratch(mg->h[r], ((size_t)(n + 127) / 128 + 1) * 16);
+		spgpuReserveScratch(mg->h[r], ((size_t)(n + 127) / 128 + 1) * 4 * 16);
 	}
 	A->rows = at;
 	cudaSetDevice(previous);
@@ -417,7 +434,7 @@ static spgpuStatus_t hell_create(spgpuMgHandle_t mg, spgpuMgMatrix_t* pA, spgpuT
 			spgpuMgMatrixDestroy(A);
 			return e == cudaErrorMemoryAllocation ? SPGPU_OUTOFMEMORY : SPGPU_UNSPECIFIED;
 		}
-		spgpuReserveScratch(mg->h[r], ((size_t)(n + 127) / 128 + 1) * 16);
+		spgpuReserveScratch(mg->h[r], ((size_t)(n + 127) / 128 + 1) * 4 * 16);
 	}
 	cudaSetDevice(previous);
 	*pA = A;
@@ -594,10 +611,18 @@ static void exchange_with_events(spgpuMgHandle_t mg, spgpuMgVector_t x)
 		if (r < mg->world - 1 && mg->doneValid[r + 1]) cudaStreamWaitEvent(s, mg->evDone[r + 1], 0);
 		if (r > 0) {
 			const size_t nb = (size_t)(A->hi[r - 1] - A->lo[r - 1]);
-			spgpuHaloPush(mg->h[r], (char*)x->ext[r - 1] + (w + nb) * es, (char*)x->ext[r] + w * es, w * es, NULL, 0);
+			void* dst = (char*)x->ext[r - 1] + (w + nb) * es;
+			if (mg->direct[r][r - 1])
+				spgpuHaloPush(mg->h[r], dst, (char*)x->ext[r] + w * es, w * es, NULL, 0);
+			else
+				cudaMemcpyPeerAsync(dst, mg->dev[r - 1], (char*)x->ext[r] + w * es, mg->dev[r], w * es, s);
 		}
-		if (r < mg->world - 1)
-			spgpuHaloPush(mg->h[r], x->ext[r + 1], (char*)x->ext[r] + n * es, w * es, NULL, 0);
+		if (r < mg->world - 1) {
+			if (mg->direct[r][r + 1])
+				spgpuHaloPush(mg->h[r], x->ext[r + 1], (char*)x->ext[r] + n * es, w * es, NULL, 0);
+			else
+				cudaMemcpyPeerAsync(x->ext[r + 1], mg->dev[r + 1], (char*)x->ext[r] + n * es, mg->dev[r], w * es, s);
+		}
 		cudaEventRecord(mg->evPush[r], s);
 	}
 	for (r = 0; r < mg->world; ++r) {

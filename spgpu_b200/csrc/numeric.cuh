@@ -131,6 +131,12 @@ template <> __device__ __forceinline__ cuDoubleComplex ld_stream64<cuDoubleCompl
 	return v;
 }
 
+/* bring the line holding *p into L2 (no register, no wait) */
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 /* read-only, cache normally (x gathers) */
 template <typename T> __device__ __forceinline__ T ld_keep(const T* p) { return __ldg(p); }
 

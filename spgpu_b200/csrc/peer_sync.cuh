@@ -120,6 +120,19 @@ __device__ __forceinline__ Acc2 peer_allreduce_sum_warp(Acc2 mine, const ArArgs&
 	return total;
 }
 
+/* partial sum a WARP of a fused SpMV + dot kernel leaves behind: one double for the real types, two for the complex ones */
+template <typename T> struct DotPartial { typedef double type; };
+template <> struct DotPartial<cuFloatComplex> { typedef Acc2 type; };
+template <> struct DotPartial<cuDoubleComplex> { typedef Acc2 type; };
+__device__ __forceinline__ Acc2 ld_partial(const double* p) { return { __ldcs(p), 0.0 }; }
+__device__ __forceinline__ Acc2 ld_partial(const Acc2* p)
+{
+	const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+	return { v.x, v.y };
+}
+__device__ __forceinline__ void acc2_to_partial(Acc2 v, double& out) { out = v.a; }
+__device__ __forceinline__ void acc2_to_partial(Acc2 v, Acc2& out) { out = v; }
+
 /* value of type T <-> the two doubles of a slot / partial */
 template <typename T> __device__ __forceinline__ Acc2 to_acc2(T v);
 template <> __device__ __forceinline__ Acc2 to_acc2<float>(float v) { return { (double)v, 0.0 }; }

@@ -45,8 +45,9 @@ typedef struct SpgpuTuning {
 	int haloTrace;       /* 1: the fused SpMV + halo kernels record per-exchange timestamps (spgpuHaloTraceRead) */
 	int l2Fetch;         /* > 0: cudaLimitMaxL2FetchGranularity of the handle's device is set to this many bytes
 	                      * (32 / 64 / 128) when the key is set -- a DEVICE-wide limit, an experiment knob */
-	int redInflight;     /* reductions: 16-byte packs a thread keeps in flight per input (2, 4 or 8; 0 = default: dot 2, one-input ops 4) */
-	int ellShortMinB;    /* ELL exact-slot-count kernel: resident CTAs per SM asked of the register allocator (0 = default) */
+	int redInflight;     /* reductions: 16-byte packs a thread keeps in flight per input (2, 4 or 8; 0 = default 4) */
+	int ellShortMinB;    /* (reserved) */
+	int hellPrefetch;    /* HELL: waves of resident CTAs ahead of which a warp prefetches its hackOffsets entry into L2 (0 = default 2, < 0 = off) */
 } SpgpuTuning;
 
 typedef struct SpgpuHandlePriv {

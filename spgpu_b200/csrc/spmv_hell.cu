@@ -187,7 +187,7 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	const int speculate = variant != 1;
 	cudaStream_t s = handle->currentStream;
 	HellArgs<T> args = { z, y, alpha, cM, rP, hackSize, hackOffsets, rS, rIdx, rows, x, beta, baseIndex, longCut, speculate,
-		0, NULL, NULL, 0 };
+		0, NULL, NULL, 0, NULL, NULL, spgpu_hell_prefetch(handle, t) };
 	/* Split mode: on for length-sorted matrices (rIdx given: their long rows sit together in a
 	 * few hacks whose warps would be the critical path), or forced with hellSplit = 1; off with
 	 * hellSplit = -1.  Costs one small extra launch per call (no memset: the header resets itself). */

@@ -35,6 +35,10 @@ struct HellArgs {
 	int workCap;
 	uint4* foldList;             /* (32-row unit, first item, items, items finished) per unit that queued */
 	T* partials;                 /* one 32-lane partial sum per item */
+	/* > 0: every warp asks L2 for the hackOffsets entry this many hacks ahead.  A warp's life is three dependent
+	 * memory round trips -- hackOffsets -> slab -> x -- and the first one is a 4-byte read per 32 rows that nobody
+	 * has touched before: HBM latency for 1 % of the bytes.  Prefetched a couple of waves ahead it is an L2 hit. */
+	int prefetchHacks;
 };
 
 #define SPGPU_WORK_INVALID 0xffffffffu
@@ -53,6 +57,11 @@ __device__ __forceinline__ void hell_warp_rows_value_x(const HellArgs<T>& a, uns
 
 	const unsigned hack = warpRow / (unsigned)hackSize;
 	const unsigned lastHack = ((unsigned)a.rows - 1u) / (unsigned)hackSize;
+	if (a.prefetchHacks > 0 && lane == 0) {
+		const unsigned ahead = hack + (unsigned)a.prefetchHacks;
+		if (ahead <= lastHack)
+			prefetch_l2(a.hackOffsets + ahead);
+	}
 	const int slab = __ldg(a.hackOffsets + hack);
 	/* slab height of this hack = slots that exist for all of its rows; the last
 	 * hack has no terminator entry, so it takes the predicated path */

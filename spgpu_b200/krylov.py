@@ -88,30 +88,37 @@ class Cg:
         return rr_new
 
     # ---- device scalars: no host synchronisation ----------------------------
-    def step_device(self):
+    def step_device(self, mark=None):
+        """one iteration; mark(label), if given, is called after each phase has been queued (bench.py records an
+        event there to time the phases)"""
         st, L, h, n = self.st, self.L, self.h, self.st.n
         s = st.s.data_ptr()
         rr, pap, rrn = s, s + 8, s + 16
         fused = self.ar_fused
+        mark = mark or (lambda _label: None)
         if self.apply_A_dot is not None:
             # SpMV (+ halo exchange) fused with p.Ap (+ its all-reduce in the fold kernel's last CTA)
             self.apply_A_dot(st.ap, st.p_ext, pap, fused.next_ref() if fused else None)
             if self.allreduce and not fused:
                 self.allreduce(st.s[1:2])
+            mark("spmv+halo+p.Ap (+fold, all-reduce)")
         else:
             self.apply_A(st.ap, st.p_ext)
             L.spgpuDdotDev(h, n, st.p.data_ptr(), st.ap.data_ptr(), pap)
             if self.allreduce:
                 self.allreduce(st.s[1:2])
+            mark("spmv, p.Ap, all-reduce")
         # x += (rr/pAp) p ;  r -= (rr/pAp) Ap ;  rr' = r.r   -- one pass (spgpuDcgUpdateDev)
         L.spgpuDcgUpdateDev(h, st.x.data_ptr(), st.r.data_ptr(), st.p.data_ptr(), st.ap.data_ptr(), n, rr, pap, rrn,
                             fused.next_ref() if fused else None)
         if self.allreduce and not fused:
             self.allreduce(st.s[2:3])
+        mark("x, r update + r.r (+all-reduce)")
         # p = r + (rr'/rr) p ; then rr <- rr'
         L.spgpuDaxpbyDev(h, st.p.data_ptr(), n, rrn, rr, 1.0, st.p.data_ptr(), 0, 0, 1.0, st.r.data_ptr())
         # through the library so that it is ordered on the HANDLE's stream whatever torch's current stream is
         L.spgpuDscal(h, rr, 1, self.T.scalar(1.0), rrn)
+        mark("p update")
 
     def residual_norm2(self):
         return float(self.st.s[0].item())

@@ -276,9 +276,9 @@ def test_argument_checks(ours):
         assert ours.spgpuMgSetExchange(mg.h, capi.MG_FUSED) == capi.SPGPU_UNSUPPORTED      # the same device twice cannot spin on itself
         assert ours.spgpuMgExchange(mg.h) == capi.MG_EVENTS
         bad = ctypes.c_void_p()
-        assert ours.spgpuMgDhellCreate(mg.h, ctypes.byref(bad), util.ptr(hell.values), util.ptr(hell.indices), 32,
-                                       util.ptr(hell.hack_offsets), util.ptr(hell.rs), 7, hell.nrows, hell.nrows + 1, 0) \\
-            == capi.SPGPU_UNSUPPORTED                                                      # not square
+        st = ours.spgpuMgDhellCreate(mg.h, ctypes.byref(bad), util.ptr(hell.values), util.ptr(hell.indices), 32,
+                                     util.ptr(hell.hack_offsets), util.ptr(hell.rs), 7, hell.nrows, hell.nrows + 1, 0)
+        assert st == capi.SPGPU_UNSUPPORTED                                                # not square
         ours.spgpuMgVectorDestroy(vx)
         ours.spgpuMgMatrixDestroy(A)
     finally:
