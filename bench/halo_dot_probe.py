@@ -16,6 +16,7 @@ def main():
     from spgpu_b200 import capi, device_build as DB
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    parts = int(os.environ.get("PROBE_PARTS", "2"))           # the slab is rank 1 of `parts` ranks (both neighbours when parts > 2)
     L = capi.lib()
     h = ctypes.c_void_p()
     assert L.spgpuCreate(ctypes.byref(h), 0) == 0
@@ -23,20 +24,23 @@ def main():
     L.spgpuSetStream(h, stream.cuda_stream)
     torch.cuda.set_stream(stream)
     plane = n * n
-    A = DB.hell_laplace3d_7pt(n, 0, n // 2, local_columns=True)
+    per = n // parts
+    A = DB.hell_laplace3d_7pt(n, per if parts > 2 else 0, 2 * per if parts > 2 else per, local_columns=True)
     rows = A.nrows
     x = torch.rand(A.ncols, dtype=torch.float64, device="cuda")
     z = torch.zeros(rows, dtype=torch.float64, device="cuda")
     res = torch.zeros(4, dtype=torch.float64, device="cuda")
     flags = torch.zeros(16, dtype=torch.int32, device="cuda")
     pflags = torch.zeros(16, dtype=torch.int32, device="cuda")
-    pz = [torch.zeros(plane, dtype=torch.float64, device="cuda") for _ in range(2)]
-    alt = torch.zeros(2 * plane, dtype=torch.float64, device="cuda")
+    pz = torch.zeros(plane, dtype=torch.float64, device="cuda")
     lk = capi.HaloLinks()
-    lk.peerHiLowerZone[0], lk.peerHiLowerZone[1] = pz[0].data_ptr(), pz[1].data_ptr()
-    lk.peerFlagsHi = pflags.data_ptr()
-    lk.myLoZoneOdd, lk.myHiZoneOdd, lk.myFlags = alt.data_ptr(), alt.data_ptr() + 8 * plane, flags.data_ptr()
-    flags[4:6] = 1 << 30                      # every exchange "has arrived"
+    lk.peerHiLowerZone, lk.peerFlagsHi = pz.data_ptr(), pflags.data_ptr()
+    if parts > 2:
+        pzl = torch.zeros(plane, dtype=torch.float64, device="cuda")
+        pfl = torch.zeros(16, dtype=torch.int32, device="cuda")
+        lk.peerLoUpperZone, lk.peerFlagsLo = pzl.data_ptr(), pfl.data_ptr()
+    lk.myFlags = flags.data_ptr()
+    flags[4:8] = 1 << 30                      # every exchange "has arrived" and every push "has been consumed"
     T = capi.TYPES["D"]
     one, zero = T.scalar(1.0), T.scalar(0.0)
     cm, rp, ho, rs = A.values.data_ptr(), A.indices.data_ptr(), A.hack_offsets.data_ptr(), A.rs.data_ptr()

@@ -4,7 +4,9 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 N=${1:-2}
 O=gpurun_out/r2n$N; mkdir -p $O
 nvidia-smi topo -m > $O/topo.txt 2>&1
+if [ "$2" != "notests" ]; then
 timeout 1200 python -m pytest tests/test_mg_multi_gpu.py tests/test_mg_capi_gpu.py tests/test_c_driver_gpu.py tests/test_mg_gpu.py tests/test_krylov_gpu.py -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -30 $O/pytest.log
+fi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531"
 SPGPU_BENCH_TRACE=1 timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-e2e > $O/bench_cfg5_trace.json 2> $O/bench_cfg5_trace.err; echo "cfg5 trace rc=$?"
 grep -E "CG phases|CG exchange" $O/bench_cfg5_trace.err; grep -E "^rank [0-9]+ seq" $O/bench_cfg5_trace.err | tail -4

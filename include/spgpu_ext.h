@@ -211,7 +211,7 @@ int spgpuDeviceFree(void* devPtr);
  *   separate-kernel protocol (spgpuHaloExchange / spgpuHaloAck / spgpuHaloPush / spgpuWaitFlag):
  *     [0] ready-from-below  [1] ready-from-above  [2] ack-from-below  [3] ack-from-above
  *   fused protocol (spgpu?{hell,hdia}spmvHalo[Dot]):
- *     [4] ready-from-below  [5] ready-from-above
+ *     [4] ready-from-below  [5] ready-from-above  [6] ack-from-below  [7] ack-from-above
  * The two protocols number their exchanges independently; both write the halo zones inside xExt, so
  * the neighbouring ranks must be synchronised (any barrier) when a caller switches between them.
  */
@@ -252,16 +252,11 @@ void spgpuHaloAck(spgpuHandle_t handle, unsigned* peerAckLo, unsigned* peerAckHi
 
 /*
  * Where the fused SpMV + halo kernels of a rank find its neighbours.  xExt = [lower zone (haloN) |
- * owned (rows) | upper zone (haloN)].  Exchanges are double-buffered: exchange seq uses zone pair
- * (seq & 1) -- the EVEN pair is the two zones inside xExt, the ODD pair a second set of zones
- * outside it (haloN elements each, anywhere in the rank's device memory).  Index [0] = even,
- * [1] = odd.  NULL peer flags = no neighbour on that side.
+ * owned (rows) | upper zone (haloN)].  NULL peer flags = no neighbour on that side.
  */
 typedef struct spgpuHaloLinks {
-	void* peerLoUpperZone[2];   /* PEER pointers: the LOWER neighbour's upper zones (this rank's first haloN owned entries go there) */
-	void* peerHiLowerZone[2];   /* PEER pointers: the UPPER neighbour's lower zones (this rank's last haloN owned entries go there)  */
-	void* myLoZoneOdd;          /* this rank's own odd lower / upper zones (the even ones are inside xExt) */
-	void* myHiZoneOdd;
+	void* peerLoUpperZone;      /* PEER pointer: the LOWER neighbour's upper zone (this rank's first haloN owned entries go there) */
+	void* peerHiLowerZone;      /* PEER pointer: the UPPER neighbour's lower zone (this rank's last haloN owned entries go there)  */
 	unsigned* myFlags;          /* this rank's flag block */
 	unsigned* peerFlagsLo;      /* PEER pointers to the neighbours' flag blocks */
 	unsigned* peerFlagsHi;
@@ -276,15 +271,16 @@ typedef struct spgpuHaloLinks {
  * seq = 1, 2, 3, ... (the same on every rank) numbers the exchanges; 0 = taken from the device counter
  * registered with spgpuSetSeqCounters.
  *
- * The first CTAs push this rank's two boundary runs into the neighbours' zones of pair (seq & 1) over
- * NVLink and publish seq; most interior row blocks are scheduled first, then the row blocks that read
- * a zone (they wait on the local ready word and read the zones with coherent loads), then a few waves
- * of interior blocks.  There are no acknowledgements: with two zone pairs a rank that starts exchange
- * seq + 2 has seen its neighbour's ready(seq + 1), which the neighbour publishes only after its kernel
- * seq has finished reading.  Requirements: every row references only columns within haloN of its own
- * position (rows [0, haloN) may read the lower zone, rows [rows - haloN, rows) the upper one -- the
- * host layers check this when they split a matrix); a rank with a neighbour owns at least haloN rows;
- * consecutive fused calls of a rank are ordered on one stream.
+ * The first CTAs tell the neighbours that this rank's previous exchange is over (the kernel runs, so the rows that
+ * read its zones have finished: the acknowledgement costs nothing), wait for the neighbours' acknowledgement of the
+ * same, push this rank's two boundary runs into the neighbours' zones over NVLink and publish seq; most interior
+ * row blocks are scheduled first, then the row blocks that read a zone (they wait on the local ready word), then a
+ * few waves of interior blocks.  Every block runs the same row walk with coherent loads of x.  Neighbours may
+ * drift most of a kernel apart without anybody waiting.
+ * Requirements: every row references only columns within haloN of its own position (rows [0, haloN) may
+ * read the lower zone, rows [rows - haloN, rows) the upper one -- the host layers check this when they
+ * split a matrix); a rank with a neighbour owns at least haloN rows; consecutive fused calls of a rank
+ * are ordered on one stream.
  *
  * ...HaloDot: alpha = 1, beta = 0, plus dRes[0] = sum_i xExt[haloN+i]*z[i] (this rank's share of p.Ap,
  * summed over all ranks when `ar` is given): per-warp partials in handle scratch + one fold kernel
@@ -337,7 +333,7 @@ int spgpuPreloadKrylovKernels(void);
  * exchanges starting at sequence number firstSeq (a ring of 1024): [0] first push CTA started,
  * [1] ready flags published (device nanoseconds, %globaltimer), [2] / [3] nanoseconds the row blocks
  * spent waiting for the lower / upper ready word (summed over blocks, waits > 2 us only), [4] / [5]
- * how many blocks waited, [6] first boundary block started, [7] last boundary block finished.
+ * how many blocks waited, [6] first boundary block started, [7] last boundary block past its wait.
  * Synchronises the stream.  0, or -1.
  */
 int spgpuHaloTraceRead(spgpuHandle_t handle, unsigned long long* hostOut, int firstSeq, int count);

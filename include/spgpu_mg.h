@@ -13,8 +13,7 @@
  * with the block's column indices remapped to x_ext positions.  Before a product the zones are
  * filled with the neighbours' boundary entries:
  *   SPGPU_MG_FUSED   the exchange travels INSIDE the SpMV launch (spgpu?hellspmvHalo, spgpu_ext.h):
- *                    peer stores over NVLink + flag words, double-buffered zones, no host
- *                    involvement; needs distinct devices with peer access;
+ *                    peer stores over NVLink + flag words, no host involvement; needs distinct devices with peer access;
  *   SPGPU_MG_EVENTS  a push kernel per rank + CUDA events between the ranks' streams; works on any
  *                    set of devices, including the same device listed several times (how the
  *                    single-GPU tests exercise the partition logic).

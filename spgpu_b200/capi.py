@@ -47,8 +47,7 @@ class SpgpuHandleStruct(ctypes.Structure):
 class HaloLinks(ctypes.Structure):
     """spgpuHaloLinks (include/spgpu_ext.h): where a rank's fused SpMV + halo kernels find the neighbours."""
     _fields_ = [
-        ("peerLoUpperZone", c_void_p * 2), ("peerHiLowerZone", c_void_p * 2),
-        ("myLoZoneOdd", c_void_p), ("myHiZoneOdd", c_void_p),
+        ("peerLoUpperZone", c_void_p), ("peerHiLowerZone", c_void_p),
         ("myFlags", c_void_p), ("peerFlagsLo", c_void_p), ("peerFlagsHi", c_void_p),
     ]
 

@@ -197,30 +197,37 @@ extern "C" void spgpuWaitFlag(spgpuHandle_t handle, const unsigned* flag, unsign
 /* ---- HELL / HDIA SpMV fused with the halo exchange: ONE kernel per partitioned SpMV ---- */
 
 /*
- * Protocol (per side; words of the per-rank flag block, spgpu_ext.h): exchange number seq = 1, 2, ...
- * uses zone pair (seq & 1): the even pair is the two halo zones inside x_ext, the odd pair a second
- * set of zones outside it (spgpuHaloLinks.my*ZoneOdd).  The push CTAs copy this rank's boundary
- * entries into the neighbours' zones of that pair and release-store seq into the neighbours' ready
- * words; the row blocks that read a zone acquire-spin on the local ready word.  There is NO
- * acknowledgement: a rank can only start exchange seq + 2 (which overwrites pair seq & 1) after its
- * own kernel seq + 1 has finished, that kernel's boundary rows have waited for the neighbour's
- * ready(seq + 1), and the neighbour publishes that from its kernel seq + 1, which starts -- same
- * stream -- after its kernel seq has read the pair for the last time.  So neighbours may drift a
- * whole kernel apart without waiting for each other, and a boundary row block costs one flag load
- * more than an interior one (no fence, no ticket).  Consecutive fused calls of a rank must be
- * ordered on ONE stream.
+ * Protocol (per side; words of the per-rank flag block, spgpu_ext.h).  Exchange number seq = 1, 2, ...:
+ *   push CTAs     (the first CTAs of the grid) tell both neighbours "my exchange seq - 1 is over" -- this kernel runs,
+ *                 so every earlier kernel of this rank's stream, including the rows that read my zones, has finished:
+ *                 the ACK costs the row blocks nothing -- then wait for the neighbour's ack of seq - 1 (it has finished
+ *                 reading the zone this rank is about to overwrite), copy this rank's boundary entries into the
+ *                 neighbour's zone over NVLink and release-store seq into the neighbour's READY word;
+ *   boundary rows (the row blocks that read a zone) acquire-spin on the local ready word before their first load and
+ *                 then multiply like every other block.
+ * A rank's push of exchange seq needs the neighbour to have STARTED its kernel seq, and its boundary rows -- scheduled
+ * late in the grid -- need the neighbour's push, i.e. the neighbour's start plus the copy: neighbours may drift most of
+ * a kernel apart without anybody waiting.  Every block -- interior or boundary -- runs the SAME inlined row walk with
+ * plain weak loads of x (ld.global: inside the memory model, ordered behind the CTA's acquire; the single-GPU kernels
+ * use ld.global.nc).  Measured alternatives (bench/halo_dot_probe.py, the 64-plane slab of one of eight ranks, plain
+ * kernel 0.275 ms): zones double-buffered by the parity of seq instead of acknowledged, the boundary rows choosing the
+ * zone per gather in an out-of-line copy of the row walk: 0.280 ms, and 0.322 ms with the dot fused in (the call
+ * spoils the register allocation of the common path); acks by a ticket per boundary warp: 0.298 ms (and round 1's
+ * barrier + fence + ticket per boundary block: + 7 us at N = 8).  Consecutive fused calls of a rank must be ordered
+ * on ONE stream.
  */
 template <typename T>
 struct HaloArgs {
-	T* dstLo[2]; const T* srcLo;            /* my first n owned entries -> lower neighbour's upper zone (even, odd) */
-	T* dstHi[2]; const T* srcHi;            /* my last n owned entries  -> upper neighbour's lower zone            */
+	T* dstLo; const T* srcLo;               /* my first n owned entries -> lower neighbour's upper zone */
+	T* dstHi; const T* srcHi;               /* my last n owned entries  -> upper neighbour's lower zone */
 	int n;
-	long long dLoOdd, dHiOdd;               /* element distance from my zones inside x_ext to my odd zones          */
-	unsigned* peerReadyLo; unsigned* peerReadyHi;        /* remote: my entries for `seq` are in place          */
-	const unsigned* myReadyLo; const unsigned* myReadyHi;/* local : the neighbour's entries for `seq` are in place */
+	const unsigned* ackLo; const unsigned* ackHi;        /* local : the neighbour has consumed my previous entries     */
+	unsigned* peerReadyLo; unsigned* peerReadyHi;        /* remote: my entries for `seq` are in place                  */
+	const unsigned* myReadyLo; const unsigned* myReadyHi;/* local : the neighbour's entries for `seq` are in place     */
+	unsigned* peerAckLo; unsigned* peerAckHi;            /* remote: I have consumed the neighbour's entries for `seq`  */
 	unsigned seq;                           /* sequence number of this exchange, or ... */
 	const unsigned* seqPtr;                 /* ... (seq == 0) device counter of COMPLETED exchanges: this one is *seqPtr + 1 */
-	unsigned* pushTicket;
+	unsigned* pushTicket;                   /* handle-owned counter, zero between launches */
 	int pushCtas;
 	unsigned headBlocks;                    /* 128-row blocks [0, headBlocks) hold a row that reads the lower zone */
 	unsigned firstHiBlock;                  /* 128-row blocks [firstHiBlock, ..) hold a row that reads the upper zone */
@@ -286,20 +293,22 @@ struct HdiaRowBody {
 
 /*
  * grid = pushCtas + ceil(rows/128).  The first pushCtas CTAs move the two boundary runs into the
- * neighbours' zones over NVLink and publish `seq`.  Every other CTA multiplies 128 rows; the CTAs
+ * neighbours' zones over NVLink (after the neighbours' acks) and publish `seq`.  Every other CTA multiplies 128 rows; the CTAs
  * are numbered so that most interior row blocks come first and the blocks that read a zone come
  * late (followed only by a few waves of interior blocks, so that a late neighbour delays nothing
  * but the blocks that need it) -- by the time the hardware schedules them the neighbours' entries
  * have normally long arrived.  A block may read both zones (a rank with fewer rows than two halo
  * widths): it then waits for both words.
  */
-/* The rows that read a halo zone, out of line: the interior path then keeps the register allocation of the plain
- * kernel (inlined next to it, the second copy of the row walk cost 32 bytes of spills in EVERY block; the call
- * costs a few dozen cycles in the ~3 % of blocks that take it). */
-template <typename T, class Body>
-__device__ __noinline__ T halo_boundary_rows(const Body body, unsigned warpRow, const XZones<T> xg)
+/* which 128-row block the CTA multiplies (the order is worked out on the host: halo_args) */
+template <typename T>
+__device__ __forceinline__ unsigned halo_row_block(const HaloArgs<T>& hx)
 {
-	return body.run(warpRow, xg);
+	const unsigned b = blockIdx.x - hx.pushCtas;
+	if (b < hx.early) return hx.nLo + b;                                            /* most of the interior first */
+	if (b < hx.early + hx.nLo) return b - hx.early;                                 /* then the lower boundary    */
+	if (b < hx.early + hx.nLo + hx.nHi) return hx.hiStart + (b - hx.early - hx.nLo);   /* the upper boundary      */
+	return b - hx.nHi;                                                              /* the rest of the interior   */
 }
 
 /*
@@ -311,22 +320,36 @@ spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, typename Do
 {
 	const unsigned rows = (unsigned)body.rows();
 	unsigned rb = blockIdx.x;
+	bool needLo = false, needHi = false;
+	unsigned seq = 0;
+	unsigned long long* tr = NULL;
 	T zval;
 	if (HALO) {
 		/* the counter is advanced by a later kernel in stream order (spgpuHaloSeqAdvance), never during this
 		 * one, so every CTA reads the same value whenever it is scheduled */
-		const unsigned seq = hx.seqPtr ? *reinterpret_cast<const volatile unsigned*>(hx.seqPtr) + 1u : hx.seq;
-		const unsigned par = seq & 1u;
-		unsigned long long* tr = hx.trace ? hx.trace + (size_t)(seq & (SPGPU_TRACE_SLOTS - 1)) * 8 : NULL;
+		seq = hx.seqPtr ? *reinterpret_cast<const volatile unsigned*>(hx.seqPtr) + 1u : hx.seq;
+		tr = hx.trace ? hx.trace + (size_t)(seq & (SPGPU_TRACE_SLOTS - 1)) * 8 : NULL;
 		if (blockIdx.x < (unsigned)hx.pushCtas) {
 			const bool toHi = (blockIdx.x & 1) != 0;
-			T* dst = toHi ? hx.dstHi[par] : hx.dstLo[par];
+			T* dst = toHi ? hx.dstHi : hx.dstLo;
 			const T* src = toHi ? hx.srcHi : hx.srcLo;
+			const unsigned* ack = toHi ? hx.ackHi : hx.ackLo;
 			if (tr && threadIdx.x == 0 && blockIdx.x == 0) {
 				for (int k = 2; k < 8; ++k)
 					tr[k] = 0ull;
 				tr[0] = global_timer_ns();
 			}
+			if (threadIdx.x == 0 && seq > 1u) {
+				/* This kernel runs, so every earlier kernel of this rank's stream has finished -- including the rows of
+				 * exchange seq - 1 that read my zones: that IS the acknowledgement, and it costs the row blocks nothing. */
+				if (blockIdx.x == 0) {
+					if (hx.peerAckLo) st_release_sys(hx.peerAckLo, seq - 1u);
+					if (hx.peerAckHi) st_release_sys(hx.peerAckHi, seq - 1u);
+				}
+				if (dst && ack)
+					spin_until(ack, seq - 1u, hx.spin);      /* the neighbour has finished reading what I am about to overwrite */
+			}
+			__syncthreads();
 			if (dst)
 				copy_bytes(dst, src, (size_t)hx.n * sizeof(T), blockIdx.x >> 1, (unsigned)hx.pushCtas >> 1);
 			__threadfence_system();
@@ -343,13 +366,9 @@ spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, typename Do
 			}
 			return;
 		}
-		const unsigned b = blockIdx.x - hx.pushCtas;
-		if (b < hx.early) rb = hx.nLo + b;                                            /* most of the interior first */
-		else if (b < hx.early + hx.nLo) rb = b - hx.early;                            /* then the lower boundary    */
-		else if (b < hx.early + hx.nLo + hx.nHi) rb = hx.hiStart + (b - hx.early - hx.nLo);   /* the upper boundary */
-		else rb = b - hx.nHi;                                                         /* the rest of the interior   */
-		const bool needLo = rb < hx.headBlocks && hx.myReadyLo != NULL;
-		const bool needHi = rb >= hx.firstHiBlock && hx.myReadyHi != NULL;
+		rb = halo_row_block(hx);
+		needLo = rb < hx.headBlocks && hx.myReadyLo != NULL;
+		needHi = rb >= hx.firstHiBlock && hx.myReadyHi != NULL;
 		if (needLo || needHi) {
 			if (threadIdx.x == 0) {
 				unsigned long long t0 = 0;
@@ -367,23 +386,22 @@ spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, typename Do
 				if (tr) {
 					const unsigned long long t1 = global_timer_ns();
 					if (needHi && t1 - t0 > 2000ull) { atomicAdd(tr + 3, t1 - t0); atomicAdd(tr + 5, 1ull); }
+					atomicMax(tr + 7, t1);          /* the last boundary block to get going */
 				}
 			}
 			__syncthreads();
-			const XZones<T> xz = { body.x(), par ? hx.dLoOdd : 0ll, par ? hx.dHiOdd : 0ll, hx.n, hx.n + (int)rows };
-			zval = halo_boundary_rows<T, Body>(body, rb * 128u + (threadIdx.x & ~31u), xz);
-			if (tr && threadIdx.x == 0)
-				atomicMax(tr + 7, global_timer_ns());
-		} else {
-			/* interior: no flags -- exactly the plain kernel */
-			const XPlain<T> xg = { body.x() };
-			zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
 		}
+		/* one row walk for every block: weak loads of x */
+		const XWeak<T> xg = { body.x() };
+		zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
 	} else {
 		const XPlain<T> xg = { body.x() };
 		zval = body.run(rb * 128u + (threadIdx.x & ~31u), xg);
 	}
 	if (DOT) {
+		/* nothing of the prologue is kept in registers across the row walk: the block is worked out again */
+		if (HALO)
+			rb = halo_row_block(hx);
 		const unsigned myRow = rb * 128u + threadIdx.x;
 		Acc2 c = { 0.0, 0.0 };
 		if (myRow < rows)
@@ -392,7 +410,7 @@ spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, typename Do
 	}
 }
 
-/* flag words (spgpu_ext.h): [4] fused-ready-from-below [5] fused-ready-from-above */
+/* flag words (spgpu_ext.h): [4] ready-from-below [5] ready-from-above [6] ack-from-below [7] ack-from-above */
 template <typename T>
 static HaloArgs<T> halo_args(spgpuHandle_t handle, T* xExt, int rows, int haloN, const spgpuHaloLinks* L, unsigned seq)
 {
@@ -405,16 +423,18 @@ static HaloArgs<T> halo_args(spgpuHandle_t handle, T* xExt, int rows, int haloN,
 	const int n = haloN < rows ? haloN : rows;
 	hx.n = haloN;
 	if (lo) {
-		hx.dstLo[0] = (T*)L->peerLoUpperZone[0]; hx.dstLo[1] = (T*)L->peerLoUpperZone[1];
+		hx.dstLo = (T*)L->peerLoUpperZone;
+		hx.ackLo = L->myFlags + 6;
 		hx.peerReadyLo = L->peerFlagsLo + 5;
 		hx.myReadyLo = L->myFlags + 4;
-		hx.dLoOdd = (const T*)L->myLoZoneOdd - xExt;
+		hx.peerAckLo = L->peerFlagsLo + 7;
 	}
 	if (hi) {
-		hx.dstHi[0] = (T*)L->peerHiLowerZone[0]; hx.dstHi[1] = (T*)L->peerHiLowerZone[1];
+		hx.dstHi = (T*)L->peerHiLowerZone;
+		hx.ackHi = L->myFlags + 7;
 		hx.peerReadyHi = L->peerFlagsHi + 4;
 		hx.myReadyHi = L->myFlags + 5;
-		hx.dHiOdd = (const T*)L->myHiZoneOdd - (xExt + haloN + rows);
+		hx.peerAckHi = L->peerFlagsHi + 6;
 	}
 	hx.srcLo = xExt + haloN;
 	hx.srcHi = xExt + rows;                                 /* last haloN owned entries */
@@ -484,17 +504,19 @@ static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 	const HellRowBody<T, UNROLL, 0> b0 = { a };
 	if (ctaPartials) {
 		if (hackSize == 32) {
-			/* The dot variants run at 48 resident warps per SM for the real types (40 registers) where the plain kernel
-			 * runs double at 40 warps: the extra code in front of and behind the row walk lengthens a warp's life, and the
-			 * kernel lives on the edge of being latency-bound.  Measured on the 512^3 slab of one of two ranks (plain
-			 * 1.080 ms): dot + halo 1.197 ms at 40 warps, 1.127 ms at 48; dot alone 1.125 -> 1.094 ms.  hellBlock = 192
-			 * selects the type's plain-kernel occupancy for an A/B. */
+			/* Occupancy of the dot variants, from measurement on the 512^3 slabs of one of two / one of eight ranks
+			 * (bench/halo_dot_probe.py; plain kernel 1.079 / 0.275 ms): without neighbours 48 resident warps per SM
+			 * for the real types (1.082 ms against 1.094 at the plain kernel's 40); with the halo code 40 warps
+			 * (1.152 / 0.300 ms against 1.231 / 0.305 at 48).  The row walk lives on the edge of being
+			 * latency-bound, and how ptxas schedules its loads changes with everything around it.  hellBlock = 192 /
+			 * 256 force the plain kernel's occupancy / 48 warps for an A/B. */
 			constexpr int MD = Num<T>::is_complex ? 8 : 12;
-			if (t->hellBlock == 192) {
-				if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-				else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-			} else if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			const bool dense = t->hellBlock >= 256 || (t->hellBlock != 192 && !halo);
+			if (dense) {
+				if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+				else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			} else if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
 		} else {
 			if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
 			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);

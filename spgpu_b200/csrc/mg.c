@@ -55,7 +55,6 @@ struct spgpuMgMatrix {
 struct spgpuMgVector {
 	spgpuMgMatrix_t A;
 	void* ext[MG_MAX_RANKS];          /* device: [halo | owned | halo] */
-	void* alt[MG_MAX_RANKS];          /* device: odd zone pair [halo | halo] (FUSED) */
 	void* full[MG_MAX_RANKS];         /* device: the whole vector (all-gather mode, allocated on first use) */
 	spgpuHaloLinks links[MG_MAX_RANKS];
 };
@@ -497,13 +496,11 @@ spgpuStatus_t spgpuMgVectorCreate(spgpuMgMatrix_t A, spgpuMgVector_t* pV)
 	cudaGetDevice(&previous);
 	for (r = 0; r < mg->world; ++r) {
 		const size_t n = (size_t)(A->hi[r] - A->lo[r]);
-		const size_t extBytes = (n + 2 * w) * es, altBytes = 2 * w * es;
+		const size_t extBytes = (n + 2 * w) * es;
 		cudaError_t e;
 		use_rank(mg, r);
 		e = cudaMalloc(&v->ext[r], extBytes ? extBytes : 16);
 		if (e == cudaSuccess) e = cudaMemset(v->ext[r], 0, extBytes);
-		if (e == cudaSuccess) e = cudaMalloc(&v->alt[r], altBytes ? altBytes : 16);
-		if (e == cudaSuccess) e = cudaMemset(v->alt[r], 0, altBytes);
 		if (e != cudaSuccess) {
 			cudaSetDevice(previous);
 			spgpuMgVectorDestroy(v);
@@ -516,19 +513,15 @@ spgpuStatus_t spgpuMgVectorCreate(spgpuMgMatrix_t A, spgpuMgVector_t* pV)
 		memset(k, 0, sizeof(*k));
 		if (w == 0 || mg->world == 1)
 			continue;
-		if (r > 0) {                       /* lower neighbour's UPPER zones */
+		if (r > 0) {                       /* lower neighbour's UPPER zone */
 			const size_t nb = (size_t)(A->hi[r - 1] - A->lo[r - 1]);
-			k->peerLoUpperZone[0] = (char*)v->ext[r - 1] + (w + nb) * es;
-			k->peerLoUpperZone[1] = (char*)v->alt[r - 1] + w * es;
+			k->peerLoUpperZone = (char*)v->ext[r - 1] + (w + nb) * es;
 			k->peerFlagsLo = mg->flags[r - 1];
 		}
-		if (r < mg->world - 1) {           /* upper neighbour's LOWER zones */
-			k->peerHiLowerZone[0] = v->ext[r + 1];
-			k->peerHiLowerZone[1] = v->alt[r + 1];
+		if (r < mg->world - 1) {           /* upper neighbour's LOWER zone */
+			k->peerHiLowerZone = v->ext[r + 1];
 			k->peerFlagsHi = mg->flags[r + 1];
 		}
-		k->myLoZoneOdd = v->alt[r];
-		k->myHiZoneOdd = (char*)v->alt[r] + w * es;
 		k->myFlags = mg->flags[r];
 	}
 	for (r = 0; r < mg->world; ++r) {
@@ -550,7 +543,6 @@ void spgpuMgVectorDestroy(spgpuMgVector_t v)
 		use_rank(v->A->mg, r);
 		cudaStreamSynchronize(rank_stream(v->A->mg, r));
 		if (v->ext[r]) cudaFree(v->ext[r]);
-		if (v->alt[r]) cudaFree(v->alt[r]);
 		if (v->full[r]) cudaFree(v->full[r]);
 	}
 	cudaSetDevice(previous);

@@ -148,25 +148,12 @@ template <typename T> struct XPlain {
 	__device__ __forceinline__ T ld(int c) const { return __ldg(x + c); }
 };
 
-/*
- * Boundary rows of the kernel fused with the halo exchange (ext_halo.cu): the two halo zones of
- * x_ext = [lower zone | owned | upper zone] are written by PEER GPUs during the launch, so they are
- * read with coherent loads (ld.global.ca after the CTA's acquire on the ready flag; .nc loads are
- * outside the memory model), and odd-numbered exchanges use a second pair of zones outside x_ext
- * (double buffering: dLo / dHi = element distance from a zone inside x_ext to its twin, 0 for even
- * exchanges).  c < loEnd addresses the lower zone, c >= hiBegin the upper one.
- */
-template <typename T> struct XZones {
+/* x entries that a PEER GPU may write during the launch (halo zones of the fused kernels, ext_halo.cu): plain weak
+ * loads (ld.global, SASS LDG.E) -- inside the memory model, ordered after the CTA's acquire on the ready flag; .nc
+ * loads are not */
+template <typename T> struct XWeak {
 	const T* x;
-	long long dLo, dHi;
-	int loEnd, hiBegin;
-	__device__ __forceinline__ T ld(int c) const
-	{
-		const T* p = x + c;
-		if (c < loEnd) p += dLo;
-		else if (c >= hiBegin) p += dHi;
-		return __ldca(p);
-	}
+	__device__ __forceinline__ T ld(int c) const { return x[c]; }
 };
 
 /* ---- warp helpers --------------------------------------------------------- */

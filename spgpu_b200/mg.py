@@ -17,9 +17,10 @@ the two halo zones are filled from the neighbours' boundary entries:
     first CTAs store this rank's boundary entries straight into the neighbours' halo
     zones through CUDA-IPC peer pointers over NVLink and publish a sequence number;
     the interior row blocks are scheduled first and the row blocks that read a halo
-    zone late (they wait on the local ready flag).  The zones are double-buffered by
-    the parity of the sequence number, so there are no acknowledgements and
-    neighbours may drift a whole kernel apart.  Transfer and multiply overlap inside
+    zone late (they wait on the local ready flag).  A rank acknowledges an exchange
+    when its NEXT fused kernel starts (stream order says the rows that read the zones
+    have finished), so the row blocks carry no tickets, fences or barriers for it.
+    Neighbours may drift most of a kernel apart.  Transfer and multiply overlap inside
     one launch.
   * mode "push":  each rank's spgpuDhaloPush kernel stores its boundary entries
     straight into the neighbour's halo zone through a CUDA-IPC peer pointer over
@@ -258,7 +259,7 @@ class HaloExchange:
 class PeerHalo:
     """NVLink peer stores + flags between the rank processes (CUDA IPC): the separate-kernel exchange
     (exchange / wait / ack, exchange_fused / ack_fused) and the links of the kernels that carry the
-    exchange inside the SpMV (spgpu?{hell,hdia}spmvHalo[Dot], double-buffered zones, no acks)."""
+    exchange inside the SpMV (spgpu?{hell,hdia}spmvHalo[Dot]: their own flag words and sequence numbers)."""
 
     def __init__(self, L, handle, rank, world, x_ext_ptr, ext_len, halo, group=None, itemsize=8):
         from .capi import HALO_FLAG_WORDS, HaloLinks
@@ -271,38 +272,33 @@ class PeerHalo:
         self.flags = flags.value
         self._flag_view = _as_tensor(self.flags, HALO_FLAG_WORDS, torch.int32)
         self._flag_view.zero_()
-        # the ODD zone pair of the fused protocol: [lower | upper], `halo` elements each
-        alt = ctypes.c_void_p()
-        assert L.spgpuDeviceAlloc(ctypes.byref(alt), max(2 * halo * itemsize, 16)) == 0
-        self.alt = alt.value
         torch.cuda.synchronize()
-        hx, hf, ha = ((ctypes.c_char * 64)() for _ in range(3))
+        hx, hf = ((ctypes.c_char * 64)() for _ in range(2))
         assert L.spgpuIpcGetHandle(x_ext_ptr, hx) == 0
         assert L.spgpuIpcGetHandle(self.flags, hf) == 0
-        assert L.spgpuIpcGetHandle(self.alt, ha) == 0
-        mine = (bytes(hx), bytes(hf), ext_len, bytes(ha))
+        mine = (bytes(hx), bytes(hf), ext_len)
         everyone = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
         self.peer = {}
         for nb in (rank - 1, rank + 1):
             if 0 <= nb < world:
                 opened = []
-                for blob in (everyone[nb][0], everyone[nb][1], everyone[nb][3]):
+                for blob in (everyone[nb][0], everyone[nb][1]):
                     q = ctypes.c_void_p()
                     rc = L.spgpuIpcOpenHandle((ctypes.c_char * 64).from_buffer_copy(blob), ctypes.byref(q))
                     assert rc == 0, f"cudaIpcOpenMemHandle -> {rc}"
                     opened.append(q.value)
-                self.peer[nb] = (opened[0], opened[1], everyone[nb][2], opened[2])
+                self.peer[nb] = (opened[0], opened[1], everyone[nb][2])
         lo, hi = self.peer.get(rank - 1), self.peer.get(rank + 1)
         w, b = halo, itemsize
         lk = HaloLinks()
-        if lo:      # the lower neighbour's UPPER zones: inside its x_ext (even), second half of its alt block (odd)
-            lk.peerLoUpperZone[0], lk.peerLoUpperZone[1] = lo[0] + b * (lo[2] - w), lo[3] + b * w
+        if lo:      # the lower neighbour's UPPER zone: the end of its x_ext
+            lk.peerLoUpperZone = lo[0] + b * (lo[2] - w)
             lk.peerFlagsLo = lo[1]
-        if hi:      # the upper neighbour's LOWER zones: start of its x_ext (even), first half of its alt block (odd)
-            lk.peerHiLowerZone[0], lk.peerHiLowerZone[1] = hi[0], hi[3]
+        if hi:      # the upper neighbour's LOWER zone: the start of its x_ext
+            lk.peerHiLowerZone = hi[0]
             lk.peerFlagsHi = hi[1]
-        lk.myLoZoneOdd, lk.myHiZoneOdd, lk.myFlags = self.alt, self.alt + b * w, self.flags
+        lk.myFlags = self.flags
         self.links = lk
         dist.barrier(group=group)
 
@@ -321,10 +317,10 @@ class PeerHalo:
             if hi_nb in self.peer:
                 L.spgpuWaitFlag(h, self.flags + 4 * 3, seq - 1)
         if lo_nb in self.peer:       # my first w owned entries -> their upper halo, their flag[1]
-            px, pf, plen, _ = self.peer[lo_nb]
+            px, pf, plen = self.peer[lo_nb]
             L.spgpuHaloPush(h, px + b * (plen - w), self.x_ptr + b * w, w * b, pf + 4 * 1, seq)
         if hi_nb in self.peer:       # my last w owned entries -> their lower halo, their flag[0]
-            px, pf, plen, _ = self.peer[hi_nb]
+            px, pf, plen = self.peer[hi_nb]
             L.spgpuHaloPush(h, px, self.x_ptr + b * n, w * b, pf + 4 * 0, seq)
 
     def wait(self):
@@ -383,10 +379,9 @@ class PeerHalo:
 
     def close(self):
         torch.cuda.synchronize()
-        for px, pf, _, pa in self.peer.values():
+        for px, pf, _ in self.peer.values():
             self.L.spgpuIpcCloseHandle(px)
             self.L.spgpuIpcCloseHandle(pf)
-            self.L.spgpuIpcCloseHandle(pa)
         self.peer = {}
 
 

@@ -38,49 +38,31 @@ def _middle_block(n=24, world=3, rank=1, sym="D"):
 
 
 class Emulated:
-    """One rank's view with emulated neighbours: flag blocks, the neighbours' zones (as plain local buffers),
-    this rank's odd zones, and the spgpuHaloLinks struct pointing at them."""
+    """One rank's view with emulated neighbours: flag blocks, the neighbours' zones (as plain local buffers) and the
+    spgpuHaloLinks struct pointing at them.  Fused protocol words: [4] ready-from-below [5] ready-from-above
+    [6] ack-from-below [7] ack-from-above."""
 
     def __init__(self, halo, tdtype, has_lo=True, has_hi=True):
         import torch
         nan = float("nan")
         self.my_flags = torch.zeros(16, dtype=torch.int32, device="cuda")
         self.pf = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(2)]
-        # [side][parity]: where my pushes land
-        self.pz = [[torch.full((max(halo, 1),), nan, dtype=tdtype, device="cuda") for _ in range(2)] for _ in range(2)]
-        self.alt = torch.full((2 * max(halo, 1),), nan, dtype=tdtype, device="cuda")
+        self.pz = [torch.full((max(halo, 1),), nan, dtype=tdtype, device="cuda") for _ in range(2)]   # where my pushes land
         lk = capi.HaloLinks()
         if has_lo:
-            lk.peerLoUpperZone[0], lk.peerLoUpperZone[1] = self.pz[0][0].data_ptr(), self.pz[0][1].data_ptr()
-            lk.peerFlagsLo = self.pf[0].data_ptr()
+            lk.peerLoUpperZone, lk.peerFlagsLo = self.pz[0].data_ptr(), self.pf[0].data_ptr()
         if has_hi:
-            lk.peerHiLowerZone[0], lk.peerHiLowerZone[1] = self.pz[1][0].data_ptr(), self.pz[1][1].data_ptr()
-            lk.peerFlagsHi = self.pf[1].data_ptr()
-        lk.myLoZoneOdd = self.alt.data_ptr()
-        lk.myHiZoneOdd = self.alt.data_ptr() + halo * self.alt.element_size()
+            lk.peerHiLowerZone, lk.peerFlagsHi = self.pz[1].data_ptr(), self.pf[1].data_ptr()
         lk.myFlags = self.my_flags.data_ptr()
         self.links, self.halo = lk, halo
 
     def ref(self):
         return ctypes.byref(self.links)
 
-    def place_halos(self, dx, x_ext, nrows, seq, tdtype):
-        """what the neighbours' pushes of exchange `seq` leave behind: even -> zones inside x_ext, odd -> the odd
-        zones; the OTHER pair is poisoned so that a read from the wrong pair shows"""
-        import torch
-        w = self.halo
-        lo = torch.from_numpy(x_ext[:w].copy()).cuda()
-        hi = torch.from_numpy(x_ext[w + nrows:].copy()).cuda()
-        nan = float("nan")
-        if seq & 1:
-            self.alt[:w] = lo
-            self.alt[w:2 * w] = hi
-            dx[:w] = nan
-            dx[w + nrows:] = nan
-        else:
-            dx[:w] = lo
-            dx[w + nrows:] = hi
-            self.alt[:] = nan
+    def arrived(self, seq):
+        """the neighbours' entries of exchange `seq` are in place and they have consumed mine of seq - 1"""
+        self.my_flags[4] = seq; self.my_flags[5] = seq
+        self.my_flags[6] = seq - 1; self.my_flags[7] = seq - 1
 
 
 @pytest.mark.parametrize("seq", [1, 4])
@@ -93,23 +75,28 @@ def test_spmv_fused_with_halo_exchange(ours, gpu_handle, seq, sym):
     dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
     dx = util.to_dev(x_ext)
     em = Emulated(plane, tdt)
-    em.place_halos(dx, x_ext, loc.nrows, seq, tdt)
-    em.my_flags[4] = seq; em.my_flags[5] = seq          # both neighbours' entries "have arrived"
+    em.arrived(seq)
     dz = torch.full((loc.nrows,), float("nan"), dtype=tdt, device="cuda")
     getattr(ours, f"spgpu{sym}hellspmvHalo")(gpu_handle, dz.data_ptr(), 0, t.scalar(1.0), dv.data_ptr(), di.data_ptr(), 32,
                                              dho.data_ptr(), drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), t.scalar(0.0), 0,
                                              plane, em.ref(), seq)
     torch.cuda.synchronize()
     util.assert_rows_close(dz.cpu().numpy(), want, scale, sym, f"fused spmv+halo {sym}")
-    # my first / last owned plane landed in the neighbours' zones of this parity, and only there
-    par = seq & 1
-    np.testing.assert_array_equal(em.pz[0][par].cpu().numpy(), x_ext[plane:2 * plane])
-    np.testing.assert_array_equal(em.pz[1][par].cpu().numpy(), x_ext[loc.nrows:loc.nrows + plane])
-    other = em.pz[0][1 - par]
-    assert torch.isnan(other.real if tdt.is_complex else other).all()
+    # my first / last owned plane landed in the neighbours' zones
+    np.testing.assert_array_equal(em.pz[0].cpu().numpy(), x_ext[plane:2 * plane])
+    np.testing.assert_array_equal(em.pz[1].cpu().numpy(), x_ext[loc.nrows:loc.nrows + plane])
     lo_f, hi_f = em.pf[0].cpu().numpy(), em.pf[1].cpu().numpy()
-    assert lo_f[5] == seq and hi_f[4] == seq            # lower neighbour: ready-from-above; upper: ready-from-below
+    assert lo_f[5] == seq and lo_f[7] == seq - 1        # lower neighbour: ready-from-above; ack-from-above of the PREVIOUS
+    assert hi_f[4] == seq and hi_f[6] == seq - 1        # exchange (this kernel started = that one is over); upper likewise
     assert lo_f[4] == 0 and hi_f[5] == 0 and not lo_f[:4].any() and not hi_f[:4].any()
+    # the next exchange: the same call again
+    em.arrived(seq + 1)
+    getattr(ours, f"spgpu{sym}hellspmvHalo")(gpu_handle, dz.data_ptr(), 0, t.scalar(1.0), dv.data_ptr(), di.data_ptr(), 32,
+                                             dho.data_ptr(), drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), t.scalar(0.0), 0,
+                                             plane, em.ref(), seq + 1)
+    torch.cuda.synchronize()
+    util.assert_rows_close(dz.cpu().numpy(), want, scale, sym, f"fused spmv+halo {sym}, second exchange")
+    assert em.pf[0].cpu().numpy()[7] == seq and em.pf[1].cpu().numpy()[6] == seq
     assert ours.spgpuGetDeviceStatus(gpu_handle, 0) == 0
 
 
@@ -143,18 +130,22 @@ def test_fused_rows_not_a_multiple_of_128_and_late_flags(ours, gpu_handle, seq):
     dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
     dx = util.to_dev(x_ext)
     em = Emulated(halo, torch.float64)
-    # both pairs poisoned for now
-    dx[:halo] = float("nan"); dx[halo + loc.nrows:] = float("nan")
+    lo_vals = torch.from_numpy(x_ext[:halo].copy()).cuda()
+    hi_vals = torch.from_numpy(x_ext[halo + loc.nrows:].copy()).cuda()
     dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
     late = torch.cuda.Stream()
+
+    def neighbours_arrive():
+        dx[:halo] = lo_vals
+        dx[halo + loc.nrows:] = hi_vals
+        em.my_flags[4:6] = seq
     with torch.cuda.stream(late):
         # run everything the late stream will do ONCE beforehand: the first launch of a kernel loads its module
         # (CUDA lazy loading), and a module load waits for running kernels -- i.e. for the spinning SpMV
         torch.cuda._sleep(1000)
-        em.place_halos(dx, x_ext, loc.nrows, seq, torch.float64)
-        em.my_flags[4:6] = seq
-        em.alt[:] = float("nan")
+        neighbours_arrive()
         em.my_flags.zero_()
+        em.my_flags[6:8] = seq - 1                        # my previous pushes have been consumed
         dx[:halo] = float("nan"); dx[halo + loc.nrows:] = float("nan")
     torch.cuda.synchronize()
     ours.spgpuSetTuning(gpu_handle, b"spinTimeoutMs", 5000)
@@ -162,8 +153,7 @@ def test_fused_rows_not_a_multiple_of_128_and_late_flags(ours, gpu_handle, seq):
                             drs.data_ptr(), 9, loc.nrows, dx.data_ptr(), 0.0, 0, halo, em.ref(), seq)
     with torch.cuda.stream(late):
         torch.cuda._sleep(200_000_000)                    # ~0.1 s: the boundary blocks are spinning by now
-        em.place_halos(dx, x_ext, loc.nrows, seq, torch.float64)
-        em.my_flags[4:6] = seq
+        neighbours_arrive()
     torch.cuda.synchronize()
     ours.spgpuSetTuning(gpu_handle, b"spinTimeoutMs", 20000)
     assert ours.spgpuGetDeviceStatus(gpu_handle, 1) == 0
@@ -175,8 +165,7 @@ def test_fused_rows_not_a_multiple_of_128_and_late_flags(ours, gpu_handle, seq):
 def test_hdia_spmv_fused_with_halo_exchange(ours, gpu_handle, seq, rank):
     """spgpuDhdiaspmvHalo on the first / a middle / the last block of a 27-point stencil split in three
     (emulated neighbours): rows equal the global product, boundary entries land in the neighbours'
-    zones of the exchange's parity, flags carry seq; also equal to the plain spgpuDhdiaspmv on the same
-    block bit for bit"""
+    zones, ready and ack words carry seq; also equal to the plain spgpuDhdiaspmv on the same block bit for bit"""
     import torch
     n, world = 16, 3
     coo = G.stencil3d_27pt(n)
@@ -194,28 +183,22 @@ def test_hdia_spmv_fused_with_halo_exchange(ours, gpu_handle, seq, rank):
     dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
     has_lo, has_hi = rank > 0, rank < world - 1
     em = Emulated(halo, torch.float64, has_lo, has_hi)
-    if has_lo and has_hi:
-        em.place_halos(dx, x_ext, loc.nrows, seq, torch.float64)
-    elif seq & 1:                                         # only the zone that has a neighbour moves to the odd pair
-        if has_lo:
-            em.alt[:halo] = dx[:halo]; dx[:halo] = float("nan")
-        if has_hi:
-            em.alt[halo:] = dx[halo + loc.nrows:]; dx[halo + loc.nrows:] = float("nan")
-    em.my_flags[4] = seq; em.my_flags[5] = seq
+    em.arrived(seq)
     ours.spgpuDhdiaspmvHalo(gpu_handle, dz.data_ptr(), dy.data_ptr(), 1.5, dv.data_ptr(), doff.data_ptr(), 32, dho.data_ptr(),
                             loc.nrows, loc.ext_len, dx.data_ptr(), -0.5, halo, em.ref(), seq)
     torch.cuda.synchronize()
     scale = util.row_scale(coo, x, y, 1.5, -0.5)[loc.lo:loc.hi]
     util.assert_rows_close(dz.cpu().numpy(), want, scale, "D", "fused hdia spmv+halo")
-    par = seq & 1
     if has_lo:
-        np.testing.assert_array_equal(em.pz[0][par].cpu().numpy(), x_ext[halo:2 * halo])
-        assert em.pf[0].cpu().numpy()[5] == seq
+        np.testing.assert_array_equal(em.pz[0].cpu().numpy(), x_ext[halo:2 * halo])
+        f = em.pf[0].cpu().numpy()
+        assert f[5] == seq and f[7] == seq - 1
     if has_hi:
-        np.testing.assert_array_equal(em.pz[1][par].cpu().numpy(), x_ext[loc.nrows:loc.nrows + halo])
-        assert em.pf[1].cpu().numpy()[4] == seq
-    # the plain kernel on the same block with every zone inside x_ext
-    dx2 = util.to_dev(x_ext)
+        np.testing.assert_array_equal(em.pz[1].cpu().numpy(), x_ext[loc.nrows:loc.nrows + halo])
+        f = em.pf[1].cpu().numpy()
+        assert f[4] == seq and f[6] == seq - 1
+    # the plain kernel on the same block
+    dx2 = dx
     dz2 = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
     T = util.TYPES["D"]
     ours.spgpuDhdiaspmv(gpu_handle, dz2.data_ptr(), dy.data_ptr(), T.scalar(1.5), dv.data_ptr(), doff.data_ptr(), 32,
@@ -360,8 +343,7 @@ def test_spmv_halo_dot_with_fused_allreduce(ours, gpu_handle, sym):
     tol = 1e-12 if sym in "DZ" else 2e-6
     for seq, ar_on in ((1, False), (2, True)):
         em = Emulated(plane, tdt)
-        em.place_halos(dx, x_ext, loc.nrows, seq, tdt)
-        em.my_flags[4] = seq; em.my_flags[5] = seq
+        em.arrived(seq)
         dz = torch.full((loc.nrows,), float("nan"), dtype=tdt, device="cuda")
         dres = torch.full((1,), float("nan"), dtype=tdt, device="cuda")
         tabs, ptrs, args = _tables(3, 1, 5, {0: (100.0, 7.0), 2: (-50.0, 1.0)})
@@ -390,9 +372,8 @@ def test_device_resident_sequence_numbers(ours, gpu_handle):
     assert ours.spgpuSetSeqCounters(gpu_handle, counters.data_ptr(), counters.data_ptr() + 4) == 0
     try:
         em = Emulated(plane, torch.float64)
-        for k in (7, 8):                                                     # two exchanges: 7 (odd pair) and 8 (even)
-            em.place_halos(dx, x_ext, loc.nrows, k, torch.float64)
-            em.my_flags[4] = k; em.my_flags[5] = k
+        for k in (7, 8):                                                     # two exchanges: 7 and 8
+            em.arrived(k)
             dz = torch.full((loc.nrows,), float("nan"), dtype=torch.float64, device="cuda")
             ours.spgpuDhellspmvHalo(gpu_handle, dz.data_ptr(), 0, 1.0, dv.data_ptr(), di.data_ptr(), 32, dho.data_ptr(),
                                     drs.data_ptr(), 7, loc.nrows, dx.data_ptr(), 0.0, 0, plane, em.ref(), 0)
@@ -401,6 +382,7 @@ def test_device_resident_sequence_numbers(ours, gpu_handle):
             util.assert_rows_close(dz.cpu().numpy(), want, scale, "D", "fused spmv+halo, device seq")
             assert int(counters[0].item()) == k
             assert em.pf[0].cpu().numpy()[5] == k and em.pf[1].cpu().numpy()[4] == k
+            assert em.pf[0].cpu().numpy()[7] == k - 1 and em.pf[1].cpu().numpy()[6] == k - 1
         # all-reduce number 11, world 2, this rank 0: the peer's slot is pre-filled
         tabs, ptrs, args = _tables(2, 0, 11, {1: (2.5, 0.0)})
         args.seq = 0
@@ -419,7 +401,7 @@ def test_halo_trace(ours, gpu_handle):
     dv, di, dho, drs = (util.to_dev(a) for a in (loc.values, loc.indices, loc.hack_offsets, loc.rs))
     dx = util.to_dev(x_ext)
     em = Emulated(plane, torch.float64)
-    em.my_flags[4] = 2; em.my_flags[5] = 2
+    em.arrived(2)
     dz = torch.zeros(loc.nrows, dtype=torch.float64, device="cuda")
     assert ours.spgpuSetTuning(gpu_handle, b"haloTrace", 1) == 0
     try:
