@@ -944,6 +944,20 @@ def main():
         ker_pairs.append((a, b))
     torch.cuda.synchronize()
     ker_ms = float(np.mean([a.elapsed_time(b) for a, b in ker_pairs]))
+    # ... and back to back, the way the timed steps run (no event between launches): what a partitioned step has to
+    # be compared with to see what the exchange costs
+    ker_b2b_ms = None
+    if not flush_l2:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(K):
+            step()
+        b.record(stream)
+        torch.cuda.synchronize()
+        tb = torch.tensor([a.elapsed_time(b) / K], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        ker_b2b_ms = float(tb.item())
     peak, peak_src = measured_peak()
     achieved = w["bytes"] / (ker_ms * 1e-3) / 1e9
     traffic = None
@@ -954,7 +968,10 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": w.get("kernel", f"{w['kind']}_spmv_kernel<{w['sym']}>"),
-                "kernel_ms": ker_ms, "algorithmic_bytes_per_launch": w["bytes"]}
+                "kernel_ms": ker_ms, "algorithmic_bytes_per_launch": w["bytes"],
+                # the same kernel launched K times back to back WITHOUT the exchange (max over ranks): the partitioned
+                # step minus this is what the halo exchange costs
+                "kernel_back_to_back_ms": ker_b2b_ms}
 
     # ---------------- the REFERENCE'S OWN kernels on the same buffers (N=1) ------
     # SURVEY 8(d) "reference on B200" column: oracle/_ref/libspgpu_ref.so = the reference's unmodified sources

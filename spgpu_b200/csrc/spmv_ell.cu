@@ -52,21 +52,21 @@ ell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
  * 64 warps per SM, ROWS = 2 (a CTA covers 256 consecutive rows; lane t owns rows t and t+128, so
  * every warp-level load stays one coalesced run) at 32-40 with twice the loads per lane.
  */
-template <typename T, int NS, int ROWS, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+template <typename T, int NS, int ROWS, int MINB, int BLOCK = 128>
+__global__ void __launch_bounds__(BLOCK, MINB * 128 / BLOCK)
 ell_spmv_short_kernel(T* __restrict__ z, const T* y, T alpha,
 	const T* __restrict__ cM, const int* __restrict__ rP, int cMPitch,
 	int rPPitch, const int* __restrict__ rS, const int* __restrict__ rIdx,
 	int rows, const T* __restrict__ x, T beta, int baseIndex)
 {
-	const unsigned first = blockIdx.x * (128u * ROWS) + threadIdx.x;
+	const unsigned first = blockIdx.x * ((unsigned)BLOCK * ROWS) + threadIdx.x;
 	const bool useBeta = Num<T>::nonzero(beta);
 	int col[ROWS][NS];
 	T a[ROWS][NS];
 	int len[ROWS];
 #pragma unroll
 	for (int r = 0; r < ROWS; ++r) {
-		const unsigned i = first + 128u * r;
+		const unsigned i = first + (unsigned)BLOCK * r;
 		const bool live = i < (unsigned)rows;
 		len[r] = live ? (rS ? ld_stream(rS + i) : NS) : 0;
 #pragma unroll
@@ -81,7 +81,7 @@ ell_spmv_short_kernel(T* __restrict__ z, const T* y, T alpha,
 	}
 #pragma unroll
 	for (int r = 0; r < ROWS; ++r) {
-		const unsigned i = first + 128u * r;
+		const unsigned i = first + (unsigned)BLOCK * r;
 		const bool live = i < (unsigned)rows;
 		const unsigned out = (live && rIdx) ? (unsigned)__ldg(rIdx + i) : i;
 		T yv = Num<T>::zero();
@@ -114,7 +114,16 @@ static void ell_spmv_short_launch(spgpuHandle_t handle, int rowsPerLane, T* z, c
 	constexpr int W = sizeof(T) / 4;
 	constexpr int MINB1 = NS * (1 + W) <= 16 ? 16 : NS * (1 + W) <= 24 ? 12 : 8;
 	constexpr int MINB2 = 2 * NS * (1 + W) <= 32 ? 10 : 2 * NS * (1 + W) <= 48 ? 8 : 5;
-	if (rowsPerLane >= 2)
+	if (rowsPerLane == 3)              /* ellRows = 3 / 4: one row per lane in CTAs of 256 / 512 threads (fewer CTA launches) */
+		ell_spmv_short_kernel<T, NS, 1, MINB1, 256><<<spgpu_ceil_div(rows, 256), 256, 0, s>>>(
+			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
+	else if (rowsPerLane == 4)
+		ell_spmv_short_kernel<T, NS, 1, MINB1, 512><<<spgpu_ceil_div(rows, 512), 512, 0, s>>>(
+			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
+	else if (rowsPerLane == 5)         /* 64-thread CTAs */
+		ell_spmv_short_kernel<T, NS, 1, MINB1, 64><<<spgpu_ceil_div(rows, 64), 64, 0, s>>>(
+			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
+	else if (rowsPerLane >= 2)
 		ell_spmv_short_kernel<T, NS, 2, MINB2><<<spgpu_ceil_div(rows, 256), 128, 0, s>>>(
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
 	else
