@@ -113,6 +113,28 @@ def algorithmic_bytes_hell(nnz, rows, hacks, ncols_read, sizeof_t, beta_nonzero=
     return nnz * (sizeof_t + 4) + 4 * rows + 4 * hacks + ncols_read * sizeof_t + rows * sizeof_t * (2 if beta_nonzero else 1)
 
 
+def hell_matrix_floor_bytes(A, sizeof_t):
+    """DRAM bytes of the matrix arrays a HELL SpMV cannot avoid at a fetch granularity of G bytes: slot k of a hack is
+    a run of hackSize values (and one of hackSize indices); a G-byte piece of that run has to come in as soon as ONE of
+    its rows is longer than k.  G = 32 is a sector, 64 what `ld.global.L2::64B` fetches, 128 the line every other
+    load flavour fetches on B200 (bench/probes/sector_probe.cu).  Returns {"32B": .., "64B": .., "128B": ..}."""
+    import torch
+    rs = A.rs.to(torch.int64)
+    hs = A.hack_size
+    pad = (-rs.numel()) % hs
+    if pad:
+        rs = torch.cat([rs, torch.zeros(pad, dtype=rs.dtype, device=rs.device)])
+    out = {}
+    for G in (32, 64, 128):
+        total = 0
+        for esz in (sizeof_t, 4):                      # the value run and the index run of every slot
+            rows_per_piece = max(1, min(hs, G // esz))
+            piece = max(G, rows_per_piece * esz) if rows_per_piece == hs else G
+            total += int(rs.view(-1, rows_per_piece).max(dim=1).values.sum().item()) * piece
+        out[f"{G}B"] = total
+    return out
+
+
 def build_workload(name, rank, world, device, n_override=None, global_columns=False):
     """Returns a dict describing this rank's share of the workload (device resident)."""
     import torch
@@ -972,6 +994,13 @@ def main():
                 # the same kernel launched K times back to back WITHOUT the exchange (max over ranks): the partitioned
                 # step minus this is what the halo exchange costs
                 "kernel_back_to_back_ms": ker_b2b_ms}
+    if w["kind"] == "hell":
+        # what the FORMAT costs at the fetch granularities the hardware has: matrix bytes only
+        try:
+            roofline["matrix_floor_bytes_by_fetch_granularity"] = hell_matrix_floor_bytes(w["A"], w["sizeof"])
+            roofline["matrix_algorithmic_bytes"] = int(w["nnz"]) * (w["sizeof"] + 4)
+        except Exception as exc:
+            print(f"matrix floor not computed: {exc!r}", file=sys.stderr, flush=True)
 
     # ---------------- the REFERENCE'S OWN kernels on the same buffers (N=1) ------
     # SURVEY 8(d) "reference on B200" column: oracle/_ref/libspgpu_ref.so = the reference's unmodified sources

@@ -507,7 +507,7 @@ static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 			/* Occupancy of the dot variants, from measurement on the 512^3 slabs of one of two / one of eight ranks
 			 * (bench/halo_dot_probe.py; plain kernel 1.079 / 0.275 ms): without neighbours 48 resident warps per SM
 			 * for the real types (1.082 ms against 1.094 at the plain kernel's 40); with the halo code 40 warps
-			 * (1.152 / 0.300 ms against 1.231 / 0.305 at 48).  The row walk lives on the edge of being
+			 * (1.152 / 0.300 ms against 1.231 / 0.305 at 48; 36 and 44 warps: 1.20 / 0.314 and 1.24 / 0.323).  The row walk lives on the edge of being
 			 * latency-bound, and how ptxas schedules its loads changes with everything around it.  hellBlock = 192 /
 			 * 256 force the plain kernel's occupancy / 48 warps for an A/B. */
 			constexpr int MD = Num<T>::is_complex ? 8 : 12;

@@ -222,3 +222,29 @@ def test_multivector_reductions_are_one_launch(ours, gpu_handle, dtype):
             getattr(ours, f"spgpu{s}mnrm2")(gpu_handle, util.ptr(outr), n, dx.data_ptr(), count, pitch)
             if count <= 148 * 4:       # same grid shape per vector only when the batch does not shrink the per-vector grid
                 assert abs(outr[v] - one) <= 1e-6 * abs(one)
+
+
+def test_set_stream_with_work_in_flight_orders_the_handle_scratch(ours, gpu_handle):
+    """The handle's reduction scratch (per-CTA partials, the ticket) is reused in stream order.  spgpuSetStream to a
+    second stream while a reduction is still running on the first must not let the next reduction overtake it
+    (reference core.c:62-72 only swaps the pointer; its static reduction arrays had the same hazard):
+    the new stream waits for an event recorded on the old one."""
+    import torch
+    n = 1 << 26
+    a = torch.rand(n, dtype=torch.float64, device="cuda")
+    b = torch.rand(1 << 20, dtype=torch.float64, device="cuda")
+    want_a, want_b = float(torch.dot(a, a).item()), float(torch.dot(b, b).item())
+    res = torch.zeros(4, dtype=torch.float64, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    try:
+        for _ in range(5):
+            ours.spgpuSetStream(gpu_handle, s1.cuda_stream)
+            ours.spgpuDdotDev(gpu_handle, n, a.data_ptr(), a.data_ptr(), res.data_ptr())           # ~0.17 ms on s1
+            ours.spgpuSetStream(gpu_handle, s2.cuda_stream)
+            ours.spgpuDdotDev(gpu_handle, b.numel(), b.data_ptr(), b.data_ptr(), res.data_ptr() + 8)   # short, on s2
+            torch.cuda.synchronize()
+            assert abs(float(res[0].item()) - want_a) <= 1e-11 * want_a
+            assert abs(float(res[1].item()) - want_b) <= 1e-11 * want_b
+    finally:
+        ours.spgpuSetStream(gpu_handle, None)
