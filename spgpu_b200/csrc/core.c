@@ -32,6 +32,7 @@ static void default_tuning(SpgpuTuning* t)
 	t->redInflight = 0;
 	t->ellShortMinB = 0;
 	t->hellPrefetch = 0;
+	t->hdiaPrefetch = 0;
 }
 
 spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
@@ -283,7 +284,8 @@ int spgpuGetDeviceStatus(spgpuHandle_t handle, int clear)
 	X(l2Fetch)                \
 	X(redInflight)            \
 	X(ellShortMinB)           \
-	X(hellPrefetch)
+	X(hellPrefetch)           \
+	X(hdiaPrefetch)
 
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value)
 {

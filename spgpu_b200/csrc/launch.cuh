@@ -27,7 +27,7 @@ static inline void spgpu_count_launch(spgpuHandle_t handle)
 
 static inline const SpgpuTuning* spgpu_tuning(spgpuHandle_t handle)
 {
-	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 0, 0, 8, 8, 20000, 0, 0, 0, 0, 0 };
+	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 0, 0, 8, 8, 20000, 0, 0, 0, 0, 0, 0 };
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	return h->magic == SPGPU_PRIV_MAGIC ? &h->tune : &fallback;
 }

@@ -47,6 +47,7 @@ typedef struct SpgpuTuning {
 	                      * (32 / 64 / 128) when the key is set -- a DEVICE-wide limit, an experiment knob */
 	int redInflight;     /* reductions: 16-byte packs a thread keeps in flight per input (2, 4 or 8; 0 = default 4) */
 	int ellShortMinB;    /* (reserved) */
+	int hdiaPrefetch;    /* HDIA: the same look-ahead for hackOffsets and the hack's slice of offsets[] (0 = default 2 waves, < 0 = off) */
 	int hellPrefetch;    /* HELL: waves of resident CTAs ahead of which a warp prefetches its hackOffsets entry into L2 (0 = default 2, < 0 = off) */
 } SpgpuTuning;
 

@@ -26,9 +26,9 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM,
 	const int* __restrict__ offsets, int hackSizeRt,
 	const int* __restrict__ hackOffsets, int rows, int cols,
-	const T* __restrict__ x, T beta)
+	const T* __restrict__ x, T beta, int prefetchHacks)
 {
-	const HdiaArgs<T> a = { z, y, alpha, dM, offsets, hackSizeRt, hackOffsets, rows, cols, x, beta };
+	const HdiaArgs<T> a = { z, y, alpha, dM, offsets, hackSizeRt, hackOffsets, rows, cols, x, beta, prefetchHacks };
 	T unused;
 	hdia_warp_rows_value<T, UNROLL, HACK, PREDICATED>(a, (blockIdx.x * BLOCK + threadIdx.x) & ~31u, unused);
 }
@@ -286,23 +286,26 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 		spgpu_count_launch(handle);
 		return;
 	}
+	/* hdiaPrefetch tuning key: waves of resident CTAs (8 per SM, 128 / hackSize hacks each) a warp looks ahead; 0 = 2, < 0 off */
+	const int pfWaves = t->hdiaPrefetch == 0 ? 2 : t->hdiaPrefetch;
+	const int pf = pfWaves < 0 ? 0 : pfWaves * 8 * handle->multiProcessorCount * (hackSize <= 128 ? 128 / hackSize : 1);
 	/* occupancy / round-size knob (registers vs resident warps): hdiaBlock >=256 -> 48 warps, 192 -> 40, 176 -> 36,
 	 * 160 -> 24 with twice the unroll, 64 -> 64-thread CTAs, 8 -> rounds of 8 diagonals, else 32 warps, rounds of 9 */
 	if (hackSize == 32 && t->hdiaVariant == 3) {
-		hdia_spmv_kernel<T, UNROLL, 32, 8, true><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		hdia_spmv_kernel<T, UNROLL, 32, 8, true><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	} else if (hackSize == 32) {
-		if (t->hdiaBlock >= 256)      hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else if (t->hdiaBlock == 224) hdia_spmv_kernel<T, 4, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else if (t->hdiaBlock == 8)   hdia_spmv_kernel<T, U8, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else if (t->hdiaBlock == 64)  hdia_spmv_kernel<T, UNROLL, 32, 16, false, 64><<<spgpu_ceil_div(rows, 64), 64, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else if (t->hdiaBlock == 176) hdia_spmv_kernel<T, UNROLL, 32, 9><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else if (t->hdiaBlock == 160) hdia_spmv_kernel<T, 2 * U8, 32, 6><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else if (t->hdiaBlock == 192) hdia_spmv_kernel<T, UNROLL, 32, 10><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
-		else                          hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		if (t->hdiaBlock >= 256)      hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 224) hdia_spmv_kernel<T, 4, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 8)   hdia_spmv_kernel<T, U8, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 64)  hdia_spmv_kernel<T, UNROLL, 32, 16, false, 64><<<spgpu_ceil_div(rows, 64), 64, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 176) hdia_spmv_kernel<T, UNROLL, 32, 9><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 160) hdia_spmv_kernel<T, 2 * U8, 32, 6><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 192) hdia_spmv_kernel<T, UNROLL, 32, 10><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else                          hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	} else if (hackSize == 64) {
-		hdia_spmv_kernel<T, UNROLL, 64, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		hdia_spmv_kernel<T, UNROLL, 64, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	} else {
-		hdia_spmv_kernel<T, UNROLL, 0, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta);
+		hdia_spmv_kernel<T, UNROLL, 0, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	}
 	spgpu_count_launch(handle);
 }

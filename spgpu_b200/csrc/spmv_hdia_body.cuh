@@ -29,6 +29,11 @@ struct HdiaArgs {
 	int cols;
 	const T* x;
 	T beta;
+	/* > 0: a warp looks this many hacks ahead -- it asks L2 for that hack's hackOffsets entry and, at the end of its
+	 * life, for that hack's slice of offsets[] (whose position it read at its start, off the critical path).  A warp
+	 * lives hackOffsets -> offsets -> rounds of (cells, x): the first two are tiny reads nobody has touched before,
+	 * HBM latency for 1 % of the bytes; prefetched a couple of waves ahead they are L2 hits. */
+	int prefetchHacks;
 };
 
 /* one round of the direct kernel: UNROLL diagonals starting at diagonal u0 of the 32 whose offsets
@@ -87,6 +92,16 @@ __device__ __forceinline__ void hdia_warp_rows_value_x(const HdiaArgs<T>& a, uns
 		yv = a.y[i];
 
 	const unsigned hack = warpRow / (unsigned)hackSize;
+	int aheadFirst = -1;
+	if (a.prefetchHacks > 0) {
+		const unsigned lastHack = ((unsigned)a.rows - 1u) / (unsigned)hackSize;
+		const unsigned ahead = hack + (unsigned)a.prefetchHacks;
+		if (ahead <= lastHack) {
+			aheadFirst = __ldg(a.hackOffsets + ahead);          /* used only at the very end */
+			if (lane == 0 && ahead + (unsigned)a.prefetchHacks <= lastHack)
+				prefetch_l2(a.hackOffsets + ahead + a.prefetchHacks);
+		}
+	}
 	const int first = __ldg(a.hackOffsets + hack);
 	const int diags = __ldg(a.hackOffsets + hack + 1) - first;
 	const T* cell = a.dM + (long long)first * hackSize + (warpRow % (unsigned)hackSize) + lane;
@@ -108,6 +123,8 @@ __device__ __forceinline__ void hdia_warp_rows_value_x(const HdiaArgs<T>& a, uns
 		zval = spmv_epilogue<T>(acc, a.alpha, a.beta, useBeta, yv);
 		a.z[i] = zval;
 	}
+	if (aheadFirst >= 0 && lane < 2)
+		prefetch_l2(a.offsets + aheadFirst + 32 * lane);        /* up to 64 diagonals of the hack ahead */
 }
 
 template <typename T, int UNROLL, int HACK, bool PREDICATED>

@@ -119,7 +119,8 @@ def test_unstructured_matrix_goes_through_the_all_gather_mode(ours, gpu_handle, 
     t = util.TYPES[s]
     nrows = 1000
     coo = G.random_coo(nrows, nrows, (0, 12), 3, dtype, 1)             # base 1, some empty rows
-    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    hell = F.ell_to_hell(F.coo_to_ell(coo, ell_base=1), 32)
+    assert hell.base == 1
     x = G.random_vector(nrows, dtype, 1, -1, 1)
     single = util.dev_spmv(ours, gpu_handle, "hell", hell, util.upload(hell), x, None, 1.0, 0.0)
     for devices, what in _device_lists()[1:]:
@@ -285,3 +286,52 @@ def test_argument_checks(ours):
         mg.close()
     h = ctypes.c_void_p()
     assert ours.spgpuMgCreate(ctypes.byref(h), (ctypes.c_int * 1)(0), 0) == capi.SPGPU_UNSUPPORTED
+
+
+@pytest.mark.parametrize("hack,base,world", [(64, 1, 2), (32, 1, 3), (96, 0, 2)])
+def test_partitioned_spmv_generic_hack_sizes_and_index_base(ours, gpu_handle, hack, base, world):
+    """a random banded matrix (rows reach at most 100 columns away; ragged rows, some empty; the row count is not a
+    multiple of 128 or of the hack size) with 1-based indices and hack sizes other than 32: the split keeps hack
+    boundaries, the remap keeps the base, the halo width is the measured reach rounded up to 32"""
+    rng = np.random.default_rng(hack + base)
+    n = 5000 + 37
+    lens = rng.integers(0, 12, n)
+    rows = np.repeat(np.arange(n), lens)
+    cols = np.clip(rows + rng.integers(-100, 101, rows.shape[0]), 0, n - 1)
+    key = np.unique(rows.astype(np.int64) * n + cols)
+    rows, cols = (key // n).astype(np.int32), (key % n).astype(np.int32)
+    vals = rng.uniform(-1, 1, rows.shape[0])
+    coo = F.Coo(rows + base, cols + base, vals, n, n, base)
+    hell = F.ell_to_hell(F.coo_to_ell(coo, ell_base=base), hack)
+    assert hell.base == base
+    x = G.random_vector(n, np.float64, 1, -1, 1)
+    y = G.random_vector(n, np.float64, 2, -1, 1)
+    T = util.TYPES["D"]
+    single = util.dev_spmv(ours, gpu_handle, "hell", hell, util.upload(hell), x, y, 1.5, -0.25)
+    want = util.oracle_spmv("hell", hell, x, y, 1.5, -0.25)
+    util.assert_rows_close(single, want, util.row_scale(coo, x, y, 1.5, -0.25), "D", "single-GPU product")
+    import torch
+    lists = [[0] * world]
+    if torch.cuda.device_count() >= world:
+        lists.append(list(range(world)))
+    for devices in lists:
+        mg = Mg(ours, devices)
+        try:
+            A = mg.matrix(hell)
+            halo = ours.spgpuMgMatrixHalo(A)
+            assert 0 < halo <= 128 and halo % 32 == 0, halo
+            lo, hi = ctypes.c_int(), ctypes.c_int()
+            for r in range(world):
+                ours.spgpuMgMatrixRowBlock(A, r, ctypes.byref(lo), ctypes.byref(hi))
+                assert lo.value % hack == 0 and (hi.value % hack == 0 or hi.value == n)
+            vx, vy, vz = mg.vector(A, x), mg.vector(A, y), mg.vector(A)
+            for _ in range(3):
+                assert ours.spgpuMgDhellspmv(mg.h, vz, vy, T.scalar(1.5), A, vx, T.scalar(-0.25)) == 0
+            assert ours.spgpuMgSynchronize(mg.h) == 0
+            got = mg.get(vz, n, np.float64)
+            assert np.array_equal(got.view(np.uint8), single.view(np.uint8)), devices
+            for v in (vx, vy, vz):
+                ours.spgpuMgVectorDestroy(v)
+            ours.spgpuMgMatrixDestroy(A)
+        finally:
+            mg.close()
