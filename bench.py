@@ -219,12 +219,24 @@ def build_workload(name, rank, world, device, n_override=None, global_columns=Fa
     elif name == "cfg4":
         R = n_override or 2_000_000
         lens, cols, vals = DB.banded_complex_entries(R, device=device)
-        A = DB.hell_from_rows(lens, cols, vals, R)
+        lo, hi, halo = 0, R, 0
+        if world > 1:
+            # row block of this rank with columns remapped into x_ext = [halo | owned | halo]; every rank generates
+            # the same matrix (same seed) and keeps its rows.  bw = 1000 -> halo 1024 (whole hacks)
+            from spgpu_b200 import mg
+            halo = 1024
+            lo, hi = mg.row_blocks(R, world, 32)[rank]
+            ends = torch.cumsum(lens, 0)
+            e0, e1 = int((ends[lo] - lens[lo]).item()), int(ends[hi - 1].item())
+            lens, cols, vals = lens[lo:hi].contiguous(), cols[e0:e1].contiguous(), vals[e0:e1].contiguous()
+            w["A_global"] = DB.hell_from_rows(lens, cols, vals, R)            # the same rows with global columns (--verify)
+            cols = cols - (lo - halo)
+        A = DB.hell_from_rows(lens, cols, vals, (hi - lo) + 2 * halo if world > 1 else R)
         del lens, cols, vals
-        w.update(kind="hell", sym="Z", A=A, rows=R, nnz=A.nnz, halo=0, x_len=R, sizeof=16,
-                 alpha=0.7 - 0.3j, beta=-0.5 + 0.25j, flops_per_nnz=8, total_rows=R, bandwidth=1000,
+        w.update(kind="hell", sym="Z", A=A, rows=hi - lo, nnz=A.nnz, halo=halo, x_len=A.ncols, sizeof=16,
+                 alpha=0.7 - 0.3j, beta=-0.5 + 0.25j, flops_per_nnz=8, total_rows=R, bandwidth=1000, lo=lo, hi=hi,
                  label=f"banded complex-double {R} rows ~40 nnz/row, HELL hackSize 32 (BASELINE configs[3])")
-        w["bytes"] = algorithmic_bytes_hell(A.nnz, R, A.hack_offsets.numel(), R, 16, beta_nonzero=True)
+        w["bytes"] = algorithmic_bytes_hell(A.nnz, hi - lo, A.hack_offsets.numel(), A.ncols, 16, beta_nonzero=True)
     else:
         raise SystemExit(f"unknown workload {name}")
     return w
@@ -711,10 +723,11 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    if args.workload not in ("cfg5", "cfg2") and world > 1:
-        raise SystemExit("only cfg5 (HELL) and cfg2 (HDIA) are row-sharded across GPUs; run the other workloads with --gpus 1")
-    if args.workload == "cfg2" and world > 1 and args.halo == "allgather":
-        args.halo = "fused"             # HDIA addresses x relative to the row: there is no global-column mode
+    if args.workload not in ("cfg5", "cfg2", "cfg4") and world > 1:
+        raise SystemExit("cfg5 (double HELL), cfg2 (double HDIA) and cfg4 (complex-double HELL) are row-sharded across GPUs; "
+                         "run the other workloads with --gpus 1")
+    if args.workload in ("cfg2", "cfg4") and world > 1 and args.halo == "allgather":
+        args.halo = "fused"             # HDIA addresses x relative to the row; cfg4 is only built with local columns
 
     L = capi.lib()
     h = ctypes.c_void_p()
@@ -744,17 +757,19 @@ def main():
     # x_ext lives in its own cudaMalloc block so it can be IPC-exported to the neighbours
     gen = torch.Generator(device=device)
     gen.manual_seed(12345 + rank)
-    if w["sym"] == "D":
-        x_ptr, x_ext = mg.raw_device_vector(L, ext_len, torch.float64)
-        x_ext.copy_(torch.rand(ext_len, generator=gen, device=device, dtype=torch.float64))
+    real = torch.float32 if w["sym"] in "SC" else torch.float64
+    if w["sym"] in "CZ":
+        x_init = torch.complex(torch.rand(ext_len, generator=gen, device=device, dtype=real),
+                               torch.rand(ext_len, generator=gen, device=device, dtype=real))
     else:
-        real = torch.float32 if w["sym"] in "SC" else torch.float64
-        if w["sym"] in "CZ":
-            x_ext = torch.complex(torch.rand(ext_len, generator=gen, device=device, dtype=real),
-                                  torch.rand(ext_len, generator=gen, device=device, dtype=real))
-        else:
-            x_ext = torch.rand(ext_len, generator=gen, device=device, dtype=real)
+        x_init = torch.rand(ext_len, generator=gen, device=device, dtype=real)
+    if w["sym"] == "D" or world > 1:
+        x_ptr, x_ext = mg.raw_device_vector(L, ext_len, tdt)
+        x_ext.copy_(x_init)
+    else:
+        x_ext = x_init
         x_ptr = x_ext.data_ptr()
+    del x_init
     z = torch.zeros(rows, dtype=tdt, device=device)
     y = None
     if w["beta"] != 0:
@@ -771,19 +786,20 @@ def main():
             return None
         A, s = w["A"], w["sym"]
         t = capi.TYPES[s]
-        one, zero = t.scalar(1.0), t.scalar(0.0)
+        one, zero = t.scalar(w["alpha"]), t.scalar(w["beta"])
+        y_ptr_ = y.data_ptr() if y is not None else 0
         links = peer.links_ref()
         if w["kind"] == "hdia":
             fn = getattr(L, f"spgpu{s}hdiaspmvHalo")
 
             def fused_hdia(seq):
-                fn(h, z_ptr_, 0, one, A.values.data_ptr(), A.offsets.data_ptr(), A.hack_size,
+                fn(h, z_ptr_, y_ptr_, one, A.values.data_ptr(), A.offsets.data_ptr(), A.hack_size,
                    A.hack_offsets.data_ptr(), rows, A.ncols, x_ptr, zero, halo, links, seq)
             return fused_hdia
         fn = getattr(L, f"spgpu{s}hellspmvHalo")
 
         def fused(seq):
-            fn(h, z_ptr_, 0, one, A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
+            fn(h, z_ptr_, y_ptr_, one, A.values.data_ptr(), A.indices.data_ptr(), A.hack_size,
                A.hack_offsets.data_ptr(), A.rs.data_ptr(), A.avg, rows, x_ptr, zero, A.base, halo, links, seq)
         return fused
 
@@ -868,6 +884,33 @@ def main():
         del Ag, z_ref, x_full
         if rank == 0:
             print(f"verify: partitioned SpMV == global-column SpMV on every rank: {verified}", file=sys.stderr, flush=True)
+
+    if args.verify and world > 1 and w.get("A_global") is not None:
+        # each rank multiplies ITS rows with global columns by the all-gathered x and compares bit for bit
+        Ag, sym_ = w["A_global"], w["sym"]
+        one_step()
+        barrier()
+        own = x_ext[halo:halo + rows].contiguous()
+        parts = [torch.empty(hi_ - lo_, dtype=tdt, device=device) for lo_, hi_ in mg.row_blocks(w["total_rows"], world, 32)]
+        if tdt.is_complex:
+            dist.all_gather([torch.view_as_real(p_) for p_ in parts], torch.view_as_real(own))
+        else:
+            dist.all_gather(parts, own)
+        x_full = torch.cat(parts)
+        z_ref = torch.full((rows,), float("nan"), dtype=tdt, device=device)
+        T = capi.TYPES[sym_]
+        getattr(L, f"spgpu{sym_}hellspmv")(h, z_ref.data_ptr(), y.data_ptr() if y is not None else 0, T.scalar(w["alpha"]),
+                                          Ag.values.data_ptr(), Ag.indices.data_ptr(), 32, Ag.hack_offsets.data_ptr(),
+                                          Ag.rs.data_ptr(), 0, Ag.avg, rows, x_full.data_ptr(), T.scalar(w["beta"]), 0)
+        torch.cuda.synchronize()
+        same = torch.equal(torch.view_as_real(z), torch.view_as_real(z_ref)) if tdt.is_complex else torch.equal(z, z_ref)
+        ok = torch.tensor([1.0 if same else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        verified = bool(ok.item() == 1.0)
+        del z_ref, x_full, parts
+        if rank == 0:
+            print(f"verify: partitioned {sym_} HELL SpMV == the same rows with global columns on every rank: {verified}", file=sys.stderr, flush=True)
+    w.pop("A_global", None)
 
     if args.verify and args.workload == "cfg2" and world > 1:
         # each rank multiplies the FULL matrix by the all-gathered x and compares its own rows

@@ -37,7 +37,7 @@ def _torchrun(n, args, timeout=900):
     return json.loads(lines[0])
 
 
-@pytest.mark.parametrize("workload,size", [("cfg5", 128), ("cfg2", 64)])
+@pytest.mark.parametrize("workload,size", [("cfg5", 128), ("cfg2", 64), ("cfg4", 200000)])
 def test_partitioned_bench_is_verified_on_two_gpus(workload, size):
     if _gpus() < 2:
         pytest.skip("needs two GPUs")
