@@ -77,6 +77,14 @@ spgpuStatus_t spgpuMgSynchronize(spgpuMgHandle_t mg);
 SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_MG_HELLCREATE)
 
 /*
+ * The partition spgpuMg?hellCreate would choose, without touching a device: bounds[0..world] = first row of every
+ * block (multiples of hackSize), *halo = halo width in elements (the furthest reach of any row outside its block, rounded
+ * up to 32), *allGather = 1 when the matrix has to be multiplied in all-gather mode (then *halo = 0).
+ */
+spgpuStatus_t spgpuMgHellPlan(int world, const __host int* rP, int hackSize, const __host int* hackOffsets,
+	const __host int* rS, int rows, int baseIndex, int* bounds, int* halo, int* allGather);
+
+/*
  * The same from per-rank blocks that are ALREADY partitioned: rank r owns blockRows[r] consecutive
  * rows (a multiple of hackSize for every rank but the last), its HELL arrays cM[r], rP[r] (elements[r]
  * entries each), hackOffsets[r], rS[r] hold LOCAL column indices into x_ext = [haloN | owned | haloN]

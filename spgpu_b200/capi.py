@@ -144,7 +144,7 @@ def ext_symbols():
 def mg_symbols():
     """Every symbol include/spgpu_mg.h declares (the C-level multi-GPU API)."""
     names = ["spgpuMgCreate", "spgpuMgDestroy", "spgpuMgWorld", "spgpuMgRankHandle", "spgpuMgSetExchange", "spgpuMgExchange",
-             "spgpuMgSynchronize", "spgpuMgHellCreateFromBlocks", "spgpuMgMatrixDestroy", "spgpuMgMatrixHalo",
+             "spgpuMgSynchronize", "spgpuMgHellPlan", "spgpuMgHellCreateFromBlocks", "spgpuMgMatrixDestroy", "spgpuMgMatrixHalo",
              "spgpuMgMatrixRows", "spgpuMgMatrixRowBlock", "spgpuMgVectorCreate", "spgpuMgVectorDestroy", "spgpuMgVectorSet",
              "spgpuMgVectorGet", "spgpuMgVectorLocal", "spgpuMgDcgCreate", "spgpuMgDcgStart", "spgpuMgDcgStep",
              "spgpuMgDcgSolution", "spgpuMgDcgDestroy"]
@@ -326,6 +326,8 @@ class SpgpuLib:
             f["spgpuMgSetExchange"] = _sig(d, "spgpuMgSetExchange", c_int, [P, c_int], optional=True)
             f["spgpuMgExchange"] = _sig(d, "spgpuMgExchange", c_int, [P], optional=True)
             f["spgpuMgSynchronize"] = _sig(d, "spgpuMgSynchronize", c_int, [P], optional=True)
+            f["spgpuMgHellPlan"] = _sig(d, "spgpuMgHellPlan", c_int,
+                [c_int, P, c_int, P, P, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)], optional=True)
             f["spgpuMgHellCreateFromBlocks"] = _sig(d, "spgpuMgHellCreateFromBlocks", c_int,
                 [P, PP, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), PP, PP, PP, PP,
                  ctypes.POINTER(ctypes.c_longlong), c_int], optional=True)

@@ -327,62 +327,87 @@ static long long hell_at(const int* hackOffsets, int hackSize, int i, int k)
 	return (long long)hackOffsets[i / hackSize] + (long long)k * hackSize + i % hackSize;
 }
 
+/*
+ * The partition of a global HELL matrix over `world` ranks, host arithmetic only (no device is touched, so it can be
+ * checked without a GPU): bounds[0..world] = first row of every block (multiples of hackSize), *halo = the furthest any
+ * row reaches outside its own block rounded up to 32 (0 on one rank), *allGather = 1 when halo mode is impossible --
+ * a block owns fewer than halo rows (a zone would need entries of a rank two hops away), or a row that is not among
+ * the first / last halo rows of its block reads a halo column (interior rows are multiplied before the zones arrive).
+ */
+spgpuStatus_t spgpuMgHellPlan(int world, const int* rP, int hackSize, const int* hackOffsets, const int* rS, int rows,
+	int baseIndex, int* bounds, int* halo, int* allGather)
+{
+	int r, i, k, banded = 1;
+	long long reach = 0;
+	if (world < 1 || world > MG_MAX_RANKS || rows < 0 || hackSize <= 0 || hackSize % 32 != 0)
+		return SPGPU_UNSUPPORTED;
+	{
+		const long long units = ((long long)rows + hackSize - 1) / hackSize;
+		for (r = 0; r < world; ++r) {
+			long long b = (units * r / world) * hackSize;
+			bounds[r] = (int)(b < rows ? b : rows);
+		}
+		bounds[world] = rows;
+	}
+	*halo = 0;
+	*allGather = 0;
+	if (world == 1)
+		return SPGPU_SUCCESS;
+	/* how far does any row reach outside its own block? */
+	for (r = 0; r < world; ++r)
+		for (i = bounds[r]; i < bounds[r + 1]; ++i)
+			for (k = 0; k < rS[i]; ++k) {
+				const long long g = (long long)rP[hell_at(hackOffsets, hackSize, i, k)] - baseIndex;
+				if (g < bounds[r] && bounds[r] - g > reach) reach = bounds[r] - g;
+				if (g >= bounds[r + 1] && g - bounds[r + 1] + 1 > reach) reach = g - bounds[r + 1] + 1;
+			}
+	if (reach > 0x7fffffe0ll)
+		reach = 0x7fffffe0ll;
+	*halo = (int)(((reach + 31) / 32) * 32);
+	if (*halo == 0)
+		*halo = 32;
+	for (r = 0; r < world && banded; ++r) {
+		const int lo = bounds[r], hi = bounds[r + 1];
+		if (hi - lo < *halo)
+			banded = 0;
+		for (i = lo; i < hi && banded; ++i)
+			for (k = 0; k < rS[i]; ++k) {
+				const long long g = (long long)rP[hell_at(hackOffsets, hackSize, i, k)] - baseIndex;
+				if ((g < lo && i - lo >= *halo) || (g >= hi && i - lo < (hi - lo) - *halo)) {
+					banded = 0;
+					break;
+				}
+			}
+	}
+	if (!banded) {
+		*allGather = 1;
+		*halo = 0;
+	}
+	return SPGPU_SUCCESS;
+}
+
 static spgpuStatus_t hell_create(spgpuMgHandle_t mg, spgpuMgMatrix_t* pA, spgpuType_t type, const void* cM,
 	const int* rP, int hackSize, const int* hackOffsets, const int* rS, int avg, int rows, int cols, int baseIndex)
 {
 	const int world = mg ? mg->world : 0;
 	const size_t esize = spgpuSizeOf(type);
-	int bound[MG_MAX_RANKS + 1], r, i, k, banded = 1, previous = 0;
-	long long reach = 0, total = 0;
+	int bound[MG_MAX_RANKS + 1], r, i, k, banded = 1, previous = 0, allGather = 0;
+	long long total = 0;
 	int halo = 0;
 	spgpuMgMatrix_t A;
 	*pA = NULL;
 	if (!mg || rows < 0 || cols != rows || hackSize <= 0 || hackSize % 32 != 0)
 		return SPGPU_UNSUPPORTED;        /* vectors are partitioned like the rows: square matrices */
-	{
-		const long long units = ((long long)rows + hackSize - 1) / hackSize;
-		for (r = 0; r < world; ++r) {
-			long long b = (units * r / world) * hackSize;
-			bound[r] = (int)(b < rows ? b : rows);
-		}
-		bound[world] = rows;
-		if (rows > 0) {
-			const int lastHack = (int)units - 1;
-			int deepest = 0;
-			for (i = lastHack * hackSize; i < rows; ++i)
-				if (rS[i] > deepest)
-					deepest = rS[i];
-			total = (long long)hackOffsets[lastHack] + (long long)deepest * hackSize;
-		}
-	}
-	/* how far does any row reach outside its own block? */
-	for (r = 0; r < world && world > 1; ++r)
-		for (i = bound[r]; i < bound[r + 1]; ++i)
-			for (k = 0; k < rS[i]; ++k) {
-				const long long g = (long long)rP[hell_at(hackOffsets, hackSize, i, k)] - baseIndex;
-				if (g < bound[r] && bound[r] - g > reach) reach = bound[r] - g;
-				if (g >= bound[r + 1] && g - bound[r + 1] + 1 > reach) reach = g - bound[r + 1] + 1;
-			}
-	if (world > 1) {
-		halo = (int)(((reach + 31) / 32) * 32);
-		if (halo == 0)
-			halo = 32;
-		/* halo mode needs: every block owns >= halo rows (its boundary entries feed a whole zone and a zone is fed
-		 * by ONE neighbour), and only the first / last halo rows of a block read a zone (interior rows are
-		 * multiplied before the zones arrive) */
-		for (r = 0; r < world && banded; ++r) {
-			const int lo = bound[r], hi = bound[r + 1];
-			if (hi - lo < halo)
-				banded = 0;
-			for (i = lo; i < hi && banded; ++i)
-				for (k = 0; k < rS[i]; ++k) {
-					const long long g = (long long)rP[hell_at(hackOffsets, hackSize, i, k)] - baseIndex;
-					if ((g < lo && i - lo >= halo) || (g >= hi && i - lo < (hi - lo) - halo)) {
-						banded = 0;
-						break;
-					}
-				}
-		}
+	if (spgpuMgHellPlan(world, rP, hackSize, hackOffsets, rS, rows, baseIndex, bound, &halo, &allGather) != SPGPU_SUCCESS)
+		return SPGPU_UNSUPPORTED;
+	banded = !allGather;
+	if (rows > 0) {
+		const int lastHack = (rows + hackSize - 1) / hackSize - 1;
+		int deepest = 0;
+		for (i = lastHack * hackSize; i < rows; ++i)
+			if (rS[i] > deepest)
+				deepest = rS[i];
+		total = (long long)hackOffsets[lastHack] + (long long)deepest * hackSize;
 	}
 	A = matrix_new(mg, type, hackSize, baseIndex, avg);
 	if (!A)

@@ -231,3 +231,71 @@ def test_allgather_mode_for_unstructured_columns(tmp_path):
     want = util.oracle_spmv("hell", hell, x, None, 1.0, 0.0)
     got = np.concatenate([np.load(tmp_path / f"z{r}.npy") for r in range(world)])
     np.testing.assert_array_equal(got, want)
+
+
+def _plan(L, hell, world):
+    import ctypes
+    bounds = (ctypes.c_int * (world + 1))()
+    halo, allg = ctypes.c_int(-7), ctypes.c_int(-7)
+    idx = np.ascontiguousarray(hell.indices, np.int32)
+    hoff = np.ascontiguousarray(hell.hack_offsets, np.int32)
+    rs = np.ascontiguousarray(hell.rs, np.int32)
+    st = L.spgpuMgHellPlan(world, idx.ctypes.data, hell.hack_size, hoff.ctypes.data, rs.ctypes.data, hell.nrows,
+                           hell.base, bounds, ctypes.byref(halo), ctypes.byref(allg))
+    return st, list(bounds), halo.value, allg.value
+
+
+def test_c_partition_plan_agrees_with_the_python_partition():
+    """spgpuMgHellPlan (the host arithmetic of spgpuMg?hellCreate, include/spgpu_mg.h) needs no device: its row
+    blocks are mg.row_blocks', its halo is the furthest reach rounded up to 32 and is accepted by mg.split_hell,
+    and a pattern mg.split_hell refuses at every width is planned as all-gather."""
+    from spgpu_b200 import capi
+    L = capi.lib()
+    cases = [(G.laplace3d_7pt(8), 32, 0), (G.laplace3d_7pt(16), 32, 1), (G.stencil3d_27pt(8), 64, 0),
+             (G.laplace2d_5pt(40, 23), 32, 0), (G.laplace2d_5pt(33, 31), 96, 1)]
+    for coo, hs, base in cases:
+        if base != coo.base:
+            coo = F.Coo(coo.rows + (base - coo.base), coo.cols + (base - coo.base), coo.vals, coo.nrows, coo.ncols, base)
+        hell = F.ell_to_hell(F.coo_to_ell(coo, ell_base=base), hs)
+        reach = int(np.abs(coo.rows.astype(np.int64) - coo.cols.astype(np.int64)).max())
+        for world in (1, 2, 3, 5):
+            st, bounds, halo, allg = _plan(L, hell, world)
+            assert st == 0
+            assert bounds == [a for a, _ in mg.row_blocks(hell.nrows, world, hs)] + [hell.nrows]
+            if world == 1:
+                assert (halo, allg) == (0, 0)
+                continue
+            smallest = min(b - a for a, b in zip(bounds, bounds[1:]))
+            # the reach OUT of a block is at most the bandwidth; blocks smaller than the halo force all-gather
+            if allg:
+                assert halo == 0 and smallest < ((reach + 31) // 32) * 32
+                with pytest.raises(ValueError):
+                    for r in range(world):
+                        mg._check_block(bounds[r], bounds[r + 1], ((reach + 31) // 32) * 32, world)
+                        mg.split_hell(hell, world, r, ((reach + 31) // 32) * 32)
+            else:
+                assert halo % 32 == 0 and 0 < halo <= ((reach + 31) // 32) * 32 and smallest >= halo
+                for r in range(world):
+                    mg.split_hell(hell, world, r, halo)          # accepted: banded within the planned width
+                if halo > 32:
+                    with pytest.raises(ValueError):              # and no narrower multiple of 32 would do
+                        for r in range(world):
+                            mg.split_hell(hell, world, r, halo - 32)
+
+
+def test_c_partition_plan_of_an_unstructured_pattern_is_all_gather():
+    from spgpu_b200 import capi
+    L = capi.lib()
+    coo = G.random_coo(640, 640, (1, 9), 5, np.float64, 0)
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    for world in (3, 4):
+        st, bounds, halo, allg = _plan(L, hell, world)
+        assert st == 0 and allg == 1 and halo == 0 and bounds[-1] == 640
+    # two ranks: every column is at most one whole block away, so the halo is the neighbour's entire block
+    st, bounds, halo, allg = _plan(L, hell, 2)
+    assert (st, allg) == (0, 0) and 0 < halo <= 320
+    for r in range(2):
+        mg.split_hell(hell, 2, r, halo)
+    assert _plan(L, hell, 0)[0] != 0 and _plan(L, hell, 17)[0] != 0
+    bad = F.Hell(hell.values, hell.indices, hell.hack_offsets, hell.rs, 48, hell.height, hell.nrows, hell.ncols, 0)
+    assert _plan(L, bad, 2)[0] != 0                              # hackSize must be a multiple of 32
