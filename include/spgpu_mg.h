@@ -85,6 +85,24 @@ spgpuStatus_t spgpuMgHellPlan(int world, const __host int* rP, int hackSize, con
 	const __host int* rS, int rows, int baseIndex, int* bounds, int* halo, int* allGather);
 
 /*
+ * The same for a GLOBAL HDIA matrix in HOST memory (the arrays cooToHdia / diaToHdia produce, reference
+ * hdia_conv.h:29-96; layout reference hdia.h:29-130).  HDIA addresses x relative to the row, so a row block is
+ * the same hacks with hackOffsets re-based and every diagonal offset raised by the halo width (local row i reads
+ * x_ext[i + offset + halo]); cells outside the matrix are stored as 0.  The halo is the furthest a NON-ZERO cell
+ * reaches outside its block.  SPGPU_UNSUPPORTED when that exceeds a neighbouring block or the non-zero cells are not
+ * banded within it (HDIA has no all-gather form: its columns are relative to the row -- convert such a matrix to HELL).
+ */
+#define SPGPU_DECL_MG_HDIACREATE(S, T, R)                                                    \
+	spgpuStatus_t spgpuMg##S##hdiaCreate(spgpuMgHandle_t mg, spgpuMgMatrix_t* pA,              \
+		const __host T* dM, const __host int* offsets, int hackSize,                           \
+		const __host int* hackOffsets, int rows, int cols);
+SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_MG_HDIACREATE)
+
+/* the partition spgpuMg?hdiaCreate would choose, without touching a device; *fits = 0 where it would refuse */
+spgpuStatus_t spgpuMgHdiaPlan(int world, spgpuType_t type, const __host void* dM, const __host int* offsets,
+	int hackSize, const __host int* hackOffsets, int rows, int cols, int* bounds, int* halo, int* fits);
+
+/*
  * The same from per-rank blocks that are ALREADY partitioned: rank r owns blockRows[r] consecutive
  * rows (a multiple of hackSize for every rank but the last), its HELL arrays cM[r], rP[r] (elements[r]
  * entries each), hackOffsets[r], rS[r] hold LOCAL column indices into x_ext = [haloN | owned | haloN]
@@ -118,11 +136,16 @@ void* spgpuMgVectorLocal(spgpuMgVector_t v, int rank);
 
 /*
  * z = alpha * A * x + beta * y over the partition (y may be NULL when beta == 0; z may be y; z must
- * not be x).  One kernel per rank in FUSED mode.  dot / nrm2 block and return the GLOBAL value
+ * not be x).  One kernel per rank in FUSED mode.  spgpuMg?hellspmv / spgpuMg?hdiaspmv accept a matrix of their
+ * own format only (SPGPU_UNSUPPORTED otherwise); spgpuMg?spmv takes either.  dot / nrm2 block and return the GLOBAL value
  * (partials added in rank order: every run gives the same bits); dot is unconjugated like spgpu?dot.
  */
 #define SPGPU_DECL_MG_OPS(S, T, R)                                                            \
 	spgpuStatus_t spgpuMg##S##hellspmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y, \
+		T alpha, spgpuMgMatrix_t A, spgpuMgVector_t x, T beta);                                 \
+	spgpuStatus_t spgpuMg##S##hdiaspmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y, \
+		T alpha, spgpuMgMatrix_t A, spgpuMgVector_t x, T beta);                                 \
+	spgpuStatus_t spgpuMg##S##spmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y,    \
 		T alpha, spgpuMgMatrix_t A, spgpuMgVector_t x, T beta);                                 \
 	spgpuStatus_t spgpuMg##S##dot(spgpuMgHandle_t mg, __host T* result, spgpuMgVector_t a,      \
 		spgpuMgVector_t b);                                                                     \
@@ -131,7 +154,7 @@ void* spgpuMgVectorLocal(spgpuMgVector_t v, int rank);
 		spgpuMgVector_t y, T alpha, spgpuMgVector_t x);
 SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_MG_OPS)
 
-/* ---- conjugate gradients on a double matrix (BASELINE configs[4]: "plus CG step") ---------------- */
+/* ---- conjugate gradients on a double matrix, HELL or HDIA (BASELINE configs[4]: "plus CG step") --- */
 
 /*
  * x = 0, r = p = b; *rr0 (may be NULL) = b.b.  Each CgStep is `iterations` iterations of

@@ -144,12 +144,13 @@ def ext_symbols():
 def mg_symbols():
     """Every symbol include/spgpu_mg.h declares (the C-level multi-GPU API)."""
     names = ["spgpuMgCreate", "spgpuMgDestroy", "spgpuMgWorld", "spgpuMgRankHandle", "spgpuMgSetExchange", "spgpuMgExchange",
-             "spgpuMgSynchronize", "spgpuMgHellPlan", "spgpuMgHellCreateFromBlocks", "spgpuMgMatrixDestroy", "spgpuMgMatrixHalo",
+             "spgpuMgSynchronize", "spgpuMgHellPlan", "spgpuMgHdiaPlan", "spgpuMgHellCreateFromBlocks", "spgpuMgMatrixDestroy", "spgpuMgMatrixHalo",
              "spgpuMgMatrixRows", "spgpuMgMatrixRowBlock", "spgpuMgVectorCreate", "spgpuMgVectorDestroy", "spgpuMgVectorSet",
              "spgpuMgVectorGet", "spgpuMgVectorLocal", "spgpuMgDcgCreate", "spgpuMgDcgStart", "spgpuMgDcgStep",
              "spgpuMgDcgSolution", "spgpuMgDcgDestroy"]
     for s in FLOAT_SYMS:
-        names += [f"spgpuMg{s}hellCreate", f"spgpuMg{s}hellspmv", f"spgpuMg{s}dot", f"spgpuMg{s}nrm2", f"spgpuMg{s}axpby"]
+        names += [f"spgpuMg{s}hellCreate", f"spgpuMg{s}hdiaCreate", f"spgpuMg{s}hellspmv", f"spgpuMg{s}hdiaspmv",
+                  f"spgpuMg{s}spmv", f"spgpuMg{s}dot", f"spgpuMg{s}nrm2", f"spgpuMg{s}axpby"]
     return names
 
 
@@ -328,6 +329,8 @@ class SpgpuLib:
             f["spgpuMgSynchronize"] = _sig(d, "spgpuMgSynchronize", c_int, [P], optional=True)
             f["spgpuMgHellPlan"] = _sig(d, "spgpuMgHellPlan", c_int,
                 [c_int, P, c_int, P, P, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)], optional=True)
+            f["spgpuMgHdiaPlan"] = _sig(d, "spgpuMgHdiaPlan", c_int,
+                [c_int, c_int, P, P, c_int, P, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)], optional=True)
             f["spgpuMgHellCreateFromBlocks"] = _sig(d, "spgpuMgHellCreateFromBlocks", c_int,
                 [P, PP, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), PP, PP, PP, PP,
                  ctypes.POINTER(ctypes.c_longlong), c_int], optional=True)
@@ -351,7 +354,10 @@ class SpgpuLib:
                 T, R = t.ctype, t.rtype
                 f[f"spgpuMg{s}hellCreate"] = _sig(d, f"spgpuMg{s}hellCreate", c_int,
                     [P, PP, P, P, c_int, P, P, c_int, c_int, c_int, c_int], optional=True)
-                f[f"spgpuMg{s}hellspmv"] = _sig(d, f"spgpuMg{s}hellspmv", c_int, [P, P, P, T, P, P, T], optional=True)
+                f[f"spgpuMg{s}hdiaCreate"] = _sig(d, f"spgpuMg{s}hdiaCreate", c_int,
+                    [P, PP, P, P, c_int, P, c_int, c_int], optional=True)
+                for op in ("hellspmv", "hdiaspmv", "spmv"):
+                    f[f"spgpuMg{s}{op}"] = _sig(d, f"spgpuMg{s}{op}", c_int, [P, P, P, T, P, P, T], optional=True)
                 f[f"spgpuMg{s}dot"] = _sig(d, f"spgpuMg{s}dot", c_int, [P, ctypes.POINTER(T), P, P], optional=True)
                 f[f"spgpuMg{s}nrm2"] = _sig(d, f"spgpuMg{s}nrm2", c_int, [P, ctypes.POINTER(R), P], optional=True)
                 f[f"spgpuMg{s}axpby"] = _sig(d, f"spgpuMg{s}axpby", c_int, [P, P, T, P, T, P], optional=True)

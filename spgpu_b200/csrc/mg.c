@@ -4,8 +4,9 @@
  *
  * One process, N ranks = N (device, spgpu handle, stream) triples.  A matrix is N self-contained HELL
  * blocks in the reference's own layout (reference hell.h:45-169) with column indices remapped into
- * each rank's x_ext = [halo | owned | halo]; the products are the library's own kernels
- * (spgpu?hellspmv, or spgpu?hellspmvHalo[Dot] of spgpu_ext.h when the halo exchange travels inside
+ * each rank's x_ext = [halo | owned | halo] -- or N HDIA blocks (reference hdia.h:29-130) whose diagonal
+ * offsets are shifted by the halo width; the products are the library's own kernels (spgpu?hellspmv /
+ * spgpu?hdiaspmv, or spgpu?{hell,hdia}spmvHalo[Dot] of spgpu_ext.h when the halo exchange travels inside
  * the launch).  What this file adds is bookkeeping: the split, the remap, the vectors with their
  * zones, sequence numbers, and -- in EVENTS mode -- the CUDA events between the ranks' streams.
  */
@@ -20,6 +21,8 @@
 #define MG_MAX_RANKS 16
 #define MG_MODE_HALO 0
 #define MG_MODE_ALLGATHER 1
+#define MG_KIND_HELL 0
+#define MG_KIND_HDIA 1
 
 struct spgpuMgContext {
 	int world;
@@ -41,14 +44,15 @@ struct spgpuMgMatrix {
 	spgpuMgHandle_t mg;
 	spgpuType_t type;
 	size_t esize;
+	int kind;                         /* MG_KIND_HELL / MG_KIND_HDIA */
 	int rows, hackSize, baseIndex, avg;
 	int mode;                         /* MG_MODE_HALO / MG_MODE_ALLGATHER */
 	int halo;
 	int lo[MG_MAX_RANKS], hi[MG_MAX_RANKS];
-	void* cM[MG_MAX_RANKS];
-	int* rP[MG_MAX_RANKS];
-	int* hackOffsets[MG_MAX_RANKS];
-	int* rS[MG_MAX_RANKS];
+	void* cM[MG_MAX_RANKS];           /* HELL values / HDIA dM */
+	int* rP[MG_MAX_RANKS];            /* HELL column indices / HDIA diagonal offsets (already + halo) */
+	int* hackOffsets[MG_MAX_RANKS];   /* HELL: element offsets, one per hack / HDIA: diagonal prefix, hacks + 1 */
+	int* rS[MG_MAX_RANKS];            /* HELL row sizes / HDIA: NULL */
 	int owned;                        /* device arrays allocated here (freed by MatrixDestroy) */
 };
 
@@ -327,6 +331,18 @@ static long long hell_at(const int* hackOffsets, int hackSize, int i, int k)
 	return (long long)hackOffsets[i / hackSize] + (long long)k * hackSize + i % hackSize;
 }
 
+/* contiguous, near-equal row blocks whose boundaries are multiples of hackSize: bounds[0..world] */
+static void block_bounds(int world, int rows, int hackSize, int* bounds)
+{
+	const long long units = ((long long)rows + hackSize - 1) / hackSize;
+	int r;
+	for (r = 0; r < world; ++r) {
+		const long long b = (units * r / world) * hackSize;
+		bounds[r] = (int)(b < rows ? b : rows);
+	}
+	bounds[world] = rows;
+}
+
 /*
  * The partition of a global HELL matrix over `world` ranks, host arithmetic only (no device is touched, so it can be
  * checked without a GPU): bounds[0..world] = first row of every block (multiples of hackSize), *halo = the furthest any
@@ -341,14 +357,7 @@ spgpuStatus_t spgpuMgHellPlan(int world, const int* rP, int hackSize, const int*
 	long long reach = 0;
 	if (world < 1 || world > MG_MAX_RANKS || rows < 0 || hackSize <= 0 || hackSize % 32 != 0)
 		return SPGPU_UNSUPPORTED;
-	{
-		const long long units = ((long long)rows + hackSize - 1) / hackSize;
-		for (r = 0; r < world; ++r) {
-			long long b = (units * r / world) * hackSize;
-			bounds[r] = (int)(b < rows ? b : rows);
-		}
-		bounds[world] = rows;
-	}
+	block_bounds(world, rows, hackSize, bounds);
 	*halo = 0;
 	*allGather = 0;
 	if (world == 1)
@@ -452,6 +461,154 @@ static spgpuStatus_t hell_create(spgpuMgHandle_t mg, spgpuMgMatrix_t* pA, spgpuT
 		if (e == cudaSuccess) e = upload((void**)&A->hackOffsets[r], hoff, (size_t)hacks * sizeof(int));
 		if (e == cudaSuccess) e = upload((void**)&A->rS[r], rS + lo, (size_t)n * sizeof(int));
 		free(idx);
+		free(hoff);
+		if (e != cudaSuccess) {
+			cudaSetDevice(previous);
+			spgpuMgMatrixDestroy(A);
+			return e == cudaErrorMemoryAllocation ? SPGPU_OUTOFMEMORY : SPGPU_UNSPECIFIED;
+		}
+		spgpuReserveScratch(mg->h[r], ((size_t)(n + 127) / 128 + 1) * 4 * 16);
+	}
+	cudaSetDevice(previous);
+	*pA = A;
+	return SPGPU_SUCCESS;
+}
+
+/* ---- HDIA ---------------------------------------------------------------------------------------- */
+
+static int cell_nonzero(spgpuType_t type, const void* p)
+{
+	switch (type) {
+	case SPGPU_TYPE_FLOAT: return *(const float*)p != 0.0f;
+	case SPGPU_TYPE_DOUBLE: return *(const double*)p != 0.0;
+	case SPGPU_TYPE_COMPLEX_FLOAT: return ((const float*)p)[0] != 0.0f || ((const float*)p)[1] != 0.0f;
+	case SPGPU_TYPE_COMPLEX_DOUBLE: return ((const double*)p)[0] != 0.0 || ((const double*)p)[1] != 0.0;
+	default: return 1;
+	}
+}
+
+/*
+ * The partition of a global HDIA matrix (reference hdia.h:29-130: hack h holds diagonals
+ * [hackOffsets[h], hackOffsets[h+1]), diagonal d is hackSize values dM[d*hackSize + j] of rows h*hackSize + j
+ * at column row + offsets[d]) over `world` ranks, host arithmetic only.  HDIA addresses x relative to the row,
+ * so a row block is the same hacks with hackOffsets re-based; the halo is the furthest a NON-ZERO cell reaches
+ * outside its block, rounded up to 32.  *fits = 0 when a block owns fewer than halo rows or a non-zero cell of a
+ * row outside the first / last halo rows reads a halo column: such a matrix is not partitioned (there is no
+ * all-gather form of HDIA: its columns are relative to the row).
+ */
+spgpuStatus_t spgpuMgHdiaPlan(int world, spgpuType_t type, const void* dM, const int* offsets, int hackSize,
+	const int* hackOffsets, int rows, int cols, int* bounds, int* halo, int* fits)
+{
+	const size_t es = spgpuSizeOf(type);
+	int r, pass;
+	long long reach = 0;
+	if (world < 1 || world > MG_MAX_RANKS || rows < 0 || cols < 0 || hackSize <= 0 || hackSize % 32 != 0 || es == 0)
+		return SPGPU_UNSUPPORTED;
+	block_bounds(world, rows, hackSize, bounds);
+	*halo = 0;
+	*fits = 1;
+	if (world == 1)
+		return SPGPU_SUCCESS;
+	/* pass 0 measures the reach, pass 1 checks the band against the halo it gives */
+	for (pass = 0; pass < 2 && *fits; ++pass) {
+		for (r = 0; r < world && *fits; ++r) {
+			const int lo = bounds[r], hi = bounds[r + 1];
+			int h;
+			if (pass == 1 && hi - lo < *halo) {
+				*fits = 0;
+				break;
+			}
+			for (h = lo / hackSize; h < (hi + hackSize - 1) / hackSize && *fits; ++h) {
+				int d, j;
+				for (d = hackOffsets[h]; d < hackOffsets[h + 1] && *fits; ++d)
+					for (j = 0; j < hackSize; ++j) {
+						const long long row = (long long)h * hackSize + j, g = row + offsets[d];
+						if (row >= hi)
+							break;
+						if (g < 0 || g >= cols || (g >= lo && g < hi))
+							continue;
+						if (!cell_nonzero(type, (const char*)dM + ((size_t)d * hackSize + j) * es))
+							continue;
+						if (pass == 0) {
+							if (g < lo && lo - g > reach) reach = lo - g;
+							if (g >= hi && g - hi + 1 > reach) reach = g - hi + 1;
+						} else if ((g < lo && row - lo >= *halo) || (g >= hi && row - lo < (hi - lo) - *halo)) {
+							*fits = 0;
+							break;
+						}
+					}
+			}
+		}
+		if (pass == 0) {
+			if (reach > 0x7fffffe0ll)
+				reach = 0x7fffffe0ll;
+			*halo = (int)(((reach + 31) / 32) * 32);
+			if (*halo == 0)
+				*halo = 32;
+		}
+	}
+	return SPGPU_SUCCESS;
+}
+
+static spgpuStatus_t hdia_create(spgpuMgHandle_t mg, spgpuMgMatrix_t* pA, spgpuType_t type, const void* dM,
+	const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols)
+{
+	const int world = mg ? mg->world : 0;
+	const size_t es = spgpuSizeOf(type);
+	int bound[MG_MAX_RANKS + 1], r, halo = 0, fits = 1, previous = 0;
+	spgpuMgMatrix_t A;
+	*pA = NULL;
+	if (!mg || rows < 0 || cols != rows)
+		return SPGPU_UNSUPPORTED;        /* vectors are partitioned like the rows: square matrices */
+	if (spgpuMgHdiaPlan(world, type, dM, offsets, hackSize, hackOffsets, rows, cols, bound, &halo, &fits) != SPGPU_SUCCESS || !fits)
+		return SPGPU_UNSUPPORTED;
+	A = matrix_new(mg, type, hackSize, 0, 1);
+	if (!A)
+		return SPGPU_OUTOFMEMORY;
+	A->kind = MG_KIND_HDIA;
+	A->mode = MG_MODE_HALO;
+	A->halo = halo;
+	A->rows = rows;
+	A->owned = 1;
+	cudaGetDevice(&previous);
+	for (r = 0; r < world; ++r) {
+		const int lo = bound[r], hi = bound[r + 1], n = hi - lo;
+		const int h0 = lo / hackSize, h1 = (hi + hackSize - 1) / hackSize, hacks = h1 - h0;
+		const int d0 = n > 0 ? hackOffsets[h0] : 0, d1 = n > 0 ? hackOffsets[h1] : 0, diags = d1 - d0;
+		const size_t cells = (size_t)diags * hackSize;
+		char* vals = (char*)malloc(cells > 0 ? cells * es : 1);
+		int* offs = (int*)malloc((diags > 0 ? diags : 1) * sizeof(int));
+		int* hoff = (int*)malloc((size_t)(hacks + 1) * sizeof(int));
+		cudaError_t e = cudaSuccess;
+		int h, d, j;
+		A->lo[r] = lo;
+		A->hi[r] = hi;
+		if (!vals || !offs || !hoff) {
+			free(vals); free(offs); free(hoff);
+			cudaSetDevice(previous);
+			spgpuMgMatrixDestroy(A);
+			return SPGPU_OUTOFMEMORY;
+		}
+		memcpy(vals, (const char*)dM + (size_t)d0 * hackSize * es, cells * es);
+		for (h = 0; h <= hacks; ++h)
+			hoff[h] = n > 0 ? hackOffsets[h0 + h] - d0 : 0;
+		for (d = 0; d < diags; ++d)
+			offs[d] = offsets[d0 + d] + halo;     /* local row i reads x_ext[i + offset + halo] */
+		/* cells outside the MATRIX now fall inside the window [0, n + 2*halo) the kernel tests: store 0 there
+		 * (the conversions do, reference hdia_conv.h:60-96, but nothing obliges a caller's array to) */
+		for (h = 0; h < hacks; ++h)
+			for (d = hoff[h]; d < hoff[h + 1]; ++d)
+				for (j = 0; j < hackSize; ++j) {
+					const long long row = (long long)lo + (long long)h * hackSize + j, g = row + offsets[d0 + d];
+					if (row >= hi || g < 0 || g >= cols)
+						memset(vals + ((size_t)d * hackSize + j) * es, 0, es);
+				}
+		use_rank(mg, r);
+		e = upload(&A->cM[r], vals, cells * es);
+		if (e == cudaSuccess) e = upload((void**)&A->rP[r], offs, (size_t)diags * sizeof(int));
+		if (e == cudaSuccess) e = upload((void**)&A->hackOffsets[r], hoff, (size_t)(hacks + 1) * sizeof(int));
+		free(vals);
+		free(offs);
 		free(hoff);
 		if (e != cudaSuccess) {
 			cudaSetDevice(previous);
@@ -715,7 +872,22 @@ static spgpuStatus_t check_launches(void)
 		return hell_create(mg, pA, TYPECODE, cM, rP, hackSize, hackOffsets, rS, avgNnzPerRow, rows, cols, \
 			baseIndex);                                                                                   \
 	}                                                                                                     \
-	spgpuStatus_t spgpuMg##S##hellspmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y, T alpha, \
+	spgpuStatus_t spgpuMg##S##hdiaCreate(spgpuMgHandle_t mg, spgpuMgMatrix_t* pA, const T* dM,            \
+		const int* offsets, int hackSize, const int* hackOffsets, int rows, int cols)                     \
+	{                                                                                                     \
+		return hdia_create(mg, pA, TYPECODE, dM, offsets, hackSize, hackOffsets, rows, cols);             \
+	}                                                                                                     \
+	/* one rank's product on a filled x_ext, with the plain entry point of the matrix's format */         \
+	static void mg_##S##_block_spmv(spgpuMgMatrix_t A, int r, T* z, const T* y, T alpha, const T* x, T beta) \
+	{                                                                                                     \
+		if (A->kind == MG_KIND_HDIA)                                                                      \
+			spgpu##S##hdiaspmv(A->mg->h[r], z, y, alpha, (const T*)A->cM[r], A->rP[r], A->hackSize,       \
+				A->hackOffsets[r], MG_ROWS(A, r), MG_ROWS(A, r) + 2 * A->halo, x, beta);                  \
+		else                                                                                              \
+			spgpu##S##hellspmv(A->mg->h[r], z, y, alpha, (const T*)A->cM[r], A->rP[r], A->hackSize,       \
+				A->hackOffsets[r], A->rS[r], NULL, A->avg, MG_ROWS(A, r), x, beta, A->baseIndex);         \
+	}                                                                                                     \
+	static spgpuStatus_t mg_##S##_spmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y, T alpha, \
 		spgpuMgMatrix_t A, spgpuMgVector_t x, T beta)                                                     \
 	{                                                                                                     \
 		int previous = 0, r;                                                                              \
@@ -728,27 +900,32 @@ static spgpuStatus_t check_launches(void)
 			st = allgather(mg, x);                                                                        \
 			for (r = 0; r < mg->world && st == SPGPU_SUCCESS; ++r) {                                      \
 				use_rank(mg, r);                                                                          \
-				spgpu##S##hellspmv(mg->h[r], (T*)owned_ptr(z, r), y ? (const T*)owned_ptr(y, r) : NULL,   \
-					alpha, (const T*)A->cM[r], A->rP[r], A->hackSize, A->hackOffsets[r], A->rS[r], NULL,  \
-					A->avg, MG_ROWS(A, r), (const T*)x->full[r], beta, A->baseIndex);                     \
+				mg_##S##_block_spmv(A, r, (T*)owned_ptr(z, r), y ? (const T*)owned_ptr(y, r) : NULL,      \
+					alpha, (const T*)x->full[r], beta);                                                   \
 			}                                                                                             \
 			mark_products_done(mg);                                                                       \
 		} else if (mg->exchange == SPGPU_MG_FUSED || mg->world == 1 || A->halo == 0) {                    \
 			const unsigned seq = ++mg->haloSeq;                                                           \
 			for (r = 0; r < mg->world; ++r) {                                                             \
+				const spgpuHaloLinks* links = mg->world > 1 ? &x->links[r] : NULL;                        \
+				T* zr = (T*)owned_ptr(z, r);                                                              \
+				const T* yr = y ? (const T*)owned_ptr(y, r) : NULL;                                       \
 				use_rank(mg, r);                                                                          \
-				spgpu##S##hellspmvHalo(mg->h[r], (T*)owned_ptr(z, r), y ? (const T*)owned_ptr(y, r) : NULL, \
-					alpha, (const T*)A->cM[r], A->rP[r], A->hackSize, A->hackOffsets[r], A->rS[r], A->avg, \
-					MG_ROWS(A, r), (T*)x->ext[r], beta, A->baseIndex, A->halo,                            \
-					mg->world > 1 ? &x->links[r] : NULL, seq);                                            \
+				if (A->kind == MG_KIND_HDIA)                                                              \
+					spgpu##S##hdiaspmvHalo(mg->h[r], zr, yr, alpha, (const T*)A->cM[r], A->rP[r],         \
+						A->hackSize, A->hackOffsets[r], MG_ROWS(A, r), MG_ROWS(A, r) + 2 * A->halo,       \
+						(T*)x->ext[r], beta, A->halo, links, seq);                                        \
+				else                                                                                      \
+					spgpu##S##hellspmvHalo(mg->h[r], zr, yr, alpha, (const T*)A->cM[r], A->rP[r],         \
+						A->hackSize, A->hackOffsets[r], A->rS[r], A->avg, MG_ROWS(A, r), (T*)x->ext[r],   \
+						beta, A->baseIndex, A->halo, links, seq);                                         \
 			}                                                                                             \
 		} else {                                                                                          \
 			exchange_with_events(mg, x);                                                                  \
 			for (r = 0; r < mg->world; ++r) {                                                             \
 				use_rank(mg, r);                                                                          \
-				spgpu##S##hellspmv(mg->h[r], (T*)owned_ptr(z, r), y ? (const T*)owned_ptr(y, r) : NULL,   \
-					alpha, (const T*)A->cM[r], A->rP[r], A->hackSize, A->hackOffsets[r], A->rS[r], NULL,  \
-					A->avg, MG_ROWS(A, r), (const T*)x->ext[r], beta, A->baseIndex);                      \
+				mg_##S##_block_spmv(A, r, (T*)owned_ptr(z, r), y ? (const T*)owned_ptr(y, r) : NULL,      \
+					alpha, (const T*)x->ext[r], beta);                                                    \
 			}                                                                                             \
 			mark_products_done(mg);                                                                       \
 		}                                                                                                 \
@@ -756,6 +933,21 @@ static spgpuStatus_t check_launches(void)
 			st = check_launches();                                                                        \
 		cudaSetDevice(previous);                                                                          \
 		return st;                                                                                        \
+	}                                                                                                     \
+	spgpuStatus_t spgpuMg##S##hellspmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y, T alpha, \
+		spgpuMgMatrix_t A, spgpuMgVector_t x, T beta)                                                     \
+	{                                                                                                     \
+		return (A && A->kind == MG_KIND_HELL) ? mg_##S##_spmv(mg, z, y, alpha, A, x, beta) : SPGPU_UNSUPPORTED; \
+	}                                                                                                     \
+	spgpuStatus_t spgpuMg##S##hdiaspmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y, T alpha, \
+		spgpuMgMatrix_t A, spgpuMgVector_t x, T beta)                                                     \
+	{                                                                                                     \
+		return (A && A->kind == MG_KIND_HDIA) ? mg_##S##_spmv(mg, z, y, alpha, A, x, beta) : SPGPU_UNSUPPORTED; \
+	}                                                                                                     \
+	spgpuStatus_t spgpuMg##S##spmv(spgpuMgHandle_t mg, spgpuMgVector_t z, spgpuMgVector_t y, T alpha,     \
+		spgpuMgMatrix_t A, spgpuMgVector_t x, T beta)                                                     \
+	{                                                                                                     \
+		return mg_##S##_spmv(mg, z, y, alpha, A, x, beta);                                                \
 	}                                                                                                     \
 	spgpuStatus_t spgpuMg##S##dot(spgpuMgHandle_t mg, T* result, spgpuMgVector_t a, spgpuMgVector_t b)    \
 	{                                                                                                     \
@@ -959,10 +1151,15 @@ spgpuStatus_t spgpuMgDcgStep(spgpuMgCg_t cg, int iterations, double* rr)
 			for (r = 0; r < mg->world; ++r) {            /* Ap = A p (+ halo of p) and p.Ap, all-reduced */
 				use_rank(mg, r);
 				ar.myRank = r;
-				spgpuDhellspmvHaloDot(mg->h[r], (double*)owned_ptr(cg->ap, r), (const double*)A->cM[r], A->rP[r],
-					A->hackSize, A->hackOffsets[r], A->rS[r], A->avg, MG_ROWS(A, r), (double*)cg->p->ext[r],
-					A->baseIndex, A->halo, mg->world > 1 ? &cg->p->links[r] : NULL, seq, cg->s[r] + 1,
-					mg->world > 1 ? &ar : NULL);
+				if (A->kind == MG_KIND_HDIA)
+					spgpuDhdiaspmvHaloDot(mg->h[r], (double*)owned_ptr(cg->ap, r), (const double*)A->cM[r], A->rP[r],
+						A->hackSize, A->hackOffsets[r], MG_ROWS(A, r), MG_ROWS(A, r) + 2 * A->halo, (double*)cg->p->ext[r],
+						A->halo, mg->world > 1 ? &cg->p->links[r] : NULL, seq, cg->s[r] + 1, mg->world > 1 ? &ar : NULL);
+				else
+					spgpuDhellspmvHaloDot(mg->h[r], (double*)owned_ptr(cg->ap, r), (const double*)A->cM[r], A->rP[r],
+						A->hackSize, A->hackOffsets[r], A->rS[r], A->avg, MG_ROWS(A, r), (double*)cg->p->ext[r],
+						A->baseIndex, A->halo, mg->world > 1 ? &cg->p->links[r] : NULL, seq, cg->s[r] + 1,
+						mg->world > 1 ? &ar : NULL);
 			}
 			ar.seq = ++mg->arSeq;
 			for (r = 0; r < mg->world; ++r) {            /* x += a p ; r -= a Ap ; rr' = r.r, all-reduced */
@@ -992,7 +1189,7 @@ spgpuStatus_t spgpuMgDcgStep(spgpuMgCg_t cg, int iterations, double* rr)
 	} else {
 		for (it = 0; it < iterations && st == SPGPU_SUCCESS; ++it) {
 			double pap = 0.0, rrNew = 0.0, a;
-			st = spgpuMgDhellspmv(mg, cg->ap, NULL, 1.0, A, cg->p, 0.0);
+			st = spgpuMgDspmv(mg, cg->ap, NULL, 1.0, A, cg->p, 0.0);
 			if (st == SPGPU_SUCCESS) st = spgpuMgDdot(mg, &pap, cg->p, cg->ap);
 			a = cg->rr / pap;
 			if (st == SPGPU_SUCCESS) st = spgpuMgDaxpby(mg, cg->x, 1.0, cg->x, a, cg->p);

@@ -45,6 +45,14 @@ class Mg:
         assert st == 0, f"spgpuMg{s}hellCreate -> {st}"
         return A
 
+    def hdia_matrix(self, hdia, expect=0):
+        s = util.sym_of(hdia.values.dtype)
+        A = ctypes.c_void_p()
+        st = getattr(self.L, f"spgpuMg{s}hdiaCreate")(self.h, ctypes.byref(A), util.ptr(hdia.values), util.ptr(hdia.offsets),
+                                                      hdia.hack_size, util.ptr(hdia.hack_offsets), hdia.nrows, hdia.ncols)
+        assert st == expect, f"spgpuMg{s}hdiaCreate -> {st}"
+        return A
+
     def vector(self, A, values=None):
         v = ctypes.c_void_p()
         assert self.L.spgpuMgVectorCreate(A, ctypes.byref(v)) == 0
@@ -173,11 +181,68 @@ def test_partitioned_blas1(ours, dtype):
         mg.close()
 
 
-def test_partitioned_cg(ours, oracle):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_partitioned_hdia_spmv_equals_the_single_gpu_product(ours, gpu_handle, dtype):
+    """the same for a matrix handed over in HDIA (spgpuMg?hdiaCreate: hacks re-based, diagonal offsets raised by the
+    halo width, cells outside the matrix stored as 0): spgpuMg?hdiaspmv and the format-agnostic spgpuMg?spmv on
+    1 / 2 / 3 ranks == spgpu?hdiaspmv on the whole matrix bit for bit == the CPU oracle within tolerance"""
+    s = util.sym_of(dtype)
+    t = util.TYPES[s]
+    n = 16
+    coo = G.stencil3d_27pt(n)
+    vals = coo.vals.astype(dtype)
+    if t.is_complex:
+        vals = (vals + 0.25j * np.random.default_rng(1).standard_normal(vals.shape[0])).astype(dtype)
+    coo = F.Coo(coo.rows, coo.cols, vals, coo.nrows, coo.ncols, coo.base)
+    hdia = F.coo_to_hdia(coo, 32)
+    x = G.random_vector(coo.nrows, dtype, 1, -1, 1)
+    y = G.random_vector(coo.nrows, dtype, 2, -1, 1)
+    alpha, beta = scalars(dtype)
+    single = util.dev_spmv(ours, gpu_handle, "hdia", hdia, util.upload(hdia), x, y, alpha, beta)
+    want = util.oracle_spmv("hdia", hdia, x, y, alpha, beta)
+    util.assert_rows_close(single, want, util.row_scale(coo, x, y, alpha, beta), s, "single-GPU product")
+    for devices, what in _device_lists():
+        mg = Mg(ours, devices)
+        try:
+            A = mg.hdia_matrix(hdia)
+            halo = ours.spgpuMgMatrixHalo(A)
+            assert halo == (0 if len(devices) == 1 else -(-(n * n + n + 1) // 32) * 32), (what, halo)
+            vx, vy, vz = mg.vector(A, x), mg.vector(A, y), mg.vector(A)
+            for k in range(3):
+                op = "hdiaspmv" if k < 2 else "spmv"
+                st = getattr(ours, f"spgpuMg{s}{op}")(mg.h, vz, vy, t.scalar(alpha), A, vx, t.scalar(beta))
+                assert st == 0
+            assert ours.spgpuMgSynchronize(mg.h) == 0
+            got = mg.get(vz, coo.nrows, dtype)
+            assert np.array_equal(got.view(np.uint8), single.view(np.uint8)), what
+            # the HELL entry point refuses an HDIA matrix
+            st = getattr(ours, f"spgpuMg{s}hellspmv")(mg.h, vz, vy, t.scalar(alpha), A, vx, t.scalar(beta))
+            assert st == capi.SPGPU_UNSUPPORTED
+            for v in (vx, vy, vz):
+                ours.spgpuMgVectorDestroy(v)
+            ours.spgpuMgMatrixDestroy(A)
+        finally:
+            mg.close()
+
+
+def test_hdia_that_does_not_fit_a_neighbouring_block_is_refused(ours):
+    """8 blocks of 64 rows cannot feed a 96-entry halo (27-point stencil on 8^3): SPGPU_UNSUPPORTED, no matrix"""
+    hdia = F.coo_to_hdia(G.stencil3d_27pt(8), 32)
+    mg = Mg(ours, [0] * 8)
+    try:
+        A = mg.hdia_matrix(hdia, expect=capi.SPGPU_UNSUPPORTED)
+        assert not A.value
+    finally:
+        mg.close()
+
+
+@pytest.mark.parametrize("fmt", ["hell", "hdia"])
+def test_partitioned_cg(ours, oracle, fmt):
     """spgpuMgDcgStart / spgpuMgDcgStep on 1 rank (device flavour: fused SpMV + dot, device scalars) and on 3 ranks
     of one device (the blocking recurrence of the EVENTS mode): same residual history as the CPU recurrence"""
     coo = G.laplace3d_7pt(14)
     hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    hdia = F.coo_to_hdia(coo, 32)
     n = coo.nrows
     b = G.random_vector(n, np.float64, 9)
     x = np.zeros(n); r = b.copy(); p = b.copy(); rr = float(r @ r)
@@ -193,7 +258,7 @@ def test_partitioned_cg(ours, oracle):
     for devices, what in _device_lists():
         mg = Mg(ours, devices)
         try:
-            A = mg.matrix(hell)
+            A = mg.matrix(hell) if fmt == "hell" else mg.hdia_matrix(hdia)
             vb = mg.vector(A, b)
             cg = ctypes.c_void_p()
             assert ours.spgpuMgDcgCreate(A, ctypes.byref(cg)) == 0

@@ -299,3 +299,41 @@ def test_c_partition_plan_of_an_unstructured_pattern_is_all_gather():
     assert _plan(L, hell, 0)[0] != 0 and _plan(L, hell, 17)[0] != 0
     bad = F.Hell(hell.values, hell.indices, hell.hack_offsets, hell.rs, 48, hell.height, hell.nrows, hell.ncols, 0)
     assert _plan(L, bad, 2)[0] != 0                              # hackSize must be a multiple of 32
+
+
+def test_c_hdia_partition_plan_agrees_with_the_python_partition():
+    """spgpuMgHdiaPlan: same row blocks, the halo is the furthest NON-ZERO cell outside its block rounded up to 32
+    (mg.split_hdia accepts it and refuses anything 32 narrower), blocks smaller than the halo do not fit"""
+    import ctypes
+    from spgpu_b200 import capi
+    L = capi.lib()
+    for coo, hs in ((G.stencil3d_27pt(8), 32), (G.laplace2d_5pt(40, 23), 32), (G.laplace3d_7pt(12), 64)):
+        for dtype in (np.float64, np.complex64):
+            hdia = F.coo_to_hdia(F.Coo(coo.rows, coo.cols, coo.vals.astype(dtype), coo.nrows, coo.ncols, coo.base), hs)
+            vals = np.ascontiguousarray(hdia.values)
+            offs = np.ascontiguousarray(hdia.offsets, np.int32)
+            hoff = np.ascontiguousarray(hdia.hack_offsets, np.int32)
+            for world in (1, 2, 3, 6):
+                bounds = (ctypes.c_int * (world + 1))()
+                halo, fits = ctypes.c_int(-1), ctypes.c_int(-1)
+                st = L.spgpuMgHdiaPlan(world, capi.TYPES[util.sym_of(dtype)].code, vals.ctypes.data, offs.ctypes.data, hs,
+                                       hoff.ctypes.data, hdia.nrows, hdia.ncols, bounds, ctypes.byref(halo), ctypes.byref(fits))
+                assert st == 0
+                assert list(bounds) == [a for a, _ in mg.row_blocks(hdia.nrows, world, hs)] + [hdia.nrows]
+                if world == 1:
+                    assert (halo.value, fits.value) == (0, 1)
+                    continue
+                reach = int(np.abs(coo.rows.astype(np.int64) - coo.cols.astype(np.int64)).max())
+                smallest = min(b - a for a, b in zip(bounds, list(bounds)[1:]))
+                if not fits.value:
+                    assert smallest < halo.value
+                    continue
+                assert halo.value % 32 == 0 and 0 < halo.value <= ((reach + 31) // 32) * 32 and smallest >= halo.value
+                for r in range(world):
+                    mg.split_hdia(hdia, world, r, halo.value)
+                if halo.value > 32:
+                    with pytest.raises(ValueError):
+                        for r in range(world):
+                            mg.split_hdia(hdia, world, r, halo.value - 32)
+    assert L.spgpuMgHdiaPlan(2, capi.TYPES["D"].code, vals.ctypes.data, offs.ctypes.data, 48, hoff.ctypes.data, 10, 10,
+                             bounds, ctypes.byref(halo), ctypes.byref(fits)) != 0
