@@ -979,7 +979,6 @@ def main():
                       f"waited lo {r_[2] / 1e3:7.1f} us in {r_[4]} blocks, hi {r_[3] / 1e3:7.1f} us in {r_[5]} blocks",
                       file=sys.stderr, flush=True)
         L.spgpuSetTuning(h, b"haloTrace", 0)
-    clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -1023,6 +1022,9 @@ def main():
         if world > 1:
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         ker_b2b_ms = float(tb.item())
+    # the sampler has been running since before the warm-up: it covers the timed steps AND the kernel-alone launches
+    # the roofline is computed from (a 40 ms timed region alone is one or two nvidia-smi samples)
+    clocks = sampler.stop() if rank == 0 else None
     peak, peak_src = measured_peak()
     achieved = w["bytes"] / (ker_ms * 1e-3) / 1e9
     traffic = None

@@ -206,7 +206,9 @@ def test_partitioned_hdia_spmv_equals_the_single_gpu_product(ours, gpu_handle, d
         try:
             A = mg.hdia_matrix(hdia)
             halo = ours.spgpuMgMatrixHalo(A)
-            assert halo == (0 if len(devices) == 1 else -(-(n * n + n + 1) // 32) * 32), (what, halo)
+            # the furthest cell OUTSIDE a block: at most the widest diagonal n*n + n + 1, less where the block boundary
+            # is a plane boundary (the rows next to it have no x+1 / y+1 neighbours)
+            assert (halo == 0) if len(devices) == 1 else (halo % 32 == 0 and n * n <= halo <= -(-(n * n + n + 1) // 32) * 32), (what, halo)
             vx, vy, vz = mg.vector(A, x), mg.vector(A, y), mg.vector(A)
             for k in range(3):
                 op = "hdiaspmv" if k < 2 else "spmv"
@@ -226,9 +228,17 @@ def test_partitioned_hdia_spmv_equals_the_single_gpu_product(ours, gpu_handle, d
 
 
 def test_hdia_that_does_not_fit_a_neighbouring_block_is_refused(ours):
-    """8 blocks of 64 rows cannot feed a 96-entry halo (27-point stencil on 8^3): SPGPU_UNSUPPORTED, no matrix"""
+    """16 blocks of 32 rows cannot feed a halo of a whole 64-row plane (27-point stencil on 8^3): SPGPU_UNSUPPORTED, no
+    matrix; 8 blocks of one plane each are fine (their rows reach exactly one block away)"""
     hdia = F.coo_to_hdia(G.stencil3d_27pt(8), 32)
     mg = Mg(ours, [0] * 8)
+    try:
+        A = mg.hdia_matrix(hdia)
+        assert ours.spgpuMgMatrixHalo(A) == 64
+        ours.spgpuMgMatrixDestroy(A)
+    finally:
+        mg.close()
+    mg = Mg(ours, [0] * 16)
     try:
         A = mg.hdia_matrix(hdia, expect=capi.SPGPU_UNSUPPORTED)
         assert not A.value
