@@ -339,6 +339,40 @@ def test_blocks_handed_over_pre_partitioned(ours, gpu_handle):
             mg.close()
 
 
+@pytest.mark.parametrize("nrows", [0, 40, 64])
+def test_fewer_hacks_than_ranks_and_the_empty_matrix(ours, gpu_handle, nrows):
+    """3 ranks, a matrix of 0 / 2 / 2 hacks: some ranks own no rows at all (a zone cannot be fed from an empty
+    block, so the plan is all-gather); every call still succeeds and the owners' rows are right"""
+    coo = G.laplace2d_5pt(8, nrows // 8) if nrows else F.Coo(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0), 0, 0, 0)
+    hell = F.ell_to_hell(F.coo_to_ell(coo), 32)
+    x = G.random_vector(nrows, np.float64, 1, -1, 1)
+    T = util.TYPES["D"]
+    single = util.dev_spmv(ours, gpu_handle, "hell", hell, util.upload(hell), x, None, 1.0, 0.0) if nrows else np.zeros(0)
+    mg = Mg(ours, [0, 0, 0])
+    try:
+        A = mg.matrix(hell)
+        assert ours.spgpuMgMatrixRows(A) == nrows
+        assert ours.spgpuMgMatrixHalo(A) == -1
+        lo, hi = ctypes.c_int(), ctypes.c_int()
+        owned = []
+        for r in range(3):
+            ours.spgpuMgMatrixRowBlock(A, r, ctypes.byref(lo), ctypes.byref(hi))
+            owned.append(hi.value - lo.value)
+        assert sum(owned) == nrows and min(owned) == 0
+        vx, vz = mg.vector(A, x), mg.vector(A)
+        for _ in range(2):
+            assert ours.spgpuMgDhellspmv(mg.h, vz, None, T.scalar(1.0), A, vx, T.scalar(0.0)) == 0
+        assert ours.spgpuMgSynchronize(mg.h) == 0
+        assert np.array_equal(mg.get(vz, nrows, np.float64), single)
+        res = ctypes.c_double(-1.0)
+        assert ours.spgpuMgDdot(mg.h, ctypes.byref(res), vx, vx) == 0
+        assert abs(res.value - float(x @ x)) <= 1e-12 * max(1.0, float(x @ x))
+        ours.spgpuMgVectorDestroy(vx); ours.spgpuMgVectorDestroy(vz)
+        ours.spgpuMgMatrixDestroy(A)
+    finally:
+        mg.close()
+
+
 def test_argument_checks(ours):
     mg = Mg(ours, [0, 0])
     try:
