@@ -31,8 +31,16 @@ unsigned long long spgpuGetLaunchCount(spgpuHandle_t handle);
 /*
  * Kernel-selection knobs (per handle).  Keys: hellVariant, hellBlock,
  * hellLongFactor, hellSplit, hdiaVariant, hdiaBlock, ellRows, ellShortMinB,
- * redBlocksPerSm, vecBlocksPerSm, spinTimeoutMs, haloTrace, l2Fetch (meanings:
- * csrc/spgpu_internal.h).  Returns 0, or -1 for an unknown key.
+ * redBlocksPerSm, vecBlocksPerSm, redInflight, hellPrefetch, hdiaPrefetch,
+ * spinTimeoutMs, haloTrace, l2Fetch, pdl (meanings: csrc/spgpu_internal.h).
+ * Returns 0, or -1 for an unknown key.
+ *
+ * pdl (default 1; the environment variable SPGPU_PDL=0/1 overrides the default at spgpuCreate):
+ * the SpMV, BLAS-1 and Krylov kernels are launched with programmatic stream serialization and
+ * begin with griddepcontrol.wait, so the CTAs of a kernel are placed while the last wave of the
+ * kernel before it in the stream drains and start the moment it has completed -- same results
+ * (tests/test_pdl_gpu.py), launch latency and ramp-up hidden.  Calls stay ordered on
+ * handle->currentStream exactly as the reference's <<< >>> launches are.
  */
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value);
 int spgpuGetTuning(spgpuHandle_t handle, const char* key);

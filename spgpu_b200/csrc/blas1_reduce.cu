@@ -103,6 +103,8 @@ reduce_kernel(const T* x, const T* y, long long n, long long pitch, Acc2* partia
 {
 	__shared__ Acc2 smem[32];
 	__shared__ bool amLast;
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long nthreads = (long long)gridDim.x * blockDim.x;
 	constexpr int N = RPack<T>::N;
@@ -199,15 +201,15 @@ static unsigned reduce_grid(long long n, long long cap, int INFL)
 }
 
 template <typename T, typename Op>
-static void reduce_dispatch(int infl, dim3 grid, cudaStream_t s, const T* x, const T* y, long long n, long long pitch,
+static void reduce_dispatch(spgpuHandle_t handle, int infl, dim3 grid, const T* x, const T* y, long long n, long long pitch,
 	Acc2* partials, unsigned* tickets, void* out, int outBytes, int finish, int outKind)
 {
 	if (infl == 8)
-		reduce_kernel<T, Op, 8><<<grid, RED_BLOCK, 0, s>>>(x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
+		spgpu_launch_dep(handle, reduce_kernel<T, Op, 8>, grid, RED_BLOCK, x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
 	else if (infl == 4)
-		reduce_kernel<T, Op, 4><<<grid, RED_BLOCK, 0, s>>>(x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
+		spgpu_launch_dep(handle, reduce_kernel<T, Op, 4>, grid, RED_BLOCK, x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
 	else
-		reduce_kernel<T, Op, 2><<<grid, RED_BLOCK, 0, s>>>(x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
+		spgpu_launch_dep(handle, reduce_kernel<T, Op, 2>, grid, RED_BLOCK, x, y, n, pitch, partials, tickets, out, outBytes, finish, outKind);
 }
 
 template <typename T, typename Op>
@@ -217,7 +219,7 @@ static void reduce_launch(spgpuHandle_t handle, const T* x, const T* y, long lon
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	const SpgpuTuning* t = spgpu_tuning(handle);
 	const long long cap = (long long)handle->multiProcessorCount * (t->redBlocksPerSm > 0 ? t->redBlocksPerSm : 8);
-	reduce_dispatch<T, Op>(reduce_inflight<Op>(t), dim3(reduce_grid<T, Op>(n, cap, reduce_inflight<Op>(t))), handle->currentStream,
+	reduce_dispatch<T, Op>(handle, reduce_inflight<Op>(t), dim3(reduce_grid<T, Op>(n, cap, reduce_inflight<Op>(t))),
 		x, y, n, 0, reinterpret_cast<Acc2*>(h->dPartials), h->dTicket, out, 0, finish, outKind);
 	spgpu_count_launch(handle);
 }
@@ -272,7 +274,7 @@ static void reduce_many(spgpuHandle_t handle, Ret* hostOut, const T* x, const T*
 	for (int v0 = 0; v0 < count; v0 += slice) {
 		const int nv = count - v0 < slice ? count - v0 : slice;
 		const long long o = (long long)v0 * pitch;
-		reduce_dispatch<T, Op>(infl, dim3(gx, (unsigned)nv), handle->currentStream,
+		reduce_dispatch<T, Op>(handle, infl, dim3(gx, (unsigned)nv),
 			x + o, y ? y + o : (const T*)0, n, pitch, reinterpret_cast<Acc2*>(base + resBytes), tickets,
 			dOut + v0, (int)sizeof(Ret), finish, outKind);
 		spgpu_count_launch(handle);

@@ -26,6 +26,8 @@ template <typename T, int NIN, typename Op>
 __global__ void __launch_bounds__(256)
 ew_kernel(T* out, const T* in0, const T* in1, const T* in2, long long n, Op op, int vec)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long nthreads = (long long)gridDim.x * blockDim.x;
 	constexpr int N = Pack<T>::N;
@@ -87,7 +89,7 @@ static void ew_launch(spgpuHandle_t handle, T* out, const T* in0, const T* in1,
 	const long long cap = (long long)handle->multiProcessorCount * (t->vecBlocksPerSm > 0 ? t->vecBlocksPerSm : 8);
 	if (cap > 0 && want > cap) want = cap;
 	if (want < 1) want = 1;
-	ew_kernel<T, NIN, Op><<<(unsigned)want, block, 0, handle->currentStream>>>(out, in0, in1, in2, n, op, vec);
+	spgpu_launch_dep(handle, ew_kernel<T, NIN, Op>, (unsigned)want, block, out, in0, in1, in2, n, op, vec);
 	spgpu_count_launch(handle);
 }
 

@@ -33,6 +33,7 @@ static void default_tuning(SpgpuTuning* t)
 	t->ellShortMinB = 0;
 	t->hellPrefetch = 0;
 	t->hdiaPrefetch = 0;
+	t->pdl = 1;               /* programmatic dependent launch on (launch.cuh); 0 = plain stream order */
 }
 
 spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
@@ -51,7 +52,10 @@ spgpuStatus_t spgpuCreate(spgpuHandle_t* pHandle, int device)
 	default_tuning(&h->tune);
 	{
 		const char* dbg = getenv("SPGPU_DEBUG");
+		const char* pdl = getenv("SPGPU_PDL");          /* overrides the default of the `pdl` tuning key (A/B runs) */
 		h->debug = dbg && dbg[0] && dbg[0] != '0';
+		if (pdl && pdl[0])
+			h->tune.pdl = pdl[0] != '0';
 	}
 
 	cudaGetDevice(&previous);
@@ -285,7 +289,8 @@ int spgpuGetDeviceStatus(spgpuHandle_t handle, int clear)
 	X(redInflight)            \
 	X(ellShortMinB)           \
 	X(hellPrefetch)           \
-	X(hdiaPrefetch)
+	X(hdiaPrefetch)           \
+	X(pdl)
 
 int spgpuSetTuning(spgpuHandle_t handle, const char* key, int value)
 {

@@ -318,6 +318,8 @@ template <typename T, class Body, int MINB, bool DOT, bool HALO>
 __global__ void __launch_bounds__(128, MINB)
 spmv_halo_kernel(const Body body, const HaloArgs<T> hx, int xOffset, typename DotPartial<T>::type* __restrict__ warpPartials /* one per 32 rows */)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const unsigned rows = (unsigned)body.rows();
 	unsigned rb = blockIdx.x;
 	bool needLo = false, needHi = false;
@@ -498,7 +500,6 @@ static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 		return;
 	}
 	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
-	cudaStream_t s = handle->currentStream;
 	constexpr int MB = HaloMinB<T>::hell;
 	const HellRowBody<T, UNROLL, 32> b32 = { a };
 	const HellRowBody<T, UNROLL, 0> b0 = { a };
@@ -513,19 +514,19 @@ static void hell_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 			constexpr int MD = Num<T>::is_complex ? 8 : 12;
 			const bool dense = t->hellBlock >= 256 || (t->hellBlock != 192 && !halo);
 			if (dense) {
-				if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-				else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-			} else if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+				if (halo) spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, true>, grid, 128, b32, hx, haloN, ctaPartials);
+				else      spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MD, true, false>, grid, 128, b32, hx, haloN, ctaPartials);
+			} else if (halo) spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, true>, grid, 128, b32, hx, haloN, ctaPartials);
+			else      spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, true, false>, grid, 128, b32, hx, haloN, ctaPartials);
 		} else {
-			if (halo) spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
-			else      spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			if (halo) spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, true>, grid, 128, b0, hx, haloN, ctaPartials);
+			else      spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, true, false>, grid, 128, b0, hx, haloN, ctaPartials);
 		}
 	} else {
 		if (hackSize == 32)
-			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, false, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 32>, MB, false, true>, grid, 128, b32, hx, haloN, ctaPartials);
 		else
-			spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, false, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			spgpu_launch_dep(handle, spmv_halo_kernel<T, HellRowBody<T, UNROLL, 0>, 8, false, true>, grid, 128, b0, hx, haloN, ctaPartials);
 	}
 	spgpu_count_launch(handle);
 }
@@ -543,22 +544,21 @@ static void hdia_spmv_halo_launch(spgpuHandle_t handle, T* z, const T* y, T alph
 		return;
 	}
 	const unsigned grid = hx.pushCtas + spgpu_ceil_div(rows, 128);
-	cudaStream_t s = handle->currentStream;
 	const HdiaRowBody<T, UNROLL, 32> b32 = { a };
 	const HdiaRowBody<T, UNROLL, 0> b0 = { a };
 	if (ctaPartials) {
 		if (hackSize == 32) {
-			if (halo) spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
-			else      spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true, false><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			if (halo) spgpu_launch_dep(handle, spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true, true>, grid, 128, b32, hx, haloN, ctaPartials);
+			else      spgpu_launch_dep(handle, spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, true, false>, grid, 128, b32, hx, haloN, ctaPartials);
 		} else {
-			if (halo) spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
-			else      spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true, false><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			if (halo) spgpu_launch_dep(handle, spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true, true>, grid, 128, b0, hx, haloN, ctaPartials);
+			else      spgpu_launch_dep(handle, spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, true, false>, grid, 128, b0, hx, haloN, ctaPartials);
 		}
 	} else {
 		if (hackSize == 32)
-			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, false, true><<<grid, 128, 0, s>>>(b32, hx, haloN, ctaPartials);
+			spgpu_launch_dep(handle, spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 32>, 8, false, true>, grid, 128, b32, hx, haloN, ctaPartials);
 		else
-			spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, false, true><<<grid, 128, 0, s>>>(b0, hx, haloN, ctaPartials);
+			spgpu_launch_dep(handle, spmv_halo_kernel<T, HdiaRowBody<T, UNROLL, 0>, 8, false, true>, grid, 128, b0, hx, haloN, ctaPartials);
 	}
 	spgpu_count_launch(handle);
 }

@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(256)
 axpby_dev_kernel(T* z, long long n, const T* bNum, const T* bDen, double bSign, const T* y,
 	const T* aNum, const T* aDen, double aSign, const T* x, int vec)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const T a = dev_quotient<T>(aNum, aDen, aSign), b = dev_quotient<T>(bNum, bDen, bSign);
 	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long nthreads = (long long)gridDim.x * blockDim.x;
@@ -80,7 +82,7 @@ static void axpby_dev_launch(spgpuHandle_t handle, T* z, int n, const T* dBetaNu
 	long long want = ((vec ? n / (2 * KPack<T>::N) : n) + 255) / 256 + 1;
 	const long long cap = (long long)handle->multiProcessorCount * (t->vecBlocksPerSm > 0 ? t->vecBlocksPerSm : 8);
 	if (cap > 0 && want > cap) want = cap;
-	axpby_dev_kernel<T><<<(unsigned)want, 256, 0, handle->currentStream>>>(z, n, dBetaNum, dBetaDen,
+	spgpu_launch_dep(handle, axpby_dev_kernel<T>, (unsigned)want, 256, z, n, dBetaNum, dBetaDen,
 		betaSign, y, dAlphaNum, dAlphaDen, alphaSign, x, vec);
 	spgpu_count_launch(handle);
 }
@@ -114,6 +116,8 @@ cg_update_kernel(T* x, T* r, const T* p, const T* ap, long long n, const T* rr, 
 {
 	__shared__ Acc2 smem[32];
 	__shared__ bool amLast;
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const T alpha = Num<T>::div(__ldg(rr), __ldg(pap));
 	const T nalpha = Num<T>::mul(Num<T>::from_real(-1), alpha);
 	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -174,7 +178,7 @@ static void cg_update_launch(spgpuHandle_t handle, T* x, T* r, const T* p, const
 	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
 	if (want > cap) want = cap;
 	if (want < 1) want = 1;
-	cg_update_kernel<T><<<(unsigned)want, 256, 0, handle->currentStream>>>(x, r, p, ap, n > 0 ? n : 0, dRr, dPAp, vec,
+	spgpu_launch_dep(handle, cg_update_kernel<T>, (unsigned)want, 256, x, r, p, ap, n > 0 ? n : 0, dRr, dPAp, vec,
 		reinterpret_cast<Acc2*>(h->dPartials), h->dTicket, dRrNew, spgpu_ar_args(handle, ar));
 	spgpu_count_launch(handle);
 }
@@ -188,6 +192,8 @@ fold_partials_kernel(const typename DotPartial<T>::type* __restrict__ in, long l
 {
 	__shared__ Acc2 smem[32];
 	__shared__ bool amLast;
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long nthreads = (long long)gridDim.x * blockDim.x;
 	Acc2 s = { 0.0, 0.0 };
@@ -219,7 +225,7 @@ void spgpu_fold_partials(spgpuHandle_t handle, const typename DotPartial<T>::typ
 	if (cap > SPGPU_RED_MAX_BLOCKS) cap = SPGPU_RED_MAX_BLOCKS;
 	if (want > cap) want = cap;
 	if (want < 1) want = 1;
-	fold_partials_kernel<T><<<(unsigned)want, 256, 0, handle->currentStream>>>(partials, n > 0 ? n : 0,
+	spgpu_launch_dep(handle, fold_partials_kernel<T>, (unsigned)want, 256, partials, n > 0 ? n : 0,
 		reinterpret_cast<Acc2*>(h->dPartials), h->dTicket, dRes, spgpu_ar_args(handle, ar));
 	spgpu_count_launch(handle);
 }

@@ -49,6 +49,8 @@ typedef struct SpgpuTuning {
 	int ellShortMinB;    /* (reserved) */
 	int hdiaPrefetch;    /* HDIA: the same look-ahead for hackOffsets and the hack's slice of offsets[] (0 = default 2 waves, < 0 = off) */
 	int hellPrefetch;    /* HELL: waves of resident CTAs ahead of which a warp prefetches its hackOffsets entry into L2 (0 = default 2, < 0 = off) */
+	int pdl;             /* > 0: the kernels that begin with grid_dependency_wait() are launched with programmatic stream
+	                      * serialization, so the next kernel's CTAs take the slots the previous kernel's tail leaves (launch.cuh) */
 } SpgpuTuning;
 
 typedef struct SpgpuHandlePriv {

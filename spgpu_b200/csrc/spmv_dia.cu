@@ -23,6 +23,8 @@ dia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ dM
 	const int* __restrict__ offsets, int dMPitch, int rows, int cols, int diags,
 	const T* __restrict__ x, T beta)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned lane = threadIdx.x & 31;
 	if (i - lane >= (unsigned)rows)
@@ -78,7 +80,7 @@ static void dia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 {
 	if (rows <= 0)
 		return;
-	dia_spmv_kernel<T, UNROLL><<<spgpu_ceil_div(rows, 128), 128, 0, handle->currentStream>>>(
+	spgpu_launch_dep(handle, dia_spmv_kernel<T, UNROLL>, spgpu_ceil_div(rows, 128), 128, 
 		z, y, alpha, dM, offsets, dMPitch, rows, cols, diags, x, beta);
 	spgpu_count_launch(handle);
 }

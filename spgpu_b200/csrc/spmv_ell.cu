@@ -23,6 +23,8 @@ ell_spmv_kernel(T* __restrict__ z, const T* y, T alpha,
 	int maxNnzPerRow, int rows, const T* __restrict__ x, T beta, int baseIndex,
 	int longCut, int allocated)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned lane = threadIdx.x & 31;
 	if (i - lane >= (unsigned)rows)
@@ -59,6 +61,8 @@ ell_spmv_short_kernel(T* __restrict__ z, const T* y, T alpha,
 	int rPPitch, const int* __restrict__ rS, const int* __restrict__ rIdx,
 	int rows, const T* __restrict__ x, T beta, int baseIndex)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const unsigned first = blockIdx.x * ((unsigned)BLOCK * ROWS) + threadIdx.x;
 	const bool useBeta = Num<T>::nonzero(beta);
 	int col[ROWS][NS];
@@ -109,25 +113,24 @@ static void ell_spmv_short_launch(spgpuHandle_t handle, int rowsPerLane, T* z, c
 	const T* cM, const int* rP, int cMPitch, int rPPitch, const int* rS, const int* rIdx,
 	int rows, const T* x, T beta, int baseIndex)
 {
-	cudaStream_t s = handle->currentStream;
 	/* registers ~ 20 + ROWS*NS*(1 + words per value) (ptxas -v): the CTA count that fits without spills */
 	constexpr int W = sizeof(T) / 4;
 	constexpr int MINB1 = NS * (1 + W) <= 16 ? 16 : NS * (1 + W) <= 24 ? 12 : 8;
 	constexpr int MINB2 = 2 * NS * (1 + W) <= 32 ? 10 : 2 * NS * (1 + W) <= 48 ? 8 : 5;
 	if (rowsPerLane == 3)              /* ellRows = 3 / 4: one row per lane in CTAs of 256 / 512 threads (fewer CTA launches) */
-		ell_spmv_short_kernel<T, NS, 1, MINB1, 256><<<spgpu_ceil_div(rows, 256), 256, 0, s>>>(
+		spgpu_launch_dep(handle, ell_spmv_short_kernel<T, NS, 1, MINB1, 256>, spgpu_ceil_div(rows, 256), 256, 
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
 	else if (rowsPerLane == 4)
-		ell_spmv_short_kernel<T, NS, 1, MINB1, 512><<<spgpu_ceil_div(rows, 512), 512, 0, s>>>(
+		spgpu_launch_dep(handle, ell_spmv_short_kernel<T, NS, 1, MINB1, 512>, spgpu_ceil_div(rows, 512), 512, 
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
 	else if (rowsPerLane == 5)         /* 64-thread CTAs */
-		ell_spmv_short_kernel<T, NS, 1, MINB1, 64><<<spgpu_ceil_div(rows, 64), 64, 0, s>>>(
+		spgpu_launch_dep(handle, ell_spmv_short_kernel<T, NS, 1, MINB1, 64>, spgpu_ceil_div(rows, 64), 64, 
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
 	else if (rowsPerLane >= 2)
-		ell_spmv_short_kernel<T, NS, 2, MINB2><<<spgpu_ceil_div(rows, 256), 128, 0, s>>>(
+		spgpu_launch_dep(handle, ell_spmv_short_kernel<T, NS, 2, MINB2>, spgpu_ceil_div(rows, 256), 128, 
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
 	else
-		ell_spmv_short_kernel<T, NS, 1, MINB1><<<spgpu_ceil_div(rows, 128), 128, 0, s>>>(
+		spgpu_launch_dep(handle, ell_spmv_short_kernel<T, NS, 1, MINB1>, spgpu_ceil_div(rows, 128), 128, 
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, rows, x, beta, baseIndex);
 	spgpu_count_launch(handle);
 }
@@ -198,11 +201,11 @@ static void ell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	if (t->hellBlock >= 256) dense = true;
 	else if (t->hellBlock > 0 && t->hellBlock <= 64) dense = false;
 	if (dense)
-		ell_spmv_kernel<T, UNROLL, 12><<<grid, block, 0, handle->currentStream>>>(
+		spgpu_launch_dep(handle, ell_spmv_kernel<T, UNROLL, 12>, grid, block, 
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow, rows, x,
 			beta, baseIndex, spgpu_long_cut(t, avgNnzPerRow), allocated);
 	else
-		ell_spmv_kernel<T, UNROLL, 8><<<grid, block, 0, handle->currentStream>>>(
+		spgpu_launch_dep(handle, ell_spmv_kernel<T, UNROLL, 8>, grid, block, 
 			z, y, alpha, cM, rP, cMPitch, rPPitch, rS, rIdx, maxNnzPerRow, rows, x,
 			beta, baseIndex, spgpu_long_cut(t, avgNnzPerRow), allocated);
 	spgpu_count_launch(handle);

@@ -28,6 +28,8 @@ hdia_spmv_kernel(T* __restrict__ z, const T* y, T alpha, const T* __restrict__ d
 	const int* __restrict__ hackOffsets, int rows, int cols,
 	const T* __restrict__ x, T beta, int prefetchHacks)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const HdiaArgs<T> a = { z, y, alpha, dM, offsets, hackSizeRt, hackOffsets, rows, cols, x, beta, prefetchHacks };
 	T unused;
 	hdia_warp_rows_value<T, UNROLL, HACK, PREDICATED>(a, (blockIdx.x * BLOCK + threadIdx.x) & ~31u, unused);
@@ -292,20 +294,20 @@ static void hdia_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	/* occupancy / round-size knob (registers vs resident warps): hdiaBlock >=256 -> 48 warps, 192 -> 40, 176 -> 36,
 	 * 160 -> 24 with twice the unroll, 64 -> 64-thread CTAs, 8 -> rounds of 8 diagonals, else 32 warps, rounds of 9 */
 	if (hackSize == 32 && t->hdiaVariant == 3) {
-		hdia_spmv_kernel<T, UNROLL, 32, 8, true><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 32, 8, true>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	} else if (hackSize == 32) {
-		if (t->hdiaBlock >= 256)      hdia_spmv_kernel<T, UNROLL, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
-		else if (t->hdiaBlock == 224) hdia_spmv_kernel<T, 4, 32, 12><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
-		else if (t->hdiaBlock == 8)   hdia_spmv_kernel<T, U8, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
-		else if (t->hdiaBlock == 64)  hdia_spmv_kernel<T, UNROLL, 32, 16, false, 64><<<spgpu_ceil_div(rows, 64), 64, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
-		else if (t->hdiaBlock == 176) hdia_spmv_kernel<T, UNROLL, 32, 9><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
-		else if (t->hdiaBlock == 160) hdia_spmv_kernel<T, 2 * U8, 32, 6><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
-		else if (t->hdiaBlock == 192) hdia_spmv_kernel<T, UNROLL, 32, 10><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
-		else                          hdia_spmv_kernel<T, UNROLL, 32, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		if (t->hdiaBlock >= 256)      spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 32, 12>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 224) spgpu_launch_dep(handle, hdia_spmv_kernel<T, 4, 32, 12>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 8)   spgpu_launch_dep(handle, hdia_spmv_kernel<T, U8, 32, 8>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 64)  spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 32, 16, false, 64>, spgpu_ceil_div(rows, 64), 64, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 176) spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 32, 9>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 160) spgpu_launch_dep(handle, hdia_spmv_kernel<T, 2 * U8, 32, 6>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else if (t->hdiaBlock == 192) spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 32, 10>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		else                          spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 32, 8>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	} else if (hackSize == 64) {
-		hdia_spmv_kernel<T, UNROLL, 64, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 64, 8>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	} else {
-		hdia_spmv_kernel<T, UNROLL, 0, 8><<<grid, 128, 0, s>>>(z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
+		spgpu_launch_dep(handle, hdia_spmv_kernel<T, UNROLL, 0, 8>, grid, 128, z, y, alpha, dM, offsets, hackSize, hackOffsets, rows, cols, x, beta, pf);
 	}
 	spgpu_count_launch(handle);
 }

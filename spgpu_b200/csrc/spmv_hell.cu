@@ -26,6 +26,8 @@ template <typename T, int UNROLL, int HACK, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 hell_spmv_kernel(const HellArgs<T> a)
 {
+	grid_dependency_wait();
+	grid_launch_dependents();
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	hell_warp_rows<T, UNROLL, HACK>(a, i - (threadIdx.x & 31));
 }
@@ -222,14 +224,14 @@ static void hell_spmv_launch(spgpuHandle_t handle, T* z, const T* y, T alpha,
 	else if (t->hellBlock == 192) level = 10;
 	else if (t->hellBlock > 0 && t->hellBlock <= 64) level = 8;
 	if (hackSize == 32) {
-		if (level == 10)      hell_spmv_kernel<T, UNROLL, 32, 10><<<grid, block, 0, s>>>(HELL_ARGS);
-		else if (level == 12) hell_spmv_kernel<T, UNROLL, 32, 12><<<grid, block, 0, s>>>(HELL_ARGS);
-		else                  hell_spmv_kernel<T, UNROLL, 32, 8><<<grid, block, 0, s>>>(HELL_ARGS);
+		if (level == 10)      spgpu_launch_dep(handle, hell_spmv_kernel<T, UNROLL, 32, 10>, grid, block, HELL_ARGS);
+		else if (level == 12) spgpu_launch_dep(handle, hell_spmv_kernel<T, UNROLL, 32, 12>, grid, block, HELL_ARGS);
+		else                  spgpu_launch_dep(handle, hell_spmv_kernel<T, UNROLL, 32, 8>, grid, block, HELL_ARGS);
 	} else if (hackSize == 64) {
-		if (level >= 10) hell_spmv_kernel<T, UNROLL, 64, 10><<<grid, block, 0, s>>>(HELL_ARGS);
-		else             hell_spmv_kernel<T, UNROLL, 64, 8><<<grid, block, 0, s>>>(HELL_ARGS);
+		if (level >= 10) spgpu_launch_dep(handle, hell_spmv_kernel<T, UNROLL, 64, 10>, grid, block, HELL_ARGS);
+		else             spgpu_launch_dep(handle, hell_spmv_kernel<T, UNROLL, 64, 8>, grid, block, HELL_ARGS);
 	} else {
-		hell_spmv_kernel<T, UNROLL, 0, 8><<<grid, block, 0, s>>>(HELL_ARGS);
+		spgpu_launch_dep(handle, hell_spmv_kernel<T, UNROLL, 0, 8>, grid, block, HELL_ARGS);
 	}
 #undef HELL_ARGS
 	spgpu_count_launch(handle);

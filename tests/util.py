@@ -184,20 +184,11 @@ def dptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def dev_spmv(L, h, fmt, A, dA, x, y, alpha, beta, base=None, ridx=None, rs_null=False, avg=None,
-             inplace=False):
-    """Run one SpMV through the C ABI of library L on device buffers.
-    dA: dict of device tensors of the format arrays.  Returns z as numpy."""
-    import torch
+def dev_spmv_ptr(L, h, fmt, A, dA, dz, dx, dy, alpha, beta, base=None, dr=None, rs_null=False, avg=None):
+    """z = alpha A x + beta y on DEVICE tensors through the C ABI of library L, asynchronous on the handle's stream
+    (dy / dr may be None)."""
     s = sym_of(A.values.dtype)
     t = TYPES[s]
-    dx = to_dev(x)
-    dy = to_dev(y)
-    if inplace:
-        dz = dy
-    else:
-        dz = torch.full((A.nrows,), float("nan"), dtype=dx.dtype, device="cuda")
-    dr = to_dev(ridx)
     a, b = t.scalar(alpha), t.scalar(beta)
     if avg is None:
         avg = max(1, int(np.ceil(A.rs.mean())) if getattr(A, "rs", None) is not None and A.nrows else 1)
@@ -217,6 +208,23 @@ def dev_spmv(L, h, fmt, A, dA, x, y, alpha, beta, base=None, ridx=None, rs_null=
                                          A.hack_size, dptr(dA["hack_offsets"]), A.nrows, A.ncols, dptr(dx), b)
     else:
         raise ValueError(fmt)
+
+
+def dev_spmv(L, h, fmt, A, dA, x, y, alpha, beta, base=None, ridx=None, rs_null=False, avg=None,
+             inplace=False):
+    """Run one SpMV through the C ABI of library L on device buffers.
+    dA: dict of device tensors of the format arrays.  Returns z as numpy."""
+    import torch
+    s = sym_of(A.values.dtype)
+    t = TYPES[s]
+    dx = to_dev(x)
+    dy = to_dev(y)
+    if inplace:
+        dz = dy
+    else:
+        dz = torch.full((A.nrows,), float("nan"), dtype=dx.dtype, device="cuda")
+    dr = to_dev(ridx)
+    dev_spmv_ptr(L, h, fmt, A, dA, dz, dx, dy, alpha, beta, base=base, dr=dr, rs_null=rs_null, avg=avg)
     torch.cuda.synchronize()
     return dz.cpu().numpy()
 
