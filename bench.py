@@ -23,6 +23,7 @@ pinned host memory and z going back to it inside the timed region.
 from __future__ import annotations
 
 import argparse
+import atexit
 import ctypes
 import json
 import os
@@ -54,6 +55,10 @@ def measured_peak():
 # --------------------------------------------------------------------------- #
 
 class ClockSampler:
+    """`nvidia-smi -lms 20` in the background.  The first query on a fresh box can take over a second, so the
+    process is started well before the timed region; `mark()` is called when the warm-up begins and only the
+    lines printed after it count.  If none has arrived by `stop()`, the GPU is kept busy with more (untimed) steps
+    until one does -- a sample taken on an idle GPU would say nothing about the clocks under load."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -61,7 +66,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []                 # (monotonic time, text)
+        self.t_mark = 0.0
 
     def start(self):
         try:
@@ -70,35 +76,55 @@ class ClockSampler:
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            atexit.register(self._kill)         # a path that leaves without stop() must not leave nvidia-smi behind
         except Exception:
             self.proc = None
 
+    def _kill(self):
+        if self.proc and self.proc.poll() is None:
+            self.proc.kill()
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        self.t_mark = time.monotonic()
+
+    def _parsed(self):
+        out = []
+        for t, ln in list(self.lines):
+            f = [x.strip() for x in ln.split(",")]
+            if t < self.t_mark or len(f) < 9:
+                continue
+            try:
+                out.append((float(f[1]), float(f[2]), f[5:9]))
+            except ValueError:
+                continue
+        return out
+
+    def stop(self, keep_busy=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        extended = False
+        t0 = time.monotonic()
+        while keep_busy is not None and not self._parsed() and time.monotonic() - t0 < 5.0 and self.proc.poll() is None:
+            keep_busy()                 # still the same kernels on the same stream, just not timed
+            extended = True
+        time.sleep(0.15 if not extended else 0.0)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = self._parsed()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
+        reasons = set()
+        for _, _, flags in rows:
+            for name, v in zip(names, flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        sm, mx = [r[0] for r in rows], [r[1] for r in rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
@@ -721,6 +747,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # the first query on a fresh box can take over a second: start long before the timed region
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     if args.workload not in ("cfg5", "cfg2", "cfg4") and world > 1:
@@ -826,7 +855,7 @@ def main():
     # working sets that are not >> L2 (126 MB): evict it between timed steps by READING a 512 MB
     # scratch (a write-flush would leave 126 MB of dirty lines whose write-back lands inside the
     # timed kernel: +19 us on kernels that take 12-80 us)
-    flush_l2 = (w["bytes"] / max(world, 1)) < 8 * 126e6
+    flush_l2 = w["bytes"] < 8 * 126e6          # w["bytes"] is what THIS rank's kernel touches per launch
     scratch = torch.zeros(64 * 1024 * 1024, dtype=torch.int64, device=device) if flush_l2 else None
 
     def flush():
@@ -938,9 +967,8 @@ def main():
     halo_trace = bool(os.environ.get("SPGPU_BENCH_TRACE")) and peer is not None and args.halo == "fused"
     if halo_trace:
         L.spgpuSetTuning(h, b"haloTrace", 1)
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()                 # nvidia-smi needs ~0.1 s to start printing: begin before the warm-up
+        sampler.mark()                  # lines printed from here on are "during the measurement"
     for _ in range(W):
         one_step()
     barrier()
@@ -1024,7 +1052,11 @@ def main():
         ker_b2b_ms = float(tb.item())
     # the sampler has been running since before the warm-up: it covers the timed steps AND the kernel-alone launches
     # the roofline is computed from (a 40 ms timed region alone is one or two nvidia-smi samples)
-    clocks = sampler.stop() if rank == 0 else None
+    def keep_busy():
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop(keep_busy) if rank == 0 else None
     peak, peak_src = measured_peak()
     achieved = w["bytes"] / (ker_ms * 1e-3) / 1e9
     traffic = None
