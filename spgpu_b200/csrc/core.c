@@ -19,7 +19,7 @@ static void default_tuning(SpgpuTuning* t)
 {
 	t->hellVariant = 0;
 	t->hellBlock = 0;          /* 0 = per-type default occupancy, <=64 force 32 warps, >=256 force 48 */
-	t->hellLongFactor = 4;     /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike */
+	t->hellLongFactor = 2;     /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike */
 	t->hellSplit = 0;
 	t->hdiaVariant = 0;
 	t->hdiaBlock = 0;

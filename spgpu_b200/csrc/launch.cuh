@@ -28,7 +28,7 @@ static inline void spgpu_count_launch(spgpuHandle_t handle)
 
 static inline const SpgpuTuning* spgpu_tuning(spgpuHandle_t handle)
 {
-	static const SpgpuTuning fallback = { 0, 0, 4, 0, 0, 0, 0, 8, 8, 20000, 0, 0, 0, 0, 0, 0, 1 };
+	static const SpgpuTuning fallback = { 0, 0, 2, 0, 0, 0, 0, 8, 8, 20000, 0, 0, 0, 0, 0, 0, 1 };
 	SpgpuHandlePriv* h = spgpuPriv(handle);
 	return h->magic == SPGPU_PRIV_MAGIC ? &h->tune : &fallback;
 }
@@ -87,10 +87,13 @@ static inline int spgpu_hell_prefetch(spgpuHandle_t handle, const SpgpuTuning* t
 	return waves * 10 * 4 * (handle->multiProcessorCount > 0 ? handle->multiProcessorCount : 148);
 }
 
-/* rows deeper than this many slots count as spikes (spmv_slots.cuh decides per warp what to do with them) */
+/* rows deeper than this many slots count as spikes (spmv_slots.cuh decides per warp what to do with them).  The factor:
+ * on Pareto row lengths (mean 8 .. 64, caps 64 .. 4096, float and double, bench/longfactor_probe.py,
+ * profiles/r2_longfactor.jsonl) 2 x the average beats 3, 4 and 6 by 1 - 14 %, and 1 x loses 11 % once the average
+ * reaches 32; uniform lengths do not care. */
 static inline int spgpu_long_cut(const SpgpuTuning* t, int avgNnzPerRow)
 {
-	long long cut = (long long)(t->hellLongFactor > 0 ? t->hellLongFactor : 4) * (avgNnzPerRow > 0 ? avgNnzPerRow : 1);
+	long long cut = (long long)(t->hellLongFactor > 0 ? t->hellLongFactor : 2) * (avgNnzPerRow > 0 ? avgNnzPerRow : 1);
 	if (cut < 32) cut = 32;
 	if (cut > (1 << 30)) cut = 1 << 30;
 	return (int)cut;

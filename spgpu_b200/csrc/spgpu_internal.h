@@ -33,7 +33,7 @@ extern "C" {
 typedef struct SpgpuTuning {
 	int hellVariant;     /* 0 auto, 1 direct loads predicated on rS, 2 direct loads with unpredicated slab reads, 3 bulk-async (TMA) pipeline */
 	int hellBlock;       /* occupancy knob: 0 per-type default, <=64 force 32 warps/SM, 192 force 40, >=256 force 48 */
-	int hellLongFactor;  /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike (default 4) */
+	int hellLongFactor;  /* a row deeper than factor x avgNnzPerRow (>= 32) slots counts as a spike (default 2: bench/longfactor_probe.py) */
 	int hellSplit;       /* long-hack split mode: 0 auto (on when rIdx is given), 1 on, -1 off, >1 on with that queue capacity */
 	int hdiaVariant;     /* 0/1 direct (unpredicated cell loads), 2 x windows staged in shared memory, 3 direct with predicated cell loads, 4 bulk-async (TMA) pipeline, 5 persistent with metadata prefetch, 6/7 per-warp slab by bulk copy with 16/32 x gathers in flight (hackSize 32) */
 	int hdiaBlock;       /* occupancy knob: 8 -> rounds of 8 diagonals instead of 9, 64 -> 64-thread CTAs, 160 -> 24 warps/SM with twice the unroll, 176 -> 36, 192 -> 40, 224 -> 48 warps with UNROLL 4, >=256 -> 48 (default 32); variants 6/7: 1..32 = diagonals per warp slice */
