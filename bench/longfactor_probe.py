@@ -15,7 +15,7 @@ def main():
     import numpy as np
     import torch
     from spgpu_b200 import capi, device_build as DB
-    L = capi.lib()
+    L = capi.SpgpuLib(os.environ["SPGPU_LIB"]) if os.environ.get("SPGPU_LIB") else capi.lib()      # A/B builds
     h = ctypes.c_void_p()
     assert L.spgpuCreate(ctypes.byref(h), 0) == 0
     stream = torch.cuda.Stream()

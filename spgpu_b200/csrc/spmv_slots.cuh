@@ -38,6 +38,13 @@
 
 #include "numeric.cuh"
 
+/* rounds of 32 slots a warp keeps in flight while it finishes a spike row (phase 2).  8 and 16 were tried to shorten the
+ * walk of a 4096-slot row: the extra registers spill (double: 12 -> 144 bytes) and EVERY matrix pays -- 14 irregular matrices
+ * 3 - 15 % slower at 8, 30 - 50 % at 16, and the 512^3 Laplacian, which never enters phase 2, 2.144 -> 2.215 ms. */
+#ifndef SPGPU_PHASE2_UNROLL
+#define SPGPU_PHASE2_UNROLL 4
+#endif
+
 template <typename T, int UNROLL, int STRIDE, class XG>
 __device__ __forceinline__ T warp_rows_dot_x(
 	const T* __restrict__ vals, const int* __restrict__ idxs,   /* already at this lane's slot 0 */
@@ -133,6 +140,8 @@ __device__ __forceinline__ T warp_rows_dot_x(
 	}
 
 	/* ---- phase 2: spike rows, all lanes on one row ---- */
+	/* One warp walks the whole row, and every round is two memory latencies (slot, then x): P2U rounds in flight. */
+	constexpr int P2U = SPGPU_PHASE2_UNROLL;
 	unsigned todo = __ballot_sync(SPGPU_FULL_MASK, rowLen > cut);
 	while (todo) {
 		const int r = __ffs(todo) - 1;
@@ -142,11 +151,11 @@ __device__ __forceinline__ T warp_rows_dot_x(
 		const T* rv = vals + (r - lane);
 		const int* ri = idxs + (r - lane);
 		T part = Num<T>::zero();
-		for (int k0 = cut + lane; k0 < len; k0 += 32 * 4) {
-			int col[4];
-			T a[4];
+		for (int k0 = cut + lane; k0 < len; k0 += 32 * P2U) {
+			int col[P2U];
+			T a[P2U];
 #pragma unroll
-			for (int u = 0; u < 4; ++u) {
+			for (int u = 0; u < P2U; ++u) {
 				const int k = k0 + 32 * u;
 				const bool on = k < len;
 				col[u] = baseIndex;
@@ -156,14 +165,17 @@ __device__ __forceinline__ T warp_rows_dot_x(
 					a[u] = ld_stream64(rv + k * valStride);
 				}
 			}
+			T xv[P2U];
 #pragma unroll
-			for (int u = 0; u < 4; ++u) {
+			for (int u = 0; u < P2U; ++u) {
 				const bool on = (k0 + 32 * u) < len;
-				T xv = Num<T>::zero();
+				xv[u] = Num<T>::zero();
 				if (on)
-					xv = xg.ld(col[u] - baseIndex);
-				part = Num<T>::fma(a[u], xv, part);
+					xv[u] = xg.ld(col[u] - baseIndex);
 			}
+#pragma unroll
+			for (int u = 0; u < P2U; ++u)
+				part = Num<T>::fma(a[u], xv[u], part);
 		}
 		part = warp_sum<T>(part);
 		if (lane == r)
