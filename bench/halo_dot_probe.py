@@ -17,7 +17,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     parts = int(os.environ.get("PROBE_PARTS", "2"))           # the slab is rank 1 of `parts` ranks (both neighbours when parts > 2)
-    L = capi.lib()
+    L = capi.SpgpuLib(os.environ["SPGPU_LIB"]) if os.environ.get("SPGPU_LIB") else capi.lib()      # A/B builds
     h = ctypes.c_void_p()
     assert L.spgpuCreate(ctypes.byref(h), 0) == 0
     stream = torch.cuda.Stream()

@@ -165,17 +165,14 @@ __device__ __forceinline__ T warp_rows_dot_x(
 					a[u] = ld_stream64(rv + k * valStride);
 				}
 			}
-			T xv[P2U];
 #pragma unroll
 			for (int u = 0; u < P2U; ++u) {
 				const bool on = (k0 + 32 * u) < len;
-				xv[u] = Num<T>::zero();
+				T xv = Num<T>::zero();
 				if (on)
-					xv[u] = xg.ld(col[u] - baseIndex);
+					xv = xg.ld(col[u] - baseIndex);
+				part = Num<T>::fma(a[u], xv, part);
 			}
-#pragma unroll
-			for (int u = 0; u < P2U; ++u)
-				part = Num<T>::fma(a[u], xv[u], part);
 		}
 		part = warp_sum<T>(part);
 		if (lane == r)
