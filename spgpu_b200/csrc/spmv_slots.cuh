@@ -96,7 +96,7 @@ __device__ __forceinline__ T warp_rows_dot_x(
 			 * coalesced -- so it continues while at least SPIKE_ROWS rows are still active:
 			 * cut = the smallest depth with fewer than SPIKE_ROWS longer rows (binary search
 			 * on ballots). */
-			constexpr int SPIKE_ROWS = 8;
+			constexpr int SPIKE_ROWS = 8;            /* 4 and 16 measure the same (bench/longfactor_probe.py, 14 matrices) */
 			int lo = longCut, hi = longest;
 			while (lo < hi) {
 				const int mid = (lo + hi) >> 1;
