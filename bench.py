@@ -1059,10 +1059,12 @@ def main():
     clocks = sampler.stop(keep_busy) if rank == 0 else None
     peak, peak_src = measured_peak()
     achieved = w["bytes"] / (ker_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, limiter = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{args.workload}_n{world}")
+            tj = json.load(f)
+        traffic = tj.get(f"{args.workload}_n{world}")
+        limiter = (tj.get("_limiters") or {}).get(f"{args.workload}_n{world}")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -1071,6 +1073,8 @@ def main():
                 # the same kernel launched K times back to back WITHOUT the exchange (max over ranks): the partitioned
                 # step minus this is what the halo exchange costs
                 "kernel_back_to_back_ms": ker_b2b_ms}
+    if limiter:
+        roofline["limiter_ncu"] = limiter          # the kernel is not DRAM-bound: what ncu says it is bound by
     if w["kind"] == "hell":
         # what the FORMAT costs at the fetch granularities the hardware has: matrix bytes only
         try:
