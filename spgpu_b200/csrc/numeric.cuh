@@ -150,11 +150,12 @@ template <typename T> struct XPlain {
 
 /* x entries that a PEER GPU may write during the launch (halo zones of the fused kernels, ext_halo.cu): plain weak
  * loads (ld.global, SASS LDG.E) -- inside the memory model, ordered after the CTA's acquire on the ready flag; .nc
- * loads are not */
+ * loads are not.  (L1::evict_last on these loads measures the same as the default policy.) */
 template <typename T> struct XWeak {
 	const T* x;
 	__device__ __forceinline__ T ld(int c) const { return x[c]; }
 };
+
 
 /* ---- warp helpers --------------------------------------------------------- */
 
