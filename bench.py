@@ -1313,7 +1313,8 @@ def main():
             allred = (lambda t: dist.all_reduce(t)) if world > 1 else None
         # the scalars of the device flavour are all-reduced by the last CTA of the kernel that produces them
         # (no separate launch) when the peer all-reduce is in use
-        cg = krylov.Cg(L, h, st, apply_A, apply_A_dot, allred, ar_fused=peer_ar if apply_A_dot is not None else None)
+        cg = krylov.Cg(L, h, st, apply_A, apply_A_dot, allred, ar_fused=peer_ar if apply_A_dot is not None else None,
+                       pingpong=True)
         bvec = torch.rand(rows, generator=gen, device=device, dtype=torch.float64)
         iters = 10
         cg_out = {"iterations": iters}
@@ -1394,6 +1395,7 @@ def main():
                                                 links, 0, dres, ar)
                         L.spgpuHaloSeqAdvance(h)
                     cg.apply_A_dot = apply_A_dot_dev
+                cg.pingpong = False                      # ONE captured iteration is replayed: its scalar slots are frozen
                 cg.start(bvec)
                 for _ in range(2):
                     cg.step_device()

@@ -66,7 +66,8 @@ struct spgpuMgVector {
 struct spgpuMgCg {
 	spgpuMgMatrix_t A;
 	spgpuMgVector_t x, r, p, ap;
-	double* s[MG_MAX_RANKS];          /* device scalars: [rr, pAp, rr', -] */
+	double* s[MG_MAX_RANKS];          /* device scalars: [rr, pAp, rr', -]; slots 0 and 2 swap roles every iteration */
+	unsigned iter;                    /* iterations done on the devices: r.r of the current iterate is in slot 2 * (iter & 1) */
 	double rr;                        /* host copy (blocking recurrence) */
 };
 
@@ -1116,6 +1117,7 @@ spgpuStatus_t spgpuMgDcgStart(spgpuMgCg_t cg, spgpuMgVector_t b, double* rr0)
 		cudaMemcpyAsync(owned_ptr(cg->p, r), owned_ptr(b, r), bytes, cudaMemcpyDeviceToDevice, s);
 	}
 	st = spgpuMgDdot(mg, &cg->rr, cg->r, cg->r);
+	cg->iter = 0;
 	for (r = 0; r < mg->world && st == SPGPU_SUCCESS; ++r) {
 		use_rank(mg, r);
 		if (cudaMemcpy(cg->s[r], &cg->rr, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -1144,6 +1146,7 @@ spgpuStatus_t spgpuMgDcgStep(spgpuMgCg_t cg, int iterations, double* rr)
 			tables[r] = mg->arTable[r];
 		for (it = 0; it < iterations; ++it) {
 			const unsigned seq = ++mg->haloSeq;
+			const int cur = 2 * (int)(cg->iter & 1u), nxt = 2 - cur;   /* "rr <- rr'" is a swap of roles, not a kernel */
 			spgpuPeerAllreduce ar;
 			ar.world = mg->world;
 			ar.tables = tables;
@@ -1167,19 +1170,20 @@ spgpuStatus_t spgpuMgDcgStep(spgpuMgCg_t cg, int iterations, double* rr)
 				ar.myRank = r;
 				spgpuDcgUpdateDev(mg->h[r], (double*)owned_ptr(cg->x, r), (double*)owned_ptr(cg->r, r),
 					(const double*)owned_ptr(cg->p, r), (const double*)owned_ptr(cg->ap, r), MG_ROWS(A, r),
-					cg->s[r], cg->s[r] + 1, cg->s[r] + 2, mg->world > 1 ? &ar : NULL);
+					cg->s[r] + cur, cg->s[r] + 1, cg->s[r] + nxt, mg->world > 1 ? &ar : NULL);
 			}
-			for (r = 0; r < mg->world; ++r) {            /* p = r + (rr'/rr) p ; rr <- rr' */
+			for (r = 0; r < mg->world; ++r) {            /* p = r + (rr'/rr) p */
 				use_rank(mg, r);
-				spgpuDaxpbyDev(mg->h[r], (double*)owned_ptr(cg->p, r), MG_ROWS(A, r), cg->s[r] + 2, cg->s[r], 1.0,
+				spgpuDaxpbyDev(mg->h[r], (double*)owned_ptr(cg->p, r), MG_ROWS(A, r), cg->s[r] + nxt, cg->s[r] + cur, 1.0,
 					(const double*)owned_ptr(cg->p, r), NULL, NULL, 1.0, (const double*)owned_ptr(cg->r, r));
-				spgpuDscal(mg->h[r], cg->s[r], 1, 1.0, cg->s[r] + 2);
 			}
+			++cg->iter;
 		}
 		st = check_launches();
 		if (rr && st == SPGPU_SUCCESS) {
 			use_rank(mg, 0);
-			if (cudaMemcpyAsync(mg->hostSlots, cg->s[0], sizeof(double), cudaMemcpyDeviceToHost, rank_stream(mg, 0)) != cudaSuccess)
+			if (cudaMemcpyAsync(mg->hostSlots, cg->s[0] + 2 * (cg->iter & 1u), sizeof(double), cudaMemcpyDeviceToHost,
+					rank_stream(mg, 0)) != cudaSuccess)
 				st = SPGPU_UNSPECIFIED;
 			if (st == SPGPU_SUCCESS)
 				st = spgpuMgSynchronize(mg);

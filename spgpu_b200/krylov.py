@@ -48,10 +48,16 @@ class Cg:
     tensor over the ranks (a collective of its own); ar_fused: a mg.PeerAllreduce whose exchange the
     producing kernels run themselves."""
 
-    def __init__(self, L, handle, state: CgState, apply_A, apply_A_dot=None, allreduce=None, ar_fused=None):
+    def __init__(self, L, handle, state: CgState, apply_A, apply_A_dot=None, allreduce=None, ar_fused=None,
+                 pingpong=False):
         self.L, self.h, self.st = L, handle, state
         self.apply_A, self.apply_A_dot, self.allreduce, self.ar_fused = apply_A, apply_A_dot, allreduce, ar_fused
         self.T = TYPES["D"]
+        # pingpong: r.r lives alternately in scalar slot 0 and slot 2, so that "rr <- rr'" is no kernel at all (4 launches
+        # per iteration instead of 5).  Off by default because a CUDA graph of ONE iteration freezes the slots; capture
+        # two iterations, or leave it off, when replaying a graph.
+        self.pingpong = pingpong
+        self.k = 0
 
     def start(self, b: torch.Tensor):
         """x = 0, r = p = b, rr = b.b"""
@@ -63,6 +69,7 @@ class Cg:
         if self.allreduce:
             self.allreduce(st.s[0:1])
         st.rr_host = float(st.s[0].item())
+        self.k = 0
         return st.rr_host
 
     # ---- reference-style: blocking dots, host scalars -----------------------
@@ -93,7 +100,9 @@ class Cg:
         event there to time the phases)"""
         st, L, h, n = self.st, self.L, self.h, self.st.n
         s = st.s.data_ptr()
-        rr, pap, rrn = s, s + 8, s + 16
+        cur = 2 * (self.k & 1) if self.pingpong else 0       # slot of r.r of the current iterate
+        nxt = 2 - cur
+        rr, pap, rrn = s + 8 * cur, s + 8, s + 8 * nxt
         fused = self.ar_fused
         mark = mark or (lambda _label: None)
         if self.apply_A_dot is not None:
@@ -112,16 +121,19 @@ class Cg:
         L.spgpuDcgUpdateDev(h, st.x.data_ptr(), st.r.data_ptr(), st.p.data_ptr(), st.ap.data_ptr(), n, rr, pap, rrn,
                             fused.next_ref() if fused else None)
         if self.allreduce and not fused:
-            self.allreduce(st.s[2:3])
+            self.allreduce(st.s[nxt:nxt + 1])
         mark("x, r update + r.r (+all-reduce)")
         # p = r + (rr'/rr) p ; then rr <- rr'
         L.spgpuDaxpbyDev(h, st.p.data_ptr(), n, rrn, rr, 1.0, st.p.data_ptr(), 0, 0, 1.0, st.r.data_ptr())
-        # through the library so that it is ordered on the HANDLE's stream whatever torch's current stream is
-        L.spgpuDscal(h, rr, 1, self.T.scalar(1.0), rrn)
+        if self.pingpong:
+            self.k += 1                                       # the slots swap roles: nothing to copy
+        else:
+            # through the library so that it is ordered on the HANDLE's stream whatever torch's current stream is
+            L.spgpuDscal(h, rr, 1, self.T.scalar(1.0), rrn)
         mark("p update")
 
     def residual_norm2(self):
-        return float(self.st.s[0].item())
+        return float(self.st.s[2 * (self.k & 1) if self.pingpong else 0].item())
 
 
 CG_BYTES_PER_ROW_VECTOR_OPS = {

@@ -72,10 +72,11 @@ def test_fused_spmv_dot(ours, gpu_handle):
     assert abs(float(dres.item()) - float(np.dot(x, want))) <= 1e-12 * scale
 
 
-@pytest.mark.parametrize("flavour", ["blocking", "device"])
+@pytest.mark.parametrize("flavour", ["blocking", "device", "device-pingpong"])
 def test_cg_converges_like_the_cpu_recurrence(ours, gpu_handle, flavour):
     """40 CG iterations on a 3-D Laplacian: same residual history as the identical
-    recurrence run with numpy + the CPU oracle, and the final x solves the system"""
+    recurrence run with numpy + the CPU oracle, and the final x solves the system
+    (device-pingpong: r.r alternates between two scalar slots instead of being copied, 4 launches per iteration)"""
     import torch
     from spgpu_b200 import krylov
     coo = G.laplace3d_7pt(16)
@@ -96,9 +97,10 @@ def test_cg_converges_like_the_cpu_recurrence(ours, gpu_handle, flavour):
     stream = torch.cuda.ExternalStream(ours.spgpuGetStream(gpu_handle))
     with torch.cuda.stream(stream):
         st = krylov.CgState(n, 0, "cuda")
-        cg = krylov.Cg(ours, gpu_handle, st, apply_A, apply_A_dot)
+        cg = krylov.Cg(ours, gpu_handle, st, apply_A, apply_A_dot, pingpong=flavour == "device-pingpong")
         rr0 = cg.start(util.to_dev(b))
         hist = []
+        launches0 = ours.spgpuGetLaunchCount(gpu_handle)
         for _ in range(40):
             if flavour == "blocking":
                 hist.append(cg.step_blocking())
@@ -106,6 +108,8 @@ def test_cg_converges_like_the_cpu_recurrence(ours, gpu_handle, flavour):
                 cg.step_device()
                 hist.append(cg.residual_norm2())
         torch.cuda.synchronize()
+        per_iteration = (ours.spgpuGetLaunchCount(gpu_handle) - launches0) / 40
+        assert per_iteration == {"blocking": 6, "device": 5, "device-pingpong": 4}[flavour]
         x_gpu = st.x.cpu().numpy()
     # CPU recurrence with the oracle SpMV
     x = np.zeros(n); r = b.copy(); p = b.copy(); rr = float(r @ r)
