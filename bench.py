@@ -1075,6 +1075,32 @@ def main():
                 "kernel_back_to_back_ms": ker_b2b_ms}
     if limiter:
         roofline["limiter_ncu"] = limiter          # the kernel is not DRAM-bound: what ncu says it is bound by
+    if flush_l2 and world == 1:
+        # SHORT problems (cfg1: 80 MB = 12 us at the long-copy peak): launch ramp, the last partial wave and the cold L2 are a
+        # visible part of the run whatever the kernel does.  The practical ceiling is a pure stream of the SAME number of
+        # bytes under the SAME protocol (flush, one event pair per launch): spgpuDscal, n doubles read + n written.
+        try:
+            ns = max(1, int(w["bytes"] // 16))
+            sx = torch.rand(ns, dtype=torch.float64, device=device)
+            sz = torch.empty(ns, dtype=torch.float64, device=device)
+            one_and_half = capi.TYPES["D"].scalar(1.5)
+            ts = []
+            for it in range(13):
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                L.spgpuDscal(h, sz.data_ptr(), ns, one_and_half, sx.data_ptr())
+                b.record(stream)
+                b.synchronize()
+                if it >= 3:
+                    ts.append(a.elapsed_time(b))
+            stream_ms = float(np.mean(ts))
+            roofline["same_size_stream"] = {"op": "spgpuDscal, the same bytes, the same protocol", "bytes": 16 * ns, "ms": stream_ms,
+                                            "frac_of_peak": 16 * ns / (stream_ms * 1e-3) / 1e9 / peak,
+                                            "kernel_vs_stream": stream_ms * (w["bytes"] / (16 * ns)) / ker_ms}
+            del sx, sz
+        except Exception as exc:
+            print(f"same-size stream not measured: {exc!r}", file=sys.stderr, flush=True)
     if w["kind"] == "hell":
         # what the FORMAT costs at the fetch granularities the hardware has: matrix bytes only
         try:
