@@ -39,9 +39,9 @@ def test_c_driver_runs_and_agrees_with_its_host_loop(tmp_path, case):
     assert p.stdout.count(" ok") == 3 and "FAILED" not in p.stdout
 
 
-def build_mg(tmp_path):
-    exe = str(tmp_path / "mg_cg")
-    cmd = ["gcc", "-O2", "-fopenmp", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "mg_cg.c"), f"-I{ROOT}/include",
+def build_mg(tmp_path, name="mg_cg"):
+    exe = str(tmp_path / name)
+    cmd = ["gcc", "-O2", "-fopenmp", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", name + ".c"), f"-I{ROOT}/include",
            "-I/usr/local/cuda/include", f"-L{ROOT}/spgpu_b200/lib", "-lspgpu", f"-Wl,-rpath,{ROOT}/spgpu_b200/lib",
            "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-o", exe]
     p = subprocess.run(cmd, capture_output=True, text=True)
@@ -51,6 +51,7 @@ def build_mg(tmp_path):
 
 def test_multi_gpu_c_driver_compiles_against_the_headers(tmp_path):
     build_mg(tmp_path)
+    build_mg(tmp_path, "mg_hdia")
 
 
 @pytest.mark.gpu
@@ -62,3 +63,14 @@ def test_multi_gpu_c_driver_runs(tmp_path, ranks):
     p = subprocess.run([exe, "32", str(ranks), "5", "40"], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "OK" in p.stdout and "FAILED" not in p.stdout and "(0 rows over 1e-12)" in p.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [1, 2, 3])
+def test_multi_gpu_hdia_c_driver_runs(tmp_path, ranks):
+    """examples/mg_hdia.c: the 27-point stencil converted with the library's own cooToHdia, partitioned by
+    spgpuMgDhdiaCreate, multiplied through spgpuMgDhdiaspmv / spgpuMgDspmv, solved with CG -- no Python"""
+    exe = build_mg(tmp_path, "mg_hdia")
+    p = subprocess.run([exe, "24", str(ranks), "5", "25"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "OK" in p.stdout and "FAILED" not in p.stdout and "(0 rows over 1e-12)" in p.stdout and "fits" in p.stdout
