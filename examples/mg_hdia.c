@@ -160,10 +160,11 @@ int main(int argc, char** argv)
 		OK(spgpuMgDhdiaspmv(mg, vb, NULL, 1.0, A, vx, 0.0));
 		OK(spgpuMgDcgCreate(A, &cg));
 		OK(spgpuMgDcgStart(cg, vb, &rr0));
+		OK(spgpuMgDcgStep(cg, 2, &rr));                      /* untimed: the first launches of a process are not the iteration's cost */
 		t0 = now();
 		OK(spgpuMgDcgStep(cg, iters, &rr));
 		dt = (now() - t0) / (iters > 0 ? iters : 1);
-		printf("CG: r.r %.6e -> %.6e after %d iterations, %.4f ms per iteration\n", rr0, rr, iters, dt * 1e3);
+		printf("CG: r.r %.6e -> %.6e after 2 + %d iterations, %.4f ms per iteration\n", rr0, rr, iters, dt * 1e3);
 		if (!(rr < rr0))
 			++bad;
 		spgpuMgDcgDestroy(cg);
