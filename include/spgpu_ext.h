@@ -314,6 +314,18 @@ typedef struct spgpuHaloLinks {
 SPGPU_FOR_FLOAT_TYPES(SPGPU_DECL_SPMV_HALO)
 
 /*
+ * The block schedule of the fused kernels, host arithmetic only (no device is touched; the CPU tests sweep it):
+ * plan[0] = headBlocks (128-row blocks [0, headBlocks) hold a row of [0, haloN): they wait for the lower zone),
+ * plan[1] = firstHiBlock (blocks from there on hold a row of [rows - haloN, rows): they wait for the upper zone;
+ * 0xffffffff without an upper neighbour), plan[2..5] = early, nLo, nHi, hiStart: CTA c (counted behind the push CTAs)
+ * multiplies block spgpuHaloBlockOf(plan, c) -- `early` interior blocks first, then the nLo lower-boundary blocks, the
+ * nHi upper-boundary blocks from hiStart, then the remaining interior blocks.  Returns 0, or -1 for bad arguments.
+ */
+int spgpuHaloBlockPlan(int rows, int haloN, int hasLowerNeighbour, int hasUpperNeighbour, int multiProcessorCount,
+	unsigned* plan /* 6 words */);
+unsigned spgpuHaloBlockOf(const unsigned* plan, unsigned cta);
+
+/*
  * Sequence numbers in device memory, so that a partitioned iteration can be captured ONCE in a CUDA
  * graph and replayed (a by-value seq would be frozen into the graph).  After spgpuSetSeqCounters the
  * fused halo kernels and the all-reduces, when called with seq == 0, take their sequence number from

@@ -126,7 +126,7 @@ def abi_symbols():
 def ext_symbols():
     """Every symbol include/spgpu_ext.h declares (additive API)."""
     names = ["spgpuB200Version", "spgpuGetLaunchCount", "spgpuSetTuning", "spgpuGetTuning",
-             "spgpuGetDeviceStatus", "spgpuReserveScratch"]
+             "spgpuGetDeviceStatus", "spgpuReserveScratch", "spgpuHaloBlockPlan", "spgpuHaloBlockOf"]
     for s in FLOAT_SYMS:
         names += [f"spgpu{s}dotDev", f"spgpu{s}nrm2sqDev", f"spgpu{s}sumDev", f"spgpu{s}allreduceSumDev",
                   f"spgpu{s}axpbyDev", f"spgpu{s}hellspmvDot", f"spgpu{s}cgUpdateDev",
@@ -267,6 +267,10 @@ class SpgpuLib:
                 f[f"spgpu{s}nrm2sqDev"] = _sig(d, f"spgpu{s}nrm2sqDev", None, [H, c_int, P, P], optional=True)
             f["spgpuGetDeviceStatus"] = _sig(d, "spgpuGetDeviceStatus", c_int, [H, c_int], optional=True)
             f["spgpuReserveScratch"] = _sig(d, "spgpuReserveScratch", c_int, [H, c_size_t], optional=True)
+            f["spgpuHaloBlockPlan"] = _sig(d, "spgpuHaloBlockPlan", c_int,
+                [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_uint)], optional=True)
+            f["spgpuHaloBlockOf"] = _sig(d, "spgpuHaloBlockOf", ctypes.c_uint, [ctypes.POINTER(ctypes.c_uint), ctypes.c_uint],
+                                         optional=True)
             LK, AR, U = ctypes.POINTER(HaloLinks), ctypes.POINTER(PeerAllreduceArgs), ctypes.c_uint
             for s in FLOAT_SYMS:
                 T = TYPES[s].ctype

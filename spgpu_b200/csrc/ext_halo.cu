@@ -301,14 +301,55 @@ struct HdiaRowBody {
  * widths): it then waits for both words.
  */
 /* which 128-row block the CTA multiplies (the order is worked out on the host: halo_args) */
+__host__ __device__ __forceinline__ unsigned halo_block_of(unsigned b, unsigned early, unsigned nLo, unsigned nHi, unsigned hiStart)
+{
+	if (b < early) return nLo + b;                                      /* most of the interior first */
+	if (b < early + nLo) return b - early;                              /* then the lower boundary    */
+	if (b < early + nLo + nHi) return hiStart + (b - early - nLo);      /* the upper boundary         */
+	return b - nHi;                                                     /* the rest of the interior   */
+}
+
 template <typename T>
 __device__ __forceinline__ unsigned halo_row_block(const HaloArgs<T>& hx)
 {
-	const unsigned b = blockIdx.x - hx.pushCtas;
-	if (b < hx.early) return hx.nLo + b;                                            /* most of the interior first */
-	if (b < hx.early + hx.nLo) return b - hx.early;                                 /* then the lower boundary    */
-	if (b < hx.early + hx.nLo + hx.nHi) return hx.hiStart + (b - hx.early - hx.nLo);   /* the upper boundary      */
-	return b - hx.nHi;                                                              /* the rest of the interior   */
+	return halo_block_of(blockIdx.x - hx.pushCtas, hx.early, hx.nLo, hx.nHi, hx.hiStart);
+}
+
+/* which row blocks wait for a zone and in which order the blocks are multiplied: host arithmetic only, shared by
+ * halo_args below and by spgpuHaloBlockPlan (spgpu_ext.h), which the CPU tests sweep over (rows, haloN) */
+struct HaloBlockPlan { unsigned headBlocks, firstHiBlock, early, nLo, nHi, hiStart; };
+
+static HaloBlockPlan halo_block_plan(int rows, int haloN, bool lo, bool hi, int multiProcessorCount)
+{
+	HaloBlockPlan p;
+	const int n = haloN < rows ? haloN : rows;
+	/* rows [0, haloN) may read the lower zone, rows [rows - haloN, rows) the upper one (band |col - row| <= haloN) */
+	p.headBlocks = lo ? (unsigned)((n + 127) / 128) : 0u;
+	p.firstHiBlock = hi ? (unsigned)((rows - n) / 128) : 0xffffffffu;
+	const unsigned rowBlocks = (unsigned)((rows + 127) / 128);
+	const unsigned fillerCap = 3u * 10u * (unsigned)multiProcessorCount;    /* about three waves */
+	p.nLo = p.headBlocks < rowBlocks ? p.headBlocks : rowBlocks;
+	p.hiStart = p.firstHiBlock < rowBlocks ? p.firstHiBlock : rowBlocks;
+	if (p.hiStart < p.nLo) p.hiStart = p.nLo;
+	p.nHi = rowBlocks - p.hiStart;
+	const unsigned interior = p.hiStart - p.nLo;
+	const unsigned filler = (interior >> 2) < fillerCap ? (interior >> 2) : fillerCap;
+	p.early = interior - filler;
+	return p;
+}
+
+extern "C" int spgpuHaloBlockPlan(int rows, int haloN, int hasLower, int hasUpper, int multiProcessorCount, unsigned* plan)
+{
+	if (rows < 0 || haloN < 0 || multiProcessorCount < 1 || !plan)
+		return -1;
+	const HaloBlockPlan p = halo_block_plan(rows, haloN, hasLower != 0 && haloN > 0, hasUpper != 0 && haloN > 0, multiProcessorCount);
+	plan[0] = p.headBlocks; plan[1] = p.firstHiBlock; plan[2] = p.early; plan[3] = p.nLo; plan[4] = p.nHi; plan[5] = p.hiStart;
+	return 0;
+}
+
+extern "C" unsigned spgpuHaloBlockOf(const unsigned* plan, unsigned cta)
+{
+	return halo_block_of(cta, plan[2], plan[3], plan[4], plan[5]);
 }
 
 /*
@@ -422,7 +463,6 @@ static HaloArgs<T> halo_args(spgpuHandle_t handle, T* xExt, int rows, int haloN,
 	const bool lo = L && L->peerFlagsLo && haloN > 0, hi = L && L->peerFlagsHi && haloN > 0;
 	/* a rank with a neighbour sends its first / last haloN OWNED entries: it must own at least that many
 	 * (the host layers check this: mg.py _check_block, spgpuMg*Create) */
-	const int n = haloN < rows ? haloN : rows;
 	hx.n = haloN;
 	if (lo) {
 		hx.dstLo = (T*)L->peerLoUpperZone;
@@ -444,21 +484,14 @@ static HaloArgs<T> halo_args(spgpuHandle_t handle, T* xExt, int rows, int haloN,
 	hx.seqPtr = (seq == 0u && h->magic == SPGPU_PRIV_MAGIC) ? h->dHaloSeq : NULL;
 	hx.pushTicket = h->dTicket + 8;
 	hx.pushCtas = (lo || hi) ? 8 : 0;
-	/* rows [0, haloN) may read the lower zone, rows [rows - haloN, rows) the upper one (band |col - row| <= haloN) */
-	hx.headBlocks = lo ? (unsigned)((n + 127) / 128) : 0u;
-	hx.firstHiBlock = hi ? (unsigned)((rows - n) / 128) : 0xffffffffu;
 	{
-		const unsigned rowBlocks = (unsigned)((rows + 127) / 128);
-		const unsigned fillerCap = 3u * 10u * (unsigned)handle->multiProcessorCount;    /* about three waves */
-		hx.nLo = hx.headBlocks < rowBlocks ? hx.headBlocks : rowBlocks;
-		hx.hiStart = hx.firstHiBlock < rowBlocks ? hx.firstHiBlock : rowBlocks;
-		if (hx.hiStart < hx.nLo) hx.hiStart = hx.nLo;
-		hx.nHi = rowBlocks - hx.hiStart;
-		{
-			const unsigned interior = hx.hiStart - hx.nLo;
-			const unsigned filler = (interior >> 2) < fillerCap ? (interior >> 2) : fillerCap;
-			hx.early = interior - filler;
-		}
+		const HaloBlockPlan p = halo_block_plan(rows, haloN, lo, hi, handle->multiProcessorCount);
+		hx.headBlocks = p.headBlocks;
+		hx.firstHiBlock = p.firstHiBlock;
+		hx.early = p.early;
+		hx.nLo = p.nLo;
+		hx.nHi = p.nHi;
+		hx.hiStart = p.hiStart;
 	}
 	hx.spin = spin_ctl(handle);
 	hx.trace = h->magic == SPGPU_PRIV_MAGIC ? h->dTrace : NULL;

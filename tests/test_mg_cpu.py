@@ -337,3 +337,58 @@ def test_c_hdia_partition_plan_agrees_with_the_python_partition():
                             mg.split_hdia(hdia, world, r, halo.value - 32)
     assert L.spgpuMgHdiaPlan(2, capi.TYPES["D"].code, vals.ctypes.data, offs.ctypes.data, 48, hoff.ctypes.data, 10, 10,
                              bounds, ctypes.byref(halo), ctypes.byref(fits)) != 0
+
+
+def test_fused_kernel_block_schedule_covers_every_block_once_and_marks_every_boundary_row():
+    """spgpuHaloBlockPlan / spgpuHaloBlockOf (csrc/ext_halo.cu: the arithmetic the fused SpMV + halo kernel runs on):
+    for a sweep of (rows, haloN, neighbours) -- rows not a multiple of 128, haloN not a multiple of 128, blocks that
+    read BOTH zones, a block as small as its halo -- the CTA -> row-block map is a permutation, every block holding a
+    row of [0, haloN) waits for the lower zone, every block holding a row of [rows - haloN, rows) for the upper one
+    (round 1's schedule missed one: ADVICE r1 'high'), no interior block waits, and the boundary blocks come after
+    the `early` interior ones"""
+    import ctypes
+    from spgpu_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(3)
+    cases = [(1000, 128), (1000, 96), (872, 128), (4096, 4096), (4096, 2048), (130, 64), (129, 129), (128, 128), (1, 1),
+             (262144 * 64, 262144), (5037, 128), (64, 32), (0, 0), (300, 0)]
+    cases += [(int(r), int(h)) for r, h in zip(rng.integers(1, 200000, 60), rng.integers(1, 3000, 60))]
+    for rows, halo in cases:
+        halo = min(halo, rows)                      # a rank with a neighbour owns at least haloN rows
+        for lo, hi in ((1, 1), (1, 0), (0, 1), (0, 0)):
+            for sms in (148, 4):
+                plan = (ctypes.c_uint * 6)()
+                assert L.spgpuHaloBlockPlan(rows, halo, lo, hi, sms, plan) == 0
+                head, first_hi, early, n_lo, n_hi, hi_start = list(plan)
+                blocks = -(-rows // 128)
+                if blocks <= 20000:
+                    order = [L.spgpuHaloBlockOf(plan, c) for c in range(blocks)]
+                    assert sorted(order) == list(range(blocks)), (rows, halo, lo, hi)
+                    pos = {b: c for c, b in enumerate(order)}
+                else:                                  # the 512^3 slab: spot-check the map instead of enumerating 2 M blocks
+                    probe = [0, 1, early - 1, early, early + n_lo - 1, early + n_lo, early + n_lo + n_hi - 1,
+                             early + n_lo + n_hi, blocks - 1]
+                    order = None
+                    seen = {L.spgpuHaloBlockOf(plan, c) for c in probe if 0 <= c < blocks}
+                    assert len(seen) == len({c for c in probe if 0 <= c < blocks}) and max(seen) < blocks
+                need_lo = lambda b: b < head
+                need_hi = lambda b: b >= first_hi
+                if lo and halo > 0:
+                    assert all(need_lo(i // 128) for i in {0, halo - 1, halo // 2})
+                    assert head == -(-halo // 128)
+                else:
+                    assert head == 0
+                if hi and halo > 0:
+                    assert all(need_hi(i // 128) for i in {rows - halo, rows - 1, rows - 1 - halo // 2})
+                    # ... and no block below the first upper-zone row's block waits for it
+                    assert first_hi == (rows - halo) // 128
+                else:
+                    assert first_hi == 0xffffffff
+                if order is not None and blocks:
+                    boundary = [b for b in range(blocks) if need_lo(b) or need_hi(b)]
+                    interior = [b for b in range(blocks) if not (need_lo(b) or need_hi(b))]
+                    assert len(interior) == (hi_start - n_lo if (lo or hi) and halo > 0 else blocks) or not boundary
+                    if boundary and interior:
+                        assert min(pos[b] for b in boundary) >= early
+                        assert sorted(pos[b] for b in interior)[:early] == list(range(early))
+    assert L.spgpuHaloBlockPlan(-1, 0, 0, 0, 148, (ctypes.c_uint * 6)()) == -1
